@@ -1,0 +1,84 @@
+"""Definitions of the golden parity cases (inputs are regenerated from seeds; outputs are committed).
+
+Each case is a dict understood by `build_inputs`; the expected outputs in tests/golden/*.npz were
+produced by the UNMODIFIED reference module (oracle/_ref) via tests/golden/make_golden.py.
+"""
+import hashlib
+
+import numpy as np
+
+CASES = {
+    # name: n1, n2, box (x,y,z | y,z None = cubic), modes, hmin, hmax, dr, frames, same, extras
+    "cfg1_shape":   dict(n1=1000, n2=1000, box=(31.04, None, None), modes=["000"], hmin=0.0, hmax=15.0, dr=0.05, frames=3, same=True, seed=1),
+    "cfg2_shape":   dict(n1=1000, n2=1000, box=(67.7, None, None), modes=["000", "110", "101", "011", "220"], hmin=0.0, hmax=30.0, dr=0.05, frames=2, same=False, seed=2),
+    "cfg3_density": dict(n1=2048, n2=2048, box=(39.42, None, None), modes=["all"], hmin=0.0, hmax=15.0, dr=0.05, frames=2, same=True, seed=3),
+    "rect_all":     dict(n1=300, n2=400, box=(40.0, None, None), modes=["all"], hmin=0.0, hmax=15.0, dr=0.05, frames=2, same=False, seed=4),
+    "rect_wide":    dict(n1=37, n2=1531, box=(52.0, None, None), modes=["all"], hmin=0.0, hmax=20.0, dr=0.1, frames=2, same=False, seed=5),
+    "self_odd":     dict(n1=257, n2=257, box=(31.04, None, None), modes=["all"], hmin=0.0, hmax=15.0, dr=0.05, frames=2, same=True, seed=6),
+    "ortho_npt":    dict(n1=333, n2=333, box=(30.0, 36.0, 41.0), modes=["all"], hmin=0.0, hmax=14.0, dr=0.05, frames=3, same=True, seed=7, npt=True),
+    "g000_nodip":   dict(n1=200, n2=500, box=(35.0, None, None), modes=["000"], hmin=0.0, hmax=15.0, dr=0.05, frames=2, same=False, seed=8, nodip=True),
+    "hmin_pos":     dict(n1=400, n2=400, box=(32.0, None, None), modes=["000", "110", "202"], hmin=2.0, hmax=12.0, dr=0.1, frames=2, same=True, seed=9),
+    "f32_bounds":   dict(n1=256, n2=256, box=(40.0, None, None), modes=["all"], hmin=0.0, hmax=15.02, dr=0.05, frames=1, same=True, seed=10),
+    "beyond_half":  dict(n1=128, n2=128, box=(20.0, None, None), modes=["all"], hmin=0.0, hmax=15.0, dr=0.05, frames=2, same=True, seed=11),
+    "unwrapped":    dict(n1=150, n2=170, box=(25.0, None, None), modes=["all"], hmin=0.0, hmax=12.0, dr=0.05, frames=2, same=False, seed=12, unwrapped=True),
+    "tiny_1x1":     dict(n1=1, n2=1, box=(40.0, None, None), modes=["all"], hmin=0.0, hmax=15.0, dr=0.05, frames=1, same=False, seed=13),
+    "tiny_1x5":     dict(n1=1, n2=5, box=(12.0, None, None), modes=["all"], hmin=0.0, hmax=5.0, dr=0.05, frames=2, same=False, seed=14),
+    "distinct_eq_subset": dict(n1=64, n2=64, box=(18.0, None, None), modes=["110", "011", "022"], hmin=0.0, hmax=8.0, dr=0.05, frames=2, same=False, seed=15),
+}
+
+
+def build_inputs(case, frame):
+    """-> (c1, c2, d1, d2, box_xyz_for_this_frame or None)."""
+    n1, n2 = case["n1"], case["n2"]
+    bx, by, bz = case["box"]
+    L = np.array([bx, by or bx, bz or bx], dtype=np.float64)
+    rng = np.random.default_rng(100003 * case["seed"] + frame)
+    newbox = None
+    if case.get("npt"):
+        s = 1.0 + 1e-3 * rng.standard_normal(3)
+        L = L * s
+        newbox = tuple(float(v) for v in L)
+    lo, span = (-1.0, 3.0) if case.get("unwrapped") else (0.0, 1.0)
+    c1 = np.ascontiguousarray((lo + span * rng.random((n1, 3))) * L)
+    d1 = np.ascontiguousarray(rng.standard_normal((n1, 3)))
+    if case["same"]:
+        c2, d2 = c1, d1
+    else:
+        c2 = np.ascontiguousarray((lo + span * rng.random((n2, 3))) * L)
+        d2 = np.ascontiguousarray(rng.standard_normal((n2, 3)))
+    if case.get("nodip"):
+        d1 = d2 = None
+    return c1, c2, d1, d2, newbox
+
+
+def input_digest(case):
+    h = hashlib.sha256()
+    for f in range(case["frames"]):
+        for a in build_inputs(case, f)[:4]:
+            if a is not None:
+                h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def make_rdf(cls, case):
+    n1, n2 = case["n1"], case["n2"]
+    bx, by, bz = case["box"]
+    return cls(case["modes"], case["hmin"], case["hmax"], case["dr"], n1, n2, n1, n2, bx, by, bz)
+
+
+def drive(rdf, case):
+    """Run all frames of a case through an RDF-like object (reference, oracle or the GPU shim)."""
+    for f in range(case["frames"]):
+        c1, c2, d1, d2, newbox = build_inputs(case, f)
+        if newbox is not None:
+            rdf.update_box(*newbox)
+        if d1 is None:
+            rdf.calcFrame(c1, c2)
+        else:
+            rdf.calcFrame(c1, c2, d1, d2)
+    return rdf
+
+
+# hand-checkable micro cases: x=(0,0,0), 0-15/0.05, L=40 -> flat indices
+MICRO = [((15.0, 0.0, 0.0), 300), ((14.999999999, 0.0, 0.0), 299), ((0.05, 0.0, 0.0), 1),
+         ((0.049999, 0.0, 0.0), None)]

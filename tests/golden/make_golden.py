@@ -1,0 +1,67 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference module (oracle/_ref).
+
+Run in the build container (needs oracle/_ref, i.e. /root/reference at build time):
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+The GPU box never runs this; it only reads the committed fixtures.
+
+Per case the fixture holds
+  raw    sum_i histogram[k][i][b]  (un-normalised, what RDF._addHisto adds; gfunction.pyx:466-480)
+  out    histogram_out after RDF.write()  (normalised; gfunction.pyx:483-550)
+  dat    the text of every written <prefix>_gXYZ.dat, keyed by mode
+  digest sha256 of the regenerated inputs (guards against generator drift)
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, HERE)
+
+import cases as C          # noqa: E402
+import oracle as O         # noqa: E402
+
+
+def main():
+    ref = O.load_ref()
+    if ref is None:
+        sys.exit("oracle/_ref is not built; run python oracle/build_ref.py first")
+    for name, case in C.CASES.items():
+        rdf = C.drive(C.make_rdf(ref.RDF, case), case)
+        raw = np.zeros(7 * int(rdf.histo_n))
+        rdf._addHisto(raw, rdf.histogram)
+        with tempfile.TemporaryDirectory() as tmp:
+            rdf.write(os.path.join(tmp, "g"))
+            dat = {m: open(os.path.join(tmp, "g_g%s.dat" % m)).read()
+                   for m in O.MODE_ORDER if int(rdf.mode_sel) & O.MODE_BITS[m]}
+        meta = dict(histo_n=int(rdf.histo_n), mode_sel=int(rdf.mode_sel), ctr=int(rdf.ctr),
+                    oneistwo=bool(rdf.oneistwo), histo_min=float(rdf.histo_min),
+                    histo_max=float(rdf.histo_max), histo_dr=float(rdf.histo_dr),
+                    histo_inv_dr=float(rdf.histo_inv_dr), volume=float(rdf.volume),
+                    digest=C.input_digest(case), dat=dat)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), raw=raw, out=rdf.histogram_out,
+                            meta=np.array(json.dumps(meta)))
+        print("%-20s histo_n=%d in-range(g000 raw)=%.0f" % (name, meta["histo_n"], raw[:meta["histo_n"]].sum()))
+
+    # micro cases: flat index hit by a single pair (quirks Q2/Q3)
+    micro = []
+    for y, _expect in C.MICRO:
+        r = ref.RDF(["000"], 0.0, 15.0, 0.05, 1, 2, 1, 2, 40.0)
+        c1 = np.zeros((1, 3))
+        c2 = np.array([y, (30.0, 30.0, 30.0)], dtype=np.float64)
+        # allocate one spare row so the Q3 spill (index 300) stays inside the array we can inspect
+        r.histogram = np.zeros(2 * int(r.histo_n) * 7)
+        r.calcFrame(c1, c2)
+        nz = np.flatnonzero(r.histogram)
+        micro.append(int(nz[0]) if nz.size else -1)
+    np.savez_compressed(os.path.join(HERE, "micro.npz"), idx=np.array(micro))
+    print("micro", micro)
+
+
+if __name__ == "__main__":
+    main()
