@@ -1,0 +1,166 @@
+/*
+ * gfn.h - C ABI of libgfn.so, the B200 (sm_100a) backend of newanalysis.gfunction.RDF.
+ *
+ * This is the drop-in boundary for ONE reference path: the per-frame pair loop of the g-function
+ * RDF class.  Every entry point cites the reference interface it replaces; all paths are relative
+ * to /root/reference/newanalysis/gfunction/gfunction.pyx.
+ *
+ *   reference native call being replaced (the Cython cdef the RDF class calls once per frame):
+ *     cdef void calcHisto(double *core_xyz, double *surr_xyz, double *core_dip, double *surr_dip,
+ *                         ndarray dest, ndarray box_dim, int ncore, int nsurround,
+ *                         float histo_min, float histo_max, int histo_n, double invdx, int mode_sel)
+ *                                                                        gfunction.pyx:110-112
+ *     call site                                                         gfunction.pyx:460-464
+ *     legacy GPU analogue  CUDA.calcHistoGPU(...)                        gfunction.pyx:104-105, 455-457
+ *
+ * Conventions: plain C, no torch / numpy types.  Every function returns an int status (GFN_OK = 0)
+ * unless stated; gfn_last_error() gives the message of the last failure on that handle.  All host
+ * pointers are caller-owned; input frames are COPIED into the library's pinned ring before
+ * gfn_enqueue_frame returns, so the caller may overwrite them immediately (analysis scripts reuse
+ * their arrays every frame).  There is NO CPU fallback: without a usable sm_100 device gfn_create
+ * fails with GFN_ENODEV.
+ *
+ * Arithmetic contract: bin assignment and all orientation weights are computed in IEEE fp64 with
+ * exactly the reference's operation order (no fused multiply-add), see DESIGN.md.  The g000 row is
+ * bit-exact; weighted rows differ from the reference only by summation order.
+ */
+#ifndef GFN_H
+#define GFN_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFN_OK        0
+#define GFN_EINVAL    1   /* bad argument                                   -> ValueError      */
+#define GFN_ECUDA     2   /* CUDA runtime failure                           -> RuntimeError    */
+#define GFN_ENCCL     3   /* NCCL failure / NCCL library not loadable       -> RuntimeError    */
+#define GFN_EZERODIV  4   /* in-range pair with a zero-norm dipole (Q5)     -> ZeroDivisionError("float division"),
+                             gfunction.pyx:155,159,163 under cdivision=False; reported at the next
+                             gfn_sync / gfn_readout after the offending frame (deferred) */
+#define GFN_ENOMEM    5
+#define GFN_ENODEV    6   /* no usable CUDA device: the product never falls back to the CPU */
+
+/* gfn_create flags */
+#define GFN_FLAG_PER_PARTICLE      1u  /* keep the reference's [mode][core i][bin] histogram on the device
+                                          (7*n1*histo_n doubles, gfunction.pyx:332) instead of [mode][bin] */
+#define GFN_FLAG_FILTER_FP64       2u  /* range pre-test in fp64 instead of the conservative fp32 pre-filter;
+                                          results are identical, only the pipe that rejects far pairs changes */
+#define GFN_FLAG_DISCARD_OVERFLOW  4u  /* pos >= histo_n (quirk Q3) is dropped instead of spilling into
+                                          bin pos-histo_n of the next row like the reference does */
+#define GFN_FLAG_HIST_GLOBAL       8u  /* force the global-atomic histogram path (default: per-warp shared-memory
+                                          replicas whenever they fit) */
+
+/* bits of mode_sel, gfunction.pyx:274-288 */
+#define GFN_MODE_000 1
+#define GFN_MODE_110 2
+#define GFN_MODE_101 4
+#define GFN_MODE_011 8
+#define GFN_MODE_220 16
+#define GFN_MODE_202 32
+#define GFN_MODE_022 64
+
+typedef struct gfn_handle gfn_t;
+
+typedef struct gfn_stats {
+    double pair_evals;        /* reference j-loop iterations submitted so far (n(n+1)/2 or n1*n2 per frame) */
+    double survivors;         /* pairs that passed the range pre-filter and were evaluated exactly in fp64 */
+    double in_range;          /* pairs that were binned (passed gfunction.pyx:149) */
+    double kernel_ms;         /* device time of all pair-kernel launches so far (CUDA events, summed over devices) */
+    double kernel_launches;   /* number of launches of library kernels so far (all kinds) */
+    double pair_launches;     /* number of pair-kernel launches */
+    double frames;            /* frames submitted */
+    double h2d_bytes;         /* bytes copied host->device */
+    double overflow;          /* pairs with pos >= histo_n (quirk Q3) */
+    int    filter_fp64;       /* 1 if the fp64 pre-test is active, 0 for the fp32 pre-filter */
+    int    hist_mode;         /* 0 shared-memory warp replicas, 1 global atomics, 2 per-particle global */
+    int    warps_per_block, blocks_per_sm, grid, smem_bytes, batch_frames, ndev;
+} gfn_stats_t;
+
+/* Number of CUDA devices visible (0 if none / no driver).  Never fails. */
+int gfn_device_count(void);
+
+/* Replaces the device-side half of RDF.__init__ (gfunction.pyx:234-364; legacy allocations :336-364).
+ *   n1,n2        selection sizes (self.n1, self.n2)                       :321-322
+ *   histo_n      number of bins  int32((max-min)/dr+0.5)                  :295
+ *   histo_min/max  passed as C float exactly like calcHisto takes them    :112, :291-292 (quirk Q4)
+ *   inv_dr       1/round(dr,5)                                            :293-294
+ *   mode_sel     bitmask                                                  :274-288
+ *   box_dim[6]   lengths then half lengths                                :297-311 (halves must equal length/2)
+ *   devices/ndev CUDA ordinals to shard frames over (NULL/0 = device 0)
+ */
+int gfn_create(gfn_t **out, int n1, int n2, int histo_n, float histo_min, float histo_max,
+               double inv_dr, int mode_sel, const double box_dim[6],
+               const int *devices, int ndev, unsigned flags);
+
+/* RDF.update_box, gfunction.pyx:367-383: applies to frames enqueued afterwards (the box travels
+ * with each frame, so NpT trajectories are safe with asynchronous batches). */
+int gfn_update_box(gfn_t *h, const double box_dim[6]);
+
+/* One frame = one call of calcHisto (gfunction.pyx:460-464).  c1 (n1,3), c2 (n2,3), d1 (n1,3), d2 (n2,3)
+ * C-contiguous float64; d1/d2 may be NULL when mode_sel does not need them (:411-415, quirk Q6).
+ * c2 == c1 (same pointer) uploads the selection once.  Asynchronous with respect to the GPU. */
+int gfn_enqueue_frame(gfn_t *h, const double *c1, const double *c2, const double *d1, const double *d2);
+
+/* Batch extension: nframes frames, frame f of every array starts stride_k doubles after frame f-1
+ * (stride 0 is not allowed).  box_dims: NULL = current box for all, else 6 doubles per frame. */
+int gfn_enqueue_frames(gfn_t *h, int nframes,
+                       const double *c1, long long stride_c1, const double *c2, long long stride_c2,
+                       const double *d1, long long stride_d1, const double *d2, long long stride_d2,
+                       const double *box_dims);
+
+/* Device-resident frames (inputs already in HBM on h's device 0; the legacy pre_*_gpu kwargs of
+ * calcFrame, gfunction.pyx:390-391,431-453, map here).  Pointers are DEVICE pointers with the same
+ * layout as gfn_enqueue_frames; nothing is copied from the host except the boxes. */
+int gfn_enqueue_device_frames(gfn_t *h, int nframes,
+                              const double *dc1, long long stride_c1, const double *dc2, long long stride_c2,
+                              const double *dd1, long long stride_d1, const double *dd2, long long stride_d2,
+                              const double *box_dims);
+
+/* Submit a partially filled batch (asynchronous). */
+int gfn_flush(gfn_t *h);
+/* Flush and wait for every submitted frame; reports deferred GFN_EZERODIV. */
+int gfn_sync(gfn_t *h);
+
+/* Replaces memcpy_dtoh + RDF._addHisto (gfunction.pyx:529-531, 466-480): flush, wait, combine the
+ * per-device histograms (one ncclAllReduce when more than one device/rank participates) and copy out.
+ *   hist      7*histo_n doubles, layout [mode k][bin], k in order 000,110,101,011,220,202,022: the
+ *             un-normalised sum over core particles of everything accumulated since the last gfn_reset
+ *             (OVERWRITES hist; the caller adds it to histogram_out like _addHisto does)
+ *   pairw     histo_n doubles or NULL: total pair weight per bin (what g000 would hold) regardless of mode_sel
+ *   overflow  1 value or NULL: number of pairs whose pos >= histo_n (quirk Q3)
+ */
+int gfn_readout(gfn_t *h, double *hist, double *pairw, unsigned long long *overflow);
+
+/* Per-particle histogram (GFN_FLAG_PER_PARTICLE only): 7*n1*histo_n doubles, reference layout :332. */
+int gfn_readout_per_particle(gfn_t *h, double *hist);
+
+/* RDF.scale (gfunction.pyx:513-515) and RDF.resetArrays (:552-557) on the device accumulators. */
+int gfn_scale(gfn_t *h, double value);
+int gfn_reset(gfn_t *h);
+
+void gfn_destroy(gfn_t *h);
+const char *gfn_last_error(const gfn_t *h);   /* h may be NULL: last gfn_create failure */
+int gfn_stats(gfn_t *h, gfn_stats_t *out);
+
+/* Multi-process frame sharding (one process per GPU): rank 0 calls gfn_comm_unique_id, ships the
+ * 128 bytes to the other ranks by any means, every rank calls gfn_comm_attach; gfn_readout then
+ * all-reduces over the ranks (ncclAllReduce, sum, fp64).  Single-process multi-device handles set
+ * up their communicator internally (ncclCommInitAll). */
+int gfn_comm_unique_id(char out[128]);
+int gfn_comm_attach(gfn_t *h, const char unique_id[128], int nranks, int rank);
+
+/* Measured pipe peaks for the roofline denominator: dependent-free DFMA / FFMA loops on every SM
+ * of device dev.  Results in TFLOP/s (an FMA counts 2). */
+int gfn_measure_peaks(int dev, double *fp64_tflops, double *fp32_tflops);
+
+/* Raw device memory helpers so a host framework without its own CUDA binding can stage
+ * device-resident frames for gfn_enqueue_device_frames (bench: inputs resident in HBM). */
+int gfn_dev_alloc(int dev, void **dptr, unsigned long long bytes);
+int gfn_dev_free(int dev, void *dptr);
+int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFN_H */

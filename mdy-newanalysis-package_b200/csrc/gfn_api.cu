@@ -1,0 +1,755 @@
+// gfn_api.cu - host side of libgfn.so: the C ABI declared in include/gfn.h.
+//
+// What lives here (reference counterparts in /root/reference/newanalysis/gfunction/gfunction.pyx):
+//   * handle = device half of RDF.__init__ (:234-364) - parameters, per-device accumulators
+//   * pinned-host frame-batch upload ring on CUDA streams: gfn_enqueue_frame copies the caller's
+//     arrays into a pinned batch slot and returns; full batches go H2D on a copy stream while the
+//     compute stream works on the previous batch (replaces the synchronous memcpy_htod per frame of
+//     the legacy branch, :429-453)
+//   * frame-sharded multi-GPU driver: batches are dealt round-robin to the handle's devices; at
+//     readout the small per-device histograms are summed with ONE ncclAllReduce (NCCL is loaded
+//     with dlopen so the library has no hard dependency when a single GPU is used)
+//   * readout / scale / reset (:529-531, :513-515, :552-557)
+#include "gfn_kernels.cuh"
+#include "../../include/gfn.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+using namespace gfn;
+
+namespace {
+
+thread_local char g_create_err[512] = "";
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (ABI of nccl.h 2.x; only what the histogram all-reduce needs)
+// ------------------------------------------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat64 = 8 };   // ncclDataType_t: ncclDouble
+enum { ncclSum = 0 };
+
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string err;
+};
+
+Nccl& nccl()
+{
+    static Nccl n;
+    static bool tried = false;
+    if (tried) return n;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (n.lib) break;
+    }
+    if (!n.lib) { n.err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return n; }
+#define GFN_SYM(field, name) *(void**)(&n.field) = dlsym(n.lib, name); if (!n.field) { n.err = std::string("missing NCCL symbol ") + name; return n; }
+    GFN_SYM(GetUniqueId, "ncclGetUniqueId")
+    GFN_SYM(CommInitRank, "ncclCommInitRank")
+    GFN_SYM(CommInitAll, "ncclCommInitAll")
+    GFN_SYM(CommDestroy, "ncclCommDestroy")
+    GFN_SYM(AllReduce, "ncclAllReduce")
+    GFN_SYM(GroupStart, "ncclGroupStart")
+    GFN_SYM(GroupEnd, "ncclGroupEnd")
+    GFN_SYM(GetErrorString, "ncclGetErrorString")
+#undef GFN_SYM
+    n.ok = true;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+constexpr int kRing = 3;
+
+struct Batch {
+    double* h_pin = nullptr;      // pinned staging: [frame][c1 | d1 | c2 | d2] (absent parts omitted)
+    double* d_raw = nullptr;      // same layout on the device
+    double* h_box = nullptr;      // pinned [frames][6]
+    double* d_box = nullptr;
+    Rec64*  recA = nullptr; Rec64* recB = nullptr;
+    float4* posA = nullptr; float4* posB = nullptr;
+    float*  maxab = nullptr;      // [2][frames]
+    cudaEvent_t uploaded = nullptr, done = nullptr, k0 = nullptr, k1 = nullptr;
+    int nframes = 0;
+    bool aliased = false;         // selection 2 is selection 1 (same pointer passed)
+    bool inflight = false;
+    bool timed = false;           // k0/k1 hold an un-harvested pair-kernel timing
+};
+
+struct Dev {
+    int dev = 0;
+    cudaStream_t copy = nullptr, comp = nullptr;
+    Batch ring[kRing];
+    int cur = 0;
+    double* gacc = nullptr;               // [8][histo_n]
+    double* gsum = nullptr;               // all-reduce result
+    double* gpp = nullptr;                // per-particle
+    double* partials = nullptr;
+    unsigned long long* counters = nullptr;
+    int* item_start = nullptr;
+    PairConfig cfg;
+    ncclComm_t comm = nullptr;
+    // device-frame scratch (gfn_enqueue_device_frames)
+    Rec64* xrecA = nullptr; Rec64* xrecB = nullptr; float4* xposA = nullptr; float4* xposB = nullptr;
+    float* xmax = nullptr; double* xbox = nullptr; int xcap = 0;
+    cudaEvent_t xk0 = nullptr, xk1 = nullptr; bool xtimed = false;
+};
+
+}  // namespace
+
+struct gfn_handle {
+    int n1, n2, histo_n, mode_sel;
+    float hmin_f, hmax_f;
+    double inv_dr;
+    double box[6];
+    unsigned flags;
+    bool need1, need2;
+    int n1_pad, n2_pad;
+    int batch_frames;
+    long long frame_doubles;      // worst case (not aliased)
+    long long off_c1, off_d1, off_c2, off_d2;   // offsets (doubles) inside a non-aliased frame
+    int n_itiles, n_jtiles, seg_tiles, items_per_frame;
+    std::vector<Dev> devs;
+    int next_dev = 0;
+    // external communicator (one process per GPU)
+    int nranks = 1, rank = 0;
+    bool ext_comm = false;
+    bool comm_ready = false;
+    // stats
+    double st_pairs = 0, st_frames = 0, st_h2d = 0, st_launches = 0, st_pair_launches = 0, st_kernel_ms = 0;
+    char err[512];
+};
+
+namespace {
+
+int fail(gfn_t* h, int code, const char* fmt, ...)
+{
+    char* dst = h ? h->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, GFN_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+int validate_box(gfn_t* h, const double* b)
+{
+    for (int k = 0; k < 3; ++k) {
+        if (!(b[k] > 0.0) || !isfinite(b[k])) return fail(h, GFN_EINVAL, "box length %d must be positive and finite", k);
+        if (b[3 + k] != b[k] / 2.0) return fail(h, GFN_EINVAL, "box_dim[%d] must equal box_dim[%d]/2 (gfunction.pyx:297-311)", 3 + k, k);
+    }
+    return GFN_OK;
+}
+
+void harvest_timing(gfn_t* h, Batch& b)
+{
+    if (b.timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, b.k0, b.k1) == cudaSuccess) h->st_kernel_ms += ms;
+        b.timed = false;
+    }
+}
+
+int wait_batch(gfn_t* h, Dev& d, Batch& b)
+{
+    if (b.inflight) {
+        CU(cudaSetDevice(d.dev));
+        CU(cudaEventSynchronize(b.done));
+        b.inflight = false;
+        harvest_timing(h, b);
+    }
+    return GFN_OK;
+}
+
+void fill_params(gfn_t* h, Dev& d, PairParams& p)
+{
+    memset(&p, 0, sizeof(p));
+    p.n1 = h->n1; p.n2 = h->n2; p.tri = (h->n1 == h->n2);
+    p.histo_n = h->histo_n; p.mode_sel = h->mode_sel;
+    p.hmin = (double)h->hmin_f; p.hmax = (double)h->hmax_f; p.invdx = h->inv_dr;
+    p.n_itiles = h->n_itiles; p.n_jtiles = h->n_jtiles; p.seg_tiles = h->seg_tiles; p.items_per_frame = h->items_per_frame;
+    p.item_start = d.item_start;
+    p.partials = d.partials; p.gacc = d.gacc; p.gpp = d.gpp; p.counters = d.counters;
+    p.flags = h->flags;
+    p.strideA = h->n1_pad; p.strideB = h->n2_pad;
+}
+
+// prep + pair + finalize for nframes frames whose raw arrays are on the device
+int launch_frames(gfn_t* h, Dev& d, int nframes,
+                  const double* c1, long long s_c1, const double* d1, long long s_d1,
+                  const double* c2, long long s_c2, const double* d2, long long s_d2, bool aliased,
+                  Rec64* recA, float4* posA, Rec64* recB, float4* posB, float* maxab, const double* d_box,
+                  cudaEvent_t k0, cudaEvent_t k1)
+{
+    cudaStream_t s = d.comp;
+    CU(cudaMemsetAsync(maxab, 0, sizeof(float) * 2 * nframes, s));
+    CU(prep_launch(c1, s_c1, h->need1 ? d1 : nullptr, s_d1, recA, posA, maxab, h->n1, h->n1_pad, nframes, s));
+    h->st_launches += 1;
+    if (!aliased) {
+        CU(prep_launch(c2, s_c2, h->need2 ? d2 : nullptr, s_d2, recB, posB, maxab + nframes, h->n2, h->n2_pad, nframes, s));
+        h->st_launches += 1;
+    }
+    PairParams p;
+    fill_params(h, d, p);
+    p.recA = recA; p.posA = posA; p.maxA = maxab;
+    p.recB = aliased ? recA : recB; p.posB = aliased ? posA : posB; p.maxB = aliased ? maxab : maxab + nframes;
+    p.box = d_box; p.nframes = nframes;
+    CU(cudaEventRecord(k0, s));
+    CU(pair_launch(d.cfg, p, s));
+    CU(cudaEventRecord(k1, s));
+    h->st_launches += 1; h->st_pair_launches += 1;
+    if (d.cfg.hist_mode == 0) {
+        CU(finalize_launch(d.partials, d.cfg.grid, h->histo_n, d.cfg.nslot, d.gacc, s));
+        h->st_launches += 1;
+    }
+    const double per = (h->n1 == h->n2) ? 0.5 * (double)h->n1 * ((double)h->n1 + 1.0) : (double)h->n1 * (double)h->n2;
+    h->st_pairs += per * nframes;
+    h->st_frames += nframes;
+    return GFN_OK;
+}
+
+int submit(gfn_t* h, Dev& d)
+{
+    Batch& b = d.ring[d.cur];
+    if (b.nframes == 0) return GFN_OK;
+    CU(cudaSetDevice(d.dev));
+    const long long fd = b.aliased ? (h->off_c2) : h->frame_doubles;    // aliased frames hold only c1|d1
+    const size_t bytes = (size_t)fd * b.nframes * sizeof(double);
+    CU(cudaMemcpyAsync(b.d_raw, b.h_pin, bytes, cudaMemcpyHostToDevice, d.copy));
+    CU(cudaMemcpyAsync(b.d_box, b.h_box, sizeof(double) * 6 * b.nframes, cudaMemcpyHostToDevice, d.copy));
+    CU(cudaEventRecord(b.uploaded, d.copy));
+    CU(cudaStreamWaitEvent(d.comp, b.uploaded, 0));
+    h->st_h2d += (double)bytes + 48.0 * b.nframes;
+    int rc = launch_frames(h, d, b.nframes,
+                           b.d_raw + h->off_c1, fd, b.d_raw + h->off_d1, fd,
+                           b.d_raw + h->off_c2, fd, b.d_raw + h->off_d2, fd, b.aliased,
+                           b.recA, b.posA, b.recB, b.posB, b.maxab, b.d_box, b.k0, b.k1);
+    if (rc) return rc;
+    b.timed = true;
+    CU(cudaEventRecord(b.done, d.comp));
+    b.inflight = true;
+    d.cur = (d.cur + 1) % kRing;
+    Batch& nb = d.ring[d.cur];
+    nb.nframes = 0;
+    return GFN_OK;
+}
+
+int check_zerodiv(gfn_t* h)
+{
+    for (Dev& d : h->devs) {
+        unsigned long long c[kCounters];
+        CU(cudaSetDevice(d.dev));
+        CU(cudaMemcpy(c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
+        if (c[1]) return fail(h, GFN_EZERODIV, "float division");
+    }
+    return GFN_OK;
+}
+
+int setup_comm(gfn_t* h)
+{
+    if (h->comm_ready) return GFN_OK;
+    const int nd = (int)h->devs.size();
+    if (nd > 1) {
+        Nccl& n = nccl();
+        if (!n.ok) return fail(h, GFN_ENCCL, "%s", n.err.c_str());
+        std::vector<ncclComm_t> comms(nd);
+        std::vector<int> ids(nd);
+        for (int i = 0; i < nd; ++i) ids[i] = h->devs[i].dev;
+        int rc = n.CommInitAll(comms.data(), nd, ids.data());
+        if (rc != ncclSuccess) return fail(h, GFN_ENCCL, "ncclCommInitAll: %s", n.GetErrorString(rc));
+        for (int i = 0; i < nd; ++i) h->devs[i].comm = comms[i];
+    }
+    h->comm_ready = true;
+    return GFN_OK;
+}
+
+void free_dev(Dev& d)
+{
+    cudaSetDevice(d.dev);
+    if (d.comp) cudaStreamSynchronize(d.comp);
+    if (d.copy) cudaStreamSynchronize(d.copy);
+    for (Batch& b : d.ring) {
+        if (b.h_pin) cudaFreeHost(b.h_pin);
+        if (b.h_box) cudaFreeHost(b.h_box);
+        cudaFree(b.d_raw); cudaFree(b.d_box); cudaFree(b.recA); cudaFree(b.recB); cudaFree(b.posA); cudaFree(b.posB); cudaFree(b.maxab);
+        if (b.uploaded) cudaEventDestroy(b.uploaded);
+        if (b.done) cudaEventDestroy(b.done);
+        if (b.k0) cudaEventDestroy(b.k0);
+        if (b.k1) cudaEventDestroy(b.k1);
+    }
+    cudaFree(d.gacc); cudaFree(d.gsum); cudaFree(d.gpp); cudaFree(d.partials); cudaFree(d.counters); cudaFree(d.item_start);
+    cudaFree(d.xrecA); cudaFree(d.xrecB); cudaFree(d.xposA); cudaFree(d.xposB); cudaFree(d.xmax); cudaFree(d.xbox);
+    if (d.xk0) cudaEventDestroy(d.xk0);
+    if (d.xk1) cudaEventDestroy(d.xk1);
+    if (d.comm && nccl().ok) nccl().CommDestroy(d.comm);
+    if (d.copy) cudaStreamDestroy(d.copy);
+    if (d.comp) cudaStreamDestroy(d.comp);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gfn_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* gfn_last_error(const gfn_t* h) { return h ? h->err : g_create_err; }
+
+int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float histo_max,
+               double inv_dr, int mode_sel, const double box_dim[6], const int* devices, int ndev, unsigned flags)
+{
+    gfn_t* h = nullptr;
+    if (!out) return fail(h, GFN_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n1 < 1 || n2 < 1) return fail(h, GFN_EINVAL, "selection sizes must be >= 1 (got %d, %d)", n1, n2);
+    if (histo_n < 1) return fail(h, GFN_EINVAL, "histo_n must be >= 1 (got %d)", histo_n);
+    if (mode_sel < 0 || mode_sel > 127) return fail(h, GFN_EINVAL, "mode_sel out of range: %d", mode_sel);
+    if (!(inv_dr > 0.0) || !isfinite(inv_dr)) return fail(h, GFN_EINVAL, "inv_dr must be positive and finite");
+    if (!box_dim) return fail(h, GFN_EINVAL, "box_dim is NULL");
+    int rc = validate_box(h, box_dim);
+    if (rc) return rc;
+    const int navail = gfn_device_count();
+    if (navail < 1) return fail(h, GFN_ENODEV, "no CUDA device available; libgfn has no CPU fallback");
+    std::vector<int> devs;
+    if (!devices || ndev <= 0) devs.push_back(0);
+    else for (int i = 0; i < ndev; ++i) {
+        if (devices[i] < 0 || devices[i] >= navail) return fail(h, GFN_EINVAL, "device ordinal %d out of range (0..%d)", devices[i], navail - 1);
+        devs.push_back(devices[i]);
+    }
+    for (int dv : devs) {
+        cudaDeviceProp pr;
+        if (cudaGetDeviceProperties(&pr, dv) != cudaSuccess) return fail(h, GFN_ECUDA, "cudaGetDeviceProperties(%d) failed", dv);
+        if (pr.major != 10) return fail(h, GFN_ENODEV, "device %d is sm_%d%d; libgfn is built for sm_100a (B200) only", dv, pr.major, pr.minor);
+    }
+    if ((flags & GFN_FLAG_PER_PARTICLE) && devs.size() > 1)
+        return fail(h, GFN_EINVAL, "GFN_FLAG_PER_PARTICLE supports a single device");
+
+    h = new gfn_handle();
+    h->err[0] = 0;
+    h->n1 = n1; h->n2 = n2; h->histo_n = histo_n; h->mode_sel = mode_sel;
+    h->hmin_f = histo_min; h->hmax_f = histo_max; h->inv_dr = inv_dr; h->flags = flags;
+    memcpy(h->box, box_dim, sizeof(h->box));
+    h->need1 = mode_sel & (2 | 4 | 16 | 32);       // gfunction.pyx:121 / :411
+    h->need2 = mode_sel & (2 | 8 | 16 | 64);       // gfunction.pyx:135 / :414
+    h->n1_pad = (n1 + kPadTo - 1) / kPadTo * kPadTo;
+    h->n2_pad = (n2 + kPadTo - 1) / kPadTo * kPadTo;
+    h->off_c1 = 0;
+    h->off_d1 = 3ll * n1;
+    h->off_c2 = h->off_d1 + (h->need1 ? 3ll * n1 : 0);
+    h->off_d2 = h->off_c2 + 3ll * n2;
+    h->frame_doubles = h->off_d2 + (h->need2 ? 3ll * n2 : 0);
+
+    // batch size: ~2^31 pair evaluations or 64 MB of frames per batch, whichever is smaller
+    const double per = (n1 == n2) ? 0.5 * (double)n1 * ((double)n1 + 1.0) : (double)n1 * (double)n2;
+    long long bf = (long long)(2147483648.0 / per);
+    const long long by_bytes = (64ll << 20) / (h->frame_doubles * 8);
+    if (bf > by_bytes) bf = by_bytes;
+    if (bf > 4096) bf = 4096;
+    if (bf < 1) bf = 1;
+    if (const char* e = getenv("GFN_BATCH_FRAMES")) { long long v = atoll(e); if (v >= 1 && v <= 65535) bf = v; }
+    h->batch_frames = (int)bf;
+
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(nullptr, GFN_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); for (Dev& dd : h->devs) free_dev(dd); delete h; return GFN_ECUDA; } } while (0)
+    h->devs.resize(devs.size());
+    for (size_t i = 0; i < devs.size(); ++i) h->devs[i].dev = devs[i];
+    for (Dev& d : h->devs) {
+        CUC(cudaSetDevice(d.dev));
+        CUC(pair_configure(d.dev, histo_n, mode_sel, flags, &d.cfg));
+    }
+    // work decomposition (identical on all devices)
+    {
+        const PairConfig& c = h->devs[0].cfg;
+        const int TI = tile_i(c);
+        h->n_itiles = (n1 + TI - 1) / TI;
+        h->n_jtiles = (n2 + kTJ - 1) / kTJ;
+        // segment length: aim at >= 8 items per CTA per batch, at least 4 and at most 64 surround tiles per item
+        const double want_items = 8.0 * c.grid;
+        double tiles_total = 0;
+        for (int t = 0; t < h->n_itiles; ++t) tiles_total += h->n_jtiles - ((n1 == n2) ? (t * TI) / kTJ : 0);
+        tiles_total *= h->batch_frames;
+        int seg = (int)(tiles_total / want_items);
+        if (seg < 4) seg = 4;
+        if (seg > 64) seg = 64;
+        if (const char* e = getenv("GFN_SEG_TILES")) { int v = atoi(e); if (v >= 1) seg = v; }
+        h->seg_tiles = seg;
+        std::vector<int> start(h->n_itiles + 1, 0);
+        for (int t = 0; t < h->n_itiles; ++t) {
+            const int first = (n1 == n2) ? (t * TI) / kTJ : 0;
+            const int tiles = h->n_jtiles - first;
+            start[t + 1] = start[t] + (tiles > 0 ? (tiles + seg - 1) / seg : 0);
+        }
+        h->items_per_frame = start[h->n_itiles];
+        for (Dev& d : h->devs) {
+            CUC(cudaSetDevice(d.dev));
+            CUC(cudaMalloc(&d.item_start, sizeof(int) * start.size()));
+            CUC(cudaMemcpy(d.item_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+        }
+    }
+    for (Dev& d : h->devs) {
+        CUC(cudaSetDevice(d.dev));
+        CUC(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+        CUC(cudaStreamCreateWithFlags(&d.comp, cudaStreamNonBlocking));
+        CUC(cudaMalloc(&d.gacc, sizeof(double) * 8 * histo_n));
+        CUC(cudaMalloc(&d.gsum, sizeof(double) * 8 * histo_n));
+        CUC(cudaMemset(d.gacc, 0, sizeof(double) * 8 * histo_n));
+        CUC(cudaMalloc(&d.counters, sizeof(unsigned long long) * kCounters));
+        CUC(cudaMemset(d.counters, 0, sizeof(unsigned long long) * kCounters));
+        if (d.cfg.hist_mode == 0) CUC(cudaMalloc(&d.partials, sizeof(double) * (size_t)d.cfg.grid * histo_n * d.cfg.nslot));
+        if (flags & GFN_FLAG_PER_PARTICLE) {
+            const size_t bytes = sizeof(double) * 7ull * n1 * histo_n;
+            CUC(cudaMalloc(&d.gpp, bytes));
+            CUC(cudaMemset(d.gpp, 0, bytes));
+        }
+        CUC(cudaEventCreateWithFlags(&d.xk0, cudaEventDefault));
+        CUC(cudaEventCreateWithFlags(&d.xk1, cudaEventDefault));
+        for (Batch& b : d.ring) {
+            const size_t fb = sizeof(double) * (size_t)h->frame_doubles * h->batch_frames;
+            CUC(cudaHostAlloc(&b.h_pin, fb, cudaHostAllocDefault));
+            CUC(cudaMalloc(&b.d_raw, fb));
+            CUC(cudaHostAlloc(&b.h_box, sizeof(double) * 6 * h->batch_frames, cudaHostAllocDefault));
+            CUC(cudaMalloc(&b.d_box, sizeof(double) * 6 * h->batch_frames));
+            CUC(cudaMalloc(&b.recA, sizeof(Rec64) * (size_t)h->n1_pad * h->batch_frames));
+            CUC(cudaMalloc(&b.posA, sizeof(float4) * (size_t)h->n1_pad * h->batch_frames));
+            CUC(cudaMalloc(&b.recB, sizeof(Rec64) * (size_t)h->n2_pad * h->batch_frames));
+            CUC(cudaMalloc(&b.posB, sizeof(float4) * (size_t)h->n2_pad * h->batch_frames));
+            CUC(cudaMalloc(&b.maxab, sizeof(float) * 2 * h->batch_frames));
+            CUC(cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming));
+            CUC(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+            CUC(cudaEventCreateWithFlags(&b.k0, cudaEventDefault));
+            CUC(cudaEventCreateWithFlags(&b.k1, cudaEventDefault));
+        }
+    }
+#undef CUC
+    *out = h;
+    return GFN_OK;
+}
+
+int gfn_update_box(gfn_t* h, const double box_dim[6])
+{
+    if (!h || !box_dim) return fail(h, GFN_EINVAL, "NULL argument");
+    int rc = validate_box(h, box_dim);
+    if (rc) return rc;
+    memcpy(h->box, box_dim, sizeof(h->box));
+    return GFN_OK;
+}
+
+int gfn_enqueue_frames(gfn_t* h, int nframes,
+                       const double* c1, long long s_c1, const double* c2, long long s_c2,
+                       const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims)
+{
+    if (!h) return GFN_EINVAL;
+    if (nframes < 0) return fail(h, GFN_EINVAL, "nframes < 0");
+    if (!c1 || !c2) return fail(h, GFN_EINVAL, "coordinate array is NULL");
+    if (h->need1 && !d1) return fail(h, GFN_EINVAL, "No dipole moment array for the first selection was passed, although the requested gfunctions need it");
+    if (h->need2 && !d2) return fail(h, GFN_EINVAL, "No dipole moment array for the second selection was passed, although the requested gfunctions need it");
+    const bool aliased = (c2 == c1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || d2 == d1) && (!h->need2 || h->need1);
+    for (int f = 0; f < nframes; ++f) {
+        Dev& d = h->devs[h->next_dev];
+        Batch* b = &d.ring[d.cur];
+        if (b->nframes > 0 && b->aliased != aliased) {      // layout change: close the batch
+            int rc = submit(h, d);
+            if (rc) return rc;
+            b = &d.ring[d.cur];
+        }
+        if (b->nframes == 0) {
+            int rc = wait_batch(h, d, *b);
+            if (rc) return rc;
+            b->aliased = aliased;
+        }
+        if (box_dims) {
+            int rc = validate_box(h, box_dims + 6ll * f);
+            if (rc) return rc;
+        }
+        const long long fd = aliased ? h->off_c2 : h->frame_doubles;
+        double* dst = b->h_pin + fd * b->nframes;
+        memcpy(dst + h->off_c1, c1 + s_c1 * f, sizeof(double) * 3 * h->n1);
+        if (h->need1) memcpy(dst + h->off_d1, d1 + s_d1 * f, sizeof(double) * 3 * h->n1);
+        if (!aliased) {
+            memcpy(dst + h->off_c2, c2 + s_c2 * f, sizeof(double) * 3 * h->n2);
+            if (h->need2) memcpy(dst + h->off_d2, d2 + s_d2 * f, sizeof(double) * 3 * h->n2);
+        }
+        memcpy(b->h_box + 6ll * b->nframes, box_dims ? box_dims + 6ll * f : h->box, sizeof(double) * 6);
+        b->nframes++;
+        if (b->nframes == h->batch_frames) {
+            int rc = submit(h, d);
+            if (rc) return rc;
+            h->next_dev = (h->next_dev + 1) % (int)h->devs.size();
+        }
+    }
+    return GFN_OK;
+}
+
+int gfn_enqueue_frame(gfn_t* h, const double* c1, const double* c2, const double* d1, const double* d2)
+{
+    return gfn_enqueue_frames(h, 1, c1, 0, c2, 0, d1, 0, d2, 0, nullptr);
+}
+
+int gfn_enqueue_device_frames(gfn_t* h, int nframes,
+                              const double* dc1, long long s_c1, const double* dc2, long long s_c2,
+                              const double* dd1, long long s_d1, const double* dd2, long long s_d2, const double* box_dims)
+{
+    if (!h) return GFN_EINVAL;
+    if (nframes < 0) return fail(h, GFN_EINVAL, "nframes < 0");
+    if (!dc1 || !dc2) return fail(h, GFN_EINVAL, "coordinate array is NULL");
+    if (h->need1 && !dd1) return fail(h, GFN_EINVAL, "dipoles of the first selection are required by mode_sel");
+    if (h->need2 && !dd2) return fail(h, GFN_EINVAL, "dipoles of the second selection are required by mode_sel");
+    Dev& d = h->devs[0];
+    CU(cudaSetDevice(d.dev));
+    const bool aliased = (dc2 == dc1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || dd2 == dd1) && (!h->need2 || h->need1);
+    const int chunk = h->batch_frames;
+    if (d.xcap < chunk) {
+        CU(cudaStreamSynchronize(d.comp));
+        cudaFree(d.xrecA); cudaFree(d.xrecB); cudaFree(d.xposA); cudaFree(d.xposB); cudaFree(d.xmax); cudaFree(d.xbox);
+        d.xrecA = d.xrecB = nullptr; d.xposA = d.xposB = nullptr; d.xmax = nullptr; d.xbox = nullptr; d.xcap = 0;
+        CU(cudaMalloc(&d.xrecA, sizeof(Rec64) * (size_t)h->n1_pad * chunk));
+        CU(cudaMalloc(&d.xposA, sizeof(float4) * (size_t)h->n1_pad * chunk));
+        CU(cudaMalloc(&d.xrecB, sizeof(Rec64) * (size_t)h->n2_pad * chunk));
+        CU(cudaMalloc(&d.xposB, sizeof(float4) * (size_t)h->n2_pad * chunk));
+        CU(cudaMalloc(&d.xmax, sizeof(float) * 2 * chunk));
+        CU(cudaMalloc(&d.xbox, sizeof(double) * 6 * chunk));
+        d.xcap = chunk;
+    }
+    std::vector<double> hb(6 * (size_t)chunk);
+    for (int f0 = 0; f0 < nframes; f0 += chunk) {
+        const int nf = nframes - f0 < chunk ? nframes - f0 : chunk;
+        for (int f = 0; f < nf; ++f) {
+            const double* src = box_dims ? box_dims + 6ll * (f0 + f) : h->box;
+            if (box_dims) { int rc = validate_box(h, src); if (rc) return rc; }
+            memcpy(&hb[6 * (size_t)f], src, sizeof(double) * 6);
+        }
+        // scratch (records, boxes) is reused chunk after chunk: stream order on d.comp serialises it
+        if (d.xtimed) { CU(cudaEventSynchronize(d.xk1)); float ms = 0.f; if (cudaEventElapsedTime(&ms, d.xk0, d.xk1) == cudaSuccess) h->st_kernel_ms += ms; d.xtimed = false; }
+        CU(cudaMemcpyAsync(d.xbox, hb.data(), sizeof(double) * 6 * nf, cudaMemcpyHostToDevice, d.comp));
+        CU(cudaStreamSynchronize(d.comp));      // hb is pageable and reused
+        int rc = launch_frames(h, d, nf,
+                               dc1 + s_c1 * f0, s_c1, dd1 ? dd1 + s_d1 * f0 : nullptr, s_d1,
+                               dc2 + s_c2 * f0, s_c2, dd2 ? dd2 + s_d2 * f0 : nullptr, s_d2, aliased,
+                               d.xrecA, d.xposA, d.xrecB, d.xposB, d.xmax, d.xbox, d.xk0, d.xk1);
+        if (rc) return rc;
+        d.xtimed = true;
+    }
+    return GFN_OK;
+}
+
+int gfn_flush(gfn_t* h)
+{
+    if (!h) return GFN_EINVAL;
+    for (Dev& d : h->devs) {
+        int rc = submit(h, d);
+        if (rc) return rc;
+    }
+    return GFN_OK;
+}
+
+int gfn_sync(gfn_t* h)
+{
+    if (!h) return GFN_EINVAL;
+    int rc = gfn_flush(h);
+    if (rc) return rc;
+    for (Dev& d : h->devs) {
+        CU(cudaSetDevice(d.dev));
+        CU(cudaStreamSynchronize(d.copy));
+        CU(cudaStreamSynchronize(d.comp));
+        for (Batch& b : d.ring) { b.inflight = false; harvest_timing(h, b); }
+        if (d.xtimed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, d.xk0, d.xk1) == cudaSuccess) h->st_kernel_ms += ms; d.xtimed = false; }
+    }
+    return check_zerodiv(h);
+}
+
+int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overflow)
+{
+    if (!h || !hist) return fail(h, GFN_EINVAL, "NULL argument");
+    int rc = gfn_sync(h);
+    if (rc && rc != GFN_EZERODIV) return rc;
+    const int zd = rc;
+    const size_t n8 = 8ull * h->histo_n;
+    const bool collective = h->devs.size() > 1 || h->ext_comm;
+    if (collective) {
+        if ((rc = setup_comm(h))) return rc;
+        Nccl& n = nccl();
+        if (h->devs.size() > 1) n.GroupStart();
+        for (Dev& d : h->devs) {
+            CU(cudaSetDevice(d.dev));
+            int nr = n.AllReduce(d.gacc, d.gsum, n8, ncclFloat64, ncclSum, d.comm, d.comp);
+            if (nr != ncclSuccess) { if (h->devs.size() > 1) n.GroupEnd(); return fail(h, GFN_ENCCL, "ncclAllReduce: %s", n.GetErrorString(nr)); }
+        }
+        if (h->devs.size() > 1) { int nr = n.GroupEnd(); if (nr != ncclSuccess) return fail(h, GFN_ENCCL, "ncclGroupEnd: %s", n.GetErrorString(nr)); }
+        h->st_launches += (double)h->devs.size();
+        for (Dev& d : h->devs) { CU(cudaSetDevice(d.dev)); CU(cudaStreamSynchronize(d.comp)); }
+    }
+    Dev& d0 = h->devs[0];
+    CU(cudaSetDevice(d0.dev));
+    std::vector<double> tmp(n8);
+    CU(cudaMemcpy(tmp.data(), collective ? d0.gsum : d0.gacc, sizeof(double) * n8, cudaMemcpyDeviceToHost));
+    memcpy(hist, tmp.data(), sizeof(double) * 7 * h->histo_n);
+    if (pairw) memcpy(pairw, tmp.data() + 7ull * h->histo_n, sizeof(double) * h->histo_n);
+    if (overflow) {
+        unsigned long long tot = 0;
+        for (Dev& d : h->devs) {
+            unsigned long long c[kCounters];
+            CU(cudaSetDevice(d.dev));
+            CU(cudaMemcpy(c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
+            tot += c[0];
+        }
+        *overflow = tot;      // local devices only; ranks of an external communicator report their own
+    }
+    return zd;
+}
+
+int gfn_readout_per_particle(gfn_t* h, double* hist)
+{
+    if (!h || !hist) return fail(h, GFN_EINVAL, "NULL argument");
+    if (!(h->flags & GFN_FLAG_PER_PARTICLE)) return fail(h, GFN_EINVAL, "handle was not created with GFN_FLAG_PER_PARTICLE");
+    int rc = gfn_sync(h);
+    if (rc && rc != GFN_EZERODIV) return rc;
+    Dev& d = h->devs[0];
+    CU(cudaSetDevice(d.dev));
+    CU(cudaMemcpy(hist, d.gpp, sizeof(double) * 7ull * h->n1 * h->histo_n, cudaMemcpyDeviceToHost));
+    return rc;
+}
+
+int gfn_scale(gfn_t* h, double value)
+{
+    if (!h) return GFN_EINVAL;
+    int rc = gfn_flush(h);
+    if (rc) return rc;
+    for (Dev& d : h->devs) {
+        CU(cudaSetDevice(d.dev));
+        CU(scale_launch(d.gacc, 8ll * h->histo_n, value, d.comp));
+        if (d.gpp) CU(scale_launch(d.gpp, 7ll * h->n1 * h->histo_n, value, d.comp));
+        h->st_launches += d.gpp ? 2 : 1;
+    }
+    return GFN_OK;
+}
+
+int gfn_reset(gfn_t* h)
+{
+    if (!h) return GFN_EINVAL;
+    int rc = gfn_flush(h);
+    if (rc) return rc;
+    for (Dev& d : h->devs) {
+        CU(cudaSetDevice(d.dev));
+        CU(cudaMemsetAsync(d.gacc, 0, sizeof(double) * 8 * h->histo_n, d.comp));
+        if (d.gpp) CU(cudaMemsetAsync(d.gpp, 0, sizeof(double) * 7ull * h->n1 * h->histo_n, d.comp));
+        CU(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounters, d.comp));
+    }
+    return GFN_OK;
+}
+
+void gfn_destroy(gfn_t* h)
+{
+    if (!h) return;
+    for (Dev& d : h->devs) free_dev(d);
+    delete h;
+}
+
+int gfn_stats(gfn_t* h, gfn_stats_t* out)
+{
+    if (!h || !out) return fail(h, GFN_EINVAL, "NULL argument");
+    memset(out, 0, sizeof(*out));
+    out->pair_evals = h->st_pairs; out->frames = h->st_frames; out->h2d_bytes = h->st_h2d;
+    out->kernel_launches = h->st_launches; out->pair_launches = h->st_pair_launches; out->kernel_ms = h->st_kernel_ms;
+    for (Dev& d : h->devs) {
+        unsigned long long c[kCounters];
+        CU(cudaSetDevice(d.dev));
+        CU(cudaMemcpy(c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
+        out->overflow += (double)c[0]; out->survivors += (double)c[2]; out->in_range += (double)c[3];
+    }
+    const PairConfig& c = h->devs[0].cfg;
+    out->filter_fp64 = c.filter_fp64; out->hist_mode = c.hist_mode; out->warps_per_block = c.warps;
+    out->blocks_per_sm = c.blocks_per_sm; out->grid = c.grid; out->smem_bytes = c.smem_bytes;
+    out->batch_frames = h->batch_frames; out->ndev = (int)h->devs.size();
+    return GFN_OK;
+}
+
+int gfn_comm_unique_id(char out[128])
+{
+    Nccl& n = nccl();
+    if (!n.ok) return fail(nullptr, GFN_ENCCL, "%s", n.err.c_str());
+    ncclUniqueId id;
+    int rc = n.GetUniqueId(&id);
+    if (rc != ncclSuccess) return fail(nullptr, GFN_ENCCL, "ncclGetUniqueId: %s", n.GetErrorString(rc));
+    memcpy(out, id.internal, 128);
+    return GFN_OK;
+}
+
+int gfn_comm_attach(gfn_t* h, const char unique_id[128], int nranks, int rank)
+{
+    if (!h || !unique_id) return fail(h, GFN_EINVAL, "NULL argument");
+    if (h->devs.size() != 1) return fail(h, GFN_EINVAL, "gfn_comm_attach needs a single-device handle (one process per GPU)");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, GFN_EINVAL, "bad rank %d of %d", rank, nranks);
+    Nccl& n = nccl();
+    if (!n.ok) return fail(h, GFN_ENCCL, "%s", n.err.c_str());
+    ncclUniqueId id;
+    memcpy(id.internal, unique_id, 128);
+    Dev& d = h->devs[0];
+    CU(cudaSetDevice(d.dev));
+    int rc = n.CommInitRank(&d.comm, nranks, id, rank);
+    if (rc != ncclSuccess) return fail(h, GFN_ENCCL, "ncclCommInitRank: %s", n.GetErrorString(rc));
+    h->nranks = nranks; h->rank = rank; h->ext_comm = true; h->comm_ready = true;
+    return GFN_OK;
+}
+
+int gfn_measure_peaks(int dev, double* fp64_tflops, double* fp32_tflops)
+{
+    gfn_t* h = nullptr;
+    CU(peaks_measure(dev, fp64_tflops, fp32_tflops));
+    return GFN_OK;
+}
+
+int gfn_dev_alloc(int dev, void** dptr, unsigned long long bytes)
+{
+    gfn_t* h = nullptr;
+    CU(cudaSetDevice(dev));
+    CU(cudaMalloc(dptr, bytes));
+    return GFN_OK;
+}
+
+int gfn_dev_free(int dev, void* dptr)
+{
+    gfn_t* h = nullptr;
+    CU(cudaSetDevice(dev));
+    CU(cudaFree(dptr));
+    return GFN_OK;
+}
+
+int gfn_dev_upload(int dev, void* dptr, const void* host, unsigned long long bytes)
+{
+    gfn_t* h = nullptr;
+    CU(cudaSetDevice(dev));
+    CU(cudaMemcpy(dptr, host, bytes, cudaMemcpyHostToDevice));
+    return GFN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,620 @@
+# cython: language_level=3, boundscheck=False, wraparound=False
+"""newanalysis.gfunction - B200 backend behind the reference's RDF class.
+
+Drop-in for the `RDF` class of /root/reference/newanalysis/gfunction/gfunction.pyx (:227-566): same
+constructor signature, mode strings, methods (calcFrame, update_box, scale, write, resetArrays,
+printInfo, _addHisto, _normHisto) and attribute names, so analysis scripts keep
+`from newanalysis.gfunction import RDF` unchanged.  What changed is below the class: instead of the
+OpenMP `calcHisto` loop (:110-165) or the PyCUDA kernel (:13-107), every frame goes through the C ABI
+of libgfn.so (include/gfn.h), i.e. hand-written sm_100a kernels fed by a pinned upload ring.
+
+There is NO CPU fallback: without a B200 the constructor raises RuntimeError (the reference printed a
+message and continued on the CPU, :262-264).
+
+Differences a user can observe (all documented in INTEGRATION.md):
+  * `calcFrame` is asynchronous; a zero-norm dipole (ZeroDivisionError, reference :155-163) is raised
+    at the next readout (`write`, `histogram`, `sync`) instead of inside `calcFrame`.
+  * `histogram` is a read-only property.  By default it is the [mode][bin] sum over core particles
+    (7*histo_n values, what `_addHisto` would produce); with NEWANALYSIS_GFN_FLAGS=per_particle (or
+    gfn_flags="per_particle") it is the reference's 7*n1*histo_n per-particle array (:332).
+  * extra, optional: `calcFrames` (many frames per call), `sync`, `stats`, `to_device`.
+"""
+import os
+
+import numpy as np
+cimport numpy as np
+
+np.import_array()
+
+cdef extern from "gfn.h":
+    ctypedef struct gfn_t:
+        pass
+    ctypedef struct gfn_stats_t:
+        double pair_evals
+        double survivors
+        double in_range
+        double kernel_ms
+        double kernel_launches
+        double pair_launches
+        double frames
+        double h2d_bytes
+        double overflow
+        int filter_fp64
+        int hist_mode
+        int warps_per_block
+        int blocks_per_sm
+        int grid
+        int smem_bytes
+        int batch_frames
+        int ndev
+    int GFN_OK, GFN_EINVAL, GFN_ECUDA, GFN_ENCCL, GFN_EZERODIV, GFN_ENOMEM, GFN_ENODEV
+    unsigned GFN_FLAG_PER_PARTICLE, GFN_FLAG_FILTER_FP64, GFN_FLAG_DISCARD_OVERFLOW, GFN_FLAG_HIST_GLOBAL
+    int gfn_device_count() nogil
+    int gfn_create(gfn_t **out, int n1, int n2, int histo_n, float histo_min, float histo_max,
+                   double inv_dr, int mode_sel, const double *box_dim, const int *devices, int ndev,
+                   unsigned flags) nogil
+    int gfn_update_box(gfn_t *h, const double *box_dim) nogil
+    int gfn_enqueue_frame(gfn_t *h, const double *c1, const double *c2, const double *d1, const double *d2) nogil
+    int gfn_enqueue_frames(gfn_t *h, int nframes, const double *c1, long long s1, const double *c2, long long s2,
+                           const double *d1, long long s3, const double *d2, long long s4, const double *boxes) nogil
+    int gfn_enqueue_device_frames(gfn_t *h, int nframes, const double *c1, long long s1, const double *c2, long long s2,
+                                  const double *d1, long long s3, const double *d2, long long s4, const double *boxes) nogil
+    int gfn_flush(gfn_t *h) nogil
+    int gfn_sync(gfn_t *h) nogil
+    int gfn_readout(gfn_t *h, double *hist, double *pairw, unsigned long long *overflow) nogil
+    int gfn_readout_per_particle(gfn_t *h, double *hist) nogil
+    int gfn_scale(gfn_t *h, double value) nogil
+    int gfn_reset(gfn_t *h) nogil
+    void gfn_destroy(gfn_t *h) nogil
+    const char *gfn_last_error(const gfn_t *h) nogil
+    int gfn_stats(gfn_t *h, gfn_stats_t *out) nogil
+    int gfn_comm_unique_id(char *out) nogil
+    int gfn_comm_attach(gfn_t *h, const char *uid, int nranks, int rank) nogil
+    int gfn_measure_peaks(int dev, double *fp64, double *fp32) nogil
+    int gfn_dev_alloc(int dev, void **dptr, unsigned long long nbytes) nogil
+    int gfn_dev_free(int dev, void *dptr) nogil
+    int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
+
+
+_FLAG_NAMES = {"per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
+
+
+def _parse_flags(spec):
+    if spec is None:
+        spec = os.environ.get("NEWANALYSIS_GFN_FLAGS", "")
+    if isinstance(spec, int):
+        return spec
+    flags = 0
+    for tok in str(spec).replace(" ", "").split(","):
+        if tok:
+            if tok not in _FLAG_NAMES:
+                raise ValueError("unknown gfn flag %r (known: %s)" % (tok, ", ".join(sorted(_FLAG_NAMES))))
+            flags |= _FLAG_NAMES[tok]
+    return flags
+
+
+def _parse_devices(spec):
+    """NEWANALYSIS_GPUS: 'all', a count ('8'), or a comma list of ordinals ('0,2,3').  Default: device 0."""
+    if spec is None:
+        spec = os.environ.get("NEWANALYSIS_GPUS", "")
+    if isinstance(spec, (list, tuple)):
+        return [int(v) for v in spec]
+    spec = str(spec).strip()
+    if not spec:
+        return [0]
+    if spec == "all":
+        return list(range(max(1, gfn_device_count())))
+    if "," in spec:
+        return [int(v) for v in spec.split(",") if v != ""]
+    return list(range(int(spec)))
+
+
+cdef object _raise(int rc, const gfn_t *h):
+    cdef const char *msg = gfn_last_error(h)
+    text = msg.decode("utf-8", "replace") if msg != NULL else ""
+    if rc == GFN_EZERODIV:
+        raise ZeroDivisionError("float division")
+    if rc == GFN_EINVAL:
+        raise ValueError(text)
+    if rc == GFN_ENOMEM:
+        raise MemoryError(text)
+    raise RuntimeError("libgfn: " + text)
+
+
+def device_count():
+    return gfn_device_count()
+
+
+def measure_peaks(int dev=0):
+    """(fp64_tflops, fp32_tflops) of dependent-free FMA loops on device dev (roofline denominators)."""
+    cdef double a = 0, b = 0
+    cdef int rc
+    with nogil:
+        rc = gfn_measure_peaks(dev, &a, &b)
+    if rc:
+        _raise(rc, NULL)
+    return a, b
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, every rank passes it to RDF.attach_comm)."""
+    cdef char buf[128]
+    cdef int rc = gfn_comm_unique_id(buf)
+    if rc:
+        _raise(rc, NULL)
+    return bytes(buf[:128])
+
+
+cdef class DeviceArray:
+    """float64 array resident in HBM (the new library's analogue of the PyCUDA allocations the
+    reference accepts as pre_*_gpu, gfunction.pyx:390-391)."""
+    cdef void *ptr
+    cdef readonly int device
+    cdef readonly tuple shape
+    cdef readonly unsigned long long nbytes
+
+    def __cinit__(self):
+        self.ptr = NULL
+
+    def __dealloc__(self):
+        if self.ptr != NULL:
+            gfn_dev_free(self.device, self.ptr)
+            self.ptr = NULL
+
+    def upload(self, arr):
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] flat = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        if <unsigned long long> flat.nbytes != self.nbytes:
+            raise ValueError("size mismatch")
+        cdef int rc = gfn_dev_upload(self.device, self.ptr, <const void *> flat.data, self.nbytes)
+        if rc:
+            _raise(rc, NULL)
+
+    @property
+    def address(self):
+        return <unsigned long long> <size_t> self.ptr
+
+
+def to_device(arr, int device=0):
+    """Upload a float64 array ((n,3) or (nframes,n,3)) once; the result can be shared by several RDF objects."""
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    cdef DeviceArray d = DeviceArray()
+    d.device = device
+    d.shape = tuple(a.shape)
+    d.nbytes = a.nbytes
+    cdef int rc = gfn_dev_alloc(device, &d.ptr, d.nbytes)
+    if rc:
+        d.ptr = NULL
+        _raise(rc, NULL)
+    d.upload(a)
+    return d
+
+
+cdef class _Backend:
+    cdef gfn_t *h
+    cdef int histo_n, n1, n2
+    cdef public list keepalive
+
+    def __cinit__(self):
+        self.h = NULL
+        self.keepalive = []
+
+    def __dealloc__(self):
+        if self.h != NULL:
+            gfn_destroy(self.h)
+            self.h = NULL
+
+    cdef int check(self, int rc) except -1:
+        if rc != GFN_OK:
+            _raise(rc, self.h)
+        return 0
+
+    def open(self, int n1, int n2, int histo_n, float hmin, float hmax, double inv_dr, int mode_sel,
+             np.ndarray[np.float64_t, ndim=1, mode="c"] box_dim, devices, unsigned flags):
+        cdef np.ndarray[np.int32_t, ndim=1, mode="c"] devs = np.ascontiguousarray(devices, dtype=np.int32)
+        cdef int rc
+        cdef int ndev = devs.shape[0]
+        rc = gfn_create(&self.h, n1, n2, histo_n, hmin, hmax, inv_dr, mode_sel, <const double *> box_dim.data,
+                        <const int *> devs.data, ndev, flags)
+        if rc != GFN_OK:
+            self.h = NULL
+            _raise(rc, NULL)
+        self.histo_n = histo_n
+        self.n1 = n1
+        self.n2 = n2
+
+    def update_box(self, np.ndarray[np.float64_t, ndim=1, mode="c"] box_dim):
+        self.check(gfn_update_box(self.h, <const double *> box_dim.data))
+
+    cdef int enqueue(self, const double *c1, const double *c2, const double *d1, const double *d2) except -1:
+        cdef int rc
+        with nogil:
+            rc = gfn_enqueue_frame(self.h, c1, c2, d1, d2)
+        return self.check(rc)
+
+    cdef int enqueue_many(self, int nframes, const double *c1, long long s1, const double *c2, long long s2,
+                          const double *d1, long long s3, const double *d2, long long s4, const double *boxes) except -1:
+        cdef int rc
+        with nogil:
+            rc = gfn_enqueue_frames(self.h, nframes, c1, s1, c2, s2, d1, s3, d2, s4, boxes)
+        return self.check(rc)
+
+    def enqueue_device(self, int nframes, DeviceArray c1, DeviceArray c2, DeviceArray d1, DeviceArray d2, boxes=None):
+        cdef const double *p1 = <const double *> c1.ptr
+        cdef const double *p2 = <const double *> c2.ptr
+        cdef const double *q1 = <const double *> d1.ptr if d1 is not None else NULL
+        cdef const double *q2 = <const double *> d2.ptr if d2 is not None else NULL
+        cdef np.ndarray[np.float64_t, ndim=2, mode="c"] bx
+        cdef const double *pb = NULL
+        if boxes is not None:
+            bx = np.ascontiguousarray(boxes, dtype=np.float64).reshape(nframes, 6)
+            pb = <const double *> bx.data
+        cdef long long s1 = 3 * self.n1, s2 = 3 * self.n2
+        cdef int rc
+        with nogil:
+            rc = gfn_enqueue_device_frames(self.h, nframes, p1, s1, p2, s2, q1, s1, q2, s2, pb)
+        self.keepalive.append((c1, c2, d1, d2))
+        self.check(rc)
+
+    def flush(self):
+        cdef int rc
+        with nogil:
+            rc = gfn_flush(self.h)
+        self.check(rc)
+
+    def sync(self):
+        cdef int rc
+        with nogil:
+            rc = gfn_sync(self.h)
+        del self.keepalive[:]
+        self.check(rc)
+
+    def readout(self):
+        """-> (hist[7*histo_n], pairw[histo_n], overflow)"""
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] hist = np.zeros(7 * self.histo_n, dtype=np.float64)
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] pw = np.zeros(self.histo_n, dtype=np.float64)
+        cdef unsigned long long ovf = 0
+        cdef int rc
+        with nogil:
+            rc = gfn_readout(self.h, <double *> hist.data, <double *> pw.data, &ovf)
+        del self.keepalive[:]
+        self.check(rc)
+        return hist, pw, int(ovf)
+
+    def readout_per_particle(self):
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] hist = np.zeros(7 * <long long> self.n1 * self.histo_n, dtype=np.float64)
+        cdef int rc
+        with nogil:
+            rc = gfn_readout_per_particle(self.h, <double *> hist.data)
+        self.check(rc)
+        return hist
+
+    def scale(self, double v):
+        self.check(gfn_scale(self.h, v))
+
+    def reset(self):
+        self.check(gfn_reset(self.h))
+
+    def attach_comm(self, bytes uid, int nranks, int rank):
+        if len(uid) != 128:
+            raise ValueError("unique id must be 128 bytes")
+        cdef const char *p = uid
+        cdef int rc
+        with nogil:
+            rc = gfn_comm_attach(self.h, p, nranks, rank)
+        self.check(rc)
+
+    def stats(self):
+        cdef gfn_stats_t s
+        self.check(gfn_stats(self.h, &s))
+        return dict(pair_evals=s.pair_evals, survivors=s.survivors, in_range=s.in_range, kernel_ms=s.kernel_ms,
+                    kernel_launches=s.kernel_launches, pair_launches=s.pair_launches, frames=s.frames,
+                    h2d_bytes=s.h2d_bytes, overflow=s.overflow, filter="fp64" if s.filter_fp64 else "fp32",
+                    hist_mode=("smem_warp_replicas", "global_atomics", "per_particle")[s.hist_mode],
+                    warps_per_block=s.warps_per_block, blocks_per_sm=s.blocks_per_sm, grid=s.grid,
+                    smem_bytes=s.smem_bytes, batch_frames=s.batch_frames, ndev=s.ndev)
+
+
+class RDF(object):
+    """
+    class RDF
+
+    A container object for calculating radial distribution functions (B200 backend).
+    """
+
+    def __init__(self, modes, histo_min, histo_max, histo_dr, sel1_n, sel2_n, sel1_nmol, sel2_nmol, box_x, box_y=None, box_z=None, use_cuda=False, norm_volume=None, gfn_flags=None, devices=None):
+        """
+        RDF.__init__(modes, histo_min, histo_max, histo_dr, sel1_n, sel2_n, sel1_nmol, sel2_nmol, box_x, box_y=None, box_z=None, use_cuda=False)
+
+        Same arguments as the reference (gfunction.pyx:234).  use_cuda is accepted and ignored: this
+        class always runs on the GPU.  gfn_flags / devices are optional extensions (see module docstring).
+        """
+        # the histogram always lives on the device; readout arrays are float64 like the reference CPU path (:268-271)
+        self.cuda = True
+        self.dtype = np.float64
+
+        cdef int mode_sel = 0
+        for mode in modes:                                   # :274-288, unknown strings are ignored
+            if mode == "all": mode_sel = mode_sel | 127
+            if mode == "000": mode_sel = mode_sel | 1
+            if mode == "110": mode_sel = mode_sel | 2
+            if mode == "101": mode_sel = mode_sel | 4
+            if mode == "011": mode_sel = mode_sel | 8
+            if mode == "220": mode_sel = mode_sel | 16
+            if mode == "202": mode_sel = mode_sel | 32
+            if mode == "022": mode_sel = mode_sel | 64
+        self.mode_sel = np.int32(mode_sel)
+
+        self.histo_min = np.float32(histo_min)               # :291-295
+        self.histo_max = np.float32(histo_max)
+        self.histo_dr = np.round(self.dtype(histo_dr), 5)
+        self.histo_inv_dr = self.dtype(1.0 / self.histo_dr)
+        self.histo_n = np.int32((histo_max - histo_min) / histo_dr + 0.5)
+
+        self.box_dim = np.zeros(6, dtype=self.dtype)         # :297-311 (box_y / box_z falsy -> cubic)
+        self.box_dim[0] = box_x
+        self.box_dim[3] = box_x / 2.0
+        if box_y:
+            self.box_dim[1] = box_y
+            self.box_dim[4] = box_y / 2.0
+        else:
+            self.box_dim[1] = self.box_dim[0]
+            self.box_dim[4] = self.box_dim[3]
+        if box_z:
+            self.box_dim[2] = box_z
+            self.box_dim[5] = box_z / 2.0
+        else:
+            self.box_dim[2] = self.box_dim[0]
+            self.box_dim[5] = self.box_dim[3]
+        self.volume = self.box_dim[0] * self.box_dim[1] * self.box_dim[2]
+        self.volume_list = []
+        self.norm_volume = norm_volume
+
+        self.n1 = np.int32(sel1_n)
+        self.n2 = np.int32(sel2_n)
+        self.nmol1 = sel1_nmol
+        self.nmol2 = sel2_nmol
+        self.oneistwo = None
+        self.ctr = 0
+
+        self.histogram_out = np.zeros(self.histo_n * 7, dtype=np.float64)   # :333
+
+        self._flags = _parse_flags(gfn_flags)
+        self._devices = _parse_devices(devices)
+        if gfn_device_count() < 1:
+            raise RuntimeError("newanalysis.gfunction (B200 backend): no CUDA device available and there is no CPU fallback")
+        self._be = _Backend()
+        self._be.open(int(self.n1), int(self.n2), int(self.histo_n), self.histo_min, self.histo_max,
+                      float(self.histo_inv_dr), mode_sel, self.box_dim, self._devices, self._flags)
+
+    # ------------------------------------------------------------------ reference API
+    def update_box(self, box_x, box_y, box_z):
+        """
+        update_box(box_x,box_y,box_z)
+
+        Update the box dimensions, when analysing NpT trajectories (:367-383).
+        """
+        self.box_dim[0] = box_x
+        self.box_dim[3] = box_x / 2.0
+        self.box_dim[1] = box_y
+        self.box_dim[4] = box_y / 2.0
+        self.box_dim[2] = box_z
+        self.box_dim[5] = box_z / 2.0
+        self._be.update_box(self.box_dim)
+        self.volume = self.box_dim[0] * self.box_dim[1] * self.box_dim[2]
+
+    def calcFrame(self,
+                  np.ndarray[np.float64_t, ndim=2, mode="c"] coor_sel1,
+                  np.ndarray[np.float64_t, ndim=2, mode="c"] coor_sel2,
+                  np.ndarray[np.float64_t, ndim=2, mode="c"] dip_sel1 = None,
+                  np.ndarray[np.float64_t, ndim=2, mode="c"] dip_sel2 = None,
+                  pre_coor_sel1_gpu=None, pre_coor_sel2_gpu=None,
+                  pre_dip_sel1_gpu=None, pre_dip_sel2_gpu=None):
+        """
+        calcFrame(coor_sel1, coor_sel2, dip_sel1=None, dip_sel2=None,
+                  pre_coor_sel1_gpu=None, pre_coor_sel2_gpu=None,
+                  pre_dip_sel1_gpu=None, pre_dip_sel2_gpu=None)
+
+        Pass the data of the current frame (:385-464).  The arrays are copied before the call returns.
+        pre_*_gpu take `DeviceArray` objects from `to_device` (shared uploads for several RDF objects).
+        """
+        cdef int m = <int> self.mode_sel
+        if dip_sel1 is None and pre_dip_sel1_gpu is None and (m & 2 or m & 4 or m & 16 or m & 32):
+            raise TypeError("No dipole moment array for the fist selection was passed, although the requested gfunctions need it!")
+        if dip_sel2 is None and pre_dip_sel2_gpu is None and (m & 2 or m & 8 or m & 16 or m & 64):
+            raise TypeError("No dipole moment array for the second selection was passed, although the requested gfunctions need it!")
+
+        if coor_sel1.shape[0] != self.n1 or coor_sel1.shape[1] != 3 or coor_sel2.shape[0] != self.n2 or coor_sel2.shape[1] != 3:
+            raise ValueError("coordinate arrays must have shapes (%d,3) and (%d,3)" % (self.n1, self.n2))
+        if dip_sel1 is not None and (dip_sel1.shape[0] != self.n1 or dip_sel1.shape[1] != 3):
+            raise ValueError("dip_sel1 must have shape (%d,3)" % self.n1)
+        if dip_sel2 is not None and (dip_sel2.shape[0] != self.n2 or dip_sel2.shape[1] != 3):
+            raise ValueError("dip_sel2 must have shape (%d,3)" % self.n2)
+
+        if self.oneistwo is None:                            # :417-421
+            if (coor_sel1[0] == coor_sel2[0]).all() and self.nmol1 == self.nmol2:
+                self.oneistwo = True
+            else:
+                self.oneistwo = False
+
+        self.ctr += 1                                        # :424
+        self.volume_list.append(self.volume)                 # :427
+
+        cdef _Backend be = self._be
+        if pre_coor_sel1_gpu is not None or pre_coor_sel2_gpu is not None or pre_dip_sel1_gpu is not None or pre_dip_sel2_gpu is not None:
+            c1 = pre_coor_sel1_gpu if pre_coor_sel1_gpu is not None else to_device(coor_sel1, self._devices[0])
+            if pre_coor_sel2_gpu is not None:
+                c2 = pre_coor_sel2_gpu
+            elif coor_sel2 is coor_sel1:
+                c2 = c1
+            else:
+                c2 = to_device(coor_sel2, self._devices[0])
+            d1 = pre_dip_sel1_gpu if pre_dip_sel1_gpu is not None else (to_device(dip_sel1, self._devices[0]) if dip_sel1 is not None else None)
+            if pre_dip_sel2_gpu is not None:
+                d2 = pre_dip_sel2_gpu
+            elif dip_sel2 is dip_sel1:
+                d2 = d1
+            else:
+                d2 = to_device(dip_sel2, self._devices[0]) if dip_sel2 is not None else None
+            be.enqueue_device(1, c1, c2, d1, d2, self.box_dim.reshape(1, 6))
+            return
+
+        be.enqueue(<const double *> coor_sel1.data, <const double *> coor_sel2.data,
+                   <const double *> dip_sel1.data if dip_sel1 is not None else NULL,
+                   <const double *> dip_sel2.data if dip_sel2 is not None else NULL)
+
+    def _addHisto(self, np.ndarray[np.float64_t, ndim=1] histo_out, np.ndarray[np.float64_t, ndim=1] histo):
+        """
+        Add the histograms of all core particles (:466-480).  `histo` may be the per-particle array
+        (7*n1*histo_n) or the already summed [mode][bin] array (7*histo_n) this backend keeps.
+        """
+        cdef int hn = self.histo_n
+        cdef long long n1 = self.n1
+        if histo.shape[0] == 7 * hn:
+            histo_out += histo
+        elif histo.shape[0] == 7 * n1 * hn:
+            histo_out += histo.reshape(7, n1, hn).sum(axis=1).reshape(-1)
+        else:
+            raise ValueError("histogram has %d elements, expected %d or %d" % (histo.shape[0], 7 * hn, 7 * n1 * hn))
+
+    def _normHisto(self):
+        """
+        Normalize the histogram (:483-511); host code, same arithmetic as the reference.
+        """
+        if self.norm_volume:
+            volume = self.norm_volume
+        else:
+            volume = 0.0
+            for v in self.volume_list:
+                volume += v
+            volume /= len(self.volume_list)
+
+        PI = 3.14159265358979323846
+        if self.oneistwo:
+            rho = float(self.nmol1 * (self.nmol1 - 1)) / volume
+        else:
+            rho = float(self.nmol1 * self.nmol2) / volume
+
+        cdef int i, j
+        for i in range(self.histo_n):
+            r = self.histo_min + float(i) * self.histo_dr
+            r_out = r + self.histo_dr
+            slice_vol = 4.0 / 3.0 * PI * (r_out**3 - r**3)
+            norm = rho * slice_vol * float(self.ctr)
+            for j in range(7):
+                self.histogram_out[j * self.histo_n + i] /= norm
+
+    def scale(self, value):
+        """:513-515"""
+        self.histogram_out[:] *= value
+        self._be.scale(float(value))
+
+    def write(self, filename="rdf"):
+        """
+        RDF.write(filename="rdf")
+
+        Norm the calculated histograms and write them to <filename>_g000.dat ... (:517-550).
+        Like the reference, calling it twice accumulates into the already normalised histogram_out.
+        """
+        self._addHisto(self.histogram_out, self.raw_histogram())
+        self._normHisto()
+
+        names = ("000", "110", "101", "011", "220", "202", "022")
+        files = {}
+        for k in range(7):
+            if self.mode_sel & (1 << k):
+                files[k] = open(filename + "_g" + names[k] + ".dat", 'w')
+        for i in range(self.histo_n):
+            r = self.histo_min + i * self.histo_dr + self.histo_dr * 0.5
+            for k in files:
+                files[k].write("%5.5f\t%5.5f\n" % (r, self.histogram_out[k * self.histo_n + i]))
+        for k in files:
+            files[k].close()
+
+    def resetArrays(self):
+        """
+        Reset histogram arrays to zero (:552-557; ctr and volume_list are kept, like the reference)
+        """
+        self.histogram_out[:] = 0.0
+        self._be.reset()
+
+    def printInfo(self):
+        """
+        Print some information about the RDF container (:560-566).
+        """
+        print("Modes: ", self.mode_sel)
+        print("Frames read: ", self.ctr)
+
+    # ------------------------------------------------------------------ extensions
+    @property
+    def histogram(self):
+        if self._flags & 1:
+            return self._be.readout_per_particle()
+        return self.raw_histogram()
+
+    def raw_histogram(self):
+        """Un-normalised [mode][bin] sums accumulated since the last resetArrays (7*histo_n float64)."""
+        hist, pw, ovf = self._be.readout()
+        self.pair_weight = pw
+        self.overflow = ovf
+        return hist
+
+    def calcFrames(self, coor_sel1, coor_sel2, dip_sel1=None, dip_sel2=None, boxes=None):
+        """Many frames per call: arrays of shape (nframes, n, 3); boxes (nframes, 3) for NpT or None."""
+        cdef np.ndarray[np.float64_t, ndim=3, mode="c"] c1 = np.ascontiguousarray(coor_sel1, dtype=np.float64)
+        cdef np.ndarray[np.float64_t, ndim=3, mode="c"] c2 = c1 if coor_sel2 is coor_sel1 else np.ascontiguousarray(coor_sel2, dtype=np.float64)
+        cdef np.ndarray[np.float64_t, ndim=3, mode="c"] d1 = None
+        cdef np.ndarray[np.float64_t, ndim=3, mode="c"] d2 = None
+        cdef np.ndarray[np.float64_t, ndim=2, mode="c"] bx = None
+        cdef int m = <int> self.mode_sel
+        cdef int nf = c1.shape[0]
+        if dip_sel1 is not None:
+            d1 = np.ascontiguousarray(dip_sel1, dtype=np.float64)
+        if dip_sel2 is not None:
+            d2 = d1 if dip_sel2 is dip_sel1 else np.ascontiguousarray(dip_sel2, dtype=np.float64)
+        if d1 is None and (m & 2 or m & 4 or m & 16 or m & 32):
+            raise TypeError("No dipole moment array for the fist selection was passed, although the requested gfunctions need it!")
+        if d2 is None and (m & 2 or m & 8 or m & 16 or m & 64):
+            raise TypeError("No dipole moment array for the second selection was passed, although the requested gfunctions need it!")
+        if c1.shape[1] != self.n1 or c1.shape[2] != 3 or c2.shape[1] != self.n2 or c2.shape[2] != 3 or c2.shape[0] != nf:
+            raise ValueError("coordinate arrays must have shapes (nframes,%d,3) and (nframes,%d,3)" % (self.n1, self.n2))
+        if nf == 0:
+            return
+        if self.oneistwo is None:
+            self.oneistwo = bool((c1[0, 0] == c2[0, 0]).all() and self.nmol1 == self.nmol2)
+        if boxes is not None:
+            b3 = np.asarray(boxes, dtype=np.float64).reshape(nf, 3)
+            bx = np.ascontiguousarray(np.concatenate([b3, b3 / 2.0], axis=1))
+            vols = list(b3[:, 0] * b3[:, 1] * b3[:, 2])
+        else:
+            vols = [self.volume] * nf
+        self.ctr += nf
+        self.volume_list.extend(vols)
+        cdef _Backend be = self._be
+        be.enqueue_many(nf, <const double *> c1.data, 3 * <long long> self.n1, <const double *> c2.data, 3 * <long long> self.n2,
+                        <const double *> d1.data if d1 is not None else NULL, 3 * <long long> self.n1,
+                        <const double *> d2.data if d2 is not None else NULL, 3 * <long long> self.n2,
+                        <const double *> bx.data if bx is not None else NULL)
+        if boxes is not None:
+            self.update_box(*[float(v) for v in b3[nf - 1]])
+
+    def calcFramesDevice(self, int nframes, c1, c2, d1=None, d2=None, boxes=None):
+        """Frames already resident in HBM (`DeviceArray`s of shape (nframes,n,3)); no host->device copy."""
+        if self.oneistwo is None:
+            self.oneistwo = bool(c1 is c2 and self.nmol1 == self.nmol2)
+        self.ctr += nframes
+        self.volume_list.extend([self.volume] * nframes)
+        self._be.enqueue_device(nframes, c1, c2, d1, d2, boxes)
+
+    def flush(self):
+        self._be.flush()
+
+    def sync(self):
+        """Wait for all enqueued frames; raises the deferred ZeroDivisionError if a zero-norm dipole was hit."""
+        self._be.sync()
+
+    def stats(self):
+        return self._be.stats()
+
+    def attach_comm(self, uid, nranks, rank):
+        """One process per GPU: join an NCCL communicator; readout then sums the histograms of all ranks."""
+        self._be.attach_comm(uid, nranks, rank)

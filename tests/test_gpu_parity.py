@@ -1,0 +1,312 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the
+reference-facing RDF class -> C ABI (libgfn.so), against
+  (1) the committed golden fixtures produced by the unmodified reference module, and
+  (2) the CPU oracle on seeded inputs, up to BASELINE.json's full single-GPU size (cfg3, n=32768).
+Bars: g000 / pair counts bit-exact; orientation-weighted rows within 1e-12 relative (fp64, summation
+order differs), with the cancellation caveat of SURVEY.md 8c: atol = 1e-12 * pair weight of the bin.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases as C
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+VARIANTS = ["", "fp64", "global", "fp64,global", "per_particle"]
+
+
+def RDF(*a, **k):
+    from newanalysis.gfunction import RDF as R
+    return R(*a, **k)
+
+
+def load_golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    return z["raw"], z["out"], json.loads(str(z["meta"]))
+
+
+def assert_hist_close(got, ref, hn, pairw=None):
+    got = np.asarray(got); ref = np.asarray(ref)
+    if pairw is None:
+        pairw = ref[:hn]
+    # count-like rows: exact wherever the reference row is integer valued (g000)
+    scale = np.maximum(np.abs(ref), np.tile(np.abs(pairw), 7))
+    err = np.abs(got - ref)
+    bad = err > RTOL * scale
+    assert not bad.any(), "max err/scale = %g at %s" % (np.max(err / np.maximum(scale, 1e-300)), np.flatnonzero(bad)[:5])
+
+
+@pytest.mark.parametrize("flags", VARIANTS)
+@pytest.mark.parametrize("name", sorted(C.CASES))
+def test_golden(golden_dir, name, flags, tmp_path):
+    raw, out, meta = load_golden(golden_dir, name)
+    case = C.CASES[name]
+    n1, n2 = case["n1"], case["n2"]
+    bx, by, bz = case["box"]
+    rdf = RDF(case["modes"], case["hmin"], case["hmax"], case["dr"], n1, n2, n1, n2, bx, by, bz, gfn_flags=flags)
+    C.drive(rdf, case)
+    hn = meta["histo_n"]
+    assert int(rdf.histo_n) == hn and int(rdf.mode_sel) == meta["mode_sel"]
+    assert float(rdf.histo_max) == meta["histo_max"] and float(rdf.histo_inv_dr) == meta["histo_inv_dr"]
+    assert bool(rdf.oneistwo) == meta["oneistwo"] and rdf.ctr == meta["ctr"]
+    got = rdf.raw_histogram()
+    if meta["mode_sel"] & 1:
+        assert np.array_equal(got[:hn], raw[:hn]), "g000 not bit-exact"
+    # pair weight row is what g000 would hold (minus Q3 spills), whatever the modes
+    assert_hist_close(got, raw, hn, pairw=np.maximum(rdf.pair_weight, raw[:hn]))
+    rdf.write(str(tmp_path / "g"))
+    if meta["mode_sel"] & 1:
+        assert np.array_equal(rdf.histogram_out[:hn], out[:hn])
+        assert (tmp_path / "g_g000.dat").read_text() == meta["dat"]["000"]
+    for mode, text in meta["dat"].items():
+        a = np.loadtxt(str(tmp_path / ("g_g%s.dat" % mode)))
+        b = np.array([[float(v) for v in ln.split()] for ln in text.strip().splitlines()])
+        assert a.shape == b.shape and np.allclose(a, b, rtol=0, atol=2e-5)
+
+
+def test_micro_cases(golden_dir):
+    idx = np.load(os.path.join(golden_dir, "micro.npz"))["idx"]
+    for (y, _), want in zip(C.MICRO, idx):
+        rdf = RDF(["000"], 0.0, 15.0, 0.05, 1, 2, 1, 2, 40.0, gfn_flags="per_particle")
+        rdf.calcFrame(np.zeros((1, 3)), np.array([y, (30.0, 30.0, 30.0)]))
+        h = rdf.histogram
+        nz = np.flatnonzero(h)
+        assert (int(nz[0]) if nz.size else -1) == want
+
+
+def test_per_particle_matches_reference_layout():
+    case = C.CASES["rect_all"]
+    a = C.drive(C.make_rdf(O.OracleRDF, case), case)
+    n1, n2 = case["n1"], case["n2"]
+    b = RDF(case["modes"], case["hmin"], case["hmax"], case["dr"], n1, n2, n1, n2, case["box"][0], gfn_flags="per_particle")
+    C.drive(b, case)
+    hp = b.histogram
+    hn = int(b.histo_n)
+    assert hp.shape == a.histogram.shape
+    assert np.array_equal(hp[:n1 * hn], a.histogram[:n1 * hn])
+    scale = np.maximum(np.abs(a.histogram), np.tile(a.histogram[:n1 * hn], 7))
+    assert np.all(np.abs(hp - a.histogram) <= RTOL * scale)
+    out = np.zeros(7 * hn)
+    b._addHisto(out, hp)
+    assert_hist_close(out, a.raw_sum(), hn)
+
+
+def _random_frame(rng, n, L, dip=True):
+    return np.ascontiguousarray(rng.random((n, 3)) * L), (np.ascontiguousarray(rng.standard_normal((n, 3))) if dip else None)
+
+
+@pytest.mark.parametrize("flags", ["", "fp64"])
+@pytest.mark.parametrize("n,L", [(8192, 62.58), (32768, 99.33)])
+def test_cfg3_shape_against_oracle(n, L, flags):
+    """BASELINE configs[2] shape (water, self, all modes, 0-15/0.05); n=32768 is the full size."""
+    rng = np.random.default_rng(3000 + n)
+    c, d = _random_frame(rng, n, L)
+    rdf = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L, gfn_flags=flags)
+    rdf.calcFrame(c, c, d, d)
+    got = rdf.raw_histogram()
+    ref = np.zeros(7 * 300)
+    box = np.array([L, L, L, L / 2, L / 2, L / 2])
+    rc, oob = O.calc_histo_rows_c(c, c, d, d, ref, box, 0.0, 15.0, 300, 20.0, 127)
+    assert rc == 0 and oob == 0
+    assert np.array_equal(got[:300], ref[:300])
+    # the rows oracle itself differs from the reference order by ~1e-13 relative: allow 2x
+    scale = np.maximum(np.abs(ref), np.tile(ref[:300], 7))
+    assert np.all(np.abs(got - ref) <= 2 * RTOL * scale)
+    st = rdf.stats()
+    assert st["pair_evals"] == n * (n + 1) / 2 and st["in_range"] * 2 - 0 >= ref[:300].sum() - 1
+
+
+def test_cfg2_shape_many_frames_batched():
+    """[C2mim][OTf] shape: 1000 x 1000 distinct selections of equal size (quirk Q1), 600 bins, 5 modes."""
+    n, L, nf = 1000, 67.7, 12
+    modes = ["000", "110", "101", "011", "220"]
+    rng = np.random.default_rng(2000)
+    c1 = rng.random((nf, n, 3)) * L; c2 = rng.random((nf, n, 3)) * L
+    d1 = rng.standard_normal((nf, n, 3)); d2 = rng.standard_normal((nf, n, 3))
+    a = RDF(modes, 0.0, 30.0, 0.05, n, n, n, n, L)
+    a.calcFrames(c1, c2, d1, d2)
+    b = RDF(modes, 0.0, 30.0, 0.05, n, n, n, n, L)
+    o = O.OracleRDF(modes, 0.0, 30.0, 0.05, n, n, n, n, L)
+    for f in range(nf):
+        b.calcFrame(c1[f], c2[f], d1[f], d2[f])
+        o.calcFrame(c1[f], c2[f], d1[f], d2[f])
+    ref = o.raw_sum()
+    ha, hb = a.raw_histogram(), b.raw_histogram()
+    assert np.array_equal(ha, hb)                      # batch call == per-frame calls, deterministic
+    assert np.array_equal(ha[:600], ref[:600])
+    assert_hist_close(ha, ref, 600)
+    assert a.ctr == nf and not a.oneistwo
+
+
+def test_threshold_edges_exact():
+    """Pairs placed within a few ulps of histo_max, of the first-bin edge 1/invdx and of bin edges,
+    straight and across the periodic boundary: the pre-filter must never lose a pair the reference
+    keeps, and bins must agree exactly."""
+    L = 40.0
+    rng = np.random.default_rng(11)
+    pts = []
+    for base in (15.0, 0.05, 7.35, 14.95, 0.1):
+        for k in range(-6, 7):
+            r = base
+            for _ in range(abs(k)):
+                r = np.nextafter(r, np.inf if k > 0 else -np.inf)
+            for _ in range(4):
+                u = rng.standard_normal(3); u /= np.linalg.norm(u)
+                pts.append(u * r)
+            pts.append(np.array([r, 0, 0])); pts.append(np.array([0, -r, 0]))
+    pts = np.array(pts)
+    origin = np.array([[39.7, 0.2, 20.0]])
+    c2 = np.ascontiguousarray((origin + pts) % L)
+    for flags in ("", "fp64"):
+        g = RDF(["000"], 0.0, 15.0, 0.05, 1, len(c2), 1, len(c2), L, gfn_flags=flags + ",per_particle" if flags else "per_particle")
+        o = O.OracleRDF(["000"], 0.0, 15.0, 0.05, 1, len(c2), 1, len(c2), L)
+        o.histogram = np.zeros(2 * 300 * 7)          # spare row so the Q3 spill stays inspectable
+        g.calcFrame(origin, c2); o.calcFrame(origin, c2)
+        hp = g.histogram
+        assert np.array_equal(hp[:300], o.histogram[:300])
+        assert hp[:300].sum() > 50
+
+
+def test_unwrapped_and_large_coordinates():
+    """Coordinates far outside the box (single-shift minimum image, quirk Q8) and a large offset:
+    the guard band scales with max|x|, results must still match the oracle exactly."""
+    n, L = 600, 30.0
+    rng = np.random.default_rng(5)
+    c = (rng.random((n, 3)) * 3 - 1) * L + 1000.0
+    d = rng.standard_normal((n, 3))
+    g = RDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L)
+    o = O.OracleRDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L)
+    g.calcFrame(c, c, d, d); o.calcFrame(c, c, d, d)
+    got, ref = g.raw_histogram(), o.raw_sum()
+    assert np.array_equal(got[:280], ref[:280]) and ref[:280].sum() > 0
+    assert_hist_close(got, ref, 280)
+
+
+def test_zero_norm_dipole_raises_deferred():
+    rdf = RDF(["all"], 0.0, 15.0, 0.05, 4, 5, 4, 5, 40.0)
+    rng = np.random.default_rng(0)
+    c1, c2 = rng.random((4, 3)) * 5, rng.random((5, 3)) * 5
+    d1, d2 = rng.standard_normal((4, 3)), rng.standard_normal((5, 3))
+    d2[2] = 0.0
+    rdf.calcFrame(c1, c2, d1, d2)
+    with pytest.raises(ZeroDivisionError, match="float division"):
+        rdf.sync()
+    assert rdf.ctr == 1
+
+
+def test_argument_errors_match_reference():
+    rdf = RDF(["110"], 0.0, 15.0, 0.05, 4, 5, 4, 5, 40.0)
+    with pytest.raises(TypeError, match="fist selection"):
+        rdf.calcFrame(np.zeros((4, 3)), np.zeros((5, 3)))
+    with pytest.raises(TypeError, match="second selection"):
+        rdf.calcFrame(np.zeros((4, 3)), np.zeros((5, 3)), np.ones((4, 3)))
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        rdf.calcFrame(np.zeros((4, 3), dtype=np.float32), np.zeros((5, 3)), np.ones((4, 3)), np.ones((5, 3)))
+    with pytest.raises(ValueError, match="not C-contiguous"):
+        rdf.calcFrame(np.zeros((3, 4)).T, np.zeros((5, 3)), np.ones((4, 3)), np.ones((5, 3)))
+
+
+def test_g000_without_dipoles_and_unknown_modes():
+    n, L = 500, 30.0
+    rng = np.random.default_rng(8)
+    c1, _ = _random_frame(rng, n, L, dip=False); c2, _ = _random_frame(rng, 300, L, dip=False)
+    g = RDF(["000", "bogus"], 0.0, 15.0, 0.05, n, 300, n, 300, L)
+    o = O.OracleRDF(["000", "bogus"], 0.0, 15.0, 0.05, n, 300, n, 300, L)
+    g.calcFrame(c1, c2); o.calcFrame(c1, c2)
+    assert np.array_equal(g.raw_histogram(), o.raw_sum())
+
+
+def test_scale_reset_write_twice_semantics(tmp_path):
+    """scale / resetArrays / non-idempotent write (quirk Q7) behave like the reference class."""
+    case = C.CASES["self_odd"]
+    g = C.drive(C.make_rdf(RDF, case), case)
+    o = C.drive(C.make_rdf(O.OracleRDF, case), case)
+    g.scale(0.5); o.scale(0.5)
+    hn = int(g.histo_n)
+    assert np.array_equal(g.raw_histogram()[:hn], o.raw_sum()[:hn])
+    g.write(str(tmp_path / "a")); o.write(str(tmp_path / "b"))
+    g.write(str(tmp_path / "a")); o.write(str(tmp_path / "b"))           # second write accumulates again
+    assert np.array_equal(g.histogram_out[:hn], o.histogram_out[:hn])
+    assert (tmp_path / "a_g000.dat").read_text() == (tmp_path / "b_g000.dat").read_text()
+    g.resetArrays(); o.resetArrays()
+    assert not g.raw_histogram().any() and not g.histogram_out.any() and g.ctr == o.ctr == case["frames"]
+    c1, c2, d1, d2, _ = C.build_inputs(case, 0)
+    g.calcFrame(c1, c2, d1, d2); o.calcFrame(c1, c2, d1, d2)
+    assert np.array_equal(g.raw_histogram()[:hn], o.raw_sum()[:hn])
+
+
+def test_linearity_and_determinism_at_full_size():
+    """Size-independent properties at cfg3's full n: H(frame A) + H(frame B) == H(A then B) exactly for
+    counts, and two runs of the same input are bit-identical in every row (fixed summation order)."""
+    n, L = 32768, 99.33
+    rng = np.random.default_rng(99)
+    fa = _random_frame(rng, n, L); fb = _random_frame(rng, n, L)
+    def run(frames):
+        r = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
+        for c, d in frames:
+            r.calcFrame(c, c, d, d)
+        return r.raw_histogram(), r
+    ha, _ = run([fa]); hb, _ = run([fb]); hab, r = run([fa, fb]); hab2, _ = run([fa, fb])
+    assert np.array_equal(hab, hab2)
+    assert np.array_equal(ha[:300] + hb[:300], hab[:300])
+    assert np.allclose(ha + hb, hab, rtol=1e-12, atol=1e-12 * hab[:300].max())
+    # checksum of counts: in-range ordered pairs == sum of g000
+    assert r.stats()["in_range"] * 2 == hab[:300].sum()            # self case: i==j never in range, every pair weight 2
+
+
+def test_ring_recycling_and_npt(monkeypatch):
+    """More batches than ring slots with a box that changes every frame."""
+    monkeypatch.setenv("GFN_BATCH_FRAMES", "2")
+    n, L, nf = 400, 30.0, 15
+    g = RDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L)
+    o = O.OracleRDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L)
+    assert g.stats()["batch_frames"] == 2
+    for f in range(nf):
+        rng = np.random.default_rng(400 + f)
+        s = L * (1 + 1e-3 * rng.standard_normal(3))
+        c = np.ascontiguousarray(rng.random((n, 3)) * s); d = rng.standard_normal((n, 3))
+        g.update_box(*s); o.update_box(*s)
+        g.calcFrame(c, c, d, d); o.calcFrame(c, c, d, d)
+        c[:] = 0; d[:] = 0          # caller reuses its arrays immediately
+    got, ref = g.raw_histogram(), o.raw_sum()
+    assert np.array_equal(got[:280], ref[:280])
+    assert_hist_close(got, ref, 280)
+    assert g.volume_list == o.volume_list
+
+
+def test_device_resident_frames_equal_host_path():
+    from newanalysis.gfunction import to_device
+    n, L, nf = 3000, 45.0, 3
+    rng = np.random.default_rng(17)
+    c = rng.random((nf, n, 3)) * L; d = rng.standard_normal((nf, n, 3))
+    a = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L); a.calcFrames(c, c, d, d)
+    b = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
+    dc, dd = to_device(c), to_device(d)
+    b.calcFramesDevice(nf, dc, dc, dd, dd)
+    assert np.array_equal(a.raw_histogram(), b.raw_histogram())
+    # legacy pre_*_gpu kwargs of calcFrame: one shared upload, two RDF objects (cfg4 pattern)
+    e = RDF(["000"], 0.0, 15.0, 0.05, n, n, n, n, L); f = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
+    pc, pd = to_device(c[0]), to_device(d[0])
+    e.calcFrame(c[0], c[0], pre_coor_sel1_gpu=pc, pre_coor_sel2_gpu=pc)
+    f.calcFrame(c[0], c[0], d[0], d[0], pre_coor_sel1_gpu=pc, pre_coor_sel2_gpu=pc, pre_dip_sel1_gpu=pd, pre_dip_sel2_gpu=pd)
+    o = O.OracleRDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L); o.calcFrame(c[0], c[0], d[0], d[0])
+    assert np.array_equal(e.raw_histogram()[:300], o.raw_sum()[:300])
+    assert np.array_equal(f.raw_histogram()[:300], o.raw_sum()[:300])
+
+
+def test_big_histogram_falls_back_to_global_atomics():
+    n, L = 700, 60.0
+    rng = np.random.default_rng(21)
+    c, d = _random_frame(rng, n, L)
+    g = RDF(["all"], 0.0, 29.0, 0.005, n, n, n, n, L)       # 5800 bins: replicas do not fit in shared memory
+    assert g.stats()["hist_mode"] == "global_atomics"
+    o = O.OracleRDF(["all"], 0.0, 29.0, 0.005, n, n, n, n, L)
+    g.calcFrame(c, c, d, d); o.calcFrame(c, c, d, d)
+    got, ref = g.raw_histogram(), o.raw_sum()
+    assert np.array_equal(got[:5800], ref[:5800])
+    assert_hist_close(got, ref, 5800)
