@@ -1,0 +1,346 @@
+#!/usr/bin/env python3
+"""bench.py - pair evaluations per second of the multipole g-function path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[2] - water, 32,768 molecules, self g-function, all
+seven multipole modes, histogram 0-15 A / 0.05 A (300 bins), cubic box L = 99.33 A, synthetic uniform
+coordinates and normal dipoles (gfn_b200/synth.py).  One STEP = one pass of the hot path over a batch
+of FRAMES_PER_STEP frames; one pair evaluation = one iteration of the reference j loop
+(gfunction.pyx:130), n(n+1)/2 per frame.
+
+  value      device-timed (CUDA events on the library's compute stream, gfn_mark) throughput with the
+             frames already resident in HBM; N ranks each process their own frames (weak scaling).
+  e2e        the same metric through the reference-facing call RDF.calcFrame with HOST numpy arrays:
+             copy into the pinned ring, H2D, kernels, and a histogram readout (D2H, plus the NCCL
+             all-reduce over ranks when N > 1) every step, wall clock between two device syncs.
+  roofline   FP64 vector pipe: algorithmic flops/eval x evals / pair-kernel time
+             (CUDA events around every pair-kernel launch, summed by the library) against the DFMA
+             peak measured in this run (gfn_measure_peaks); nominal 37.2 TFLOP/s beside it.
+  cpu_baseline  the UNMODIFIED reference module (oracle/_ref, kind "reference"; else the C port) timed on
+             this box's host cores on a bounded sample of the same workload.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref) on the same config, one
+frame per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "mdy-newanalysis-package_b200")
+for p in (PKG, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from gfn_b200 import synth  # noqa: E402
+
+METRIC = "pair evals/sec (1e9), multipole g-function"
+UNIT = "1e9 pair evals/s"
+WORKLOAD = "cfg3"
+FRAMES_PER_STEP = 64
+POOL_FRAMES = 128
+NOMINAL_FP64_TFLOPS = 37.2
+
+
+def cfg():
+    c = dict(synth.CONFIGS[WORKLOAD])
+    n = int(os.environ.get("GFN_BENCH_N", c["n1"]))
+    if n != c["n1"]:                     # reduced-size dry runs only (never the reported number)
+        c["L"] = c["L"] * (n / c["n1"]) ** (1.0 / 3.0)
+        c["n1"] = c["n2"] = n
+    return c
+
+
+def make_pool(c, nframes, rank):
+    n = c["n1"]
+    co = np.empty((nframes, n, 3)); di = np.empty((nframes, n, 3))
+    for f in range(nframes):
+        co[f], di[f] = synth.frame(c["cfg"], f, n, c["L"], stream=1000 * rank)
+    return co, di
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="gfn_clocks_", suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                parts = [x.strip() for x in ln.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0])); mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_rdf(c):
+    """(RDF-like object, kind): the unmodified reference class if oracle/_ref is present, else the port."""
+    import oracle as O
+    ref = O.load_ref()
+    n = c["n1"]
+    args = (c["modes"], c["hmin"], c["hmax"], c["dr"], n, n, n, n, c["L"])
+    if ref is not None:
+        return ref.RDF(*args), "reference"
+    return O.OracleRDF(*args), "port"
+
+
+def time_reference(c, steps, warmup, rank=0):
+    """One frame per step through the reference's own RDF.calcFrame on the host cores."""
+    rdf, kind = reference_rdf(c)
+    n = c["n1"]
+    per = synth.pair_evals(n, n)
+    frames = [synth.frame(c["cfg"], f, n, c["L"], stream=1000 * rank) for f in range(min(4, warmup + steps))]
+    for s in range(warmup):
+        x, d = frames[s % len(frames)]
+        rdf.calcFrame(x, x, d, d)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        x, d = frames[(warmup + s) % len(frames)]
+        rdf.calcFrame(x, x, d, d)
+    dt = time.perf_counter() - t0
+    return per * steps / dt / 1e9, dt, kind, "%d full frames of %s (n=%d, %d pair evals each), %d warm-up" % (steps, WORKLOAD, n, per, warmup)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    c = cfg()
+    val, dt, kind, sample = time_reference(c, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n": c["n1"], "modes": "all", "bins": 300, "frames_per_step": 1,
+                   "note": "reference Cython/OpenMP calcHisto on host cores, one full frame per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": host_threads(), "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import newanalysis.gfunction as G          # fails loudly if the CUDA extension is missing
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    c = cfg()
+    n, L = c["n1"], c["L"]
+    per = synth.pair_evals(n, n)
+    F, K, W = args.frames_per_step, args.steps, args.warmup
+    flags = "fp64" if args.filter == "fp64" else ""
+    mk = lambda: G.RDF(c["modes"], c["hmin"], c["hmax"], c["dr"], n, n, n, n, L, devices=[local_rank], gfn_flags=flags)  # noqa: E731
+
+    uid = None
+    if world > 1:
+        import torch
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(G.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    pool_c, pool_d = make_pool(c, POOL_FRAMES, rank)
+    fp64_peak, fp32_peak = G.measure_peaks(local_rank)
+
+    # ---------------- arm 1: inputs resident in HBM, device-timed ------------------------------------
+    r = mk()
+    if uid is not None:
+        r.attach_comm(uid, world, rank)
+    dc, dd = G.to_device(pool_c, local_rank), G.to_device(pool_d, local_rank)
+
+    def dev_step(s):
+        first = (s * F) % (POOL_FRAMES - F + 1) if POOL_FRAMES > F else 0
+        r.calcFramesDevice(F, dc, dc, dd, dd, first=first)
+
+    for s in range(W):
+        dev_step(s)
+    r.sync()
+    st0 = r.stats()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    r.mark(0)
+    for s in range(K):
+        dev_step(W + s)
+    r.mark(1)
+    r.sync()
+    ms = allmax(r.mark_elapsed_ms())
+    barrier()
+    clocks = sampler.stop()
+    st1 = r.stats()
+    hist = r.raw_histogram()                     # includes the NCCL all-reduce over ranks when world > 1
+    hn = 300
+    frames_done = (W + K) * F * world
+    assert abs(hist[:hn].sum() - 2.0 * st1["in_range"] * (world if world > 1 else 1)) <= 0.02 * hist[:hn].sum() + 1, \
+        "g000 checksum does not match the in-range pair count"
+    value = world * K * F * per / (ms * 1e-3) / 1e9
+    kernel_ms = st1["kernel_ms"] - st0["kernel_ms"]
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    pair_launches = st1["pair_launches"] - st0["pair_launches"]
+    f_in = (st1["in_range"] - st0["in_range"]) / (st1["pair_evals"] - st0["pair_evals"])
+    f_surv = (st1["survivors"] - st0["survivors"]) / (st1["pair_evals"] - st0["pair_evals"])
+    flops_eval = synth.flops_per_eval(127, f_in)
+    achieved = flops_eval * K * F * per / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else None
+
+    # ---------------- arm 2: end to end through RDF.calcFrame with host arrays -----------------------
+    e = mk()
+    if uid is not None:
+        e.attach_comm(uid, world, rank)
+
+    def host_step(s):
+        first = (s * F) % (POOL_FRAMES - F + 1) if POOL_FRAMES > F else 0
+        for f in range(first, first + F):
+            e.calcFrame(pool_c[f], pool_c[f], pool_d[f], pool_d[f])
+        return e.raw_histogram()
+
+    for s in range(W):
+        host_step(s)
+    e.sync()
+    se0 = e.stats()
+    barrier()
+    sampler2 = ClockSampler(local_rank)
+    sampler2.start()
+    t0 = time.perf_counter()
+    for s in range(K):
+        host_step(W + s)
+    e.sync()
+    dt = allmax(time.perf_counter() - t0)
+    barrier()
+    clocks_e2e = sampler2.stop()
+    se1 = e.stats()
+    e2e_value = world * K * F * per / dt / 1e9
+    h2d = (se1["h2d_bytes"] - se0["h2d_bytes"]) / K
+    d2h = 8 * hn * 8 + 8 * 8
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        val, cdt, kind, sample = time_reference(c, 2, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": host_threads(), "kind": kind, "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n": n, "L": L, "modes": "all", "bins": hn, "frames_per_step": F,
+                   "pair_evals_per_step": F * per, "parallelism": "frames sharded over %d GPU(s), one NCCL all-reduce at readout" % world,
+                   "l2": "inputs exceed L2: %d-frame pool (%.0f MB fp64) cycled, records re-derived every step" % (POOL_FRAMES, 2 * pool_c.nbytes / 1e6),
+                   "filter": st1["filter"], "hist": st1["hist_mode"], "batch_frames": st1["batch_frames"], "grid": st1["grid"],
+                   "warps_per_block": st1["warps_per_block"], "smem_bytes": st1["smem_bytes"]},
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": (achieved / fp64_peak) if achieved else None, "traffic": None,
+                     "peak_source": "measured in this run: dependent-free DFMA loop (gfn_measure_peaks); nominal %.1f" % NOMINAL_FP64_TFLOPS,
+                     "frac_of_nominal": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None,
+                     "flops_per_eval": flops_eval, "in_range_fraction": f_in, "survivor_fraction": f_surv,
+                     "kernel": "pair_kernel", "kernel_ms_per_launch": kernel_ms / max(pair_launches, 1),
+                     "kernel_share_of_step": kernel_ms / ms, "fp32_peak_tflops": fp32_peak,
+                     "lever": "fp32 conservative pre-filter + exact fp64 survivors" if st1["filter"] == "fp32" else "fp64 pre-test + exact fp64 survivors"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": dt / K * 1e3, "api": "newanalysis.gfunction.RDF.calcFrame (host numpy arrays) + readout per step"},
+        "gpu_launches": int(launches),
+        "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                   "samples": clocks["samples"], "e2e": clocks_e2e},
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--filter", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

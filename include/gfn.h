@@ -150,6 +150,12 @@ int gfn_stats(gfn_t *h, gfn_stats_t *out);
 int gfn_comm_unique_id(char out[128]);
 int gfn_comm_attach(gfn_t *h, const char unique_id[128], int nranks, int rank);
 
+/* Device-side stopwatch for benchmarks: gfn_mark records a CUDA event on the compute stream of the
+ * handle's first device (after flushing pending frames), gfn_mark_elapsed_ms waits for mark 1 and
+ * returns the device time between mark 0 and mark 1. */
+int gfn_mark(gfn_t *h, int which);
+int gfn_mark_elapsed_ms(gfn_t *h, double *ms);
+
 /* Measured pipe peaks for the roofline denominator: dependent-free DFMA / FFMA loops on every SM
  * of device dev.  Results in TFLOP/s (an FMA counts 2). */
 int gfn_measure_peaks(int dev, double *fp64_tflops, double *fp32_tflops);

@@ -82,6 +82,7 @@ Nccl& nccl()
 // handle
 // ------------------------------------------------------------------------------------------------
 constexpr int kRing = 3;
+constexpr int kXRing = 4;
 
 struct Batch {
     double* h_pin = nullptr;      // pinned staging: [frame][c1 | d1 | c2 | d2] (absent parts omitted)
@@ -113,8 +114,11 @@ struct Dev {
     ncclComm_t comm = nullptr;
     // device-frame scratch (gfn_enqueue_device_frames)
     Rec64* xrecA = nullptr; Rec64* xrecB = nullptr; float4* xposA = nullptr; float4* xposB = nullptr;
-    float* xmax = nullptr; double* xbox = nullptr; int xcap = 0;
-    cudaEvent_t xk0 = nullptr, xk1 = nullptr; bool xtimed = false;
+    float* xmax = nullptr; int xcap = 0;
+    struct XSlot { double* h_box = nullptr; double* d_box = nullptr; cudaEvent_t k0 = nullptr, k1 = nullptr; bool timed = false; };
+    XSlot xs[kXRing];
+    int xcur = 0;
+    cudaEvent_t mark[2] = {nullptr, nullptr};
 };
 
 }  // namespace
@@ -302,9 +306,14 @@ void free_dev(Dev& d)
         if (b.k1) cudaEventDestroy(b.k1);
     }
     cudaFree(d.gacc); cudaFree(d.gsum); cudaFree(d.gpp); cudaFree(d.partials); cudaFree(d.counters); cudaFree(d.item_start);
-    cudaFree(d.xrecA); cudaFree(d.xrecB); cudaFree(d.xposA); cudaFree(d.xposB); cudaFree(d.xmax); cudaFree(d.xbox);
-    if (d.xk0) cudaEventDestroy(d.xk0);
-    if (d.xk1) cudaEventDestroy(d.xk1);
+    cudaFree(d.xrecA); cudaFree(d.xrecB); cudaFree(d.xposA); cudaFree(d.xposB); cudaFree(d.xmax);
+    for (Dev::XSlot& x : d.xs) {
+        if (x.h_box) cudaFreeHost(x.h_box);
+        cudaFree(x.d_box);
+        if (x.k0) cudaEventDestroy(x.k0);
+        if (x.k1) cudaEventDestroy(x.k1);
+    }
+    for (cudaEvent_t e : d.mark) if (e) cudaEventDestroy(e);
     if (d.comm && nccl().ok) nccl().CommDestroy(d.comm);
     if (d.copy) cudaStreamDestroy(d.copy);
     if (d.comp) cudaStreamDestroy(d.comp);
@@ -431,8 +440,14 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
             CUC(cudaMalloc(&d.gpp, bytes));
             CUC(cudaMemset(d.gpp, 0, bytes));
         }
-        CUC(cudaEventCreateWithFlags(&d.xk0, cudaEventDefault));
-        CUC(cudaEventCreateWithFlags(&d.xk1, cudaEventDefault));
+        for (Dev::XSlot& x : d.xs) {
+            CUC(cudaEventCreateWithFlags(&x.k0, cudaEventDefault));
+            CUC(cudaEventCreateWithFlags(&x.k1, cudaEventDefault));
+            CUC(cudaHostAlloc(&x.h_box, sizeof(double) * 6 * h->batch_frames, cudaHostAllocDefault));
+            CUC(cudaMalloc(&x.d_box, sizeof(double) * 6 * h->batch_frames));
+        }
+        CUC(cudaEventCreateWithFlags(&d.mark[0], cudaEventDefault));
+        CUC(cudaEventCreateWithFlags(&d.mark[1], cudaEventDefault));
         for (Batch& b : d.ring) {
             const size_t fb = sizeof(double) * (size_t)h->frame_doubles * h->batch_frames;
             CUC(cudaHostAlloc(&b.h_pin, fb, cudaHostAllocDefault));
@@ -529,35 +544,36 @@ int gfn_enqueue_device_frames(gfn_t* h, int nframes,
     const bool aliased = (dc2 == dc1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || dd2 == dd1) && (!h->need2 || h->need1);
     const int chunk = h->batch_frames;
     if (d.xcap < chunk) {
-        CU(cudaStreamSynchronize(d.comp));
-        cudaFree(d.xrecA); cudaFree(d.xrecB); cudaFree(d.xposA); cudaFree(d.xposB); cudaFree(d.xmax); cudaFree(d.xbox);
-        d.xrecA = d.xrecB = nullptr; d.xposA = d.xposB = nullptr; d.xmax = nullptr; d.xbox = nullptr; d.xcap = 0;
         CU(cudaMalloc(&d.xrecA, sizeof(Rec64) * (size_t)h->n1_pad * chunk));
         CU(cudaMalloc(&d.xposA, sizeof(float4) * (size_t)h->n1_pad * chunk));
         CU(cudaMalloc(&d.xrecB, sizeof(Rec64) * (size_t)h->n2_pad * chunk));
         CU(cudaMalloc(&d.xposB, sizeof(float4) * (size_t)h->n2_pad * chunk));
         CU(cudaMalloc(&d.xmax, sizeof(float) * 2 * chunk));
-        CU(cudaMalloc(&d.xbox, sizeof(double) * 6 * chunk));
         d.xcap = chunk;
     }
-    std::vector<double> hb(6 * (size_t)chunk);
     for (int f0 = 0; f0 < nframes; f0 += chunk) {
         const int nf = nframes - f0 < chunk ? nframes - f0 : chunk;
+        Dev::XSlot& x = d.xs[d.xcur];
+        d.xcur = (d.xcur + 1) % kXRing;
+        if (x.timed) {          // slot reuse: its previous launch is kXRing chunks old
+            CU(cudaEventSynchronize(x.k1));
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms;
+            x.timed = false;
+        }
         for (int f = 0; f < nf; ++f) {
             const double* src = box_dims ? box_dims + 6ll * (f0 + f) : h->box;
             if (box_dims) { int rc = validate_box(h, src); if (rc) return rc; }
-            memcpy(&hb[6 * (size_t)f], src, sizeof(double) * 6);
+            memcpy(x.h_box + 6ll * f, src, sizeof(double) * 6);
         }
-        // scratch (records, boxes) is reused chunk after chunk: stream order on d.comp serialises it
-        if (d.xtimed) { CU(cudaEventSynchronize(d.xk1)); float ms = 0.f; if (cudaEventElapsedTime(&ms, d.xk0, d.xk1) == cudaSuccess) h->st_kernel_ms += ms; d.xtimed = false; }
-        CU(cudaMemcpyAsync(d.xbox, hb.data(), sizeof(double) * 6 * nf, cudaMemcpyHostToDevice, d.comp));
-        CU(cudaStreamSynchronize(d.comp));      // hb is pageable and reused
+        // record scratch is reused chunk after chunk: stream order on d.comp serialises it
+        CU(cudaMemcpyAsync(x.d_box, x.h_box, sizeof(double) * 6 * nf, cudaMemcpyHostToDevice, d.comp));
         int rc = launch_frames(h, d, nf,
                                dc1 + s_c1 * f0, s_c1, dd1 ? dd1 + s_d1 * f0 : nullptr, s_d1,
                                dc2 + s_c2 * f0, s_c2, dd2 ? dd2 + s_d2 * f0 : nullptr, s_d2, aliased,
-                               d.xrecA, d.xposA, d.xrecB, d.xposB, d.xmax, d.xbox, d.xk0, d.xk1);
+                               d.xrecA, d.xposA, d.xrecB, d.xposB, d.xmax, x.d_box, x.k0, x.k1);
         if (rc) return rc;
-        d.xtimed = true;
+        x.timed = true;
     }
     return GFN_OK;
 }
@@ -582,7 +598,7 @@ int gfn_sync(gfn_t* h)
         CU(cudaStreamSynchronize(d.copy));
         CU(cudaStreamSynchronize(d.comp));
         for (Batch& b : d.ring) { b.inflight = false; harvest_timing(h, b); }
-        if (d.xtimed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, d.xk0, d.xk1) == cudaSuccess) h->st_kernel_ms += ms; d.xtimed = false; }
+        for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms; x.timed = false; }
     }
     return check_zerodiv(h);
 }
@@ -721,6 +737,29 @@ int gfn_comm_attach(gfn_t* h, const char unique_id[128], int nranks, int rank)
     return GFN_OK;
 }
 
+int gfn_mark(gfn_t* h, int which)
+{
+    if (!h || which < 0 || which > 1) return fail(h, GFN_EINVAL, "gfn_mark: which must be 0 or 1");
+    int rc = gfn_flush(h);
+    if (rc) return rc;
+    Dev& d = h->devs[0];
+    CU(cudaSetDevice(d.dev));
+    CU(cudaEventRecord(d.mark[which], d.comp));
+    return GFN_OK;
+}
+
+int gfn_mark_elapsed_ms(gfn_t* h, double* ms)
+{
+    if (!h || !ms) return fail(h, GFN_EINVAL, "NULL argument");
+    Dev& d = h->devs[0];
+    CU(cudaSetDevice(d.dev));
+    CU(cudaEventSynchronize(d.mark[1]));
+    float f = 0.f;
+    CU(cudaEventElapsedTime(&f, d.mark[0], d.mark[1]));
+    *ms = f;
+    return GFN_OK;
+}
+
 int gfn_measure_peaks(int dev, double* fp64_tflops, double* fp32_tflops)
 {
     gfn_t* h = nullptr;
@@ -748,6 +787,7 @@ int gfn_dev_upload(int dev, void* dptr, const void* host, unsigned long long byt
 {
     gfn_t* h = nullptr;
     CU(cudaSetDevice(dev));
+    CU(cudaDeviceSynchronize());      // frames enqueued earlier may still be reading this buffer
     CU(cudaMemcpy(dptr, host, bytes, cudaMemcpyHostToDevice));
     return GFN_OK;
 }

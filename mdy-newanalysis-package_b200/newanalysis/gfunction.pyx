@@ -71,6 +71,8 @@ cdef extern from "gfn.h":
     int gfn_comm_unique_id(char *out) nogil
     int gfn_comm_attach(gfn_t *h, const char *uid, int nranks, int rank) nogil
     int gfn_measure_peaks(int dev, double *fp64, double *fp32) nogil
+    int gfn_mark(gfn_t *h, int which) nogil
+    int gfn_mark_elapsed_ms(gfn_t *h, double *ms) nogil
     int gfn_dev_alloc(int dev, void **dptr, unsigned long long nbytes) nogil
     int gfn_dev_free(int dev, void *dptr) nogil
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
@@ -238,11 +240,14 @@ cdef class _Backend:
             rc = gfn_enqueue_frames(self.h, nframes, c1, s1, c2, s2, d1, s3, d2, s4, boxes)
         return self.check(rc)
 
-    def enqueue_device(self, int nframes, DeviceArray c1, DeviceArray c2, DeviceArray d1, DeviceArray d2, boxes=None):
-        cdef const double *p1 = <const double *> c1.ptr
-        cdef const double *p2 = <const double *> c2.ptr
-        cdef const double *q1 = <const double *> d1.ptr if d1 is not None else NULL
-        cdef const double *q2 = <const double *> d2.ptr if d2 is not None else NULL
+    def enqueue_device(self, int nframes, DeviceArray c1, DeviceArray c2, DeviceArray d1, DeviceArray d2, boxes=None, long long first=0):
+        cdef long long o1 = first * 3 * self.n1, o2 = first * 3 * self.n2
+        if first < 0 or <unsigned long long> ((first + nframes) * 3 * self.n1 * 8) > c1.nbytes or <unsigned long long> ((first + nframes) * 3 * self.n2 * 8) > c2.nbytes:
+            raise ValueError("frames [%d, %d) exceed the device array" % (first, first + nframes))
+        cdef const double *p1 = <const double *> c1.ptr + o1
+        cdef const double *p2 = <const double *> c2.ptr + o2
+        cdef const double *q1 = (<const double *> d1.ptr + o1) if d1 is not None else NULL
+        cdef const double *q2 = (<const double *> d2.ptr + o2) if d2 is not None else NULL
         cdef np.ndarray[np.float64_t, ndim=2, mode="c"] bx
         cdef const double *pb = NULL
         if boxes is not None:
@@ -293,6 +298,17 @@ cdef class _Backend:
 
     def reset(self):
         self.check(gfn_reset(self.h))
+
+    def mark(self, int which):
+        self.check(gfn_mark(self.h, which))
+
+    def mark_elapsed_ms(self):
+        cdef double ms = 0
+        cdef int rc
+        with nogil:
+            rc = gfn_mark_elapsed_ms(self.h, &ms)
+        self.check(rc)
+        return ms
 
     def attach_comm(self, bytes uid, int nranks, int rank):
         if len(uid) != 128:
@@ -597,13 +613,13 @@ class RDF(object):
         if boxes is not None:
             self.update_box(*[float(v) for v in b3[nf - 1]])
 
-    def calcFramesDevice(self, int nframes, c1, c2, d1=None, d2=None, boxes=None):
-        """Frames already resident in HBM (`DeviceArray`s of shape (nframes,n,3)); no host->device copy."""
+    def calcFramesDevice(self, int nframes, c1, c2, d1=None, d2=None, boxes=None, first=0):
+        """Frames already resident in HBM (`DeviceArray`s of shape (>=first+nframes,n,3)); no host->device copy."""
         if self.oneistwo is None:
             self.oneistwo = bool(c1 is c2 and self.nmol1 == self.nmol2)
         self.ctr += nframes
         self.volume_list.extend([self.volume] * nframes)
-        self._be.enqueue_device(nframes, c1, c2, d1, d2, boxes)
+        self._be.enqueue_device(nframes, c1, c2, d1, d2, boxes, first)
 
     def flush(self):
         self._be.flush()
@@ -614,6 +630,13 @@ class RDF(object):
 
     def stats(self):
         return self._be.stats()
+
+    def mark(self, which):
+        """Record device-side stopwatch mark 0 or 1 on the compute stream (benchmarks)."""
+        self._be.mark(which)
+
+    def mark_elapsed_ms(self):
+        return self._be.mark_elapsed_ms()
 
     def attach_comm(self, uid, nranks, rank):
         """One process per GPU: join an NCCL communicator; readout then sums the histograms of all ranks."""

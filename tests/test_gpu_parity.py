@@ -230,9 +230,12 @@ def test_scale_reset_write_twice_semantics(tmp_path):
     hn = int(g.histo_n)
     assert np.array_equal(g.raw_histogram()[:hn], o.raw_sum()[:hn])
     g.write(str(tmp_path / "a")); o.write(str(tmp_path / "b"))
-    g.write(str(tmp_path / "a")); o.write(str(tmp_path / "b"))           # second write accumulates again
     assert np.array_equal(g.histogram_out[:hn], o.histogram_out[:hn])
     assert (tmp_path / "a_g000.dat").read_text() == (tmp_path / "b_g000.dat").read_text()
+    g.write(str(tmp_path / "a")); o.write(str(tmp_path / "b"))           # second write accumulates again
+    # the reference adds the n1 rows one by one onto the already normalised (non-integer) values, this
+    # backend adds their sum: same value up to rounding, not bit-identical (documented in INTEGRATION.md)
+    assert np.allclose(g.histogram_out[:hn], o.histogram_out[:hn], rtol=1e-12, atol=0)
     g.resetArrays(); o.resetArrays()
     assert not g.raw_histogram().any() and not g.histogram_out.any() and g.ctr == o.ctr == case["frames"]
     c1, c2, d1, d2, _ = C.build_inputs(case, 0)
