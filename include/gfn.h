@@ -74,7 +74,7 @@ typedef struct gfn_stats {
     double overflow;          /* pairs with pos >= histo_n (quirk Q3) */
     int    filter_fp64;       /* 1 if the fp64 pre-test is active, 0 for the fp32 pre-filter */
     int    hist_mode;         /* 0 shared-memory warp replicas, 1 global atomics, 2 per-particle global */
-    int    warps_per_block, blocks_per_sm, grid, smem_bytes, batch_frames, ndev;
+    int    warps_per_block, blocks_per_sm, grid, smem_bytes, batch_frames, ndev, hist_replicas;
 } gfn_stats_t;
 
 /* Number of CUDA devices visible (0 if none / no driver).  Never fails. */

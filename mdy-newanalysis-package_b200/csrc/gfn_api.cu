@@ -89,8 +89,7 @@ struct Batch {
     double* d_raw = nullptr;      // same layout on the device
     double* h_box = nullptr;      // pinned [frames][6]
     double* d_box = nullptr;
-    Rec64*  recA = nullptr; Rec64* recB = nullptr;
-    float4* posA = nullptr; float4* posB = nullptr;
+    Site* siteA = nullptr; Site* siteB = nullptr;
     float*  maxab = nullptr;      // [2][frames]
     cudaEvent_t uploaded = nullptr, done = nullptr, k0 = nullptr, k1 = nullptr;
     int nframes = 0;
@@ -113,7 +112,7 @@ struct Dev {
     PairConfig cfg;
     ncclComm_t comm = nullptr;
     // device-frame scratch (gfn_enqueue_device_frames)
-    Rec64* xrecA = nullptr; Rec64* xrecB = nullptr; float4* xposA = nullptr; float4* xposB = nullptr;
+    Site* xsiteA = nullptr; Site* xsiteB = nullptr;
     float* xmax = nullptr; int xcap = 0;
     struct XSlot { double* h_box = nullptr; double* d_box = nullptr; cudaEvent_t k0 = nullptr, k1 = nullptr; bool timed = false; };
     XSlot xs[kXRing];
@@ -199,6 +198,7 @@ void fill_params(gfn_t* h, Dev& d, PairParams& p)
     p.item_start = d.item_start;
     p.partials = d.partials; p.gacc = d.gacc; p.gpp = d.gpp; p.counters = d.counters;
     p.flags = h->flags;
+    p.nrep = d.cfg.nrep;
     p.strideA = h->n1_pad; p.strideB = h->n2_pad;
 }
 
@@ -206,21 +206,21 @@ void fill_params(gfn_t* h, Dev& d, PairParams& p)
 int launch_frames(gfn_t* h, Dev& d, int nframes,
                   const double* c1, long long s_c1, const double* d1, long long s_d1,
                   const double* c2, long long s_c2, const double* d2, long long s_d2, bool aliased,
-                  Rec64* recA, float4* posA, Rec64* recB, float4* posB, float* maxab, const double* d_box,
+                  Site* siteA, Site* siteB, float* maxab, const double* d_box,
                   cudaEvent_t k0, cudaEvent_t k1)
 {
     cudaStream_t s = d.comp;
     CU(cudaMemsetAsync(maxab, 0, sizeof(float) * 2 * nframes, s));
-    CU(prep_launch(c1, s_c1, h->need1 ? d1 : nullptr, s_d1, recA, posA, maxab, h->n1, h->n1_pad, nframes, s));
+    CU(prep_launch(c1, s_c1, h->need1 ? d1 : nullptr, s_d1, siteA, maxab, h->n1, h->n1_pad, nframes, s));
     h->st_launches += 1;
     if (!aliased) {
-        CU(prep_launch(c2, s_c2, h->need2 ? d2 : nullptr, s_d2, recB, posB, maxab + nframes, h->n2, h->n2_pad, nframes, s));
+        CU(prep_launch(c2, s_c2, h->need2 ? d2 : nullptr, s_d2, siteB, maxab + nframes, h->n2, h->n2_pad, nframes, s));
         h->st_launches += 1;
     }
     PairParams p;
     fill_params(h, d, p);
-    p.recA = recA; p.posA = posA; p.maxA = maxab;
-    p.recB = aliased ? recA : recB; p.posB = aliased ? posA : posB; p.maxB = aliased ? maxab : maxab + nframes;
+    p.siteA = siteA; p.maxA = maxab;
+    p.siteB = aliased ? siteA : siteB; p.maxB = aliased ? maxab : maxab + nframes;
     p.box = d_box; p.nframes = nframes;
     CU(cudaEventRecord(k0, s));
     CU(pair_launch(d.cfg, p, s));
@@ -251,7 +251,7 @@ int submit(gfn_t* h, Dev& d)
     int rc = launch_frames(h, d, b.nframes,
                            b.d_raw + h->off_c1, fd, b.d_raw + h->off_d1, fd,
                            b.d_raw + h->off_c2, fd, b.d_raw + h->off_d2, fd, b.aliased,
-                           b.recA, b.posA, b.recB, b.posB, b.maxab, b.d_box, b.k0, b.k1);
+                           b.siteA, b.siteB, b.maxab, b.d_box, b.k0, b.k1);
     if (rc) return rc;
     b.timed = true;
     CU(cudaEventRecord(b.done, d.comp));
@@ -299,14 +299,14 @@ void free_dev(Dev& d)
     for (Batch& b : d.ring) {
         if (b.h_pin) cudaFreeHost(b.h_pin);
         if (b.h_box) cudaFreeHost(b.h_box);
-        cudaFree(b.d_raw); cudaFree(b.d_box); cudaFree(b.recA); cudaFree(b.recB); cudaFree(b.posA); cudaFree(b.posB); cudaFree(b.maxab);
+        cudaFree(b.d_raw); cudaFree(b.d_box); cudaFree(b.siteA); cudaFree(b.siteB); cudaFree(b.maxab);
         if (b.uploaded) cudaEventDestroy(b.uploaded);
         if (b.done) cudaEventDestroy(b.done);
         if (b.k0) cudaEventDestroy(b.k0);
         if (b.k1) cudaEventDestroy(b.k1);
     }
     cudaFree(d.gacc); cudaFree(d.gsum); cudaFree(d.gpp); cudaFree(d.partials); cudaFree(d.counters); cudaFree(d.item_start);
-    cudaFree(d.xrecA); cudaFree(d.xrecB); cudaFree(d.xposA); cudaFree(d.xposB); cudaFree(d.xmax);
+    cudaFree(d.xsiteA); cudaFree(d.xsiteB); cudaFree(d.xmax);
     for (Dev::XSlot& x : d.xs) {
         if (x.h_box) cudaFreeHost(x.h_box);
         cudaFree(x.d_box);
@@ -379,9 +379,9 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
     h->off_d2 = h->off_c2 + 3ll * n2;
     h->frame_doubles = h->off_d2 + (h->need2 ? 3ll * n2 : 0);
 
-    // batch size: ~2^31 pair evaluations or 64 MB of frames per batch, whichever is smaller
+    // batch size: ~2^33 pair evaluations or 64 MB of frames per batch, whichever is smaller
     const double per = (n1 == n2) ? 0.5 * (double)n1 * ((double)n1 + 1.0) : (double)n1 * (double)n2;
-    long long bf = (long long)(2147483648.0 / per);
+    long long bf = (long long)(8589934592.0 / per);
     const long long by_bytes = (64ll << 20) / (h->frame_doubles * 8);
     if (bf > by_bytes) bf = by_bytes;
     if (bf > 4096) bf = 4096;
@@ -454,10 +454,8 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
             CUC(cudaMalloc(&b.d_raw, fb));
             CUC(cudaHostAlloc(&b.h_box, sizeof(double) * 6 * h->batch_frames, cudaHostAllocDefault));
             CUC(cudaMalloc(&b.d_box, sizeof(double) * 6 * h->batch_frames));
-            CUC(cudaMalloc(&b.recA, sizeof(Rec64) * (size_t)h->n1_pad * h->batch_frames));
-            CUC(cudaMalloc(&b.posA, sizeof(float4) * (size_t)h->n1_pad * h->batch_frames));
-            CUC(cudaMalloc(&b.recB, sizeof(Rec64) * (size_t)h->n2_pad * h->batch_frames));
-            CUC(cudaMalloc(&b.posB, sizeof(float4) * (size_t)h->n2_pad * h->batch_frames));
+            CUC(cudaMalloc(&b.siteA, sizeof(Site) * (size_t)h->n1_pad * h->batch_frames));
+            CUC(cudaMalloc(&b.siteB, sizeof(Site) * (size_t)h->n2_pad * h->batch_frames));
             CUC(cudaMalloc(&b.maxab, sizeof(float) * 2 * h->batch_frames));
             CUC(cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming));
             CUC(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
@@ -544,10 +542,8 @@ int gfn_enqueue_device_frames(gfn_t* h, int nframes,
     const bool aliased = (dc2 == dc1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || dd2 == dd1) && (!h->need2 || h->need1);
     const int chunk = h->batch_frames;
     if (d.xcap < chunk) {
-        CU(cudaMalloc(&d.xrecA, sizeof(Rec64) * (size_t)h->n1_pad * chunk));
-        CU(cudaMalloc(&d.xposA, sizeof(float4) * (size_t)h->n1_pad * chunk));
-        CU(cudaMalloc(&d.xrecB, sizeof(Rec64) * (size_t)h->n2_pad * chunk));
-        CU(cudaMalloc(&d.xposB, sizeof(float4) * (size_t)h->n2_pad * chunk));
+        CU(cudaMalloc(&d.xsiteA, sizeof(Site) * (size_t)h->n1_pad * chunk));
+        CU(cudaMalloc(&d.xsiteB, sizeof(Site) * (size_t)h->n2_pad * chunk));
         CU(cudaMalloc(&d.xmax, sizeof(float) * 2 * chunk));
         d.xcap = chunk;
     }
@@ -571,7 +567,7 @@ int gfn_enqueue_device_frames(gfn_t* h, int nframes,
         int rc = launch_frames(h, d, nf,
                                dc1 + s_c1 * f0, s_c1, dd1 ? dd1 + s_d1 * f0 : nullptr, s_d1,
                                dc2 + s_c2 * f0, s_c2, dd2 ? dd2 + s_d2 * f0 : nullptr, s_d2, aliased,
-                               d.xrecA, d.xposA, d.xrecB, d.xposB, d.xmax, x.d_box, x.k0, x.k1);
+                               d.xsiteA, d.xsiteB, d.xmax, x.d_box, x.k0, x.k1);
         if (rc) return rc;
         x.timed = true;
     }
@@ -703,7 +699,7 @@ int gfn_stats(gfn_t* h, gfn_stats_t* out)
         out->overflow += (double)c[0]; out->survivors += (double)c[2]; out->in_range += (double)c[3];
     }
     const PairConfig& c = h->devs[0].cfg;
-    out->filter_fp64 = c.filter_fp64; out->hist_mode = c.hist_mode; out->warps_per_block = c.warps;
+    out->filter_fp64 = c.filter_fp64; out->hist_mode = c.hist_mode; out->warps_per_block = c.warps; out->hist_replicas = c.nrep;
     out->blocks_per_sm = c.blocks_per_sm; out->grid = c.grid; out->smem_bytes = c.smem_bytes;
     out->batch_frames = h->batch_frames; out->ndev = (int)h->devs.size();
     return GFN_OK;

@@ -25,6 +25,7 @@
 #include "../../include/gfn.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace gfn {
 
@@ -57,13 +58,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* __restrict__ dip, long long stride_dip,
-            Rec64* __restrict__ rec, float4* __restrict__ pos, float* __restrict__ maxabs, int n, int n_pad)
+            Site* __restrict__ site, float* __restrict__ maxabs, int n, int n_pad)
 {
     const int f = blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_pad) return;
-    Rec64 r;
-    float4 p;
+    Site r;
     float m = 0.f;
     if (s < n) {
         const double* c = xyz + (long long)f * stride_xyz + 3ll * s;
@@ -76,28 +76,28 @@ prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* 
         } else {
             r.px = r.py = r.pz = 0.0; r.norm = 0.0;
         }
-        r.pad = 0.0;
-        p = make_float4(__double2float_rn(r.x), __double2float_rn(r.y), __double2float_rn(r.z), 0.f);
+        r.spare = 0.0;
+        r.fx = __double2float_rn(r.x); r.fy = __double2float_rn(r.y); r.fz = __double2float_rn(r.z); r.fw = 0.f;
         m = fmaxf(fmaxf(__double2float_ru(fabs(r.x)), __double2float_ru(fabs(r.y))), __double2float_ru(fabs(r.z)));
     } else {
-        r.x = r.y = r.z = r.px = r.py = r.pz = r.norm = r.pad = 0.0;
-        p = make_float4(1e30f, 1e30f, 1e30f, 0.f);   // padding never passes the pre-filter against a finite site
+        // padding: never passes the fp32 pre-filter against a finite site; the fp64 pre-test masks it by index
+        r.x = r.y = r.z = r.px = r.py = r.pz = r.norm = r.spare = 0.0;
+        r.fx = r.fy = r.fz = 1e30f; r.fw = 0.f;
     }
-    rec[(long long)f * n_pad + s] = r;
-    pos[(long long)f * n_pad + s] = p;
+    site[(long long)f * n_pad + s] = r;
     unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like their bits
     if ((threadIdx.x & 31) == 0 && mb) atomicMax(reinterpret_cast<unsigned*>(maxabs) + f, mb);
 }
 
 cudaError_t prep_launch(const double* xyz, long long stride_xyz, const double* dip, long long stride_dip,
-                        Rec64* rec, float4* pos, float* maxabs, int n, int n_pad, int nframes, cudaStream_t s)
+                        Site* site, float* maxabs, int n, int n_pad, int nframes, cudaStream_t s)
 {
     for (int f0 = 0; f0 < nframes; f0 += 65535) {
         int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
         dim3 grid((n_pad + 255) / 256, nf);
         prep_kernel<<<grid, 256, 0, s>>>(xyz + (long long)f0 * stride_xyz, stride_xyz,
                                          dip ? dip + (long long)f0 * stride_dip : nullptr, stride_dip,
-                                         rec + (long long)f0 * n_pad, pos + (long long)f0 * n_pad, maxabs + f0, n, n_pad);
+                                         site + (long long)f0 * n_pad, maxabs + f0, n, n_pad);
     }
     return cudaGetLastError();
 }
@@ -144,21 +144,31 @@ struct Box { double Lx, Ly, Lz, hx, hy, hz; };
 
 // Adds one value into the global accumulators, reproducing where the reference's flat index
 // ix_mode + i*histo_n + pos lands (quirk Q3: pos may reach past the row).
-__device__ __forceinline__ void global_add(const PairParams& P, int hist_mode, int k, int i, int pos, double v, bool& lost)
+__device__ __forceinline__ void global_add(const PairParams& P, int hist_mode, int k, int i, int pos, double v)
 {
     const long long hn = P.histo_n;
     if (hist_mode == 2) {   // per-particle: literal reference index, bounds-checked
         const long long ix = (long long)k * P.n1 * hn + (long long)i * hn + pos;
-        if (ix < 7ll * P.n1 * hn) atomicAdd(P.gpp + ix, v); else lost = true;
+        if (ix < 7ll * P.n1 * hn) atomicAdd(P.gpp + ix, v);
     }
     // compact [mode][bin]: the sum over rows of wherever the reference wrote
-    long long flat = (long long)i * hn + pos;
-    int kk = k;
-    if (flat >= (long long)P.n1 * hn) { kk = k + 1; }
-    int bin = pos >= hn ? (int)(pos - hn) : pos;
+    const long long flat = (long long)i * hn + pos;
+    const int kk = flat >= (long long)P.n1 * hn ? k + 1 : k;
+    const int bin = pos >= hn ? (int)(pos - hn) : pos;
     if (kk < 7 && bin < hn) atomicAdd(P.gacc + (long long)kk * hn + bin, v);
-    else if (hist_mode != 2) lost = true;
 }
+
+// reference minimum image, gfunction.pyx:145-147:  if fabs(d) > half: d = d - sign(d)*L
+// (|d| > half > 0 implies d != 0, so sign(d)*L == copysign(L, d) exactly; one rounding in the subtraction)
+__device__ __forceinline__ double min_image(double d, double L, double half)
+{
+    const double t = DSUB(d, copysign(L, d));
+    return fabs(d) > half ? t : d;
+}
+
+// 16-byte chunk c (0..3) of bin pos inside a replica with 8 slots per bin: chunks are XOR-swizzled
+// with bits 1..2 of pos so that lanes holding different bins hit different 4-bank groups.
+__device__ __forceinline__ int hist_chunk(int pos, int c) { return pos * 4 + (c ^ ((pos >> 1) & 3)); }
 
 template <typename F, int NW, int NSLOT, int HIST>
 __global__ void __launch_bounds__(NW * 32, 1)
@@ -166,36 +176,44 @@ pair_kernel(const PairParams P)
 {
     constexpr int TI = NW * 32 * kIPT;
     constexpr int TJ = kTJ;
+    constexpr int S = kStages;
     constexpr bool kF32 = sizeof(F) == 4;
+    constexpr uint32_t kTileBytes = TJ * (uint32_t)sizeof(Site);
 
     extern __shared__ __align__(128) unsigned char smem[];
-    Rec64*  irec = reinterpret_cast<Rec64*>(smem);                               // [TI]
-    Rec64*  jrec = irec + TI;                                                    // [2][TJ]
-    float4* jpos = reinterpret_cast<float4*>(jrec + 2 * TJ);                     // [2][TJ]
-    unsigned short* queue = reinterpret_cast<unsigned short*>(jpos + 2 * TJ);    // [NW][kQCap]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(queue + NW * kQCap);            // full[2], ifull
-    double* hist = reinterpret_cast<double*>(bars + 4);                          // [NW][histo_n*NSLOT] (HIST==0)
+    Site* isite = reinterpret_cast<Site*>(smem);                                  // [TI]
+    Site* jsite = isite + TI;                                                     // [S][TJ]
+    unsigned short* queue = reinterpret_cast<unsigned short*>(jsite + S * TJ);    // [NW][kQCap]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(queue + NW * kQCap);             // full[S], ifull
+    int* done_cnt = reinterpret_cast<int*>(bars + 4);                             // [S] warps finished with stage
+    int* locks = done_cnt + 4;                                                    // [NW] replica locks
+    double* hist = reinterpret_cast<double*>(locks + 20);                         // [nrep][histo_n*NSLOT] (HIST==0)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hn = P.histo_n;
     const int hsz = hn * NSLOT;
-    double* hist_w = hist + (size_t)warp * hsz;
+    const int nrep = P.nrep;
+    const int rep = warp % nrep;
+    const bool use_lock = nrep < NW;
+    double* hist_w = hist + (size_t)rep * hsz;
     unsigned short* q = queue + warp * kQCap;
 
     if (HIST == 0) {
-        for (int k = tid; k < NW * hsz; k += NW * 32) hist[k] = 0.0;
+        for (int k = tid; k < nrep * hsz; k += NW * 32) hist[k] = 0.0;
     }
+    if (tid < 4) done_cnt[tid] = 0;
+    if (tid < NW) locks[tid] = 0;
     if (tid == 0) {
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        for (int k = 0; k < 4; ++k) mbar_init(&bars[k], 1);
         mbar_fence_init();
     }
     __syncthreads();
 
     const int mode_sel = P.mode_sel;
     const bool m_cs = mode_sel & (2 | 16), m_cd = mode_sel & (4 | 32), m_sd = mode_sel & (8 | 64);
-    unsigned tcount = 0;        // surround tiles consumed so far by this CTA (stage = tcount&1, parity = (tcount>>1)&1)
+    unsigned tcount = 0;        // surround tiles consumed so far by this CTA (stage = tcount % S, parity = (tcount / S) & 1)
     unsigned icount = 0;        // items consumed (parity of the core-tile barrier)
-    unsigned long long n_surv = 0, n_inr = 0, n_ovf = 0;
+    unsigned n_surv = 0, n_inr = 0, n_ovf = 0;
     bool zerodiv = false;
 
     const long long total_items = (long long)P.items_per_frame * P.nframes;
@@ -213,20 +231,17 @@ pair_kernel(const PairParams P)
         const int jt_end = min(jt_begin + P.seg_tiles, P.n_jtiles);
         const int ntiles = jt_end - jt_begin;
 
-        const Rec64*  recA = P.recA + (long long)f * P.strideA;
-        const Rec64*  recB = P.recB + (long long)f * P.strideB;
-        const float4* posB = P.posB + (long long)f * P.strideB;
+        const Site* siteA = P.siteA + (long long)f * P.strideA;
+        const Site* siteB = P.siteB + (long long)f * P.strideB;
 
-        __syncthreads();     // previous item fully consumed: irec / jrec stages are free
+        __syncthreads();     // previous item fully consumed: the core tile and every stage are free
         if (tid == 0) {
-            mbar_expect_tx(&bars[2], TI * (uint32_t)sizeof(Rec64));
-            bulk_g2s(irec, recA + i0, TI * (uint32_t)sizeof(Rec64), &bars[2]);
-            for (int pre = 0; pre < 2 && pre < ntiles; ++pre) {
-                const int st = (tcount + pre) & 1;
-                const uint32_t bytes = TJ * (uint32_t)sizeof(Rec64) + (kF32 ? TJ * (uint32_t)sizeof(float4) : 0u);
-                mbar_expect_tx(&bars[st], bytes);
-                bulk_g2s(jrec + st * TJ, recB + (long long)(jt_begin + pre) * TJ, TJ * (uint32_t)sizeof(Rec64), &bars[st]);
-                if (kF32) bulk_g2s(jpos + st * TJ, posB + (long long)(jt_begin + pre) * TJ, TJ * (uint32_t)sizeof(float4), &bars[st]);
+            mbar_expect_tx(&bars[3], TI * (uint32_t)sizeof(Site));
+            bulk_g2s(isite, siteA + i0, TI * (uint32_t)sizeof(Site), &bars[3]);
+            for (int pre = 0; pre < S && pre < ntiles; ++pre) {
+                const int st = (tcount + pre) % S;
+                mbar_expect_tx(&bars[st], kTileBytes);
+                bulk_g2s(jsite + st * TJ, siteB + (long long)(jt_begin + pre) * TJ, kTileBytes, &bars[st]);
             }
         }
 
@@ -245,77 +260,76 @@ pair_kernel(const PairParams P)
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
             const int il = warp * (32 * kIPT) + k * 32 + lane;
-            if (kF32) {
-                const float4 c = P.posA[(long long)f * P.strideA + i0 + il];
-                cx[k] = (F)c.x; cy[k] = (F)c.y; cz[k] = (F)c.z;
-            } else {
-                const Rec64* c = recA + i0 + il;
-                if (i0 + il < P.n1) { cx[k] = (F)c->x; cy[k] = (F)c->y; cz[k] = (F)c->z; }
-                else { cx[k] = cy[k] = cz[k] = (F)1e30; }
-            }
+            const Site* c = siteA + i0 + il;
+            if (kF32) { cx[k] = (F)c->fx; cy[k] = (F)c->fy; cz[k] = (F)c->fz; }
+            else if (i0 + il < P.n1) { cx[k] = (F)c->x; cy[k] = (F)c->y; cz[k] = (F)c->z; }
+            else { cx[k] = cy[k] = cz[k] = (F)1e30; }
         }
         const int my_i_min = i0 + warp * (32 * kIPT);     // smallest core index of this warp
 
-        mbar_wait(&bars[2], icount & 1);
+        mbar_wait(&bars[3], icount & 1);
         ++icount;
 
         int qcount = 0;   // warp-uniform
         for (int t = 0; t < ntiles; ++t) {
-            const int st = (tcount + t) & 1;
+            const unsigned g = tcount + t;
+            const int st = g % S;
             const int j0 = (jt_begin + t) * TJ;
-            mbar_wait(&bars[st], ((tcount + t) >> 1) & 1);
-            const Rec64*  jr = jrec + st * TJ;
-            const float4* jp = jpos + st * TJ;
+            mbar_wait(&bars[st], (g / S) & 1);
+            const Site* js = jsite + st * TJ;
 
             // ---- exact evaluation of up to 32 queued survivors (one per lane) -------------------------
             auto drain = [&](int cnt) {
                 const bool have = lane < cnt;
                 const unsigned e = have ? q[qcount - cnt + lane] : 0u;
                 __syncwarp();          // all lanes have read their entry before anyone pushes again
-                const int il = e >> 7, jl = e & 127;
+                const int il = warp * (32 * kIPT) + (int)(e >> 7), jl = e & 127;
                 const int i = i0 + il, j = j0 + jl;
                 bool ok = have && i < P.n1 && j < P.n2 && !(P.tri && j < i);
                 int pos = 0;
                 double w = 1.0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, v6 = 0;
                 if (ok) {
-                    const Rec64 a = irec[il];
-                    const Rec64 b = jr[jl];
-                    double dx = DSUB(b.x, a.x), dy = DSUB(b.y, a.y), dz = DSUB(b.z, a.z);            // :141-143
-                    if (fabs(dx) > bx.hx) dx = DSUB(dx, DMUL((double)((0.0 < dx) - (dx < 0.0)), bx.Lx));   // :145
-                    if (fabs(dy) > bx.hy) dy = DSUB(dy, DMUL((double)((0.0 < dy) - (dy < 0.0)), bx.Ly));   // :146
-                    if (fabs(dz) > bx.hz) dz = DSUB(dz, DMUL((double)((0.0 < dz) - (dz < 0.0)), bx.Lz));   // :147
+                    const double2* ap = reinterpret_cast<const double2*>(isite + il);
+                    const double2* bp = reinterpret_cast<const double2*>(js + jl);
+                    const double2 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];   // x y | z px | py pz | norm -
+                    const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+                    const double dx = min_image(DSUB(b0.x, a0.x), bx.Lx, bx.hx);                     // :141-147
+                    const double dy = min_image(DSUB(b0.y, a0.y), bx.Ly, bx.hy);
+                    const double dz = min_image(DSUB(b1.x, a1.x), bx.Lz, bx.hz);
                     const double dist = __dsqrt_rn(DOT3(dx, dy, dz, dx, dy, dz));                      // :148
                     ++n_surv;
-                    // :149 literally; a NaN distance is rejected
-                    if (dist < P.hmin || dist > P.hmax || floor(DMUL(dist, P.invdx)) == 0.0 || !(dist == dist)) {
+                    // :149  dist<hmin | dist>hmax | floor(dist*invdx)==0  (dist >= 0, so floor(x)==0 <=> x<1); NaN rejected
+                    if (!(dist >= P.hmin) || dist > P.hmax || DMUL(dist, P.invdx) < 1.0) {
                         ok = false;
                     } else {
-                        pos = (int)floor(DMUL(DSUB(dist, P.hmin), P.invdx));                          // :150
+                        pos = __double2int_rd(DMUL(DSUB(dist, P.hmin), P.invdx));                     // :150
                         w = (P.tri && i != j) ? 2.0 : 1.0;                                            // :131-134
                         ++n_inr;
+                        const double apx = a1.y, apy = a2.x, apz = a2.y, an = a3.x;
+                        const double bpx = b1.y, bpy = b2.x, bpz = b2.y, bn = b3.x;
                         if (m_cs) {                                                                   // :154-157
-                            const double den = DMUL(a.norm, b.norm);
+                            const double den = DMUL(an, bn);
                             if (den == 0.0) zerodiv = true;
                             else {
-                                const double c = DDIV(DOT3(a.px, a.py, a.pz, b.px, b.py, b.pz), den);
+                                const double c = DDIV(DOT3(apx, apy, apz, bpx, bpy, bpz), den);
                                 v1 = DMUL(c, w);
                                 v4 = DMUL(DSUB(DMUL(DMUL(1.5, c), c), 0.5), w);
                             }
                         }
                         if (m_cd) {                                                                   // :158-161
-                            const double den = DMUL(a.norm, dist);
+                            const double den = DMUL(an, dist);
                             if (den == 0.0) zerodiv = true;
                             else {
-                                const double c = DDIV(DOT3(a.px, a.py, a.pz, dx, dy, dz), den);
+                                const double c = DDIV(DOT3(apx, apy, apz, dx, dy, dz), den);
                                 v2 = DMUL(c, w);
                                 v5 = DMUL(DSUB(DMUL(DMUL(1.5, c), c), 0.5), w);
                             }
                         }
                         if (m_sd) {                                                                   // :162-165
-                            const double den = DMUL(b.norm, dist);
+                            const double den = DMUL(bn, dist);
                             if (den == 0.0) zerodiv = true;
                             else {
-                                const double c = DDIV(DOT3(b.px, b.py, b.pz, dx, dy, dz), den);
+                                const double c = DDIV(DOT3(bpx, bpy, bpz, dx, dy, dz), den);
                                 v3 = DMUL(c, w);
                                 v6 = DMUL(DSUB(DMUL(DMUL(1.5, c), c), 0.5), w);
                             }
@@ -331,22 +345,18 @@ pair_kernel(const PairParams P)
                 if (!(mode_sel & 64)) v6 = 0.0;
 
                 const bool spill = ok && pos >= hn;          // quirk Q3
-                if (HIST != 0 || spill) {
-                    if (ok) {
-                        bool lost = false;
-                        if (spill) ++n_ovf;
-                        if (!(spill && (P.flags & GFN_FLAG_DISCARD_OVERFLOW))) {
-                            const int hm = HIST == 0 ? 1 : HIST;
-                            if (mode_sel & 1)  global_add(P, hm, 0, i, pos, v0, lost);
-                            if (mode_sel & 2)  global_add(P, hm, 1, i, pos, v1, lost);
-                            if (mode_sel & 4)  global_add(P, hm, 2, i, pos, v2, lost);
-                            if (mode_sel & 8)  global_add(P, hm, 3, i, pos, v3, lost);
-                            if (mode_sel & 16) global_add(P, hm, 4, i, pos, v4, lost);
-                            if (mode_sel & 32) global_add(P, hm, 5, i, pos, v5, lost);
-                            if (mode_sel & 64) global_add(P, hm, 6, i, pos, v6, lost);
-                            if (!spill) atomicAdd(P.gacc + 7ll * hn + pos, w);      // pair weight row
-                        }
-                        (void)lost;
+                if ((HIST != 0 && ok) || spill) {
+                    if (spill) ++n_ovf;
+                    if (!(spill && (P.flags & GFN_FLAG_DISCARD_OVERFLOW))) {
+                        const int hm = HIST == 0 ? 1 : HIST;
+                        if (mode_sel & 1)  global_add(P, hm, 0, i, pos, v0);
+                        if (mode_sel & 2)  global_add(P, hm, 1, i, pos, v1);
+                        if (mode_sel & 4)  global_add(P, hm, 2, i, pos, v2);
+                        if (mode_sel & 8)  global_add(P, hm, 3, i, pos, v3);
+                        if (mode_sel & 16) global_add(P, hm, 4, i, pos, v4);
+                        if (mode_sel & 32) global_add(P, hm, 5, i, pos, v5);
+                        if (mode_sel & 64) global_add(P, hm, 6, i, pos, v6);
+                        if (!spill) atomicAdd(P.gacc + 7ll * hn + pos, w);      // pair weight row
                     }
                 }
                 if (HIST == 0) {
@@ -355,20 +365,30 @@ pair_kernel(const PairParams P)
                     const unsigned grp = __match_any_sync(0xffffffffu, key);
                     const int rank = __popc(grp & ((1u << lane) - 1u));
                     const int maxr = __reduce_max_sync(0xffffffffu, add ? (unsigned)rank : 0u);
-                    double* hp = hist_w + (size_t)pos * NSLOT;
+                    if (use_lock) {
+                        if (lane == 0) { while (atomicCAS(&locks[rep], 0, 1) != 0) __nanosleep(40); }
+                        __syncwarp();
+                        __threadfence_block();
+                    }
                     for (int rr = 0; rr <= maxr; ++rr) {
                         if (add && rank == rr) {
                             if (NSLOT == 1) {
-                                hp[0] += w;
+                                hist_w[pos] += w;
                             } else {
-                                double2* h2 = reinterpret_cast<double2*>(hp);
-                                double2 a0 = h2[0], a1 = h2[1], a2 = h2[2], a3 = h2[3];
-                                a0.x += v0; a0.y += v1; a1.x += v2; a1.y += v3;
-                                a2.x += v4; a2.y += v5; a3.x += v6; a3.y += w;
-                                h2[0] = a0; h2[1] = a1; h2[2] = a2; h2[3] = a3;
+                                double2* h2 = reinterpret_cast<double2*>(hist_w);
+                                const int c0 = hist_chunk(pos, 0), c1 = hist_chunk(pos, 1), c2 = hist_chunk(pos, 2), c3 = hist_chunk(pos, 3);
+                                double2 h0 = h2[c0], h1 = h2[c1], hh2 = h2[c2], h3 = h2[c3];
+                                h0.x += v0; h0.y += v1; h1.x += v2; h1.y += v3;
+                                hh2.x += v4; hh2.y += v5; h3.x += v6; h3.y += w;
+                                h2[c0] = h0; h2[c1] = h1; h2[c2] = hh2; h2[c3] = h3;
                             }
                         }
                         __syncwarp();
+                    }
+                    if (use_lock) {
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) atomicExch(&locks[rep], 0);
                     }
                 }
                 qcount -= cnt;
@@ -385,10 +405,12 @@ pair_kernel(const PairParams P)
 #pragma unroll 16
                 for (int jj = 0; jj < 32; ++jj) {
                     F sx, sy, sz;
-                    if (kF32) { const float4 s = jp[jbase + jj]; sx = (F)s.x; sy = (F)s.y; sz = (F)s.z; }
-                    else {
-                        const double2 sxy = *reinterpret_cast<const double2*>(&jr[jbase + jj].x);
-                        sx = (F)sxy.x; sy = (F)sxy.y; sz = (F)jr[jbase + jj].z;
+                    if (kF32) {
+                        const float4 s = *reinterpret_cast<const float4*>(&js[jbase + jj].fx);
+                        sx = (F)s.x; sy = (F)s.y; sz = (F)s.z;
+                    } else {
+                        const double2 sxy = *reinterpret_cast<const double2*>(&js[jbase + jj].x);
+                        sx = (F)sxy.x; sy = (F)sxy.y; sz = (F)js[jbase + jj].z;
                         if (j0 + jbase + jj >= P.n2) { sx = sy = sz = (F)-1e30; }
                     }
 #pragma unroll
@@ -402,25 +424,29 @@ pair_kernel(const PairParams P)
                         msk[k] = __funnelshift_l(FOps<F>::signword(tt), msk[k], 1);    // first jj ends at bit 31
                     }
                 }
-                // ---- compact survivors into the warp queue -----------------------------------------
+                // ---- compact survivors into the warp queue (one packed scan for both core slots) ---------
+                static_assert(kIPT == 2, "the packed scan below assumes two core sites per thread");
+                if (!__any_sync(0xffffffffu, (msk[0] | msk[1]) != 0u)) continue;
+                const unsigned cnt2 = (unsigned)__popc(msk[0]) | ((unsigned)__popc(msk[1]) << 16);
+                unsigned incl = cnt2;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                const unsigned tot2 = __shfl_sync(0xffffffffu, incl, 31);
+                const unsigned excl = incl - cnt2;
 #pragma unroll
                 for (int k = 0; k < kIPT; ++k) {
+                    const int total = (tot2 >> (16 * k)) & 0xffff;
+                    if (total == 0) continue;
                     unsigned m = msk[k];
-                    if (!__any_sync(0xffffffffu, m != 0u)) continue;
-                    const int c = __popc(m);
-                    int incl = c;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int up = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += up;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    int at = qcount + incl - c;
-                    const unsigned il = warp * (32 * kIPT) + k * 32 + lane;
+                    int at = qcount + (int)((excl >> (16 * k)) & 0xffff);
+                    const unsigned tag = (unsigned)(k * 32 + lane) << 7;
                     while (m) {
                         const int jj = __clz(m);
                         m &= ~(0x80000000u >> jj);
-                        q[at++] = (unsigned short)((il << 7) | (unsigned)(jbase + jj));
+                        q[at++] = (unsigned short)(tag | (unsigned)(jbase + jj));
                     }
                     qcount += total;
                     __syncwarp();
@@ -429,12 +455,18 @@ pair_kernel(const PairParams P)
             }
             if (qcount > 0) drain(qcount);   // the stage buffer is recycled next: empty the queue
 
-            __syncthreads();                 // every warp is done with stage st
-            if (tid == 0 && t + 2 < ntiles) {
-                const uint32_t bytes = TJ * (uint32_t)sizeof(Rec64) + (kF32 ? TJ * (uint32_t)sizeof(float4) : 0u);
-                mbar_expect_tx(&bars[st], bytes);
-                bulk_g2s(jrec + st * TJ, recB + (long long)(jt_begin + t + 2) * TJ, TJ * (uint32_t)sizeof(Rec64), &bars[st]);
-                if (kF32) bulk_g2s(jpos + st * TJ, posB + (long long)(jt_begin + t + 2) * TJ, TJ * (uint32_t)sizeof(float4), &bars[st]);
+            // ---- release the stage: the last warp to finish refills it -----------------------------------
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                const int old = atomicAdd(&done_cnt[st], 1);
+                if (old == NW - 1) {
+                    atomicExch(&done_cnt[st], 0);
+                    if (t + S < ntiles) {
+                        mbar_expect_tx(&bars[st], kTileBytes);
+                        bulk_g2s(jsite + st * TJ, siteB + (long long)(jt_begin + t + S) * TJ, kTileBytes, &bars[st]);
+                    }
+                }
             }
         }
         tcount += ntiles;
@@ -445,9 +477,11 @@ pair_kernel(const PairParams P)
     if (HIST == 0) {
         double* out = P.partials + (size_t)blockIdx.x * hsz;
         for (int k = tid; k < hsz; k += NW * 32) {
+            // k = bin*NSLOT + slot in the un-swizzled layout the finalize kernel expects
+            int src = k;
+            if (NSLOT == 8) { const int bin = k >> 3, sl = k & 7; src = hist_chunk(bin, sl >> 1) * 2 + (sl & 1); }
             double s = 0.0;
-#pragma unroll
-            for (int wv = 0; wv < NW; ++wv) s += hist[(size_t)wv * hsz + k];
+            for (int wv = 0; wv < nrep; ++wv) s += hist[(size_t)wv * hsz + src];
             out[k] = s;
         }
     }
@@ -459,9 +493,9 @@ pair_kernel(const PairParams P)
     }
     const bool anyz = __any_sync(0xffffffffu, zerodiv);
     if (lane == 0) {
-        if (n_surv) atomicAdd(P.counters + 2, n_surv);
-        if (n_inr)  atomicAdd(P.counters + 3, n_inr);
-        if (n_ovf)  atomicAdd(P.counters + 0, n_ovf);
+        if (n_surv) atomicAdd(P.counters + 2, (unsigned long long)n_surv);
+        if (n_inr)  atomicAdd(P.counters + 3, (unsigned long long)n_inr);
+        if (n_ovf)  atomicAdd(P.counters + 0, (unsigned long long)n_ovf);
         if (anyz)   atomicOr(P.counters + 1, 1ull);
     }
 }
@@ -510,14 +544,11 @@ cudaError_t scale_launch(double* a, long long n, double v, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // variant selection
 // ------------------------------------------------------------------------------------------------
-template <int NW>
-static size_t smem_bytes_for(int histo_n, int nslot, bool smem_hist)
+static size_t smem_fixed_bytes(int nw)
 {
-    constexpr int TI = NW * 32 * kIPT;
-    size_t b = (size_t)TI * sizeof(Rec64) + 2 * (size_t)kTJ * sizeof(Rec64) + 2 * (size_t)kTJ * sizeof(float4)
-             + (size_t)NW * kQCap * sizeof(unsigned short) + 4 * sizeof(uint64_t);
-    if (smem_hist) b += (size_t)NW * histo_n * nslot * sizeof(double);
-    return b;
+    const size_t ti = (size_t)nw * 32 * kIPT;
+    return ti * sizeof(Site) + (size_t)kStages * kTJ * sizeof(Site) + (size_t)nw * kQCap * sizeof(unsigned short)
+         + 4 * sizeof(uint64_t) + 4 * sizeof(int) + 20 * sizeof(int);
 }
 
 typedef void (*pair_fn_t)(const PairParams);
@@ -526,11 +557,11 @@ template <typename F>
 static pair_fn_t pick_fn(int hist_mode, int warps, int nslot)
 {
     if (hist_mode == 0) {
-        if (warps == 8) return nslot == 1 ? pair_kernel<F, 8, 1, 0> : pair_kernel<F, 8, 8, 0>;
-        return nslot == 1 ? pair_kernel<F, 4, 1, 0> : pair_kernel<F, 4, 8, 0>;
+        if (warps == 16) return nslot == 1 ? pair_kernel<F, 16, 1, 0> : pair_kernel<F, 16, 8, 0>;
+        return nslot == 1 ? pair_kernel<F, 8, 1, 0> : pair_kernel<F, 8, 8, 0>;
     }
-    if (hist_mode == 1) return pair_kernel<F, 8, 8, 1>;
-    return pair_kernel<F, 8, 8, 2>;
+    if (hist_mode == 1) return pair_kernel<F, 16, 8, 1>;
+    return pair_kernel<F, 16, 8, 2>;
 }
 
 static pair_fn_t pick(const PairConfig& c)
@@ -548,16 +579,33 @@ cudaError_t pair_configure(int dev, int histo_n, int mode_sel, unsigned flags, P
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     cfg->filter_fp64 = (flags & GFN_FLAG_FILTER_FP64) ? 1 : 0;
     cfg->nslot = (mode_sel == 1) ? 1 : 8;
-    if (flags & GFN_FLAG_PER_PARTICLE) { cfg->hist_mode = 2; cfg->warps = 8; cfg->nslot = 8; }
-    else if (flags & GFN_FLAG_HIST_GLOBAL) { cfg->hist_mode = 1; cfg->warps = 8; cfg->nslot = 8; }
+    cfg->nrep = 1;
+    if (flags & GFN_FLAG_PER_PARTICLE) { cfg->hist_mode = 2; cfg->warps = 16; cfg->nslot = 8; }
+    else if (flags & GFN_FLAG_HIST_GLOBAL) { cfg->hist_mode = 1; cfg->warps = 16; cfg->nslot = 8; }
     else {
+        // per-replica bytes; replicas = as many as fit (<= warps); warps sharing a replica serialise on a lock
+        const long long rb = (long long)histo_n * cfg->nslot * (long long)sizeof(double);
+        const long long r16 = ((long long)max_smem - (long long)smem_fixed_bytes(16)) / rb;
+        const long long r8  = ((long long)max_smem - (long long)smem_fixed_bytes(8)) / rb;
         cfg->hist_mode = 0;
-        if (smem_bytes_for<8>(histo_n, cfg->nslot, true) <= (size_t)max_smem) cfg->warps = 8;
-        else if (smem_bytes_for<4>(histo_n, cfg->nslot, true) <= (size_t)max_smem) cfg->warps = 4;
-        else { cfg->hist_mode = 1; cfg->warps = 8; cfg->nslot = 8; }
+        if (r16 >= 4)      { cfg->warps = 16; cfg->nrep = (int)(r16 > 16 ? 16 : r16); }
+        else if (r8 >= 2)  { cfg->warps = 8;  cfg->nrep = (int)(r8 > 8 ? 8 : r8); }
+        else if (r16 >= 1) { cfg->warps = 16; cfg->nrep = (int)r16; }
+        else { cfg->hist_mode = 1; cfg->warps = 16; cfg->nslot = 8; }
+        if (const char* env = getenv("GFN_WARPS")) {
+            const int w = atoi(env);
+            if (cfg->hist_mode == 0 && (w == 16 || w == 8)) {
+                const long long rr = w == 16 ? r16 : r8;
+                if (rr >= 1) { cfg->warps = w; cfg->nrep = (int)(rr > w ? w : rr); }
+            }
+        }
+        if (const char* env = getenv("GFN_NREP")) {
+            const int r = atoi(env);
+            if (cfg->hist_mode == 0 && r >= 1 && r <= cfg->nrep) cfg->nrep = r;
+        }
     }
     const bool sh = cfg->hist_mode == 0;
-    cfg->smem_bytes = (int)(cfg->warps == 8 ? smem_bytes_for<8>(histo_n, cfg->nslot, sh) : smem_bytes_for<4>(histo_n, cfg->nslot, sh));
+    cfg->smem_bytes = (int)(smem_fixed_bytes(cfg->warps) + (sh ? (size_t)cfg->nrep * histo_n * cfg->nslot * sizeof(double) : 0));
     pair_fn_t fn = pick(*cfg);
     if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes)) != cudaSuccess) return e;
     int occ = 0;

@@ -7,24 +7,30 @@
 
 namespace gfn {
 
-// One site of a selection as the pair kernel consumes it: 64 bytes, so a tile of T consecutive
-// sites is one contiguous 64*T-byte run that a single 1-D TMA bulk copy moves into shared memory.
+// One site of a selection as the pair kernel consumes it: 80 bytes, so a tile of T consecutive
+// sites is one contiguous 80*T-byte run that a single 1-D TMA bulk copy moves into shared memory.
+// The 80-byte stride also spreads the 16-byte chunks of randomly indexed records over all eight
+// 4-bank groups (80*i mod 128 takes 8 values), so survivor gathers are bank-conflict free.
 //   x,y,z     coordinates exactly as passed to calcFrame (fp64)          gfunction.pyx:141-143
 //   px,py,pz  dipole (0 when the modes do not need it)                   :122-124 / :136-138
 //   norm      sqrt(px*px+py*py+pz*pz), un-fused like the reference       :125 / :139
-struct __align__(16) Rec64 {
-    double x, y, z, px, py, pz, norm, pad;
+//   fx,fy,fz  coordinates rounded to fp32 for the range pre-filter (1e30 for padding sites)
+struct __align__(16) Site {
+    double x, y, z, px, py, pz, norm, spare;
+    float fx, fy, fz, fw;
 };
+static_assert(sizeof(Site) == 80, "Site must be 80 bytes");
 
 constexpr int kTJ      = 128;    // surround sites per shared-memory stage
+constexpr int kStages  = 3;      // surround stages in flight
 constexpr int kIPT     = 2;      // core sites held in registers per thread
 constexpr int kPadTo   = 1024;   // selections are padded to a multiple of this many sites on the device
 constexpr int kQCap    = 32 + 32 * 32;  // per-warp survivor queue capacity (entries of 16 bit)
 constexpr int kCounters = 8;     // 0 overflow, 1 zerodiv flag, 2 survivors, 3 in-range pairs
 
 struct PairParams {
-    const Rec64*  recA;  const float4* posA;  const float* maxA;   // selection 1 (core)
-    const Rec64*  recB;  const float4* posB;  const float* maxB;   // selection 2 (surround)
+    const Site* siteA;  const float* maxA;   // selection 1 (core)
+    const Site* siteB;  const float* maxB;   // selection 2 (surround)
     const double* box;              // [nframes][6] lengths, half lengths
     long long strideA, strideB;     // padded sites per frame
     int n1, n2, nframes, tri;       // tri: n1 == n2 (reference keys the triangle on sizes, quirk Q1)
@@ -37,12 +43,14 @@ struct PairParams {
     double* gpp;                    // [7][n1][histo_n] per-particle histogram or nullptr
     unsigned long long* counters;   // [kCounters]
     unsigned flags;                 // GFN_FLAG_DISCARD_OVERFLOW
+    int nrep;                       // histogram replicas in shared memory
 };
 
 struct PairConfig {
     int filter_fp64;   // 0 fp32 pre-filter, 1 fp64 pre-test
     int hist_mode;     // 0 shared-memory warp replicas, 1 global atomics, 2 per-particle global atomics
-    int warps;         // 8 or 4
+    int warps;         // worker warps per CTA (16 or 8)
+    int nrep;          // shared-memory histogram replicas per CTA (warps sharing one take a lock)
     int nslot;         // 1 (g000 only) or 8
     int blocks_per_sm;
     int grid;
@@ -54,9 +62,9 @@ struct PairConfig {
 cudaError_t pair_configure(int dev, int histo_n, int mode_sel, unsigned flags, PairConfig* cfg);
 cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
 
-// Converts nframes frames of one selection into Rec64 / float4 records and the per-frame max |coordinate|.
+// Converts nframes frames of one selection into Site records and the per-frame max |coordinate|.
 cudaError_t prep_launch(const double* xyz, long long stride_xyz, const double* dip, long long stride_dip,
-                        Rec64* rec, float4* pos, float* maxabs, int n, int n_pad, int nframes, cudaStream_t s);
+                        Site* site, float* maxabs, int n, int n_pad, int nframes, cudaStream_t s);
 
 // partials[grid][histo_n*nslot] -> gacc, blocks summed in ascending order (deterministic).
 cudaError_t finalize_launch(const double* partials, int grid, int histo_n, int nslot, double* gacc, cudaStream_t s);

@@ -47,6 +47,7 @@ cdef extern from "gfn.h":
         int smem_bytes
         int batch_frames
         int ndev
+        int hist_replicas
     int GFN_OK, GFN_EINVAL, GFN_ECUDA, GFN_ENCCL, GFN_EZERODIV, GFN_ENOMEM, GFN_ENODEV
     unsigned GFN_FLAG_PER_PARTICLE, GFN_FLAG_FILTER_FP64, GFN_FLAG_DISCARD_OVERFLOW, GFN_FLAG_HIST_GLOBAL
     int gfn_device_count() nogil
@@ -327,7 +328,7 @@ cdef class _Backend:
                     h2d_bytes=s.h2d_bytes, overflow=s.overflow, filter="fp64" if s.filter_fp64 else "fp32",
                     hist_mode=("smem_warp_replicas", "global_atomics", "per_particle")[s.hist_mode],
                     warps_per_block=s.warps_per_block, blocks_per_sm=s.blocks_per_sm, grid=s.grid,
-                    smem_bytes=s.smem_bytes, batch_frames=s.batch_frames, ndev=s.ndev)
+                    smem_bytes=s.smem_bytes, batch_frames=s.batch_frames, ndev=s.ndev, hist_replicas=s.hist_replicas)
 
 
 class RDF(object):
