@@ -160,6 +160,11 @@ int gfn_mark_elapsed_ms(gfn_t *h, double *ms);
  * of device dev.  Results in TFLOP/s (an FMA counts 2). */
 int gfn_measure_peaks(int dev, double *fp64_tflops, double *fp32_tflops);
 
+/* Self-test of the kernel's straight-line fp64 division / square-root sequences against the IEEE
+ * built-ins (__ddiv_rn, __dsqrt_rn) on n_operands random operand sets with exponents in the range the
+ * kernel uses them for.  mismatches = {division, square root, near-tie cases}; all must be 0. */
+int gfn_selftest_arith(int dev, unsigned long long seed, long long n_operands, unsigned long long mismatches[3]);
+
 /* Raw device memory helpers so a host framework without its own CUDA binding can stage
  * device-resident frames for gfn_enqueue_device_frames (bench: inputs resident in HBM). */
 int gfn_dev_alloc(int dev, void **dptr, unsigned long long bytes);

@@ -394,7 +394,7 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
     for (size_t i = 0; i < devs.size(); ++i) h->devs[i].dev = devs[i];
     for (Dev& d : h->devs) {
         CUC(cudaSetDevice(d.dev));
-        CUC(pair_configure(d.dev, histo_n, mode_sel, flags, &d.cfg));
+        CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, &d.cfg));
     }
     // work decomposition (identical on all devices)
     {
@@ -760,6 +760,14 @@ int gfn_measure_peaks(int dev, double* fp64_tflops, double* fp32_tflops)
 {
     gfn_t* h = nullptr;
     CU(peaks_measure(dev, fp64_tflops, fp32_tflops));
+    return GFN_OK;
+}
+
+int gfn_selftest_arith(int dev, unsigned long long seed, long long n_operands, unsigned long long mismatches[3])
+{
+    gfn_t* h = nullptr;
+    if (!mismatches) return fail(h, GFN_EINVAL, "NULL argument");
+    CU(arith_selftest(dev, seed, n_operands, mismatches));
     return GFN_OK;
 }
 

@@ -166,313 +166,498 @@ __device__ __forceinline__ double min_image(double d, double L, double half)
     return fabs(d) > half ? t : d;
 }
 
+// ---- straight-line fp64 division / square root ---------------------------------------------------
+// The CUDA built-ins (__ddiv_rn, __dsqrt_rn) are a serial block each: a seed from the MUFU unit, a
+// Newton chain of dependent DFMAs and a branch to a subroutine for out-of-range operands.  Those
+// branches stop ptxas from interleaving the chains of several survivors, and the exact path then runs
+// at ~0.1 instructions per cycle.  The two functions below are the built-ins' own in-range sequences
+// (read off the SASS nvcc 12.9 emits for sm_100a) without the branch; they return the correctly rounded
+// IEEE result for operands inside the ranges checked by div_in_range / sqrt_in_range (verified against the
+// built-ins on 2^32 random operands by gfn_selftest_arith, tests/test_gpu_parity.py).  A warp whose
+// operands are not all in range takes the built-in path instead.
+__device__ __forceinline__ double rcp64h(double b) { double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b)); return y; }
+__device__ __forceinline__ double rsq64h(double x) { double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+
+__device__ __forceinline__ double div_inrange(double a, double b)
+{
+    double y = rcp64h(b);
+    double e = fma(-b, y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    const double q = __dmul_rn(a, y);
+    const double r = fma(-b, q, a);
+    return fma(y, r, q);
+}
+
+__device__ __forceinline__ double sqrt_inrange(double x)
+{
+    double y = rsq64h(x);
+    const double t = __dmul_rn(y, y);
+    const double e = fma(x, -t, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    const double u = __dmul_rn(y, e);
+    y = fma(p, u, y);
+    const double g = __dmul_rn(x, y);
+    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));   // y / 2
+    const double d = fma(g, -g, x);
+    return fma(d, h, g);
+}
+
+// |x| in [2^-300, 2^300]: far inside the range where the sequences above are exact (no intermediate can
+// overflow, underflow or lose bits to subnormals)
+__device__ __forceinline__ bool mid_range(double x)
+{
+    const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+    return ex - 723u <= 600u;       // biased exponent in [723, 1323]
+}
+
 // 16-byte chunk c (0..3) of bin pos inside a replica with 8 slots per bin: chunks are XOR-swizzled
 // with bits 1..2 of pos so that lanes holding different bins hit different 4-bank groups.
 __device__ __forceinline__ int hist_chunk(int pos, int c) { return pos * 4 + (c ^ ((pos >> 1) & 3)); }
 
-template <typename F, int NW, int NSLOT, int HIST>
-__global__ void __launch_bounds__(NW * 32, 1)
+struct Item { int f, i0, jt_begin, ntiles; };
+
+__device__ __forceinline__ Item decode_item(const PairParams& P, long long item, int TI)
+{
+    Item it;
+    it.f = (int)(item / P.items_per_frame);
+    const int r = (int)(item - (long long)it.f * P.items_per_frame);
+    int lo = 0, hi = P.n_itiles;      // core tile ti with item_start[ti] <= r < item_start[ti+1]
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.item_start[mid] <= r) lo = mid; else hi = mid; }
+    const int seg = r - P.item_start[lo];
+    it.i0 = lo * TI;
+    const int jt_first = P.tri ? (it.i0 / kTJ) : 0;
+    it.jt_begin = jt_first + seg * P.seg_tiles;
+    it.ntiles = min(it.jt_begin + P.seg_tiles, P.n_jtiles) - it.jt_begin;
+    return it;
+}
+
+// Shared-memory control block of one CTA (after the data arrays).
+struct Ctrl {
+    uint64_t full[kStages];      // TMA landed in stage s
+    uint64_t ifull;              // TMA landed in the core tile
+    int done_cnt[4];             // warps finished with stage s (the last one refills it)
+    int locks[4];                // replica locks (only when fewer replicas than drain warps)
+    volatile unsigned tail[16];  // ring w: entries published by filter warp w
+    volatile unsigned head[16];  // ring w: entries consumed by its drain warp
+    volatile unsigned tdone[16]; // ring w: number of surround tiles completely filtered
+    volatile unsigned tend[16][4];   // ring w: tail at the end of tile g (slot g & 3)
+};
+
+// The last warp (filter or drain) to finish with a stage refills it with the tile S steps ahead.
+__device__ __forceinline__ void release_stage(Ctrl* c, Site* jsite, const Site* siteB, int st, int nwarps,
+                                              int t, int ntiles, int jt_begin, int lane)
+{
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        const int old = atomicAdd(&c->done_cnt[st], 1);
+        if (old == nwarps - 1) {
+            atomicExch(&c->done_cnt[st], 0);
+            if (t + kStages < ntiles) {
+                mbar_expect_tx(&c->full[st], kTJ * (uint32_t)sizeof(Site));
+                bulk_g2s(jsite + st * kTJ, siteB + (long long)(jt_begin + t + kStages) * kTJ, kTJ * (uint32_t)sizeof(Site), &c->full[st]);
+            }
+        }
+    }
+}
+
+// Warp-specialised pair kernel.  Warps [0,NF) are FILTER warps: fp32 (or fp64) range pre-filter over
+// 64 core sites x the surround stage, survivors published into a per-warp single-producer ring.
+// Warps [NF,NF+4) are DRAIN warps (one per SM sub-partition): they consume the rings of filter warps
+// w = d, d+4, d+8 in that fixed order, evaluate two survivors per lane exactly in fp64 and add them
+// into their private histogram replica.  Registers are re-balanced with setmaxnreg.
+template <typename F, int NF, int NSLOT, int HIST, bool ALLM>
+__global__ void __launch_bounds__((NF + kND) * 32, 1)
 pair_kernel(const PairParams P)
 {
-    constexpr int TI = NW * 32 * kIPT;
+    constexpr int NW = NF + kND;
+    constexpr int TI = NF * 32 * kIPT;
     constexpr int TJ = kTJ;
     constexpr int S = kStages;
     constexpr bool kF32 = sizeof(F) == 4;
-    constexpr uint32_t kTileBytes = TJ * (uint32_t)sizeof(Site);
+    constexpr unsigned RMASK = kRingCap - 1;
+    static_assert(kIPT == 2, "two core sites per filter thread");
+    constexpr int kU = kDrainILP;
 
     extern __shared__ __align__(128) unsigned char smem[];
     Site* isite = reinterpret_cast<Site*>(smem);                                  // [TI]
     Site* jsite = isite + TI;                                                     // [S][TJ]
-    unsigned short* queue = reinterpret_cast<unsigned short*>(jsite + S * TJ);    // [NW][kQCap]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(queue + NW * kQCap);             // full[S], ifull
-    int* done_cnt = reinterpret_cast<int*>(bars + 4);                             // [S] warps finished with stage
-    int* locks = done_cnt + 4;                                                    // [NW] replica locks
-    double* hist = reinterpret_cast<double*>(locks + 20);                         // [nrep][histo_n*NSLOT] (HIST==0)
+    unsigned short* rings = reinterpret_cast<unsigned short*>(jsite + S * TJ);    // [NF][kRingCap]
+    Ctrl* ctrl = reinterpret_cast<Ctrl*>(rings + NF * kRingCap);
+    double* hist = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ctrl) + kCtrlBytes);   // [nrep][hn*NSLOT]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hn = P.histo_n;
     const int hsz = hn * NSLOT;
     const int nrep = P.nrep;
-    const int rep = warp % nrep;
-    const bool use_lock = nrep < NW;
-    double* hist_w = hist + (size_t)rep * hsz;
-    unsigned short* q = queue + warp * kQCap;
 
     if (HIST == 0) {
         for (int k = tid; k < nrep * hsz; k += NW * 32) hist[k] = 0.0;
     }
-    if (tid < 4) done_cnt[tid] = 0;
-    if (tid < NW) locks[tid] = 0;
+    if (tid < 16) { ctrl->tail[tid] = 0; ctrl->head[tid] = 0; ctrl->tdone[tid] = 0; }
+    if (tid < 4) { ctrl->done_cnt[tid] = 0; ctrl->locks[tid] = 0; }
     if (tid == 0) {
-        for (int k = 0; k < 4; ++k) mbar_init(&bars[k], 1);
+        for (int k = 0; k < S; ++k) mbar_init(&ctrl->full[k], 1);
+        mbar_init(&ctrl->ifull, 1);
         mbar_fence_init();
     }
     __syncthreads();
 
-    const int mode_sel = P.mode_sel;
-    const bool m_cs = mode_sel & (2 | 16), m_cd = mode_sel & (4 | 32), m_sd = mode_sel & (8 | 64);
-    unsigned tcount = 0;        // surround tiles consumed so far by this CTA (stage = tcount % S, parity = (tcount / S) & 1)
-    unsigned icount = 0;        // items consumed (parity of the core-tile barrier)
-    unsigned n_surv = 0, n_inr = 0, n_ovf = 0;
-    bool zerodiv = false;
-
     const long long total_items = (long long)P.items_per_frame * P.nframes;
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int f = (int)(item / P.items_per_frame);
-        const int r = (int)(item - (long long)f * P.items_per_frame);
-        // core tile ti with item_start[ti] <= r < item_start[ti+1]
-        int lo = 0, hi = P.n_itiles;
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.item_start[mid] <= r) lo = mid; else hi = mid; }
-        const int ti = lo;
-        const int seg = r - P.item_start[ti];
-        const int i0 = ti * TI;
-        const int jt_first = P.tri ? (i0 / TJ) : 0;
-        const int jt_begin = jt_first + seg * P.seg_tiles;
-        const int jt_end = min(jt_begin + P.seg_tiles, P.n_jtiles);
-        const int ntiles = jt_end - jt_begin;
+    unsigned tcount = 0;        // surround tiles consumed so far by this CTA (stage = g % S, parity = (g / S) & 1)
 
-        const Site* siteA = P.siteA + (long long)f * P.strideA;
-        const Site* siteB = P.siteB + (long long)f * P.strideB;
+    if (warp < NF) {
+        // =========================================== FILTER ===========================================
+        if (kF32) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        else      asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        unsigned short* q = rings + warp * kRingCap;
+        unsigned tail = 0, head_seen = 0;
 
-        __syncthreads();     // previous item fully consumed: the core tile and every stage are free
-        if (tid == 0) {
-            mbar_expect_tx(&bars[3], TI * (uint32_t)sizeof(Site));
-            bulk_g2s(isite, siteA + i0, TI * (uint32_t)sizeof(Site), &bars[3]);
-            for (int pre = 0; pre < S && pre < ntiles; ++pre) {
-                const int st = (tcount + pre) % S;
-                mbar_expect_tx(&bars[st], kTileBytes);
-                bulk_g2s(jsite + st * TJ, siteB + (long long)(jt_begin + pre) * TJ, kTileBytes, &bars[st]);
+        for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const Item it = decode_item(P, item, TI);
+            const Site* siteA = P.siteA + (long long)it.f * P.strideA;
+            const Site* siteB = P.siteB + (long long)it.f * P.strideB;
+
+            __syncthreads();     // previous item fully consumed: the core tile and every stage are free
+            if (tid == 0) {
+                mbar_expect_tx(&ctrl->ifull, TI * (uint32_t)sizeof(Site));
+                bulk_g2s(isite, siteA + it.i0, TI * (uint32_t)sizeof(Site), &ctrl->ifull);
+                for (int pre = 0; pre < S && pre < it.ntiles; ++pre) {
+                    const int st = (tcount + pre) % S;
+                    mbar_expect_tx(&ctrl->full[st], TJ * (uint32_t)sizeof(Site));
+                    bulk_g2s(jsite + st * TJ, siteB + (long long)(it.jt_begin + pre) * TJ, TJ * (uint32_t)sizeof(Site), &ctrl->full[st]);
+                }
             }
-        }
+            // frame constants (uniform)
+            const double* b = P.box + 6ll * it.f;
+            const double M = (double)fmaxf(P.maxA[it.f], P.maxB[it.f]) * (1.0 + 1.2e-7);
+            const F Tg = guard_threshold<F>(P.hmax, M, fmax(b[3], fmax(b[4], b[5])));
+            const F hxf = (F)b[3], hyf = (F)b[4], hzf = (F)b[5];
 
-        // frame constants (uniform)
-        Box bx;
-        {
-            const double* b = P.box + 6ll * f;
-            bx.Lx = b[0]; bx.Ly = b[1]; bx.Lz = b[2]; bx.hx = b[3]; bx.hy = b[4]; bx.hz = b[5];
-        }
-        const double M = (double)fmaxf(P.maxA[f], P.maxB[f]) * (1.0 + 1.2e-7);
-        const F Tg = guard_threshold<F>(P.hmax, M, fmax(bx.hx, fmax(bx.hy, bx.hz)));
-        const F hxf = (F)bx.hx, hyf = (F)bx.hy, hzf = (F)bx.hz;
-
-        // this thread's core positions: local index il(k) = warp*32*IPT + k*32 + lane
-        F cx[kIPT], cy[kIPT], cz[kIPT];
+            // this thread's core positions: local index il(k) = warp*64 + k*32 + lane
+            F cx[kIPT], cy[kIPT], cz[kIPT];
 #pragma unroll
-        for (int k = 0; k < kIPT; ++k) {
-            const int il = warp * (32 * kIPT) + k * 32 + lane;
-            const Site* c = siteA + i0 + il;
-            if (kF32) { cx[k] = (F)c->fx; cy[k] = (F)c->fy; cz[k] = (F)c->fz; }
-            else if (i0 + il < P.n1) { cx[k] = (F)c->x; cy[k] = (F)c->y; cz[k] = (F)c->z; }
-            else { cx[k] = cy[k] = cz[k] = (F)1e30; }
-        }
-        const int my_i_min = i0 + warp * (32 * kIPT);     // smallest core index of this warp
+            for (int k = 0; k < kIPT; ++k) {
+                const int il = warp * (32 * kIPT) + k * 32 + lane;
+                const Site* c = siteA + it.i0 + il;
+                if (kF32) { cx[k] = (F)c->fx; cy[k] = (F)c->fy; cz[k] = (F)c->fz; }
+                else if (it.i0 + il < P.n1) { cx[k] = (F)c->x; cy[k] = (F)c->y; cz[k] = (F)c->z; }
+                else { cx[k] = cy[k] = cz[k] = (F)1e30; }
+            }
+            const int my_i_min = it.i0 + warp * (32 * kIPT);     // smallest core index of this warp
 
-        mbar_wait(&bars[3], icount & 1);
-        ++icount;
+            for (int t = 0; t < it.ntiles; ++t) {
+                const unsigned g = tcount + t;
+                const int st = g % S;
+                const int j0 = (it.jt_begin + t) * TJ;
+                mbar_wait(&ctrl->full[st], (g / S) & 1);
+                const Site* js = jsite + st * TJ;
 
-        int qcount = 0;   // warp-uniform
-        for (int t = 0; t < ntiles; ++t) {
-            const unsigned g = tcount + t;
-            const int st = g % S;
-            const int j0 = (jt_begin + t) * TJ;
-            mbar_wait(&bars[st], (g / S) & 1);
-            const Site* js = jsite + st * TJ;
-
-            // ---- exact evaluation of up to 32 queued survivors (one per lane) -------------------------
-            auto drain = [&](int cnt) {
-                const bool have = lane < cnt;
-                const unsigned e = have ? q[qcount - cnt + lane] : 0u;
-                __syncwarp();          // all lanes have read their entry before anyone pushes again
-                const int il = warp * (32 * kIPT) + (int)(e >> 7), jl = e & 127;
-                const int i = i0 + il, j = j0 + jl;
-                bool ok = have && i < P.n1 && j < P.n2 && !(P.tri && j < i);
-                int pos = 0;
-                double w = 1.0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, v6 = 0;
-                if (ok) {
-                    const double2* ap = reinterpret_cast<const double2*>(isite + il);
-                    const double2* bp = reinterpret_cast<const double2*>(js + jl);
-                    const double2 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];   // x y | z px | py pz | norm -
-                    const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-                    const double dx = min_image(DSUB(b0.x, a0.x), bx.Lx, bx.hx);                     // :141-147
-                    const double dy = min_image(DSUB(b0.y, a0.y), bx.Ly, bx.hy);
-                    const double dz = min_image(DSUB(b1.x, a1.x), bx.Lz, bx.hz);
-                    const double dist = __dsqrt_rn(DOT3(dx, dy, dz, dx, dy, dz));                      // :148
-                    ++n_surv;
-                    // :149  dist<hmin | dist>hmax | floor(dist*invdx)==0  (dist >= 0, so floor(x)==0 <=> x<1); NaN rejected
-                    if (!(dist >= P.hmin) || dist > P.hmax || DMUL(dist, P.invdx) < 1.0) {
-                        ok = false;
-                    } else {
-                        pos = __double2int_rd(DMUL(DSUB(dist, P.hmin), P.invdx));                     // :150
-                        w = (P.tri && i != j) ? 2.0 : 1.0;                                            // :131-134
-                        ++n_inr;
-                        const double apx = a1.y, apy = a2.x, apz = a2.y, an = a3.x;
-                        const double bpx = b1.y, bpy = b2.x, bpz = b2.y, bn = b3.x;
-                        if (m_cs) {                                                                   // :154-157
-                            const double den = DMUL(an, bn);
-                            if (den == 0.0) zerodiv = true;
-                            else {
-                                const double c = DDIV(DOT3(apx, apy, apz, bpx, bpy, bpz), den);
-                                v1 = DMUL(c, w);
-                                v4 = DMUL(DSUB(DMUL(DMUL(1.5, c), c), 0.5), w);
-                            }
-                        }
-                        if (m_cd) {                                                                   // :158-161
-                            const double den = DMUL(an, dist);
-                            if (den == 0.0) zerodiv = true;
-                            else {
-                                const double c = DDIV(DOT3(apx, apy, apz, dx, dy, dz), den);
-                                v2 = DMUL(c, w);
-                                v5 = DMUL(DSUB(DMUL(DMUL(1.5, c), c), 0.5), w);
-                            }
-                        }
-                        if (m_sd) {                                                                   // :162-165
-                            const double den = DMUL(bn, dist);
-                            if (den == 0.0) zerodiv = true;
-                            else {
-                                const double c = DDIV(DOT3(bpx, bpy, bpz, dx, dy, dz), den);
-                                v3 = DMUL(c, w);
-                                v6 = DMUL(DSUB(DMUL(DMUL(1.5, c), c), 0.5), w);
-                            }
-                        }
-                    }
-                }
-                const double v0 = (mode_sel & 1) ? w : 0.0;                                           // :152
-                if (!(mode_sel & 2)) v1 = 0.0;
-                if (!(mode_sel & 4)) v2 = 0.0;
-                if (!(mode_sel & 8)) v3 = 0.0;
-                if (!(mode_sel & 16)) v4 = 0.0;
-                if (!(mode_sel & 32)) v5 = 0.0;
-                if (!(mode_sel & 64)) v6 = 0.0;
-
-                const bool spill = ok && pos >= hn;          // quirk Q3
-                if ((HIST != 0 && ok) || spill) {
-                    if (spill) ++n_ovf;
-                    if (!(spill && (P.flags & GFN_FLAG_DISCARD_OVERFLOW))) {
-                        const int hm = HIST == 0 ? 1 : HIST;
-                        if (mode_sel & 1)  global_add(P, hm, 0, i, pos, v0);
-                        if (mode_sel & 2)  global_add(P, hm, 1, i, pos, v1);
-                        if (mode_sel & 4)  global_add(P, hm, 2, i, pos, v2);
-                        if (mode_sel & 8)  global_add(P, hm, 3, i, pos, v3);
-                        if (mode_sel & 16) global_add(P, hm, 4, i, pos, v4);
-                        if (mode_sel & 32) global_add(P, hm, 5, i, pos, v5);
-                        if (mode_sel & 64) global_add(P, hm, 6, i, pos, v6);
-                        if (!spill) atomicAdd(P.gacc + 7ll * hn + pos, w);      // pair weight row
-                    }
-                }
-                if (HIST == 0) {
-                    const bool add = ok && !spill;
-                    const unsigned key = add ? (unsigned)pos : (0x40000000u | lane);
-                    const unsigned grp = __match_any_sync(0xffffffffu, key);
-                    const int rank = __popc(grp & ((1u << lane) - 1u));
-                    const int maxr = __reduce_max_sync(0xffffffffu, add ? (unsigned)rank : 0u);
-                    if (use_lock) {
-                        if (lane == 0) { while (atomicCAS(&locks[rep], 0, 1) != 0) __nanosleep(40); }
-                        __syncwarp();
-                        __threadfence_block();
-                    }
-                    for (int rr = 0; rr <= maxr; ++rr) {
-                        if (add && rank == rr) {
-                            if (NSLOT == 1) {
-                                hist_w[pos] += w;
-                            } else {
-                                double2* h2 = reinterpret_cast<double2*>(hist_w);
-                                const int c0 = hist_chunk(pos, 0), c1 = hist_chunk(pos, 1), c2 = hist_chunk(pos, 2), c3 = hist_chunk(pos, 3);
-                                double2 h0 = h2[c0], h1 = h2[c1], hh2 = h2[c2], h3 = h2[c3];
-                                h0.x += v0; h0.y += v1; h1.x += v2; h1.y += v3;
-                                hh2.x += v4; hh2.y += v5; h3.x += v6; h3.y += w;
-                                h2[c0] = h0; h2[c1] = h1; h2[c2] = hh2; h2[c3] = h3;
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    if (use_lock) {
-                        __threadfence_block();
-                        __syncwarp();
-                        if (lane == 0) atomicExch(&locks[rep], 0);
-                    }
-                }
-                qcount -= cnt;
-            };
-
-            // ---- pre-filter over the TJ surround sites of this stage --------------------------------
-            for (int jc = 0; jc < TJ / 32; ++jc) {
-                const int jbase = jc * 32;
-                if (j0 + jbase >= P.n2) break;                              // padding only
-                if (P.tri && j0 + jbase + 31 < my_i_min) continue;         // chunk entirely below this warp's rows
-                unsigned msk[kIPT];
-#pragma unroll
-                for (int k = 0; k < kIPT; ++k) msk[k] = 0u;
+                for (int jc = 0; jc < TJ / 32; ++jc) {
+                    const int jbase = jc * 32;
+                    if (j0 + jbase >= P.n2) break;                              // padding only
+                    if (P.tri && j0 + jbase + 31 < my_i_min) continue;         // chunk entirely below this warp's rows
+                    unsigned m0 = 0u, m1 = 0u;
 #pragma unroll 16
-                for (int jj = 0; jj < 32; ++jj) {
-                    F sx, sy, sz;
-                    if (kF32) {
-                        const float4 s = *reinterpret_cast<const float4*>(&js[jbase + jj].fx);
-                        sx = (F)s.x; sy = (F)s.y; sz = (F)s.z;
-                    } else {
-                        const double2 sxy = *reinterpret_cast<const double2*>(&js[jbase + jj].x);
-                        sx = (F)sxy.x; sy = (F)sxy.y; sz = (F)js[jbase + jj].z;
-                        if (j0 + jbase + jj >= P.n2) { sx = sy = sz = (F)-1e30; }
+                    for (int jj = 0; jj < 32; ++jj) {
+                        F sx, sy, sz;
+                        if (kF32) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(&js[jbase + jj].fx);
+                            sx = (F)s4.x; sy = (F)s4.y; sz = (F)s4.z;
+                        } else {
+                            const double2 sxy = *reinterpret_cast<const double2*>(&js[jbase + jj].x);
+                            sx = (F)sxy.x; sy = (F)sxy.y; sz = (F)js[jbase + jj].z;
+                            if (j0 + jbase + jj >= P.n2) { sx = sy = sz = (F)-1e30; }
+                        }
+#pragma unroll
+                        for (int k = 0; k < kIPT; ++k) {
+                            const F dx = sx - cx[k], dy = sy - cy[k], dz = sz - cz[k];
+                            const F vx = FOps<F>::abs(dx) - hxf, vy = FOps<F>::abs(dy) - hyf, vz = FOps<F>::abs(dz) - hzf;
+                            const F wx = hxf - FOps<F>::abs(vx), wy = hyf - FOps<F>::abs(vy), wz = hzf - FOps<F>::abs(vz);
+                            F tt = FOps<F>::fma(wx, wx, -Tg);
+                            tt = FOps<F>::fma(wy, wy, tt);
+                            tt = FOps<F>::fma(wz, wz, tt);
+                            if (k == 0) m0 = __funnelshift_l(FOps<F>::signword(tt), m0, 1);    // first jj ends at bit 31
+                            else        m1 = __funnelshift_l(FOps<F>::signword(tt), m1, 1);
+                        }
                     }
+                    // ---- publish survivors into this warp's ring (one packed scan for both core slots) ----
+                    if (!__any_sync(0xffffffffu, (m0 | m1) != 0u)) continue;
+                    const unsigned cnt2 = (unsigned)__popc(m0) | ((unsigned)__popc(m1) << 16);
+                    unsigned incl = cnt2;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += up;
+                    }
+                    const unsigned tot2 = __shfl_sync(0xffffffffu, incl, 31);
+                    const unsigned excl = incl - cnt2;
 #pragma unroll
                     for (int k = 0; k < kIPT; ++k) {
-                        const F dx = sx - cx[k], dy = sy - cy[k], dz = sz - cz[k];
-                        const F vx = FOps<F>::abs(dx) - hxf, vy = FOps<F>::abs(dy) - hyf, vz = FOps<F>::abs(dz) - hzf;
-                        const F wx = hxf - FOps<F>::abs(vx), wy = hyf - FOps<F>::abs(vy), wz = hzf - FOps<F>::abs(vz);
-                        F tt = FOps<F>::fma(wx, wx, -Tg);
-                        tt = FOps<F>::fma(wy, wy, tt);
-                        tt = FOps<F>::fma(wz, wz, tt);
-                        msk[k] = __funnelshift_l(FOps<F>::signword(tt), msk[k], 1);    // first jj ends at bit 31
+                        const unsigned total = (tot2 >> (16 * k)) & 0xffffu;
+                        if (total == 0) continue;
+                        while (tail + total - head_seen > (unsigned)kRingCap) {      // ring full: wait for the drain warp
+                            head_seen = ctrl->head[warp];
+                            if (tail + total - head_seen > (unsigned)kRingCap) __nanosleep(64);
+                        }
+                        unsigned m = k == 0 ? m0 : m1;
+                        unsigned at = tail + ((excl >> (16 * k)) & 0xffffu);
+                        const unsigned tag = (unsigned)(k * 32 + lane) << 7;
+                        while (m) {
+                            const int jj = __clz(m);
+                            m &= ~(0x80000000u >> jj);
+                            q[(at++) & RMASK] = (unsigned short)(tag | (unsigned)(jbase + jj));
+                        }
+                        tail += total;
+                        __syncwarp();
+                        if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
                     }
                 }
-                // ---- compact survivors into the warp queue (one packed scan for both core slots) ---------
-                static_assert(kIPT == 2, "the packed scan below assumes two core sites per thread");
-                if (!__any_sync(0xffffffffu, (msk[0] | msk[1]) != 0u)) continue;
-                const unsigned cnt2 = (unsigned)__popc(msk[0]) | ((unsigned)__popc(msk[1]) << 16);
-                unsigned incl = cnt2;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += up;
+                // ---- tile finished: tell the drain warp where it ends, release the stage ----------------
+                __syncwarp();
+                if (lane == 0) {
+                    ctrl->tend[warp][g & 3] = tail;
+                    __threadfence_block();
+                    ctrl->tdone[warp] = g + 1;
                 }
-                const unsigned tot2 = __shfl_sync(0xffffffffu, incl, 31);
-                const unsigned excl = incl - cnt2;
-#pragma unroll
-                for (int k = 0; k < kIPT; ++k) {
-                    const int total = (tot2 >> (16 * k)) & 0xffff;
-                    if (total == 0) continue;
-                    unsigned m = msk[k];
-                    int at = qcount + (int)((excl >> (16 * k)) & 0xffff);
-                    const unsigned tag = (unsigned)(k * 32 + lane) << 7;
-                    while (m) {
-                        const int jj = __clz(m);
-                        m &= ~(0x80000000u >> jj);
-                        q[at++] = (unsigned short)(tag | (unsigned)(jbase + jj));
-                    }
-                    qcount += total;
-                    __syncwarp();
-                    while (qcount >= 32) drain(32);
-                }
+                release_stage(ctrl, jsite, siteB, st, NW, t, it.ntiles, it.jt_begin, lane);
             }
-            if (qcount > 0) drain(qcount);   // the stage buffer is recycled next: empty the queue
-
-            // ---- release the stage: the last warp to finish refills it -----------------------------------
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                const int old = atomicAdd(&done_cnt[st], 1);
-                if (old == NW - 1) {
-                    atomicExch(&done_cnt[st], 0);
-                    if (t + S < ntiles) {
-                        mbar_expect_tx(&bars[st], kTileBytes);
-                        bulk_g2s(jsite + st * TJ, siteB + (long long)(jt_begin + t + S) * TJ, kTileBytes, &bars[st]);
-                    }
-                }
-            }
+            tcount += it.ntiles;
         }
-        tcount += ntiles;
+    } else {
+        // =========================================== DRAIN ============================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int dw = warp - NF;                   // drain warp 0..3
+        const int rep = dw % nrep;
+        const bool use_lock = nrep < kND;
+        double* hist_w = hist + (size_t)rep * hsz;
+        const int mode_sel = ALLM ? 127 : P.mode_sel;       // ALLM: all seven modes selected, masks fold away
+        const bool m_cs = mode_sel & (2 | 16), m_cd = mode_sel & (4 | 32), m_sd = mode_sel & (8 | 64);
+        unsigned n_surv = 0, n_inr = 0, n_ovf = 0;
+        bool zerodiv = false;
+        const double t_small = 0.25 / (P.invdx * P.invdx);       // (0.5/invdx)^2
+
+        for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const Item it = decode_item(P, item, TI);
+            const Site* siteB = P.siteB + (long long)it.f * P.strideB;
+            __syncthreads();
+            Box bx;
+            {
+                const double* b = P.box + 6ll * it.f;
+                bx.Lx = b[0]; bx.Ly = b[1]; bx.Lz = b[2]; bx.hx = b[3]; bx.hy = b[4]; bx.hz = b[5];
+            }
+            mbar_wait(&ctrl->ifull, (unsigned)((item - blockIdx.x) / gridDim.x) & 1);
+
+            for (int t = 0; t < it.ntiles; ++t) {
+                const unsigned g = tcount + t;
+                const int st = g % S;
+                const int j0 = (it.jt_begin + t) * TJ;
+                mbar_wait(&ctrl->full[st], (g / S) & 1);
+                const Site* js = jsite + st * TJ;
+
+#pragma unroll 1
+                for (int fw = dw; fw < NF; fw += kND) {     // rings of filter warps dw, dw+4, dw+8 in this fixed order
+                    const unsigned short* q = rings + fw * kRingCap;
+                    unsigned head = ctrl->head[fw];         // this warp is its only writer
+                    for (;;) {
+                        const bool fin = ctrl->tdone[fw] > g;
+                        __threadfence_block();
+                        const unsigned limit = fin ? ctrl->tend[fw][g & 3] : ctrl->tail[fw];
+                        const unsigned avail = limit - head;
+                        // full batches of 32*kU; the partial one only when the producer has finished the tile, so the
+                        // grouping (and with it the summation order) does not depend on timing.  The ring holds
+                        // kRingCap >= 32*kU-1 + 32*32 entries, so a blocked producer always sees space again.
+                        if (avail < 32u * kU && !(fin && avail > 0u)) {
+                            if (fin) break;
+                            __nanosleep(100);
+                            continue;
+                        }
+                        __threadfence_block();
+                        const int n = (int)min(avail, 32u * kU);
+
+                        // ---- exact evaluation: kU survivors per lane, branch-free so that ptxas interleaves
+                        //      the dependent fp64 chains of all of them ---------------------------------------
+                        bool ok[kU]; int pos[kU], gi[kU]; double w[kU], v[kU][6];
+                        double dxa[kU], dya[kU], dza[kU], d2[kU], dist[kU];
+                        double apx[kU], apy[kU], apz[kU], an[kU], bpx[kU], bpy[kU], bpz[kU], bn[kU];
+                        bool self_pair[kU];
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            const int idx = lane + 32 * u;
+                            const bool have = idx < n;
+                            const unsigned e = have ? q[(head + idx) & RMASK] : 0u;
+                            const int il = fw * (32 * kIPT) + (int)(e >> 7), jl = e & 127;
+                            const int i = it.i0 + il, j = j0 + jl;
+                            gi[u] = i;
+                            self_pair[u] = (i == j);
+                            ok[u] = have && i < P.n1 && j < P.n2 && !(P.tri && j < i);
+                            const double2* ap = reinterpret_cast<const double2*>(isite + il);
+                            const double2* bp = reinterpret_cast<const double2*>(js + jl);
+                            const double2 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];   // x y | z px | py pz | norm -
+                            const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+                            apx[u] = a1.y; apy[u] = a2.x; apz[u] = a2.y; an[u] = a3.x;
+                            bpx[u] = b1.y; bpy[u] = b2.x; bpz[u] = b2.y; bn[u] = b3.x;
+                            dxa[u] = min_image(DSUB(b0.x, a0.x), bx.Lx, bx.hx);                     // :141-147
+                            dya[u] = min_image(DSUB(b0.y, a0.y), bx.Ly, bx.hy);
+                            dza[u] = min_image(DSUB(b1.x, a1.x), bx.Lz, bx.hz);
+                            d2[u] = DOT3(dxa[u], dya[u], dza[u], dxa[u], dya[u], dza[u]);
+                            // pairs closer than half the first bin edge are rejected by :149 whatever the rounding
+                            // (floor(dist*invdx)==0); dropping them here keeps d2 = 0 (i == j) away from the sqrt
+                            ok[u] = ok[u] && d2[u] >= t_small;           // false for NaN too
+                        }
+                        unsigned ns = 0;
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) ns += ok[u] ? 1u : 0u;
+                        n_surv += ns;
+                        // --- distance :148
+                        bool rng = true;
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) { if (!ok[u]) d2[u] = 1.0; rng = rng && mid_range(d2[u]); }
+                        if (__all_sync(0xffffffffu, rng)) {
+#pragma unroll
+                            for (int u = 0; u < kU; ++u) dist[u] = sqrt_inrange(d2[u]);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < kU; ++u) dist[u] = __dsqrt_rn(d2[u]);
+                        }
+                        // --- range test :149, bin :150, weight :131-134
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            // dist<hmin | dist>hmax | floor(dist*invdx)==0  (dist >= 0: floor(x)==0 <=> x<1)
+                            ok[u] = ok[u] && dist[u] >= P.hmin && !(dist[u] > P.hmax) && !(DMUL(dist[u], P.invdx) < 1.0);
+                            pos[u] = __double2int_rd(DMUL(DSUB(dist[u], P.hmin), P.invdx));
+                            w[u] = (P.tri && !self_pair[u]) ? 2.0 : 1.0;
+                            n_inr += ok[u] ? 1u : 0u;
+                        }
+                        if (NSLOT == 8) {
+                            // --- orientation weights :154-165, all three cosines (unselected ones are masked below)
+                            double den[kU][3], num[kU][3], c[kU][3];
+                            bool drng = true;
+#pragma unroll
+                            for (int u = 0; u < kU; ++u) {
+                                den[u][0] = DMUL(an[u], bn[u]);
+                                den[u][1] = DMUL(an[u], dist[u]);
+                                den[u][2] = DMUL(bn[u], dist[u]);
+                                num[u][0] = DOT3(apx[u], apy[u], apz[u], bpx[u], bpy[u], bpz[u]);
+                                num[u][1] = DOT3(apx[u], apy[u], apz[u], dxa[u], dya[u], dza[u]);
+                                num[u][2] = DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]);
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) {
+                                    const bool sel = k == 0 ? m_cs : (k == 1 ? m_cd : m_sd);
+                                    if (ok[u] && sel && den[u][k] == 0.0) zerodiv = true;          // quirk Q5
+                                    if (!ok[u] || !sel || den[u][k] == 0.0) { den[u][k] = 1.0; num[u][k] = 0.0; }
+                                    drng = drng && mid_range(den[u][k]);
+                                }
+                            }
+                            if (__all_sync(0xffffffffu, drng)) {
+#pragma unroll
+                                for (int u = 0; u < kU; ++u)
+#pragma unroll
+                                    for (int k = 0; k < 3; ++k) c[u][k] = div_inrange(num[u][k], den[u][k]);
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < kU; ++u)
+#pragma unroll
+                                    for (int k = 0; k < 3; ++k) c[u][k] = DDIV(num[u][k], den[u][k]);
+                            }
+#pragma unroll
+                            for (int u = 0; u < kU; ++u)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) {
+                                    v[u][k] = DMUL(c[u][k], w[u]);                                          // incr*off_diag
+                                    v[u][3 + k] = DMUL(DSUB(DMUL(DMUL(1.5, c[u][k]), c[u][k]), 0.5), w[u]);   // (1.5*incr*incr-0.5)*off_diag
+                                }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < kU; ++u)
+#pragma unroll
+                                for (int k = 0; k < 6; ++k) v[u][k] = 0.0;
+                        }
+                        __syncwarp();
+                        head += (unsigned)n;
+                        if (lane == 0) ctrl->head[fw] = head;       // entries are in registers: the producer may reuse them
+
+                        // ---- accumulate ----------------------------------------------------------------------
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            const double v0 = (mode_sel & 1) ? w[u] : 0.0;                                    // :152
+                            const double v1 = (mode_sel & 2) ? v[u][0] : 0.0, v2 = (mode_sel & 4) ? v[u][1] : 0.0;
+                            const double v3 = (mode_sel & 8) ? v[u][2] : 0.0, v4 = (mode_sel & 16) ? v[u][3] : 0.0;
+                            const double v5 = (mode_sel & 32) ? v[u][4] : 0.0, v6 = (mode_sel & 64) ? v[u][5] : 0.0;
+                            const bool spill = ok[u] && pos[u] >= hn;          // quirk Q3
+                            if ((HIST != 0 && ok[u]) || spill) {
+                                if (spill) ++n_ovf;
+                                if (!(spill && (P.flags & GFN_FLAG_DISCARD_OVERFLOW))) {
+                                    const int hm = HIST == 0 ? 1 : HIST;
+                                    if (mode_sel & 1)  global_add(P, hm, 0, gi[u], pos[u], v0);
+                                    if (mode_sel & 2)  global_add(P, hm, 1, gi[u], pos[u], v1);
+                                    if (mode_sel & 4)  global_add(P, hm, 2, gi[u], pos[u], v2);
+                                    if (mode_sel & 8)  global_add(P, hm, 3, gi[u], pos[u], v3);
+                                    if (mode_sel & 16) global_add(P, hm, 4, gi[u], pos[u], v4);
+                                    if (mode_sel & 32) global_add(P, hm, 5, gi[u], pos[u], v5);
+                                    if (mode_sel & 64) global_add(P, hm, 6, gi[u], pos[u], v6);
+                                    if (!spill) atomicAdd(P.gacc + 7ll * hn + pos[u], w[u]);      // pair weight row
+                                }
+                            }
+                            if (HIST == 0) {
+                                if (32 * u >= n) continue;                // warp-uniform: this half of the batch is empty
+                                const bool add = ok[u] && !spill;
+                                const unsigned key = add ? (unsigned)pos[u] : (0x40000000u | lane);
+                                const unsigned grp = __match_any_sync(0xffffffffu, key);
+                                const int rank = __popc(grp & ((1u << lane) - 1u));
+                                const int maxr = __reduce_max_sync(0xffffffffu, add ? (unsigned)rank : 0u);
+                                if (use_lock) {
+                                    if (lane == 0) { while (atomicCAS(&ctrl->locks[rep], 0, 1) != 0) __nanosleep(40); }
+                                    __syncwarp();
+                                    __threadfence_block();
+                                }
+                                for (int rr = 0; rr <= maxr; ++rr) {
+                                    if (add && rank == rr) {
+                                        if (NSLOT == 1) {
+                                            hist_w[pos[u]] += w[u];
+                                        } else {
+                                            double2* h2 = reinterpret_cast<double2*>(hist_w);
+                                            const int c0 = hist_chunk(pos[u], 0), c1 = hist_chunk(pos[u], 1), c2 = hist_chunk(pos[u], 2), c3 = hist_chunk(pos[u], 3);
+                                            double2 h0 = h2[c0], h1 = h2[c1], hh2 = h2[c2], h3 = h2[c3];
+                                            h0.x += v0; h0.y += v1; h1.x += v2; h1.y += v3;
+                                            hh2.x += v4; hh2.y += v5; h3.x += v6; h3.y += w[u];
+                                            h2[c0] = h0; h2[c1] = h1; h2[c2] = hh2; h2[c3] = h3;
+                                        }
+                                    }
+                                    __syncwarp();
+                                }
+                                if (use_lock) {
+                                    __threadfence_block();
+                                    __syncwarp();
+                                    if (lane == 0) atomicExch(&ctrl->locks[rep], 0);
+                                }
+                            }
+                        }
+                    }
+                }
+                release_stage(ctrl, jsite, siteB, st, NW, t, it.ntiles, it.jt_begin, lane);
+            }
+            tcount += it.ntiles;
+        }
+        // counters: warp-reduce then one atomic per warp
+        for (int d = 16; d; d >>= 1) {
+            n_surv += __shfl_xor_sync(0xffffffffu, n_surv, d);
+            n_inr  += __shfl_xor_sync(0xffffffffu, n_inr, d);
+            n_ovf  += __shfl_xor_sync(0xffffffffu, n_ovf, d);
+        }
+        const bool anyz = __any_sync(0xffffffffu, zerodiv);
+        if (lane == 0) {
+            if (n_surv) atomicAdd(P.counters + 2, (unsigned long long)n_surv);
+            if (n_inr)  atomicAdd(P.counters + 3, (unsigned long long)n_inr);
+            if (n_ovf)  atomicAdd(P.counters + 0, (unsigned long long)n_ovf);
+            if (anyz)   atomicOr(P.counters + 1, 1ull);
+        }
     }
 
-    // ---- flush -----------------------------------------------------------------------------------
+    // ---- flush: replicas summed in a fixed order -> this CTA's partial histogram -------------------------
     __syncthreads();
     if (HIST == 0) {
         double* out = P.partials + (size_t)blockIdx.x * hsz;
@@ -484,19 +669,6 @@ pair_kernel(const PairParams P)
             for (int wv = 0; wv < nrep; ++wv) s += hist[(size_t)wv * hsz + src];
             out[k] = s;
         }
-    }
-    // counters: warp-reduce then one atomic per warp
-    for (int d = 16; d; d >>= 1) {
-        n_surv += __shfl_xor_sync(0xffffffffu, n_surv, d);
-        n_inr  += __shfl_xor_sync(0xffffffffu, n_inr, d);
-        n_ovf  += __shfl_xor_sync(0xffffffffu, n_ovf, d);
-    }
-    const bool anyz = __any_sync(0xffffffffu, zerodiv);
-    if (lane == 0) {
-        if (n_surv) atomicAdd(P.counters + 2, (unsigned long long)n_surv);
-        if (n_inr)  atomicAdd(P.counters + 3, (unsigned long long)n_inr);
-        if (n_ovf)  atomicAdd(P.counters + 0, (unsigned long long)n_ovf);
-        if (anyz)   atomicOr(P.counters + 1, 1ull);
     }
 }
 
@@ -544,75 +716,73 @@ cudaError_t scale_launch(double* a, long long n, double v, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // variant selection
 // ------------------------------------------------------------------------------------------------
-static size_t smem_fixed_bytes(int nw)
+static size_t smem_fixed_bytes(int nf)
 {
-    const size_t ti = (size_t)nw * 32 * kIPT;
-    return ti * sizeof(Site) + (size_t)kStages * kTJ * sizeof(Site) + (size_t)nw * kQCap * sizeof(unsigned short)
-         + 4 * sizeof(uint64_t) + 4 * sizeof(int) + 20 * sizeof(int);
+    const size_t ti = (size_t)nf * 32 * kIPT;
+    return ti * sizeof(Site) + (size_t)kStages * kTJ * sizeof(Site) + (size_t)nf * kRingCap * sizeof(unsigned short) + kCtrlBytes;
 }
 
 typedef void (*pair_fn_t)(const PairParams);
 
 template <typename F>
-static pair_fn_t pick_fn(int hist_mode, int warps, int nslot)
+static pair_fn_t pick_fn(int hist_mode, int nf, int nslot, bool allm)
 {
     if (hist_mode == 0) {
-        if (warps == 16) return nslot == 1 ? pair_kernel<F, 16, 1, 0> : pair_kernel<F, 16, 8, 0>;
-        return nslot == 1 ? pair_kernel<F, 8, 1, 0> : pair_kernel<F, 8, 8, 0>;
+        if (nslot == 1) return nf == 12 ? pair_kernel<F, 12, 1, 0, false> : pair_kernel<F, 8, 1, 0, false>;
+        if (allm) return nf == 12 ? pair_kernel<F, 12, 8, 0, true> : pair_kernel<F, 8, 8, 0, true>;
+        return nf == 12 ? pair_kernel<F, 12, 8, 0, false> : pair_kernel<F, 8, 8, 0, false>;
     }
-    if (hist_mode == 1) return pair_kernel<F, 16, 8, 1>;
-    return pair_kernel<F, 16, 8, 2>;
+    if (hist_mode == 1) return nf == 12 ? pair_kernel<F, 12, 8, 1, false> : pair_kernel<F, 8, 8, 1, false>;
+    return nf == 12 ? pair_kernel<F, 12, 8, 2, false> : pair_kernel<F, 8, 8, 2, false>;
 }
 
 static pair_fn_t pick(const PairConfig& c)
 {
-    return c.filter_fp64 ? pick_fn<double>(c.hist_mode, c.warps, c.nslot) : pick_fn<float>(c.hist_mode, c.warps, c.nslot);
+    const int nf = c.warps - kND;
+    return c.filter_fp64 ? pick_fn<double>(c.hist_mode, nf, c.nslot, c.all_modes != 0) : pick_fn<float>(c.hist_mode, nf, c.nslot, c.all_modes != 0);
 }
 
-int tile_i(const PairConfig& cfg) { return cfg.warps * 32 * kIPT; }
+int tile_i(const PairConfig& cfg) { return (cfg.warps - kND) * 32 * kIPT; }
 
-cudaError_t pair_configure(int dev, int histo_n, int mode_sel, unsigned flags, PairConfig* cfg)
+cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, PairConfig* cfg)
 {
+    static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block does not fit");
     cudaError_t e;
     int max_smem = 0, sms = 0;
     if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     cfg->filter_fp64 = (flags & GFN_FLAG_FILTER_FP64) ? 1 : 0;
+    // core tile: 12 filter warps (768 sites) unless 8 (512 sites) wastes less padding on this selection size
+    const double waste12 = (double)((n1 + 767) / 768 * 768) / n1, waste8 = (double)((n1 + 511) / 512 * 512) / n1;
+    int nf = waste8 < waste12 * 0.97 ? 8 : 12;
+    if (const char* env = getenv("GFN_FILTER_WARPS")) { const int w = atoi(env); if (w == 8 || w == 12) nf = w; }
+    cfg->warps = nf + kND;
     cfg->nslot = (mode_sel == 1) ? 1 : 8;
+    cfg->all_modes = (mode_sel == 127) ? 1 : 0;
     cfg->nrep = 1;
-    if (flags & GFN_FLAG_PER_PARTICLE) { cfg->hist_mode = 2; cfg->warps = 16; cfg->nslot = 8; }
-    else if (flags & GFN_FLAG_HIST_GLOBAL) { cfg->hist_mode = 1; cfg->warps = 16; cfg->nslot = 8; }
+    if (flags & GFN_FLAG_PER_PARTICLE) { cfg->hist_mode = 2; cfg->nslot = 8; }
+    else if (flags & GFN_FLAG_HIST_GLOBAL) { cfg->hist_mode = 1; cfg->nslot = 8; }
     else {
-        // per-replica bytes; replicas = as many as fit (<= warps); warps sharing a replica serialise on a lock
+        // one replica per drain warp when they fit; fewer replicas are shared under a lock
         const long long rb = (long long)histo_n * cfg->nslot * (long long)sizeof(double);
-        const long long r16 = ((long long)max_smem - (long long)smem_fixed_bytes(16)) / rb;
-        const long long r8  = ((long long)max_smem - (long long)smem_fixed_bytes(8)) / rb;
+        long long fit = ((long long)max_smem - (long long)smem_fixed_bytes(nf)) / rb;
+        if (fit < 1 && nf == 12) { nf = 8; cfg->warps = nf + kND; fit = ((long long)max_smem - (long long)smem_fixed_bytes(nf)) / rb; }
         cfg->hist_mode = 0;
-        if (r16 >= 4)      { cfg->warps = 16; cfg->nrep = (int)(r16 > 16 ? 16 : r16); }
-        else if (r8 >= 2)  { cfg->warps = 8;  cfg->nrep = (int)(r8 > 8 ? 8 : r8); }
-        else if (r16 >= 1) { cfg->warps = 16; cfg->nrep = (int)r16; }
-        else { cfg->hist_mode = 1; cfg->warps = 16; cfg->nslot = 8; }
-        if (const char* env = getenv("GFN_WARPS")) {
-            const int w = atoi(env);
-            if (cfg->hist_mode == 0 && (w == 16 || w == 8)) {
-                const long long rr = w == 16 ? r16 : r8;
-                if (rr >= 1) { cfg->warps = w; cfg->nrep = (int)(rr > w ? w : rr); }
-            }
-        }
+        if (fit >= kND) cfg->nrep = kND;
+        else if (fit >= 2) cfg->nrep = 2;
+        else if (fit >= 1) cfg->nrep = 1;
+        else { cfg->hist_mode = 1; cfg->nslot = 8; }
         if (const char* env = getenv("GFN_NREP")) {
             const int r = atoi(env);
-            if (cfg->hist_mode == 0 && r >= 1 && r <= cfg->nrep) cfg->nrep = r;
+            if (cfg->hist_mode == 0 && (r == 1 || r == 2 || r == 4) && r <= cfg->nrep) cfg->nrep = r;
         }
     }
     const bool sh = cfg->hist_mode == 0;
-    cfg->smem_bytes = (int)(smem_fixed_bytes(cfg->warps) + (sh ? (size_t)cfg->nrep * histo_n * cfg->nslot * sizeof(double) : 0));
+    cfg->smem_bytes = (int)(smem_fixed_bytes(nf) + (sh ? (size_t)cfg->nrep * histo_n * cfg->nslot * sizeof(double) : 0));
     pair_fn_t fn = pick(*cfg);
     if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes)) != cudaSuccess) return e;
-    int occ = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cfg->warps * 32, cfg->smem_bytes)) != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorInvalidConfiguration;
-    cfg->blocks_per_sm = occ;
-    cfg->grid = sms * occ;
+    cfg->blocks_per_sm = 1;
+    cfg->grid = sms;
     return cudaSuccess;
 }
 
@@ -624,6 +794,65 @@ cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t
     if (cfg.hist_mode != 0 && items < grid) grid = (int)(items > 0 ? items : 1);   // partials need the full grid only in smem mode
     fn<<<grid, cfg.warps * 32, cfg.smem_bytes, s>>>(p);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// arithmetic self-test: in-range division / square-root sequences against the IEEE built-ins
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long& x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// random double with a uniformly random mantissa and sign, biased exponent uniform in [723, 1323] (mid_range)
+__device__ __forceinline__ double rand_mid(unsigned long long& st, bool positive)
+{
+    const unsigned long long r = splitmix(st);
+    const unsigned long long man = r & 0x000fffffffffffffull;
+    const unsigned long long ex = 723ull + (splitmix(st) % 601ull);
+    const unsigned long long sg = positive ? 0ull : (r >> 63);
+    return __longlong_as_double((long long)((sg << 63) | (ex << 52) | man));
+}
+
+__global__ void arith_selftest_kernel(unsigned long long seed, int per_thread, unsigned long long* mism)
+{
+    unsigned long long st = seed + 0x1234567ull * (blockIdx.x * blockDim.x + threadIdx.x);
+    unsigned long long bad_div = 0, bad_sqrt = 0, bad_near = 0;
+    for (int k = 0; k < per_thread; ++k) {
+        const double a = rand_mid(st, false), b = rand_mid(st, false), x = rand_mid(st, true);
+        if (__double_as_longlong(div_inrange(a, b)) != __double_as_longlong(__ddiv_rn(a, b))) ++bad_div;
+        if (__double_as_longlong(sqrt_inrange(x)) != __double_as_longlong(__dsqrt_rn(x))) ++bad_sqrt;
+        // operands close to each other / to perfect squares stress the final rounding
+        const double b2 = __longlong_as_double(__double_as_longlong(a) + (long long)(splitmix(st) % 1024ull) - 512ll);
+        if (mid_range(b2) && __double_as_longlong(div_inrange(a, b2)) != __double_as_longlong(__ddiv_rn(a, b2))) ++bad_near;
+        const double sq = __dmul_rn(x, x);
+        const double sq2 = __longlong_as_double(__double_as_longlong(sq) + (long long)(splitmix(st) % 8ull) - 4ll);
+        if (mid_range(sq2) && __double_as_longlong(sqrt_inrange(sq2)) != __double_as_longlong(__dsqrt_rn(sq2))) ++bad_near;
+    }
+    if (bad_div) atomicAdd(mism + 0, bad_div);
+    if (bad_sqrt) atomicAdd(mism + 1, bad_sqrt);
+    if (bad_near) atomicAdd(mism + 2, bad_near);
+}
+
+cudaError_t arith_selftest(int dev, unsigned long long seed, long long n_operands, unsigned long long out[3])
+{
+    cudaError_t e;
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) return e;
+    unsigned long long* d = nullptr;
+    if ((e = cudaMalloc(&d, 3 * sizeof(unsigned long long))) != cudaSuccess) return e;
+    cudaMemset(d, 0, 3 * sizeof(unsigned long long));
+    const int blocks = 148 * 8, threads = 256;
+    long long per = n_operands / ((long long)blocks * threads);
+    if (per < 1) per = 1;
+    if (per > 1000000) per = 1000000;
+    arith_selftest_kernel<<<blocks, threads>>>(seed, (int)per, d);
+    e = cudaMemcpy(out, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

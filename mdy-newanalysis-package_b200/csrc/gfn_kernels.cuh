@@ -25,7 +25,10 @@ constexpr int kTJ      = 128;    // surround sites per shared-memory stage
 constexpr int kStages  = 3;      // surround stages in flight
 constexpr int kIPT     = 2;      // core sites held in registers per thread
 constexpr int kPadTo   = 1024;   // selections are padded to a multiple of this many sites on the device
-constexpr int kQCap    = 32 + 32 * 32;  // per-warp survivor queue capacity (entries of 16 bit)
+constexpr int kDrainILP = 2;     // survivors evaluated per drain lane per batch
+constexpr int kND      = 4;      // drain warps per CTA (one per SM sub-partition)
+constexpr int kRingCap = 2048;   // survivor ring entries (16 bit) per filter warp: one push (<= 32*32) always fits behind < 64 unread ones
+constexpr int kCtrlBytes = 640;  // shared-memory control block
 constexpr int kCounters = 8;     // 0 overflow, 1 zerodiv flag, 2 survivors, 3 in-range pairs
 
 struct PairParams {
@@ -49,9 +52,10 @@ struct PairParams {
 struct PairConfig {
     int filter_fp64;   // 0 fp32 pre-filter, 1 fp64 pre-test
     int hist_mode;     // 0 shared-memory warp replicas, 1 global atomics, 2 per-particle global atomics
-    int warps;         // worker warps per CTA (16 or 8)
-    int nrep;          // shared-memory histogram replicas per CTA (warps sharing one take a lock)
+    int warps;         // warps per CTA: 12 or 8 filter warps + 4 drain warps
+    int nrep;          // shared-memory histogram replicas per CTA (drain warps sharing one take a lock)
     int nslot;         // 1 (g000 only) or 8
+    int all_modes;     // mode_sel == 127: the kernel variant without mode masks
     int blocks_per_sm;
     int grid;
     int smem_bytes;
@@ -59,7 +63,7 @@ struct PairConfig {
 
 // Chooses kernel variant, grid and shared-memory size for a histogram of histo_n bins; sets the
 // function attributes.  Returns cudaSuccess or the failing error.
-cudaError_t pair_configure(int dev, int histo_n, int mode_sel, unsigned flags, PairConfig* cfg);
+cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, PairConfig* cfg);
 cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
 
 // Converts nframes frames of one selection into Site records and the per-frame max |coordinate|.
@@ -72,6 +76,10 @@ cudaError_t finalize_launch(const double* partials, int grid, int histo_n, int n
 cudaError_t scale_launch(double* a, long long n, double v, cudaStream_t s);
 
 cudaError_t peaks_measure(int dev, double* fp64_tflops, double* fp32_tflops);
+
+// Compares the kernel's in-range fp64 division / square-root sequences with the IEEE built-ins on
+// n_operands random operand sets; out = {division mismatches, sqrt mismatches, near-tie mismatches}.
+cudaError_t arith_selftest(int dev, unsigned long long seed, long long n_operands, unsigned long long out[3]);
 
 int tile_i(const PairConfig& cfg);   // core sites per block tile
 

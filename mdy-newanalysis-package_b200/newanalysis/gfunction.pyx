@@ -73,6 +73,7 @@ cdef extern from "gfn.h":
     int gfn_comm_attach(gfn_t *h, const char *uid, int nranks, int rank) nogil
     int gfn_measure_peaks(int dev, double *fp64, double *fp32) nogil
     int gfn_mark(gfn_t *h, int which) nogil
+    int gfn_selftest_arith(int dev, unsigned long long seed, long long n, unsigned long long *mism) nogil
     int gfn_mark_elapsed_ms(gfn_t *h, double *ms) nogil
     int gfn_dev_alloc(int dev, void **dptr, unsigned long long nbytes) nogil
     int gfn_dev_free(int dev, void *dptr) nogil
@@ -137,6 +138,17 @@ def measure_peaks(int dev=0):
     if rc:
         _raise(rc, NULL)
     return a, b
+
+
+def selftest_arith(int dev=0, unsigned long long seed=1, long long n_operands=1 << 30):
+    """(division, sqrt, near-tie) mismatch counts of the kernel's in-range fp64 sequences vs the IEEE built-ins."""
+    cdef unsigned long long m[3]
+    cdef int rc
+    with nogil:
+        rc = gfn_selftest_arith(dev, seed, n_operands, m)
+    if rc:
+        _raise(rc, NULL)
+    return int(m[0]), int(m[1]), int(m[2])
 
 
 def comm_unique_id():

@@ -137,7 +137,11 @@ def test_cfg2_shape_many_frames_batched():
         o.calcFrame(c1[f], c2[f], d1[f], d2[f])
     ref = o.raw_sum()
     ha, hb = a.raw_histogram(), b.raw_histogram()
-    assert np.array_equal(ha, hb)                      # batch call == per-frame calls, deterministic
+    assert np.array_equal(ha[:600], hb[:600])          # batch call == per-frame calls
+    if a.stats()["hist_replicas"] == 4:
+        assert np.array_equal(ha, hb)                  # private replicas: fixed summation order, bit-identical
+    else:
+        assert_hist_close(ha, hb, 600)                 # replicas shared under a lock: order may differ
     assert np.array_equal(ha[:600], ref[:600])
     assert_hist_close(ha, ref, 600)
     assert a.ctr == nf and not a.oneistwo
@@ -313,3 +317,11 @@ def test_big_histogram_falls_back_to_global_atomics():
     got, ref = g.raw_histogram(), o.raw_sum()
     assert np.array_equal(got[:5800], ref[:5800])
     assert_hist_close(got, ref, 5800)
+
+
+def test_inrange_div_sqrt_sequences_equal_ieee_builtins():
+    """The drain path's branch-free division / square-root sequences must return exactly what the
+    correctly rounded built-ins return (bin assignment and per-pair increments depend on it)."""
+    from newanalysis.gfunction import selftest_arith
+    for seed in (1, 2, 3):
+        assert selftest_arith(0, seed, 1 << 31) == (0, 0, 0)
