@@ -196,7 +196,7 @@ def run_ours(args, rank, world, local_rank):
     n, L = c["n1"], c["L"]
     per = synth.pair_evals(n, n)
     F, K, W = args.frames_per_step, args.steps, args.warmup
-    flags = "fp64" if args.filter == "fp64" else ""
+    flags = ("fp64" if args.filter == "fp64" else "") + ("," + args.flags if args.flags else "")
     mk = lambda: G.RDF(c["modes"], c["hmin"], c["hmax"], c["dr"], n, n, n, n, L, devices=[local_rank], gfn_flags=flags)  # noqa: E731
 
     uid = None
@@ -330,6 +330,7 @@ def main():
     ap.add_argument("--filter", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", default="", help="extra gfn flags (experiments)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -213,10 +213,6 @@ __device__ __forceinline__ bool mid_range(double x)
     return ex - 723u <= 600u;       // biased exponent in [723, 1323]
 }
 
-// 16-byte chunk c (0..3) of bin pos inside a replica with 8 slots per bin: chunks are XOR-swizzled
-// with bits 1..2 of pos so that lanes holding different bins hit different 4-bank groups.
-__device__ __forceinline__ int hist_chunk(int pos, int c) { return pos * 4 + (c ^ ((pos >> 1) & 3)); }
-
 struct Item { int f, i0, jt_begin, ntiles; };
 
 __device__ __forceinline__ Item decode_item(const PairParams& P, long long item, int TI)
@@ -239,12 +235,23 @@ struct Ctrl {
     uint64_t full[kStages];      // TMA landed in stage s
     uint64_t ifull;              // TMA landed in the core tile
     int done_cnt[4];             // warps finished with stage s (the last one refills it)
-    int locks[4];                // replica locks (only when fewer replicas than drain warps)
+    int locks[8];                // replica locks (only when fewer replicas than drain warps)
     volatile unsigned tail[16];  // ring w: entries published by filter warp w
     volatile unsigned head[16];  // ring w: entries consumed by its drain warp
     volatile unsigned tdone[16]; // ring w: number of surround tiles completely filtered
     volatile unsigned tend[16][4];   // ring w: tail at the end of tile g (slot g & 3)
 };
+
+// Shared-memory histogram replica of one drain warp (or of several under a lock):
+//   wsum[bin][6]  fp64 sums of g110,g101,g011,g220,g202,g022 (48-byte bins: 48*pos mod 128 takes 8 values,
+//                 so lanes holding different bins spread over all 4-bank groups)        -- only when WEIGHTS
+//   cnt[bin]      u32 pair weight (1 or 2 per pair, native shared-memory integer atomics; it is g000 and the
+//                 weight row at once, exact)
+__host__ __device__ inline size_t replica_bytes(int hn, bool weights)
+{
+    size_t b = (size_t)hn * (weights ? 48 + 4 : 4);
+    return (b + 15) & ~(size_t)15;
+}
 
 // The last warp (filter or drain) to finish with a stage refills it with the tile S steps ahead.
 __device__ __forceinline__ void release_stage(Ctrl* c, Site* jsite, const Site* siteB, int st, int nwarps,
@@ -269,11 +276,12 @@ __device__ __forceinline__ void release_stage(Ctrl* c, Site* jsite, const Site* 
 // Warps [NF,NF+4) are DRAIN warps (one per SM sub-partition): they consume the rings of filter warps
 // w = d, d+4, d+8 in that fixed order, evaluate two survivors per lane exactly in fp64 and add them
 // into their private histogram replica.  Registers are re-balanced with setmaxnreg.
-template <typename F, int NF, int NSLOT, int HIST, bool ALLM>
-__global__ void __launch_bounds__((NF + kND) * 32, 1)
+template <typename F, int NF, int ND, bool WEIGHTS, int HIST, bool ALLM>
+__global__ void __launch_bounds__((NF + ND) * 32, 1)
 pair_kernel(const PairParams P)
 {
-    constexpr int NW = NF + kND;
+    constexpr int NW = NF + ND;
+    static_assert(ND == 4 || (ND == 8 && NF == 8), "4 drain warps (rings d, d+4, d+8), or 8 behind 8 filter warps (ring d)");
     constexpr int TI = NF * 32 * kIPT;
     constexpr int TJ = kTJ;
     constexpr int S = kStages;
@@ -287,18 +295,20 @@ pair_kernel(const PairParams P)
     Site* jsite = isite + TI;                                                     // [S][TJ]
     unsigned short* rings = reinterpret_cast<unsigned short*>(jsite + S * TJ);    // [NF][kRingCap]
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(rings + NF * kRingCap);
-    double* hist = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ctrl) + kCtrlBytes);   // [nrep][hn*NSLOT]
+    unsigned char* hist = reinterpret_cast<unsigned char*>(ctrl) + kCtrlBytes;                         // [nrep] replicas
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hn = P.histo_n;
-    const int hsz = hn * NSLOT;
+    const size_t rbytes = replica_bytes(hn, WEIGHTS);
     const int nrep = P.nrep;
 
     if (HIST == 0) {
-        for (int k = tid; k < nrep * hsz; k += NW * 32) hist[k] = 0.0;
+        unsigned* z = reinterpret_cast<unsigned*>(hist);
+        for (size_t k = tid; k < (size_t)nrep * rbytes / 4; k += NW * 32) z[k] = 0u;
     }
     if (tid < 16) { ctrl->tail[tid] = 0; ctrl->head[tid] = 0; ctrl->tdone[tid] = 0; }
-    if (tid < 4) { ctrl->done_cnt[tid] = 0; ctrl->locks[tid] = 0; }
+    if (tid < 4) ctrl->done_cnt[tid] = 0;
+    if (tid < 8) ctrl->locks[tid] = 0;
     if (tid == 0) {
         for (int k = 0; k < S; ++k) mbar_init(&ctrl->full[k], 1);
         mbar_init(&ctrl->ifull, 1);
@@ -311,8 +321,9 @@ pair_kernel(const PairParams P)
 
     if (warp < NF) {
         // =========================================== FILTER ===========================================
-        if (kF32) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        else      asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        if (ND == 8)   asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        else if (kF32) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        else           asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         unsigned short* q = rings + warp * kRingCap;
         unsigned tail = 0, head_seen = 0;
 
@@ -429,11 +440,13 @@ pair_kernel(const PairParams P)
         }
     } else {
         // =========================================== DRAIN ============================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-        const int dw = warp - NF;                   // drain warp 0..3
+        if (ND == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        else         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int dw = warp - NF;                   // drain warp: serves the rings of filter warps dw, dw+ND, ...
         const int rep = dw % nrep;
-        const bool use_lock = nrep < kND;
-        double* hist_w = hist + (size_t)rep * hsz;
+        const bool use_lock = nrep < ND;
+        double* wsum = reinterpret_cast<double*>(hist + (size_t)rep * rbytes);
+        unsigned* cnt = reinterpret_cast<unsigned*>(hist + (size_t)rep * rbytes + (WEIGHTS ? (size_t)hn * 48 : 0));
         const int mode_sel = ALLM ? 127 : P.mode_sel;       // ALLM: all seven modes selected, masks fold away
         const bool m_cs = mode_sel & (2 | 16), m_cd = mode_sel & (4 | 32), m_sd = mode_sel & (8 | 64);
         unsigned n_surv = 0, n_inr = 0, n_ovf = 0;
@@ -459,7 +472,7 @@ pair_kernel(const PairParams P)
                 const Site* js = jsite + st * TJ;
 
 #pragma unroll 1
-                for (int fw = dw; fw < NF; fw += kND) {     // rings of filter warps dw, dw+4, dw+8 in this fixed order
+                for (int fw = dw; fw < NF; fw += ND) {      // this warp's rings, in this fixed order
                     const unsigned short* q = rings + fw * kRingCap;
                     unsigned head = ctrl->head[fw];         // this warp is its only writer
                     for (;;) {
@@ -532,7 +545,7 @@ pair_kernel(const PairParams P)
                             w[u] = (P.tri && !self_pair[u]) ? 2.0 : 1.0;
                             n_inr += ok[u] ? 1u : 0u;
                         }
-                        if (NSLOT == 8) {
+                        if (WEIGHTS) {
                             // --- orientation weights :154-165, all three cosines (unselected ones are masked below)
                             double den[kU][3], num[kU][3], c[kU][3];
                             bool drng = true;
@@ -583,56 +596,56 @@ pair_kernel(const PairParams P)
                         // ---- accumulate ----------------------------------------------------------------------
 #pragma unroll
                         for (int u = 0; u < kU; ++u) {
-                            const double v0 = (mode_sel & 1) ? w[u] : 0.0;                                    // :152
-                            const double v1 = (mode_sel & 2) ? v[u][0] : 0.0, v2 = (mode_sel & 4) ? v[u][1] : 0.0;
-                            const double v3 = (mode_sel & 8) ? v[u][2] : 0.0, v4 = (mode_sel & 16) ? v[u][3] : 0.0;
-                            const double v5 = (mode_sel & 32) ? v[u][4] : 0.0, v6 = (mode_sel & 64) ? v[u][5] : 0.0;
                             const bool spill = ok[u] && pos[u] >= hn;          // quirk Q3
                             if ((HIST != 0 && ok[u]) || spill) {
+                                const double v0 = (mode_sel & 1) ? w[u] : 0.0;                                // :152
                                 if (spill) ++n_ovf;
                                 if (!(spill && (P.flags & GFN_FLAG_DISCARD_OVERFLOW))) {
                                     const int hm = HIST == 0 ? 1 : HIST;
                                     if (mode_sel & 1)  global_add(P, hm, 0, gi[u], pos[u], v0);
-                                    if (mode_sel & 2)  global_add(P, hm, 1, gi[u], pos[u], v1);
-                                    if (mode_sel & 4)  global_add(P, hm, 2, gi[u], pos[u], v2);
-                                    if (mode_sel & 8)  global_add(P, hm, 3, gi[u], pos[u], v3);
-                                    if (mode_sel & 16) global_add(P, hm, 4, gi[u], pos[u], v4);
-                                    if (mode_sel & 32) global_add(P, hm, 5, gi[u], pos[u], v5);
-                                    if (mode_sel & 64) global_add(P, hm, 6, gi[u], pos[u], v6);
+                                    if (mode_sel & 2)  global_add(P, hm, 1, gi[u], pos[u], v[u][0]);
+                                    if (mode_sel & 4)  global_add(P, hm, 2, gi[u], pos[u], v[u][1]);
+                                    if (mode_sel & 8)  global_add(P, hm, 3, gi[u], pos[u], v[u][2]);
+                                    if (mode_sel & 16) global_add(P, hm, 4, gi[u], pos[u], v[u][3]);
+                                    if (mode_sel & 32) global_add(P, hm, 5, gi[u], pos[u], v[u][4]);
+                                    if (mode_sel & 64) global_add(P, hm, 6, gi[u], pos[u], v[u][5]);
                                     if (!spill) atomicAdd(P.gacc + 7ll * hn + pos[u], w[u]);      // pair weight row
                                 }
                             }
                             if (HIST == 0) {
-                                if (32 * u >= n) continue;                // warp-uniform: this half of the batch is empty
+                                if (32 * u >= n) continue;                // warp-uniform: this part of the batch is empty
                                 const bool add = ok[u] && !spill;
-                                const unsigned key = add ? (unsigned)pos[u] : (0x40000000u | lane);
-                                const unsigned grp = __match_any_sync(0xffffffffu, key);
-                                const int rank = __popc(grp & ((1u << lane) - 1u));
-                                const int maxr = __reduce_max_sync(0xffffffffu, add ? (unsigned)rank : 0u);
-                                if (use_lock) {
-                                    if (lane == 0) { while (atomicCAS(&ctrl->locks[rep], 0, 1) != 0) __nanosleep(40); }
-                                    __syncwarp();
-                                    __threadfence_block();
-                                }
-                                for (int rr = 0; rr <= maxr; ++rr) {
-                                    if (add && rank == rr) {
-                                        if (NSLOT == 1) {
-                                            hist_w[pos[u]] += w[u];
-                                        } else {
-                                            double2* h2 = reinterpret_cast<double2*>(hist_w);
-                                            const int c0 = hist_chunk(pos[u], 0), c1 = hist_chunk(pos[u], 1), c2 = hist_chunk(pos[u], 2), c3 = hist_chunk(pos[u], 3);
-                                            double2 h0 = h2[c0], h1 = h2[c1], hh2 = h2[c2], h3 = h2[c3];
-                                            h0.x += v0; h0.y += v1; h1.x += v2; h1.y += v3;
-                                            hh2.x += v4; hh2.y += v5; h3.x += v6; h3.y += w[u];
-                                            h2[c0] = h0; h2[c1] = h1; h2[c2] = hh2; h2[c3] = h3;
-                                        }
+                                if (add) atomicAdd(cnt + pos[u], (P.tri && !self_pair[u]) ? 2u : 1u);   // :152 and the weight row
+                                if (WEIGHTS) {
+                                    // lanes that hit the same bin take turns in lane order (deterministic, no fp64 atomics)
+                                    const unsigned key = add ? (unsigned)pos[u] : (0x40000000u | lane);
+                                    const unsigned grp = __match_any_sync(0xffffffffu, key);
+                                    const int rank = __popc(grp & ((1u << lane) - 1u));
+                                    const int maxr = __reduce_max_sync(0xffffffffu, add ? (unsigned)rank : 0u);
+                                    if (use_lock) {
+                                        if (lane == 0) { while (atomicCAS(&ctrl->locks[rep], 0, 1) != 0) __nanosleep(40); }
+                                        __syncwarp();
+                                        __threadfence_block();
                                     }
-                                    __syncwarp();
-                                }
-                                if (use_lock) {
-                                    __threadfence_block();
-                                    __syncwarp();
-                                    if (lane == 0) atomicExch(&ctrl->locks[rep], 0);
+                                    double2* hp = reinterpret_cast<double2*>(wsum + (size_t)pos[u] * 6);
+                                    for (int rr = 0; rr <= maxr; ++rr) {
+                                        if (add && rank == rr) {
+                                            double2 h0 = hp[0], h1 = hp[1], h2 = hp[2];
+                                            if (ALLM || (mode_sel & 2))  h0.x += v[u][0];       // g110
+                                            if (ALLM || (mode_sel & 4))  h0.y += v[u][1];       // g101
+                                            if (ALLM || (mode_sel & 8))  h1.x += v[u][2];       // g011
+                                            if (ALLM || (mode_sel & 16)) h1.y += v[u][3];       // g220
+                                            if (ALLM || (mode_sel & 32)) h2.x += v[u][4];       // g202
+                                            if (ALLM || (mode_sel & 64)) h2.y += v[u][5];       // g022
+                                            hp[0] = h0; hp[1] = h1; hp[2] = h2;
+                                        }
+                                        __syncwarp();
+                                    }
+                                    if (use_lock) {
+                                        __threadfence_block();
+                                        __syncwarp();
+                                        if (lane == 0) atomicExch(&ctrl->locks[rep], 0);
+                                    }
                                 }
                             }
                         }
@@ -657,16 +670,24 @@ pair_kernel(const PairParams P)
         }
     }
 
-    // ---- flush: replicas summed in a fixed order -> this CTA's partial histogram -------------------------
+    // ---- flush: replicas summed in a fixed order -> this CTA's partial histogram ------------------------
+    // partial layout: WEIGHTS ? [bin][8] = {g000, g110, g101, g011, g220, g202, g022, pair weight} : [bin] = pair weight
     __syncthreads();
     if (HIST == 0) {
-        double* out = P.partials + (size_t)blockIdx.x * hsz;
-        for (int k = tid; k < hsz; k += NW * 32) {
-            // k = bin*NSLOT + slot in the un-swizzled layout the finalize kernel expects
-            int src = k;
-            if (NSLOT == 8) { const int bin = k >> 3, sl = k & 7; src = hist_chunk(bin, sl >> 1) * 2 + (sl & 1); }
+        constexpr int PS = WEIGHTS ? 8 : 1;
+        double* out = P.partials + (size_t)blockIdx.x * hn * PS;
+        for (int k = tid; k < hn * PS; k += NW * 32) {
+            const int bin = k / PS, sl = k - bin * PS;
             double s = 0.0;
-            for (int wv = 0; wv < nrep; ++wv) s += hist[(size_t)wv * hsz + src];
+            for (int r = 0; r < nrep; ++r) {
+                const unsigned char* base = hist + (size_t)r * rbytes;
+                if (!WEIGHTS || sl == 0 || sl == 7) {
+                    const unsigned c = reinterpret_cast<const unsigned*>(base + (WEIGHTS ? (size_t)hn * 48 : 0))[bin];
+                    if (!WEIGHTS || sl == 7 || (P.mode_sel & 1)) s += (double)c;
+                } else {
+                    s += reinterpret_cast<const double*>(base)[(size_t)bin * 6 + (sl - 1)];
+                }
+            }
             out[k] = s;
         }
     }
@@ -724,25 +745,28 @@ static size_t smem_fixed_bytes(int nf)
 
 typedef void (*pair_fn_t)(const PairParams);
 
-template <typename F>
-static pair_fn_t pick_fn(int hist_mode, int nf, int nslot, bool allm)
+template <typename F, int NF, int ND>
+static pair_fn_t pick_shape(int hist_mode, bool weights, bool allm)
 {
     if (hist_mode == 0) {
-        if (nslot == 1) return nf == 12 ? pair_kernel<F, 12, 1, 0, false> : pair_kernel<F, 8, 1, 0, false>;
-        if (allm) return nf == 12 ? pair_kernel<F, 12, 8, 0, true> : pair_kernel<F, 8, 8, 0, true>;
-        return nf == 12 ? pair_kernel<F, 12, 8, 0, false> : pair_kernel<F, 8, 8, 0, false>;
+        if (!weights) return pair_kernel<F, NF, ND, false, 0, false>;
+        return allm ? pair_kernel<F, NF, ND, true, 0, true> : pair_kernel<F, NF, ND, true, 0, false>;
     }
-    if (hist_mode == 1) return nf == 12 ? pair_kernel<F, 12, 8, 1, false> : pair_kernel<F, 8, 8, 1, false>;
-    return nf == 12 ? pair_kernel<F, 12, 8, 2, false> : pair_kernel<F, 8, 8, 2, false>;
+    return hist_mode == 1 ? pair_kernel<F, NF, ND, true, 1, false> : pair_kernel<F, NF, ND, true, 2, false>;
 }
 
-static pair_fn_t pick(const PairConfig& c)
+template <typename F>
+static pair_fn_t pick_fn(const PairConfig& c)
 {
-    const int nf = c.warps - kND;
-    return c.filter_fp64 ? pick_fn<double>(c.hist_mode, nf, c.nslot, c.all_modes != 0) : pick_fn<float>(c.hist_mode, nf, c.nslot, c.all_modes != 0);
+    const int nf = c.warps - c.drain_warps;
+    const bool weights = c.nslot == 8, allm = c.all_modes != 0;
+    if (c.drain_warps == 8) return pick_shape<F, 8, 8>(c.hist_mode, weights, allm);
+    return nf == 12 ? pick_shape<F, 12, 4>(c.hist_mode, weights, allm) : pick_shape<F, 8, 4>(c.hist_mode, weights, allm);
 }
 
-int tile_i(const PairConfig& cfg) { return (cfg.warps - kND) * 32 * kIPT; }
+static pair_fn_t pick(const PairConfig& c) { return c.filter_fp64 ? pick_fn<double>(c) : pick_fn<float>(c); }
+
+int tile_i(const PairConfig& cfg) { return (cfg.warps - cfg.drain_warps) * 32 * kIPT; }
 
 cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, PairConfig* cfg)
 {
@@ -752,33 +776,44 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
     if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     cfg->filter_fp64 = (flags & GFN_FLAG_FILTER_FP64) ? 1 : 0;
-    // core tile: 12 filter warps (768 sites) unless 8 (512 sites) wastes less padding on this selection size
-    const double waste12 = (double)((n1 + 767) / 768 * 768) / n1, waste8 = (double)((n1 + 511) / 512 * 512) / n1;
-    int nf = waste8 < waste12 * 0.97 ? 8 : 12;
-    if (const char* env = getenv("GFN_FILTER_WARPS")) { const int w = atoi(env); if (w == 8 || w == 12) nf = w; }
-    cfg->warps = nf + kND;
     cfg->nslot = (mode_sel == 1) ? 1 : 8;
     cfg->all_modes = (mode_sel == 127) ? 1 : 0;
     cfg->nrep = 1;
+    // CTA shapes in order of preference: 8 filter + 8 drain warps, 12 + 4, 8 + 4
+    const int shapes[3][2] = {{8, 8}, {12, 4}, {8, 4}};
+    int force_nf = 0, force_nd = 0;
+    if (const char* env = getenv("GFN_FILTER_WARPS")) force_nf = atoi(env);
+    if (const char* env = getenv("GFN_DRAIN_WARPS")) force_nd = atoi(env);
+    const double waste12 = (double)((n1 + 767) / 768 * 768) / n1, waste8 = (double)((n1 + 511) / 512 * 512) / n1;
+    int nf = 8, nd = 8;
     if (flags & GFN_FLAG_PER_PARTICLE) { cfg->hist_mode = 2; cfg->nslot = 8; }
     else if (flags & GFN_FLAG_HIST_GLOBAL) { cfg->hist_mode = 1; cfg->nslot = 8; }
     else {
-        // one replica per drain warp when they fit; fewer replicas are shared under a lock
-        const long long rb = (long long)histo_n * cfg->nslot * (long long)sizeof(double);
-        long long fit = ((long long)max_smem - (long long)smem_fixed_bytes(nf)) / rb;
-        if (fit < 1 && nf == 12) { nf = 8; cfg->warps = nf + kND; fit = ((long long)max_smem - (long long)smem_fixed_bytes(nf)) / rb; }
+        const long long rb = (long long)replica_bytes(histo_n, cfg->nslot == 8);
         cfg->hist_mode = 0;
-        if (fit >= kND) cfg->nrep = kND;
-        else if (fit >= 2) cfg->nrep = 2;
-        else if (fit >= 1) cfg->nrep = 1;
-        else { cfg->hist_mode = 1; cfg->nslot = 8; }
+        int best = -1; long long best_fit = 0;
+        for (int k = 0; k < 3; ++k) {
+            const int f = shapes[k][0], d = shapes[k][1];
+            if ((force_nf && force_nf != f) || (force_nd && force_nd != d)) continue;
+            if (f == 12 && waste8 < waste12 * 0.97) continue;            // 768-site core tiles would be mostly padding
+            const long long fit = ((long long)max_smem - (long long)smem_fixed_bytes(f)) / rb;
+            if (fit >= d) { best = k; best_fit = d; break; }              // a private replica per drain warp
+            if (best < 0 && fit >= 1) { best = k; best_fit = fit >= 4 ? 4 : (fit >= 2 ? 2 : 1); }   // shared under a lock
+        }
+        if (best < 0) { cfg->hist_mode = 1; cfg->nslot = 8; }
+        else { nf = shapes[best][0]; nd = shapes[best][1]; cfg->nrep = (int)best_fit; }
         if (const char* env = getenv("GFN_NREP")) {
             const int r = atoi(env);
-            if (cfg->hist_mode == 0 && (r == 1 || r == 2 || r == 4) && r <= cfg->nrep) cfg->nrep = r;
+            if (cfg->hist_mode == 0 && r >= 1 && r <= cfg->nrep) cfg->nrep = r;
         }
     }
+    if (cfg->hist_mode != 0) {
+        if (force_nf == 12 || force_nd == 4) { nf = force_nf == 8 ? 8 : 12; nd = 4; }
+    }
+    cfg->drain_warps = nd;
+    cfg->warps = nf + nd;
     const bool sh = cfg->hist_mode == 0;
-    cfg->smem_bytes = (int)(smem_fixed_bytes(nf) + (sh ? (size_t)cfg->nrep * histo_n * cfg->nslot * sizeof(double) : 0));
+    cfg->smem_bytes = (int)(smem_fixed_bytes(nf) + (sh ? (size_t)cfg->nrep * replica_bytes(histo_n, cfg->nslot == 8) : 0));
     pair_fn_t fn = pick(*cfg);
     if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes)) != cudaSuccess) return e;
     cfg->blocks_per_sm = 1;

@@ -26,7 +26,6 @@ constexpr int kStages  = 3;      // surround stages in flight
 constexpr int kIPT     = 2;      // core sites held in registers per thread
 constexpr int kPadTo   = 1024;   // selections are padded to a multiple of this many sites on the device
 constexpr int kDrainILP = 2;     // survivors evaluated per drain lane per batch
-constexpr int kND      = 4;      // drain warps per CTA (one per SM sub-partition)
 constexpr int kRingCap = 2048;   // survivor ring entries (16 bit) per filter warp: one push (<= 32*32) always fits behind < 64 unread ones
 constexpr int kCtrlBytes = 640;  // shared-memory control block
 constexpr int kCounters = 8;     // 0 overflow, 1 zerodiv flag, 2 survivors, 3 in-range pairs
@@ -52,7 +51,8 @@ struct PairParams {
 struct PairConfig {
     int filter_fp64;   // 0 fp32 pre-filter, 1 fp64 pre-test
     int hist_mode;     // 0 shared-memory warp replicas, 1 global atomics, 2 per-particle global atomics
-    int warps;         // warps per CTA: 12 or 8 filter warps + 4 drain warps
+    int warps;         // warps per CTA: filter warps (12 or 8) + drain warps
+    int drain_warps;   // 4, or 8 working in pairs on 4 replicas
     int nrep;          // shared-memory histogram replicas per CTA (drain warps sharing one take a lock)
     int nslot;         // 1 (g000 only) or 8
     int all_modes;     // mode_sel == 127: the kernel variant without mode masks

@@ -80,7 +80,7 @@ cdef extern from "gfn.h":
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
 
 
-_FLAG_NAMES = {"per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
+_FLAG_NAMES = {"x_atomics": 256, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
 
 
 def _parse_flags(spec):
