@@ -133,7 +133,7 @@ struct gfn_handle {
     int batch_frames;
     long long frame_doubles;      // worst case (not aliased)
     long long off_c1, off_d1, off_c2, off_d2;   // offsets (doubles) inside a non-aliased frame
-    int n_itiles, n_jtiles, seg_tiles, items_per_frame;
+    int n_itiles, n_jtiles, tiles_per_frame;
     std::vector<Dev> devs;
     int next_dev = 0;
     // external communicator (one process per GPU)
@@ -194,8 +194,8 @@ void fill_params(gfn_t* h, Dev& d, PairParams& p)
     p.n1 = h->n1; p.n2 = h->n2; p.tri = (h->n1 == h->n2);
     p.histo_n = h->histo_n; p.mode_sel = h->mode_sel;
     p.hmin = (double)h->hmin_f; p.hmax = (double)h->hmax_f; p.invdx = h->inv_dr;
-    p.n_itiles = h->n_itiles; p.n_jtiles = h->n_jtiles; p.seg_tiles = h->seg_tiles; p.items_per_frame = h->items_per_frame;
-    p.item_start = d.item_start;
+    p.n_itiles = h->n_itiles; p.n_jtiles = h->n_jtiles; p.tiles_per_frame = h->tiles_per_frame;
+    p.tile_start = d.item_start;
     p.partials = d.partials; p.gacc = d.gacc; p.gpp = d.gpp; p.counters = d.counters;
     p.flags = h->flags;
     p.nrep = d.cfg.nrep;
@@ -402,23 +402,14 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
         const int TI = tile_i(c);
         h->n_itiles = (n1 + TI - 1) / TI;
         h->n_jtiles = (n2 + kTJ - 1) / kTJ;
-        // segment length: aim at >= 8 items per CTA per batch, at least 4 and at most 64 surround tiles per item
-        const double want_items = 8.0 * c.grid;
-        double tiles_total = 0;
-        for (int t = 0; t < h->n_itiles; ++t) tiles_total += h->n_jtiles - ((n1 == n2) ? (t * TI) / kTJ : 0);
-        tiles_total *= h->batch_frames;
-        int seg = (int)(tiles_total / want_items);
-        if (seg < 4) seg = 4;
-        if (seg > 64) seg = 64;
-        if (const char* e = getenv("GFN_SEG_TILES")) { int v = atoi(e); if (v >= 1) seg = v; }
-        h->seg_tiles = seg;
+        // prefix of surround-tile visits per core tile (the triangle starts at the tile holding the diagonal)
         std::vector<int> start(h->n_itiles + 1, 0);
         for (int t = 0; t < h->n_itiles; ++t) {
             const int first = (n1 == n2) ? (t * TI) / kTJ : 0;
             const int tiles = h->n_jtiles - first;
-            start[t + 1] = start[t] + (tiles > 0 ? (tiles + seg - 1) / seg : 0);
+            start[t + 1] = start[t] + (tiles > 0 ? tiles : 0);
         }
-        h->items_per_frame = start[h->n_itiles];
+        h->tiles_per_frame = start[h->n_itiles];
         for (Dev& d : h->devs) {
             CUC(cudaSetDevice(d.dev));
             CUC(cudaMalloc(&d.item_start, sizeof(int) * start.size()));

@@ -213,20 +213,26 @@ __device__ __forceinline__ bool mid_range(double x)
     return ex - 723u <= 600u;       // biased exponent in [723, 1323]
 }
 
+// Work decomposition: all surround-tile visits of a launch form one flat sequence ordered by
+// (frame, core tile, surround tile); CTA c owns the contiguous slice [T*c/grid, T*(c+1)/grid), so every
+// CTA gets the same number of tiles (+-1) whatever the triangle looks like, and the assignment is static
+// (deterministic summation).  A "run" is the part of a slice that stays inside one (frame, core tile).
 struct Item { int f, i0, jt_begin, ntiles; };
 
-__device__ __forceinline__ Item decode_item(const PairParams& P, long long item, int TI)
+__device__ __forceinline__ Item decode_run(const PairParams& P, long long cur, long long end, int TI)
 {
     Item it;
-    it.f = (int)(item / P.items_per_frame);
-    const int r = (int)(item - (long long)it.f * P.items_per_frame);
-    int lo = 0, hi = P.n_itiles;      // core tile ti with item_start[ti] <= r < item_start[ti+1]
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.item_start[mid] <= r) lo = mid; else hi = mid; }
-    const int seg = r - P.item_start[lo];
+    it.f = (int)(cur / P.tiles_per_frame);
+    const int r = (int)(cur - (long long)it.f * P.tiles_per_frame);
+    int lo = 0, hi = P.n_itiles;      // core tile ti with tile_start[ti] <= r < tile_start[ti+1]
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.tile_start[mid] <= r) lo = mid; else hi = mid; }
+    const int off = r - P.tile_start[lo];
+    const int row = P.tile_start[lo + 1] - P.tile_start[lo];
     it.i0 = lo * TI;
     const int jt_first = P.tri ? (it.i0 / kTJ) : 0;
-    it.jt_begin = jt_first + seg * P.seg_tiles;
-    it.ntiles = min(it.jt_begin + P.seg_tiles, P.n_jtiles) - it.jt_begin;
+    it.jt_begin = jt_first + off;
+    const long long left = end - cur;
+    it.ntiles = (long long)(row - off) < left ? row - off : (int)left;
     return it;
 }
 
@@ -316,7 +322,9 @@ pair_kernel(const PairParams P)
     }
     __syncthreads();
 
-    const long long total_items = (long long)P.items_per_frame * P.nframes;
+    const long long total_tiles = (long long)P.tiles_per_frame * P.nframes;
+    const long long slice_begin = total_tiles * blockIdx.x / gridDim.x;
+    const long long slice_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
     unsigned tcount = 0;        // surround tiles consumed so far by this CTA (stage = g % S, parity = (g / S) & 1)
 
     if (warp < NF) {
@@ -327,8 +335,9 @@ pair_kernel(const PairParams P)
         unsigned short* q = rings + warp * kRingCap;
         unsigned tail = 0, head_seen = 0;
 
-        for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-            const Item it = decode_item(P, item, TI);
+        for (long long cur = slice_begin; cur < slice_end; ) {
+            const Item it = decode_run(P, cur, slice_end, TI);
+            cur += it.ntiles;
             const Site* siteA = P.siteA + (long long)it.f * P.strideA;
             const Site* siteB = P.siteB + (long long)it.f * P.strideB;
 
@@ -453,8 +462,10 @@ pair_kernel(const PairParams P)
         bool zerodiv = false;
         const double t_small = 0.25 / (P.invdx * P.invdx);       // (0.5/invdx)^2
 
-        for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-            const Item it = decode_item(P, item, TI);
+        unsigned icount = 0;
+        for (long long cur = slice_begin; cur < slice_end; ) {
+            const Item it = decode_run(P, cur, slice_end, TI);
+            cur += it.ntiles;
             const Site* siteB = P.siteB + (long long)it.f * P.strideB;
             __syncthreads();
             Box bx;
@@ -462,7 +473,8 @@ pair_kernel(const PairParams P)
                 const double* b = P.box + 6ll * it.f;
                 bx.Lx = b[0]; bx.Ly = b[1]; bx.Lz = b[2]; bx.hx = b[3]; bx.hy = b[4]; bx.hz = b[5];
             }
-            mbar_wait(&ctrl->ifull, (unsigned)((item - blockIdx.x) / gridDim.x) & 1);
+            mbar_wait(&ctrl->ifull, icount & 1);
+            ++icount;
 
             for (int t = 0; t < it.ntiles; ++t) {
                 const unsigned g = tcount + t;
@@ -485,7 +497,9 @@ pair_kernel(const PairParams P)
                         // kRingCap >= 32*kU-1 + 32*32 entries, so a blocked producer always sees space again.
                         if (avail < 32u * kU && !(fin && avail > 0u)) {
                             if (fin) break;
-                            __nanosleep(100);
+                            // a ring fills at a few entries per microsecond: sleep long enough that polling does not
+                            // steal issue slots from the filter warps of this sub-partition
+                            __nanosleep(avail < 16u * kU ? 1000 : 400);
                             continue;
                         }
                         __threadfence_block();
@@ -824,9 +838,9 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
 cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s)
 {
     pair_fn_t fn = pick(cfg);
-    long long items = (long long)p.items_per_frame * p.nframes;
+    long long tiles = (long long)p.tiles_per_frame * p.nframes;
     int grid = cfg.grid;
-    if (cfg.hist_mode != 0 && items < grid) grid = (int)(items > 0 ? items : 1);   // partials need the full grid only in smem mode
+    if (cfg.hist_mode != 0 && tiles < grid) grid = (int)(tiles > 0 ? tiles : 1);   // partials need the full grid only in smem mode
     fn<<<grid, cfg.warps * 32, cfg.smem_bytes, s>>>(p);
     return cudaGetLastError();
 }

@@ -38,8 +38,8 @@ struct PairParams {
     int n1, n2, nframes, tri;       // tri: n1 == n2 (reference keys the triangle on sizes, quirk Q1)
     int histo_n, mode_sel;
     double hmin, hmax, invdx;       // hmin/hmax = (double)(float)histo_min/max  (quirk Q4)
-    int n_itiles, n_jtiles, seg_tiles, items_per_frame;
-    const int* item_start;          // [n_itiles+1] prefix of j segments per core tile
+    int n_itiles, n_jtiles, tiles_per_frame;
+    const int* tile_start;          // [n_itiles+1] prefix of surround-tile visits per core tile
     double* partials;               // [grid][histo_n*NSLOT] block partial histograms (shared-memory mode)
     double* gacc;                   // [8][histo_n] device accumulators: 7 modes + pair weight
     double* gpp;                    // [7][n1][histo_n] per-particle histogram or nullptr
