@@ -39,7 +39,7 @@ for p in (PKG, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-from gfn_b200 import synth  # noqa: E402
+from gfn_b200 import sharding, synth  # noqa: E402
 
 METRIC = "pair evals/sec (1e9), multipole g-function"
 UNIT = "1e9 pair evals/s"
@@ -185,12 +185,7 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
 
     def allmax(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return x if dist is None else sharding.allreduce_max(dist, x, device="cuda")
 
     c = cfg()
     n, L = c["n1"], c["L"]
@@ -199,14 +194,7 @@ def run_ours(args, rank, world, local_rank):
     flags = ("fp64" if args.filter == "fp64" else "") + ("," + args.flags if args.flags else "")
     mk = lambda: G.RDF(c["modes"], c["hmin"], c["hmax"], c["dr"], n, n, n, n, L, devices=[local_rank], gfn_flags=flags)  # noqa: E731
 
-    uid = None
-    if world > 1:
-        import torch
-        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(G.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
+    uid = sharding.broadcast_unique_id(dist, G.comm_unique_id, device="cuda") if world > 1 else None
 
     pool_c, pool_d = make_pool(c, POOL_FRAMES, rank)
     fp64_peak, fp32_peak = G.measure_peaks(local_rank)
