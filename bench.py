@@ -135,8 +135,21 @@ def reference_rdf(c):
     return O.OracleRDF(*args), "port"
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the reference's prange must get every host core."""
+    n = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def time_reference(c, steps, warmup, rank=0):
     """One frame per step through the reference's own RDF.calcFrame on the host cores."""
+    use_all_host_threads()
     rdf, kind = reference_rdf(c)
     n = c["n1"]
     per = synth.pair_evals(n, n)
@@ -241,8 +254,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- arm 2: end to end through RDF.calcFrame with host arrays -----------------------
     e = mk()
-    if uid is not None:
-        e.attach_comm(uid, world, rank)
+    if world > 1:           # an NCCL unique id makes exactly one communicator: a second handle needs its own
+        e.attach_comm(sharding.broadcast_unique_id(dist, G.comm_unique_id, device="cuda"), world, rank)
 
     def host_step(s):
         first = (s * F) % (POOL_FRAMES - F + 1) if POOL_FRAMES > F else 0
