@@ -499,7 +499,10 @@ pair_kernel(const PairParams P)
                             if (fin) break;
                             // a ring fills at a few entries per microsecond: sleep long enough that polling does not
                             // steal issue slots from the filter warps of this sub-partition
-                            __nanosleep(avail < 16u * kU ? 1000 : 400);
+                            // (one nanosleep returns after well under 100 ns on B200 whatever its argument, and a poll
+                            // is ~15 instructions with three shared-memory reads: chain several sleeps per poll)
+#pragma unroll 1
+                            for (int z = P.poll_reps; z > 0; --z) __nanosleep(P.poll_ns);
                             continue;
                         }
                         __threadfence_block();

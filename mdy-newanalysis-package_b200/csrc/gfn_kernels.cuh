@@ -46,6 +46,7 @@ struct PairParams {
     unsigned long long* counters;   // [kCounters]
     unsigned flags;                 // GFN_FLAG_DISCARD_OVERFLOW
     int nrep;                       // histogram replicas in shared memory
+    unsigned poll_ns; int poll_reps; // drain-warp back-off while its ring holds less than a batch
 };
 
 struct PairConfig {

@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Throughput of the BASELINE.json configurations other than the bench workload (device-resident frames,
+device-timed with gfn_mark): python profiles/run_configs.py [cfg1 cfg2 cfg3 cfg4 cfg5]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "mdy-newanalysis-package_b200"))
+import newanalysis.gfunction as G          # noqa: E402
+from gfn_b200 import synth                 # noqa: E402
+
+
+def run(name, n1, n2, L, modes, hmax, nframes, reps, self_pairs, flags=""):
+    rng = np.random.default_rng(5)
+    c1 = rng.random((nframes, n1, 3)) * L; d1 = rng.standard_normal((nframes, n1, 3))
+    r = G.RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags)
+    dc1, dd1 = G.to_device(c1), G.to_device(d1)
+    if self_pairs:
+        dc2, dd2 = dc1, dd1
+    else:
+        c2 = rng.random((nframes, n2, 3)) * L; d2 = rng.standard_normal((nframes, n2, 3))
+        dc2, dd2 = G.to_device(c2), G.to_device(d2)
+    need_d = modes != ["000"]
+    r.calcFramesDevice(nframes, dc1, dc2, dd1 if need_d else None, dd2 if need_d else None); r.sync()
+    st0 = r.stats()
+    r.mark(0)
+    for _ in range(reps):
+        r.calcFramesDevice(nframes, dc1, dc2, dd1 if need_d else None, dd2 if need_d else None)
+    r.mark(1); r.sync()
+    ms = r.mark_elapsed_ms(); st = r.stats()
+    evals = st["pair_evals"] - st0["pair_evals"]
+    f_in = (st["in_range"] - st0["in_range"]) / evals
+    out = dict(config=name, n1=n1, n2=n2, modes=modes, frames=nframes * reps, gpair_per_s=evals / ms / 1e6,
+               in_range_fraction=f_in, kernel_ms=st["kernel_ms"] - st0["kernel_ms"], wall_ms=ms, hist=st["hist_mode"],
+               warps=st["warps_per_block"], replicas=st["hist_replicas"], batch_frames=st["batch_frames"], filter=st["filter"])
+    print(json.dumps(out), flush=True)
+
+
+CONFIGS = {
+    "cfg1": lambda: run("cfg1 SPC/E 1000 O-O g000", 1000, 1000, 31.04, ["000"], 15.0, 100, 20, True),
+    "cfg2": lambda: run("cfg2 [C2mim][OTf] 1000x1000 5 modes 600 bins", 1000, 1000, 67.7, ["000", "110", "101", "011", "220"], 30.0, 500, 4, False),
+    "cfg3": lambda: run("cfg3 water 32768 all modes", 32768, 32768, 99.33, ["all"], 15.0, 15, 4, True),
+    "cfg3_g000": lambda: run("cfg3 shape, g000 only", 32768, 32768, 99.33, ["000"], 15.0, 15, 4, True),
+    "cfg4a": lambda: run("cfg4 solute COM 1024 x solvent 81920 all", 1024, 81920, 143.6, ["all"], 15.0, 16, 4, False),
+    "cfg4b": lambda: run("cfg4 solvent 81920 self all", 81920, 81920, 143.6, ["all"], 15.0, 2, 3, True),
+    "cfg4c": lambda: run("cfg4 solute atoms 4096 x solvent O 81920 g000", 4096, 81920, 143.6, ["000"], 15.0, 8, 4, False),
+    "cfg5": lambda: run("cfg5 1M sites self all", 1048576, 1048576, 315.4, ["all"], 15.0, 1, 1, True),
+}
+
+if __name__ == "__main__":
+    for k in (sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg3_g000", "cfg4a", "cfg4b", "cfg4c"]):
+        t0 = time.time()
+        CONFIGS[k]()
