@@ -325,3 +325,28 @@ def test_inrange_div_sqrt_sequences_equal_ieee_builtins():
     from newanalysis.gfunction import selftest_arith
     for seed in (1, 2, 3):
         assert selftest_arith(0, seed, 1 << 31) == (0, 0, 0)
+
+
+def _ngpu():
+    from newanalysis.gfunction import device_count
+    return device_count()
+
+
+@pytest.mark.skipif("_ngpu() < 2")
+def test_single_process_two_devices_frame_sharding(monkeypatch):
+    """NEWANALYSIS_GPUS=2: one handle deals frame batches round-robin to two GPUs and sums the per-device
+    histograms with one ncclAllReduce (communicator from ncclCommInitAll) at readout."""
+    monkeypatch.setenv("GFN_BATCH_FRAMES", "2")
+    n, L, nf = 900, 40.0, 9
+    rng = np.random.default_rng(123)
+    c = rng.random((nf, n, 3)) * L; d = rng.standard_normal((nf, n, 3))
+    one = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
+    two = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L, devices=[0, 1])
+    assert two.stats()["ndev"] == 2
+    for f in range(nf):
+        one.calcFrame(c[f], c[f], d[f], d[f]); two.calcFrame(c[f], c[f], d[f], d[f])
+    a, b = one.raw_histogram(), two.raw_histogram()
+    assert np.array_equal(a[:300], b[:300])
+    assert_hist_close(b, a, 300)
+    two.calcFrame(c[0], c[0], d[0], d[0]); one.calcFrame(c[0], c[0], d[0], d[0])     # accumulation continues after a readout
+    assert np.array_equal(one.raw_histogram()[:300], two.raw_histogram()[:300])
