@@ -160,6 +160,23 @@ int gfn_mark_elapsed_ms(gfn_t *h, double *ms);
  * of device dev.  Results in TFLOP/s (an FMA counts 2). */
 int gfn_measure_peaks(int dev, double *fp64_tflops, double *fp32_tflops);
 
+/* ---- N1: per-residue centre of mass and dipole on the device --------------------------------
+ * Replaces helpers.comByResidue (/root/reference/newanalysis/helpers/helpers.pyx:71-98), dipByResidue (:101-123)
+ * and, being the same arithmetic on velocities, velcomByResidue (:41-68).  Results are bit-identical to the
+ * reference (same atom order, un-fused multiply/add, IEEE division).
+ *   apr[i]  atoms of residue i, rfa[i] index of its first atom (the reference's atoms_per_residue / residue_first_atom)
+ *   coor    nframes x natoms x 3 float64;  outputs nframes x nres x 3 float64 */
+typedef struct gfn_residues gfn_residues_t;
+int gfn_residues_create(gfn_residues_t **out, int dev, int natoms, int nres, const int *apr, const int *rfa,
+                        const double *masses, const double *charges /* NULL: centres of mass only */);
+void gfn_residues_destroy(gfn_residues_t *r);
+/* host arrays: com_in == NULL computes the centres of mass (returned in com_out if not NULL); dip_out != NULL
+ * computes dipoles relative to com_in (or to the computed centres of mass) */
+int gfn_residues_com_dip(gfn_residues_t *r, int nframes, const double *coor, const double *com_in,
+                         double *com_out, double *dip_out);
+/* device arrays in and out (feed them to gfn_enqueue_device_frames); ddip may be NULL */
+int gfn_residues_com_dip_device(gfn_residues_t *r, int nframes, const double *dcoor, double *dcom, double *ddip);
+
 /* Self-test of the kernel's straight-line fp64 division / square-root sequences against the IEEE
  * built-ins (__ddiv_rn, __dsqrt_rn) on n_operands random operand sets with exponents in the range the
  * kernel uses them for.  mismatches = {division, square root, near-tie cases}; all must be 0. */

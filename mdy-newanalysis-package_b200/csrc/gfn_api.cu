@@ -757,6 +757,94 @@ int gfn_measure_peaks(int dev, double* fp64_tflops, double* fp32_tflops)
     return GFN_OK;
 }
 
+// ---- N1: residue map (topology on the device) ----------------------------------------------------------
+}  // extern "C"
+
+struct gfn_residues {
+    int dev, natoms, nres;
+    int* apr = nullptr; int* rfa = nullptr;
+    double* masses = nullptr; double* charges = nullptr;
+    double* scratch = nullptr; size_t scratch_bytes = 0;     // staging for host-side calls
+    char err[256];
+};
+
+extern "C" {
+
+int gfn_residues_create(gfn_residues_t** out, int dev, int natoms, int nres, const int* apr, const int* rfa,
+                        const double* masses, const double* charges)
+{
+    gfn_t* h = nullptr;
+    if (!out || !apr || !rfa || !masses) return fail(h, GFN_EINVAL, "NULL argument");
+    *out = nullptr;
+    if (natoms < 1 || nres < 1) return fail(h, GFN_EINVAL, "natoms and nres must be >= 1");
+    for (int i = 0; i < nres; ++i)
+        if (apr[i] < 0 || rfa[i] < 0 || (long long)rfa[i] + apr[i] > natoms)
+            return fail(h, GFN_EINVAL, "residue %d (first atom %d, %d atoms) exceeds natoms = %d", i, rfa[i], apr[i], natoms);
+    if (gfn_device_count() < 1) return fail(h, GFN_ENODEV, "no CUDA device available; libgfn has no CPU fallback");
+    CU(cudaSetDevice(dev));
+    gfn_residues* r = new gfn_residues();
+    r->dev = dev; r->natoms = natoms; r->nres = nres; r->err[0] = 0;
+#define CUR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(nullptr, GFN_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); gfn_residues_destroy(r); return GFN_ECUDA; } } while (0)
+    CUR(cudaMalloc(&r->apr, sizeof(int) * nres));
+    CUR(cudaMalloc(&r->rfa, sizeof(int) * nres));
+    CUR(cudaMalloc(&r->masses, sizeof(double) * natoms));
+    CUR(cudaMemcpy(r->apr, apr, sizeof(int) * nres, cudaMemcpyHostToDevice));
+    CUR(cudaMemcpy(r->rfa, rfa, sizeof(int) * nres, cudaMemcpyHostToDevice));
+    CUR(cudaMemcpy(r->masses, masses, sizeof(double) * natoms, cudaMemcpyHostToDevice));
+    if (charges) {
+        CUR(cudaMalloc(&r->charges, sizeof(double) * natoms));
+        CUR(cudaMemcpy(r->charges, charges, sizeof(double) * natoms, cudaMemcpyHostToDevice));
+    }
+#undef CUR
+    *out = r;
+    return GFN_OK;
+}
+
+void gfn_residues_destroy(gfn_residues_t* r)
+{
+    if (!r) return;
+    cudaSetDevice(r->dev);
+    cudaFree(r->apr); cudaFree(r->rfa); cudaFree(r->masses); cudaFree(r->charges); cudaFree(r->scratch);
+    delete r;
+}
+
+// device pointers in, device pointers out (chained into gfn_enqueue_device_frames without touching the host)
+int gfn_residues_com_dip_device(gfn_residues_t* r, int nframes, const double* dcoor, double* dcom, double* ddip)
+{
+    gfn_t* h = nullptr;
+    if (!r || !dcoor || !dcom) return fail(h, GFN_EINVAL, "NULL argument");
+    if (ddip && !r->charges) return fail(h, GFN_EINVAL, "dipoles requested but the residue map was created without charges");
+    CU(cudaSetDevice(r->dev));
+    CU(residue_com_launch(dcoor, 3ll * r->natoms, r->masses, r->apr, r->rfa, r->nres, nframes, dcom, 0));
+    if (ddip) CU(residue_dip_launch(dcoor, 3ll * r->natoms, r->charges, r->apr, r->rfa, r->nres, nframes, dcom, ddip, 0));
+    CU(cudaStreamSynchronize(0));     // the RDF handles consume these arrays on their own (non-blocking) streams
+    return GFN_OK;
+}
+
+// host arrays in, host arrays out: comByResidue (com_in == NULL: com is computed and returned in com_out) and
+// dipByResidue (dip_out != NULL; com_in, if given, is the reference point array the caller passes, helpers.pyx:101)
+int gfn_residues_com_dip(gfn_residues_t* r, int nframes, const double* coor, const double* com_in, double* com_out, double* dip_out)
+{
+    gfn_t* h = nullptr;
+    if (!r || !coor || nframes < 1) return fail(h, GFN_EINVAL, "bad argument");
+    if (dip_out && !r->charges) return fail(h, GFN_EINVAL, "dipoles requested but the residue map was created without charges");
+    CU(cudaSetDevice(r->dev));
+    const size_t cb = sizeof(double) * 3 * (size_t)r->natoms * nframes, ob = sizeof(double) * 3 * (size_t)r->nres * nframes;
+    if (r->scratch_bytes < cb + 2 * ob) {
+        cudaFree(r->scratch); r->scratch = nullptr; r->scratch_bytes = 0;
+        CU(cudaMalloc(&r->scratch, cb + 2 * ob));
+        r->scratch_bytes = cb + 2 * ob;
+    }
+    double* dcoor = r->scratch; double* dcom = dcoor + 3ll * r->natoms * nframes; double* ddip = dcom + 3ll * r->nres * nframes;
+    CU(cudaMemcpy(dcoor, coor, cb, cudaMemcpyHostToDevice));
+    if (com_in) CU(cudaMemcpy(dcom, com_in, ob, cudaMemcpyHostToDevice));
+    else CU(residue_com_launch(dcoor, 3ll * r->natoms, r->masses, r->apr, r->rfa, r->nres, nframes, dcom, 0));
+    if (dip_out) CU(residue_dip_launch(dcoor, 3ll * r->natoms, r->charges, r->apr, r->rfa, r->nres, nframes, dcom, ddip, 0));
+    if (com_out) CU(cudaMemcpy(com_out, dcom, ob, cudaMemcpyDeviceToHost));
+    if (dip_out) CU(cudaMemcpy(dip_out, ddip, ob, cudaMemcpyDeviceToHost));
+    return GFN_OK;
+}
+
 int gfn_selftest_arith(int dev, unsigned long long seed, long long n_operands, unsigned long long mismatches[3])
 {
     gfn_t* h = nullptr;

@@ -76,6 +76,12 @@ cudaError_t finalize_launch(const double* partials, int grid, int histo_n, int n
 
 cudaError_t scale_launch(double* a, long long n, double v, cudaStream_t s);
 
+// N1 producers (helpers.pyx:71-123): nframes frames of natoms x 3 coordinates -> nres x 3 centres of mass / dipoles.
+cudaError_t residue_com_launch(const double* coor, long long stride_coor, const double* masses, const int* apr, const int* rfa,
+                               int nres, int nframes, double* com, cudaStream_t s);
+cudaError_t residue_dip_launch(const double* coor, long long stride_coor, const double* charges, const int* apr, const int* rfa,
+                               int nres, int nframes, const double* com, double* dip, cudaStream_t s);
+
 cudaError_t peaks_measure(int dev, double* fp64_tflops, double* fp32_tflops);
 
 // Compares the kernel's in-range fp64 division / square-root sequences with the IEEE built-ins on

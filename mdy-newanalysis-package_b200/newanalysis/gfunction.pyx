@@ -75,6 +75,14 @@ cdef extern from "gfn.h":
     int gfn_mark(gfn_t *h, int which) nogil
     int gfn_selftest_arith(int dev, unsigned long long seed, long long n, unsigned long long *mism) nogil
     int gfn_mark_elapsed_ms(gfn_t *h, double *ms) nogil
+    ctypedef struct gfn_residues_t:
+        pass
+    int gfn_residues_create(gfn_residues_t **out, int dev, int natoms, int nres, const int *apr, const int *rfa,
+                            const double *masses, const double *charges) nogil
+    void gfn_residues_destroy(gfn_residues_t *r) nogil
+    int gfn_residues_com_dip(gfn_residues_t *r, int nframes, const double *coor, const double *com_in,
+                             double *com_out, double *dip_out) nogil
+    int gfn_residues_com_dip_device(gfn_residues_t *r, int nframes, const double *dcoor, double *dcom, double *ddip) nogil
     int gfn_dev_alloc(int dev, void **dptr, unsigned long long nbytes) nogil
     int gfn_dev_free(int dev, void *dptr) nogil
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
@@ -202,6 +210,135 @@ def to_device(arr, int device=0):
         _raise(rc, NULL)
     d.upload(a)
     return d
+
+
+cdef DeviceArray _device_empty(tuple shape, int device):
+    cdef DeviceArray d = DeviceArray()
+    cdef unsigned long long n = 8
+    for v in shape:
+        n *= <unsigned long long> v
+    d.device = device
+    d.shape = shape
+    d.nbytes = n
+    cdef int rc = gfn_dev_alloc(device, &d.ptr, n)
+    if rc:
+        d.ptr = NULL
+        _raise(rc, NULL)
+    return d
+
+
+cdef class ResidueMap:
+    """Topology of a selection on the device (atoms per residue, first atom, masses, charges) for the GPU
+    versions of helpers.comByResidue / dipByResidue / velcomByResidue
+    (/root/reference/newanalysis/helpers/helpers.pyx:41-123).  Results are bit-identical to the reference."""
+    cdef gfn_residues_t *r
+    cdef readonly int natoms
+    cdef readonly int nres
+    cdef readonly int device
+    cdef readonly bint has_charges
+
+    def __cinit__(self):
+        self.r = NULL
+
+    def __init__(self, masses, apr, rfa, charges=None, int device=0):
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] m = np.ascontiguousarray(masses, dtype=np.float64)
+        cdef np.ndarray[np.int32_t, ndim=1, mode="c"] a = np.ascontiguousarray(apr, dtype=np.int32)
+        cdef np.ndarray[np.int32_t, ndim=1, mode="c"] f = np.ascontiguousarray(rfa, dtype=np.int32)
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] q = None
+        if a.shape[0] != f.shape[0]:
+            raise ValueError("apr and rfa must have one entry per residue")
+        if charges is not None:
+            q = np.ascontiguousarray(charges, dtype=np.float64)
+            if q.shape[0] != m.shape[0]:
+                raise ValueError("charges and masses must have one entry per atom")
+        self.natoms = m.shape[0]
+        self.nres = a.shape[0]
+        self.device = device
+        self.has_charges = q is not None
+        cdef int rc = gfn_residues_create(&self.r, device, self.natoms, self.nres, <const int *> a.data, <const int *> f.data,
+                                          <const double *> m.data, <const double *> q.data if q is not None else NULL)
+        if rc:
+            self.r = NULL
+            _raise(rc, NULL)
+
+    def __dealloc__(self):
+        if self.r != NULL:
+            gfn_residues_destroy(self.r)
+            self.r = NULL
+
+    def com(self, coor):
+        """(natoms,3) or (nframes,natoms,3) host array -> centres of mass (…,nres,3)."""
+        return self._run(coor, None, True, False)[0]
+
+    def dip(self, coor, com=None):
+        """Dipoles relative to `com` (default: the centres of mass)."""
+        return self._run(coor, com, False, True)[1]
+
+    def com_dip(self, coor):
+        return self._run(coor, None, True, True)
+
+    def _run(self, coor, com_in, bint want_com, bint want_dip):
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] c = np.ascontiguousarray(coor, dtype=np.float64).reshape(-1)
+        sh = np.shape(coor)
+        lead = tuple(sh[:len(sh) - 2])
+        cdef int nframes = 1
+        for v in lead:
+            nframes *= v
+        if c.shape[0] != <long long> nframes * self.natoms * 3:
+            raise ValueError("coordinates must have shape (..., %d, 3)" % self.natoms)
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] ci = None
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] co = np.zeros(<long long> nframes * self.nres * 3)
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] do = None
+        if com_in is not None:
+            ci = np.ascontiguousarray(com_in, dtype=np.float64).reshape(-1)
+            if ci.shape[0] != co.shape[0]:
+                raise ValueError("com must have shape (..., %d, 3)" % self.nres)
+        if want_dip:
+            do = np.zeros(<long long> nframes * self.nres * 3)
+        cdef int rc
+        cdef const double *pc = <const double *> c.data
+        cdef const double *pci = <const double *> ci.data if ci is not None else NULL
+        cdef double *pco = <double *> co.data
+        cdef double *pdo = <double *> do.data if do is not None else NULL
+        with nogil:
+            rc = gfn_residues_com_dip(self.r, nframes, pc, pci, pco, pdo)
+        if rc:
+            _raise(rc, NULL)
+        shape = lead + (self.nres, 3)
+        return (co.reshape(shape) if (want_com or com_in is None) else None), (do.reshape(shape) if want_dip else None)
+
+    def com_dip_device(self, DeviceArray coor, bint want_dip=True):
+        """Device-resident coordinates (nframes,natoms,3) -> (DeviceArray com, DeviceArray dip) of shape
+        (nframes,nres,3), ready for RDF.calcFramesDevice / the pre_*_gpu arguments of RDF.calcFrame."""
+        cdef long long per = 3 * <long long> self.natoms * 8
+        if coor.nbytes % per:
+            raise ValueError("device array does not hold whole frames of %d atoms" % self.natoms)
+        cdef int nframes = <int> (coor.nbytes // per)
+        cdef DeviceArray com = _device_empty((nframes, self.nres, 3), self.device)
+        cdef DeviceArray dip = _device_empty((nframes, self.nres, 3), self.device) if want_dip else None
+        cdef int rc
+        cdef double *pd = <double *> dip.ptr if dip is not None else NULL
+        with nogil:
+            rc = gfn_residues_com_dip_device(self.r, nframes, <const double *> coor.ptr, <double *> com.ptr, pd)
+        if rc:
+            _raise(rc, NULL)
+        return com, dip
+
+
+def comByResidue(coor, masses, int nres, apr, rfa):
+    """helpers.comByResidue(coor,masses,nres,apr,rfa) on the GPU (helpers.pyx:71-98), same result bit for bit.
+    Builds a ResidueMap per call; keep a ResidueMap yourself when calling it every frame."""
+    return ResidueMap(masses, np.asarray(apr)[:nres], np.asarray(rfa)[:nres]).com(np.asarray(coor, dtype=np.float64))
+
+
+def velcomByResidue(vels, masses, int nres, apr, rfa):
+    """helpers.velcomByResidue (helpers.pyx:41-68): the same arithmetic as comByResidue, applied to velocities."""
+    return comByResidue(vels, masses, nres, apr, rfa)
+
+
+def dipByResidue(coor, charges, masses, int nres, apr, rfa, com):
+    """helpers.dipByResidue(coor,charges,masses,nres,apr,rfa,com) on the GPU (helpers.pyx:101-123)."""
+    return ResidueMap(masses, np.asarray(apr)[:nres], np.asarray(rfa)[:nres], charges).dip(np.asarray(coor, dtype=np.float64), com)
 
 
 cdef class _Backend:

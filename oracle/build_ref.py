@@ -71,6 +71,43 @@ def build(reference="/root/reference", force=False):
     return built_module()
 
 
+SETUP_HELPERS = r"""
+import numpy, sys
+from setuptools import setup, Extension
+from Cython.Build import cythonize
+ext = Extension('helpers', ['helpers.pyx', 'BertholdHorn.cpp'], language='c++',
+                extra_compile_args=['-fopenmp', '-O2', '-ffp-contract=off'], extra_link_args=['-fopenmp'],
+                include_dirs=[numpy.get_include(), '.'],
+                define_macros=[('NPY_NO_DEPRECATED_API', 'NPY_1_7_API_VERSION')])
+setup(name='helpers_ref', ext_modules=cythonize([ext], language_level=3, quiet=True))
+"""
+
+
+def build_helpers(reference="/root/reference", force=False):
+    """The reference helpers module (comByResidue / dipByResidue, next-row N1): helpers.pyx + BertholdHorn.cpp,
+    read from /root/reference, built in /tmp, only the .so lands in oracle/_ref/."""
+    hits = sorted(glob.glob(os.path.join(OUT, "helpers*.so")))
+    if hits and not force:
+        return hits[0]
+    src = os.path.join(reference, "newanalysis", "helpers")
+    if not os.path.isfile(os.path.join(src, "helpers.pyx")):
+        return None
+    os.makedirs(OUT, exist_ok=True)
+    with tempfile.TemporaryDirectory(prefix="gfn_ref_helpers_") as tmp:
+        for f in ("helpers.pyx", "BertholdHorn.cpp", "BertholdHorn.h"):
+            shutil.copyfile(os.path.join(src, f), os.path.join(tmp, f))
+        with open(os.path.join(tmp, "setup.py"), "w") as fh:
+            fh.write(SETUP_HELPERS)
+        env = dict(os.environ, CC="/usr/bin/gcc", CXX="/usr/bin/g++", LDSHARED="/usr/bin/g++ -shared")
+        res = subprocess.run([sys.executable, "setup.py", "build_ext", "--build-lib", OUT, "--build-temp", os.path.join(tmp, "bt")],
+                             cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout[-3000:])
+            raise RuntimeError("reference helpers.pyx failed to build")
+    hits = sorted(glob.glob(os.path.join(OUT, "helpers*.so")))
+    return hits[0] if hits else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -81,6 +118,7 @@ def main():
         print("reference tree not present and no prebuilt oracle/_ref module", file=sys.stderr)
         sys.exit(3)
     print(so)
+    print(build_helpers(a.reference, a.force))
 
 
 if __name__ == "__main__":

@@ -19,6 +19,7 @@
  *   gfn_oracle_calc_histo   <- cdef void calcHisto               :110-165
  *   gfn_oracle_add_histo    <- RDF._addHisto                     :466-480
  *   gfn_oracle_calc_histo_ts<- def calcHistoTS                   :168-192   (next-row N3)
+ *   gfn_oracle_com_by_residue / gfn_oracle_dip_by_residue <- newanalysis/helpers/helpers.pyx:71-98, :101-123 (next-row N1)
  */
 #include <math.h>
 #include <stddef.h>
@@ -244,4 +245,40 @@ int gfn_oracle_calc_histo_rows(const double *core_xyz, const double *surr_xyz,
     }
     if (oob) *oob += n_oob;
     return zerodiv;
+}
+
+
+/* comByResidue, newanalysis/helpers/helpers.pyx:71-98 (velcomByResidue :41-68 is the same arithmetic on velocities):
+ * com[i][k] = (sum_j coor[rfa[i]+j][k] * masses[rfa[i]+j]) / (sum_j masses[rfa[i]+j]), j ascending. */
+void gfn_oracle_com_by_residue(const double *coor, const double *masses, int nres, const int *apr, const int *rfa, double *com)
+{
+    int i;
+#pragma omp parallel for schedule(static)
+    for (i = 0; i < nres; i++) {
+        double tot = 0.0, s[3] = {0.0, 0.0, 0.0};
+        int j, k;
+        for (j = 0; j < apr[i]; j++) {
+            const int a = rfa[i] + j;
+            for (k = 0; k < 3; k++) s[k] += coor[3 * (long long)a + k] * masses[a];
+            tot += masses[a];
+        }
+        for (k = 0; k < 3; k++) com[3 * (long long)i + k] = s[k] / tot;
+    }
+}
+
+/* dipByResidue, helpers.pyx:101-123: dip[i][k] = sum_j (coor[a][k] - com[i][k]) * charges[a]. */
+void gfn_oracle_dip_by_residue(const double *coor, const double *charges, int nres, const int *apr, const int *rfa,
+                               const double *com, double *dip)
+{
+    int i;
+#pragma omp parallel for schedule(static)
+    for (i = 0; i < nres; i++) {
+        double s[3] = {0.0, 0.0, 0.0};
+        int j, k;
+        for (j = 0; j < apr[i]; j++) {
+            const int a = rfa[i] + j;
+            for (k = 0; k < 3; k++) s[k] += (coor[3 * (long long)a + k] - com[3 * (long long)i + k]) * charges[a];
+        }
+        for (k = 0; k < 3; k++) dip[3 * (long long)i + k] = s[k];
+    }
 }

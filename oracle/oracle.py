@@ -84,6 +84,48 @@ def load_ref():
     return mod
 
 
+def load_ref_helpers():
+    """The unmodified reference helpers module (oracle/_ref/helpers*.so, newanalysis/helpers/helpers.pyx) or None.
+    Its import line `from scipy.special import sph_harm` fails on scipy >= 1.17 (the name was removed); the
+    loader provides a placeholder for that one unrelated name instead of touching the reference source."""
+    hits = sorted(glob.glob(os.path.join(HERE, "_ref", "helpers*.so")))
+    if not hits:
+        return None
+    import scipy.special
+    if not hasattr(scipy.special, "sph_harm"):
+        scipy.special.sph_harm = None
+    spec = importlib.util.spec_from_file_location("helpers", hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def com_by_residue_c(coor, masses, apr, rfa):
+    """C restatement of helpers.comByResidue (helpers.pyx:71-98)."""
+    lib = load_c()
+    coor = _c64(coor); masses = _c64(masses)
+    apr = np.ascontiguousarray(apr, dtype=np.int32); rfa = np.ascontiguousarray(rfa, dtype=np.int32)
+    com = np.zeros((apr.shape[0], 3))
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.gfn_oracle_com_by_residue.restype = None
+    lib.gfn_oracle_com_by_residue(_dptr(coor), _dptr(masses), ctypes.c_int(apr.shape[0]), apr.ctypes.data_as(ip),
+                                  rfa.ctypes.data_as(ip), _dptr(com))
+    return com
+
+
+def dip_by_residue_c(coor, charges, apr, rfa, com):
+    """C restatement of helpers.dipByResidue (helpers.pyx:101-123)."""
+    lib = load_c()
+    coor = _c64(coor); charges = _c64(charges); com = _c64(com)
+    apr = np.ascontiguousarray(apr, dtype=np.int32); rfa = np.ascontiguousarray(rfa, dtype=np.int32)
+    dip = np.zeros((apr.shape[0], 3))
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.gfn_oracle_dip_by_residue.restype = None
+    lib.gfn_oracle_dip_by_residue(_dptr(coor), _dptr(charges), ctypes.c_int(apr.shape[0]), apr.ctypes.data_as(ip),
+                                  rfa.ctypes.data_as(ip), _dptr(com), _dptr(dip))
+    return dip
+
+
 def _dptr(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
 

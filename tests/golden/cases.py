@@ -82,3 +82,33 @@ def drive(rdf, case):
 # hand-checkable micro cases: x=(0,0,0), 0-15/0.05, L=40 -> flat indices
 MICRO = [((15.0, 0.0, 0.0), 300), ((14.999999999, 0.0, 0.0), 299), ((0.05, 0.0, 0.0), 1),
          ((0.049999, 0.0, 0.0), None)]
+
+
+# N1 producers (helpers.comByResidue / dipByResidue): residues of ragged size, incl. single-atom and empty ones
+RESIDUE_CASES = {
+    "water":   dict(nres=500, apr=("const", 3), L=30.0, seed=21),
+    "ragged":  dict(nres=333, apr=("range", 1, 40), L=45.0, seed=22),
+    "ions":    dict(nres=64, apr=("range", 1, 2), L=20.0, seed=23),
+    "gaps":    dict(nres=100, apr=("range", 0, 6), L=25.0, seed=24, gaps=True),
+}
+
+
+def build_residues(case):
+    """-> (coor (natoms,3), masses, charges, apr int32, rfa int32).  'gaps' leaves unused atoms between
+    residues and lets residues be empty (apr = 0: the reference then divides 0 by 0 -> nan, reproduced)."""
+    rng = np.random.default_rng(900001 * case["seed"])
+    nres = case["nres"]
+    kind = case["apr"]
+    apr = np.full(nres, kind[1], dtype=np.int32) if kind[0] == "const" else rng.integers(kind[1], kind[2] + 1, nres).astype(np.int32)
+    gap = rng.integers(0, 3, nres) if case.get("gaps") else np.zeros(nres, dtype=np.int64)
+    rfa = np.zeros(nres, dtype=np.int32)
+    pos = 0
+    for i in range(nres):
+        pos += int(gap[i])
+        rfa[i] = pos
+        pos += int(apr[i])
+    natoms = max(pos, 1)
+    coor = np.ascontiguousarray(rng.random((natoms, 3)) * case["L"])
+    masses = np.ascontiguousarray(1.0 + 15.0 * rng.random(natoms))
+    charges = np.ascontiguousarray(rng.standard_normal(natoms))
+    return coor, masses, charges, apr, rfa

@@ -62,6 +62,21 @@ def main():
     np.savez_compressed(os.path.join(HERE, "micro.npz"), idx=np.array(micro))
     print("micro", micro)
 
+    # N1 producers: comByResidue / dipByResidue / velcomByResidue of the unmodified reference helpers module
+    H = O.load_ref_helpers()
+    if H is None:
+        sys.exit("oracle/_ref/helpers*.so is not built; run python oracle/build_ref.py first")
+    out = {}
+    for name in sorted(C.RESIDUE_CASES):
+        coor, masses, charges, apr, rfa = C.build_residues(C.RESIDUE_CASES[name])
+        nres = apr.shape[0]
+        com = H.comByResidue(coor, masses, nres, apr, rfa)
+        dip = H.dipByResidue(coor, charges, masses, nres, apr, rfa, com)
+        vel = H.velcomByResidue(coor * 0.37, masses, nres, apr, rfa)
+        out[name + "_com"] = com; out[name + "_dip"] = dip; out[name + "_vel"] = vel
+        print("residues %-10s nres=%d natoms=%d" % (name, nres, coor.shape[0]))
+    np.savez_compressed(os.path.join(HERE, "residues.npz"), **out)
+
 
 if __name__ == "__main__":
     main()

@@ -350,3 +350,42 @@ def test_single_process_two_devices_frame_sharding(monkeypatch):
     assert_hist_close(b, a, 300)
     two.calcFrame(c[0], c[0], d[0], d[0]); one.calcFrame(c[0], c[0], d[0], d[0])     # accumulation continues after a readout
     assert np.array_equal(one.raw_histogram()[:300], two.raw_histogram()[:300])
+
+
+# ---- N1: centre of mass / dipole producers on the device ------------------------------------------------
+@pytest.mark.parametrize("name", sorted(C.RESIDUE_CASES))
+def test_residue_producers_bit_exact(golden_dir, name):
+    from newanalysis.helpers import comByResidue, dipByResidue, velcomByResidue
+    z = np.load(os.path.join(golden_dir, "residues.npz"))
+    coor, masses, charges, apr, rfa = C.build_residues(C.RESIDUE_CASES[name])
+    nres = apr.shape[0]
+    com = comByResidue(coor, masses, nres, apr, rfa)
+    assert np.array_equal(com, z[name + "_com"], equal_nan=True)
+    assert np.array_equal(dipByResidue(coor, charges, masses, nres, apr, rfa, com), z[name + "_dip"], equal_nan=True)
+    assert np.array_equal(velcomByResidue(coor * 0.37, masses, nres, apr, rfa), z[name + "_vel"], equal_nan=True)
+
+
+def test_atoms_to_gfunction_on_device():
+    """Raw atom coordinates -> (device) centres of mass + dipoles -> RDF, without a host round trip, equals the
+    host pipeline of the reference (comByResidue, dipByResidue, calcFrame) bit for bit in the counts."""
+    from newanalysis.gfunction import ResidueMap, to_device
+    nres, L, nf = 2000, 40.0, 3
+    rng = np.random.default_rng(31)
+    apr = np.full(nres, 3, dtype=np.int32); rfa = (3 * np.arange(nres)).astype(np.int32)
+    masses = np.tile([15.999, 1.008, 1.008], nres); charges = np.tile([-0.8476, 0.4238, 0.4238], nres)
+    centre = rng.random((nf, nres, 1, 3)) * L
+    coor = np.ascontiguousarray((centre + rng.standard_normal((nf, nres, 3, 3)) * 0.6).reshape(nf, 3 * nres, 3))
+    rm = ResidueMap(masses, apr, rfa, charges)
+    com, dip = rm.com_dip(coor)
+    for f in range(nf):
+        assert np.array_equal(com[f], O.com_by_residue_c(coor[f], masses, apr, rfa))
+        assert np.array_equal(dip[f], O.dip_by_residue_c(coor[f], charges, apr, rfa, com[f]))
+    dcom, ddip = rm.com_dip_device(to_device(coor))
+    a = RDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+    a.calcFramesDevice(nf, dcom, dcom, ddip, ddip)
+    o = O.OracleRDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+    for f in range(nf):
+        o.calcFrame(com[f], com[f], dip[f], dip[f])
+    got, ref = a.raw_histogram(), o.raw_sum()
+    assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 0
+    assert_hist_close(got, ref, 300)

@@ -128,3 +128,25 @@ def test_reference_module_agrees_when_present():
     a = C.drive(C.make_rdf(ref.RDF, case), case)
     b = C.drive(C.make_rdf(O.OracleRDF, case), case)
     assert np.array_equal(a.histogram, b.histogram)
+
+
+# ---- N1 producers -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(C.RESIDUE_CASES))
+def test_residue_oracle_matches_golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "residues.npz"))
+    coor, masses, charges, apr, rfa = C.build_residues(C.RESIDUE_CASES[name])
+    com = O.com_by_residue_c(coor, masses, apr, rfa)
+    assert np.array_equal(com, z[name + "_com"], equal_nan=True)
+    assert np.array_equal(O.dip_by_residue_c(coor, charges, apr, rfa, com), z[name + "_dip"], equal_nan=True)
+    assert np.array_equal(O.com_by_residue_c(coor * 0.37, masses, apr, rfa), z[name + "_vel"], equal_nan=True)
+
+
+def test_residue_oracle_matches_reference_module_when_present():
+    H = O.load_ref_helpers()
+    if H is None:
+        pytest.skip("oracle/_ref/helpers not built")
+    coor, masses, charges, apr, rfa = C.build_residues(C.RESIDUE_CASES["ragged"])
+    com = H.comByResidue(coor, masses, apr.shape[0], apr, rfa)
+    assert np.array_equal(com, O.com_by_residue_c(coor, masses, apr, rfa))
+    assert np.array_equal(H.dipByResidue(coor, charges, masses, apr.shape[0], apr, rfa, com),
+                          O.dip_by_residue_c(coor, charges, apr, rfa, com))
