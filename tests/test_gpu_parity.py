@@ -389,3 +389,21 @@ def test_atoms_to_gfunction_on_device():
     got, ref = a.raw_histogram(), o.raw_sum()
     assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 0
     assert_hist_close(got, ref, 300)
+
+
+def test_cfg5_row_block_against_oracle():
+    """BASELINE configs[4] shape (1M-site box, L = 315.4 A): a rectangular row block of 1,024 core sites
+    against 262,144 surround sites (a quarter of the box population, same density region) vs the CPU oracle."""
+    n1, n2, L = 1024, 262144, 315.4
+    rng = np.random.default_rng(5005)
+    c1, d1 = _random_frame(rng, n1, L); c2, d2 = _random_frame(rng, n2, L)
+    rdf = RDF(["all"], 0.0, 15.0, 0.05, n1, n2, n1, n2, L)
+    rdf.calcFrame(c1, c2, d1, d2)
+    got = rdf.raw_histogram()
+    ref = np.zeros(7 * 300)
+    box = np.array([L, L, L, L / 2, L / 2, L / 2])
+    rc, oob = O.calc_histo_rows_c(c1, c2, d1, d2, ref, box, 0.0, 15.0, 300, 20.0, 127)
+    assert rc == 0 and oob == 0
+    assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 1000
+    scale = np.maximum(np.abs(ref), np.tile(ref[:300], 7))
+    assert np.all(np.abs(got - ref) <= 2 * RTOL * scale)
