@@ -204,7 +204,7 @@ def run_ours(args, rank, world, local_rank):
     n, L = c["n1"], c["L"]
     per = synth.pair_evals(n, n)
     F, K, W = args.frames_per_step, args.steps, args.warmup
-    flags = ("fp64" if args.filter == "fp64" else "") + ("," + args.flags if args.flags else "")
+    flags = ("" if args.filter == "auto" else args.filter) + ("," + args.flags if args.flags else "")
     mk = lambda: G.RDF(c["modes"], c["hmin"], c["hmax"], c["dr"], n, n, n, n, L, devices=[local_rank], gfn_flags=flags)  # noqa: E731
 
     uid = sharding.broadcast_unique_id(dist, G.comm_unique_id, device="cuda") if world > 1 else None
@@ -308,7 +308,9 @@ def run_ours(args, rank, world, local_rank):
                      "flops_per_eval": flops_eval, "in_range_fraction": f_in, "survivor_fraction": f_surv,
                      "kernel": "pair_kernel", "kernel_ms_per_launch": kernel_ms / max(pair_launches, 1),
                      "kernel_share_of_step": kernel_ms / ms, "fp32_peak_tflops": fp32_peak,
-                     "lever": "fp32 conservative pre-filter + exact fp64 survivors" if st1["filter"] == "fp32" else "fp64 pre-test + exact fp64 survivors"},
+                     "lever": {"fp32": "fp32 conservative pre-filter + exact fp64 survivors",
+                               "fp16x2": "packed-fp16 conservative pre-filter (two core sites per instruction) + exact fp64 survivors",
+                               "fp64": "fp64 pre-test + exact fp64 survivors"}[st1["filter"]]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": dt / K * 1e3, "api": "newanalysis.gfunction.RDF.calcFrame (host numpy arrays) + readout per step"},
         "gpu_launches": int(launches),
@@ -328,7 +330,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--filter", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--filter", default="auto", choices=["auto", "fp16", "fp32", "fp64"],
+                    help="range pre-filter: auto = what the RDF class picks itself (fp16x2 for in-box coordinates)")
     ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", default="", help="extra gfn flags (experiments)")

@@ -48,7 +48,9 @@ extern "C" {
                                           results are identical, only the pipe that rejects far pairs changes */
 #define GFN_FLAG_DISCARD_OVERFLOW  4u  /* pos >= histo_n (quirk Q3) is dropped instead of spilling into
                                           bin pos-histo_n of the next row like the reference does */
-#define GFN_FLAG_HIST_GLOBAL       8u  /* force the global-atomic histogram path (default: per-warp shared-memory
+#define GFN_FLAG_HIST_GLOBAL       8u
+#define GFN_FLAG_FILTER_FP16       16u  /* range pre-filter in packed fp16 (two core sites per instruction, coordinates in box
+                                          units, wider guard band); results identical, see DESIGN.md */  /* force the global-atomic histogram path (default: per-warp shared-memory
                                           replicas whenever they fit) */
 
 /* bits of mode_sel, gfunction.pyx:274-288 */

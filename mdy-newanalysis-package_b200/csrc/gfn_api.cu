@@ -214,10 +214,11 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
 {
     cudaStream_t s = d.comp;
     CU(cudaMemsetAsync(maxab, 0, sizeof(float) * 2 * nframes, s));
-    CU(prep_launch(c1, s_c1, h->need1 ? d1 : nullptr, s_d1, siteA, maxab, h->n1, h->n1_pad, nframes, s));
+    const int hf = d.cfg.filter_fp64 == 2;
+    CU(prep_launch(c1, s_c1, h->need1 ? d1 : nullptr, s_d1, siteA, maxab, h->n1, h->n1_pad, nframes, d_box, hf, d.counters, s));
     h->st_launches += 1;
     if (!aliased) {
-        CU(prep_launch(c2, s_c2, h->need2 ? d2 : nullptr, s_d2, siteB, maxab + nframes, h->n2, h->n2_pad, nframes, s));
+        CU(prep_launch(c2, s_c2, h->need2 ? d2 : nullptr, s_d2, siteB, maxab + nframes, h->n2, h->n2_pad, nframes, d_box, hf, d.counters, s));
         h->st_launches += 1;
     }
     PairParams p;
@@ -271,7 +272,8 @@ int check_zerodiv(gfn_t* h)
         unsigned long long c[kCounters];
         CU(cudaSetDevice(d.dev));
         CU(cudaMemcpy(c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
-        if (c[1]) return fail(h, GFN_EZERODIV, "float division");
+        if (c[1] & 2ull) return fail(h, GFN_EINVAL, "coordinates lie more than 30000 box lengths from the origin: the fp16 pre-filter cannot represent them, create the handle without GFN_FLAG_FILTER_FP16");
+        if (c[1] & 1ull) return fail(h, GFN_EZERODIV, "float division");
     }
     return GFN_OK;
 }

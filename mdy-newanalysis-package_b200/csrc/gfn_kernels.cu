@@ -24,8 +24,10 @@
 #include "gfn_kernels.cuh"
 #include "../../include/gfn.h"
 
+#include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace gfn {
 
@@ -58,7 +60,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* __restrict__ dip, long long stride_dip,
-            Site* __restrict__ site, float* __restrict__ maxabs, int n, int n_pad)
+            Site* __restrict__ site, float* __restrict__ maxabs, int n, int n_pad, const double* __restrict__ box, int half_filter,
+            unsigned long long* __restrict__ counters)
 {
     const int f = blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,12 +80,28 @@ prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* 
             r.px = r.py = r.pz = 0.0; r.norm = 0.0;
         }
         r.spare = 0.0;
-        r.fx = __double2float_rn(r.x); r.fy = __double2float_rn(r.y); r.fz = __double2float_rn(r.z); r.fw = 0.f;
+        if (half_filter) {
+            // fp16 filter: coordinates in units of the longest box edge, each duplicated into both halves of a
+            // half2 so that one broadcast LDS.128 feeds the two core sites a filter thread keeps in one register
+            const double* bb = box + 6ll * f;
+            const double invS = 1.0 / fmax(bb[0], fmax(bb[1], bb[2]));
+            // beyond ~3e4 box lengths fp16 overflows and the filter would no longer be conservative: refuse loudly
+            if (fmax(fabs(r.x), fmax(fabs(r.y), fabs(r.z))) * invS > 30000.0) atomicOr(counters + 1, 2ull);
+            const __half hx = __double2half(r.x * invS), hy = __double2half(r.y * invS), hz = __double2half(r.z * invS);
+            const __half2 xx = __halves2half2(hx, hx), yy = __halves2half2(hy, hy), zz = __halves2half2(hz, hz);
+            r.fx = __uint_as_float(*reinterpret_cast<const unsigned*>(&xx));
+            r.fy = __uint_as_float(*reinterpret_cast<const unsigned*>(&yy));
+            r.fz = __uint_as_float(*reinterpret_cast<const unsigned*>(&zz));
+            r.fw = 0.f;
+        } else {
+            r.fx = __double2float_rn(r.x); r.fy = __double2float_rn(r.y); r.fz = __double2float_rn(r.z); r.fw = 0.f;
+        }
         m = fmaxf(fmaxf(__double2float_ru(fabs(r.x)), __double2float_ru(fabs(r.y))), __double2float_ru(fabs(r.z)));
     } else {
         // padding: never passes the fp32 pre-filter against a finite site; the fp64 pre-test masks it by index
         r.x = r.y = r.z = r.px = r.py = r.pz = r.norm = r.spare = 0.0;
         r.fx = r.fy = r.fz = 1e30f; r.fw = 0.f;
+        if (half_filter) r.fx = r.fy = r.fz = __uint_as_float(0x73537353u);     // half2(15000, 15000): squares overflow to +inf
     }
     site[(long long)f * n_pad + s] = r;
     unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like their bits
@@ -90,14 +109,15 @@ prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* 
 }
 
 cudaError_t prep_launch(const double* xyz, long long stride_xyz, const double* dip, long long stride_dip,
-                        Site* site, float* maxabs, int n, int n_pad, int nframes, cudaStream_t s)
+                        Site* site, float* maxabs, int n, int n_pad, int nframes, const double* box, int half_filter,
+                        unsigned long long* counters, cudaStream_t s)
 {
     for (int f0 = 0; f0 < nframes; f0 += 65535) {
         int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
         dim3 grid((n_pad + 255) / 256, nf);
         prep_kernel<<<grid, 256, 0, s>>>(xyz + (long long)f0 * stride_xyz, stride_xyz,
                                          dip ? dip + (long long)f0 * stride_dip : nullptr, stride_dip,
-                                         site + (long long)f0 * n_pad, maxabs + f0, n, n_pad);
+                                         site + (long long)f0 * n_pad, maxabs + f0, n, n_pad, box + 6ll * f0, half_filter, counters);
     }
     return cudaGetLastError();
 }
@@ -119,6 +139,10 @@ template <> struct FOps<double> {
     static __device__ __forceinline__ unsigned signword(double a) { return (unsigned)__double2hiint(a); }
     static constexpr double kU = 1.1102230246251565e-16;   // 2^-53
     static __device__ __forceinline__ double up(double t) { return t * (1.0 + 1e-15); }
+};
+
+template <> struct FOps<__half> {
+    static constexpr double kU = 4.8828125e-04;            // 2^-11
 };
 
 // Guard-banded squared cut-off of the pre-filter (see DESIGN.md "filter guard band" for the proof).
@@ -291,7 +315,8 @@ pair_kernel(const PairParams P)
     constexpr int TI = NF * 32 * kIPT;
     constexpr int TJ = kTJ;
     constexpr int S = kStages;
-    constexpr bool kF32 = sizeof(F) == 4;
+    constexpr bool kF32 = std::is_same<F, float>::value;
+    constexpr bool kH16 = std::is_same<F, __half>::value;
     constexpr unsigned RMASK = kRingCap - 1;
     static_assert(kIPT == 2, "two core sites per filter thread");
     constexpr int kU = kDrainILP;
@@ -330,7 +355,7 @@ pair_kernel(const PairParams P)
     if (warp < NF) {
         // =========================================== FILTER ===========================================
         if (ND == 8)   asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-        else if (kF32) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        else if (kF32 || kH16) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         else           asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         unsigned short* q = rings + warp * kRingCap;
         unsigned tail = 0, head_seen = 0;
@@ -354,18 +379,44 @@ pair_kernel(const PairParams P)
             // frame constants (uniform)
             const double* b = P.box + 6ll * it.f;
             const double M = (double)fmaxf(P.maxA[it.f], P.maxB[it.f]) * (1.0 + 1.2e-7);
-            const F Tg = guard_threshold<F>(P.hmax, M, fmax(b[3], fmax(b[4], b[5])));
-            const F hxf = (F)b[3], hyf = (F)b[4], hzf = (F)b[5];
-
-            // this thread's core positions: local index il(k) = warp*64 + k*32 + lane
-            F cx[kIPT], cy[kIPT], cz[kIPT];
+            // ---- filter constants and this thread's two core positions ------------------------------------
+            // scalar filters (fp32 / fp64): Tg, half box lengths and positions in the filter type
+            // fp16x2 filter: everything in units of the longest box edge S; the two core sites share a half2
+            typedef typename std::conditional<kH16, float, F>::type FS;          // scalar type of the non-half paths
+            FS Tg = 0, hxf = 0, hyf = 0, hzf = 0;
+            FS cx[kIPT], cy[kIPT], cz[kIPT];
+            __half2 hTg, hhx, hhy, hhz, hcx, hcy, hcz;
+            if (kH16) {
+                const double S = fmax(b[0], fmax(b[1], b[2])), invS = 1.0 / S;
+                const double u = FOps<__half>::kU;
+                // component error of the fp16 fold for pairs near the cut-off (tight form):
+                //   e_w <= u (2 M' + 5 h' + 3 hmax') + O(u^2)   (primes: in units of S; M' enters only through the
+                //   rounding of the two coordinates because an in-range pair has |dx'| <= 2h' + hmax')
+                const double hm = P.hmax * invS;
+                const double ew = u * (2.1 * M * invS + 5.2 * fmax(b[3], fmax(b[4], b[5])) * invS + 3.2 * hm);
+                const double T = (hm * hm * (1.0 + 1e-12) + 3.5 * ew * hm + 3.0 * ew * ew + 4.0 * 5.9604644775390625e-08) * (1.0 + 8.0 * u);
+                __half th = __double2half(T);
+                if (__half2float(th) <= (float)T) th = __ushort_as_half((unsigned short)(__half_as_ushort(th) + 1));   // round up
+                hTg = __halves2half2(__hneg(th), __hneg(th));
+                const __half a = __double2half(b[3] * invS), bq = __double2half(b[4] * invS), cq = __double2half(b[5] * invS);
+                hhx = __halves2half2(a, a); hhy = __halves2half2(bq, bq); hhz = __halves2half2(cq, cq);
+                const Site* c0 = siteA + it.i0 + warp * (32 * kIPT) + lane;
+                const Site* c1 = c0 + 32;
+                const unsigned x0 = __float_as_uint(c0->fx), y0 = __float_as_uint(c0->fy), z0 = __float_as_uint(c0->fz);
+                const unsigned x1 = __float_as_uint(c1->fx), y1 = __float_as_uint(c1->fy), z1 = __float_as_uint(c1->fz);
+                const unsigned px = __byte_perm(x0, x1, 0x5410), py = __byte_perm(y0, y1, 0x5410), pz = __byte_perm(z0, z1, 0x5410);
+                hcx = *reinterpret_cast<const __half2*>(&px); hcy = *reinterpret_cast<const __half2*>(&py); hcz = *reinterpret_cast<const __half2*>(&pz);
+            } else {
+                Tg = (FS)guard_threshold<FS>(P.hmax, M, fmax(b[3], fmax(b[4], b[5])));
+                hxf = (FS)b[3]; hyf = (FS)b[4]; hzf = (FS)b[5];
 #pragma unroll
-            for (int k = 0; k < kIPT; ++k) {
-                const int il = warp * (32 * kIPT) + k * 32 + lane;
-                const Site* c = siteA + it.i0 + il;
-                if (kF32) { cx[k] = (F)c->fx; cy[k] = (F)c->fy; cz[k] = (F)c->fz; }
-                else if (it.i0 + il < P.n1) { cx[k] = (F)c->x; cy[k] = (F)c->y; cz[k] = (F)c->z; }
-                else { cx[k] = cy[k] = cz[k] = (F)1e30; }
+                for (int k = 0; k < kIPT; ++k) {
+                    const int il = warp * (32 * kIPT) + k * 32 + lane;
+                    const Site* c = siteA + it.i0 + il;
+                    if (kF32) { cx[k] = (FS)c->fx; cy[k] = (FS)c->fy; cz[k] = (FS)c->fz; }
+                    else if (it.i0 + il < P.n1) { cx[k] = (FS)c->x; cy[k] = (FS)c->y; cz[k] = (FS)c->z; }
+                    else { cx[k] = cy[k] = cz[k] = (FS)1e30; }
+                }
             }
             const int my_i_min = it.i0 + warp * (32 * kIPT);     // smallest core index of this warp
 
@@ -381,27 +432,44 @@ pair_kernel(const PairParams P)
                     if (j0 + jbase >= P.n2) break;                              // padding only
                     if (P.tri && j0 + jbase + 31 < my_i_min) continue;         // chunk entirely below this warp's rows
                     unsigned m0 = 0u, m1 = 0u;
+                    if (kH16) {
+                        // 9 HADD2 (with |.| modifiers) + 3 HFMA2 + 3 shifts per TWO pairs
 #pragma unroll 16
-                    for (int jj = 0; jj < 32; ++jj) {
-                        F sx, sy, sz;
-                        if (kF32) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(&js[jbase + jj].fx);
-                            sx = (F)s4.x; sy = (F)s4.y; sz = (F)s4.z;
-                        } else {
-                            const double2 sxy = *reinterpret_cast<const double2*>(&js[jbase + jj].x);
-                            sx = (F)sxy.x; sy = (F)sxy.y; sz = (F)js[jbase + jj].z;
-                            if (j0 + jbase + jj >= P.n2) { sx = sy = sz = (F)-1e30; }
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const uint4 s4 = *reinterpret_cast<const uint4*>(&js[jbase + jj].fx);
+                            const __half2 sx = *reinterpret_cast<const __half2*>(&s4.x), sy = *reinterpret_cast<const __half2*>(&s4.y), sz = *reinterpret_cast<const __half2*>(&s4.z);
+                            const __half2 dx = __hsub2(sx, hcx), dy = __hsub2(sy, hcy), dz = __hsub2(sz, hcz);
+                            const __half2 wx = __hsub2(hhx, __habs2(__hsub2(__habs2(dx), hhx)));
+                            const __half2 wy = __hsub2(hhy, __habs2(__hsub2(__habs2(dy), hhy)));
+                            const __half2 wz = __hsub2(hhz, __habs2(__hsub2(__habs2(dz), hhz)));
+                            const __half2 tt = __hfma2(wz, wz, __hfma2(wy, wy, __hfma2(wx, wx, hTg)));
+                            const unsigned tb = *reinterpret_cast<const unsigned*>(&tt);
+                            m0 = __funnelshift_l(tb << 16, m0, 1);      // sign of the low half: core site k = 0
+                            m1 = __funnelshift_l(tb, m1, 1);            // sign of the high half: core site k = 1
                         }
+                    } else {
+#pragma unroll 16
+                        for (int jj = 0; jj < 32; ++jj) {
+                            FS sx, sy, sz;
+                            if (kF32) {
+                                const float4 s4 = *reinterpret_cast<const float4*>(&js[jbase + jj].fx);
+                                sx = (FS)s4.x; sy = (FS)s4.y; sz = (FS)s4.z;
+                            } else {
+                                const double2 sxy = *reinterpret_cast<const double2*>(&js[jbase + jj].x);
+                                sx = (FS)sxy.x; sy = (FS)sxy.y; sz = (FS)js[jbase + jj].z;
+                                if (j0 + jbase + jj >= P.n2) { sx = sy = sz = (FS)-1e30; }
+                            }
 #pragma unroll
-                        for (int k = 0; k < kIPT; ++k) {
-                            const F dx = sx - cx[k], dy = sy - cy[k], dz = sz - cz[k];
-                            const F vx = FOps<F>::abs(dx) - hxf, vy = FOps<F>::abs(dy) - hyf, vz = FOps<F>::abs(dz) - hzf;
-                            const F wx = hxf - FOps<F>::abs(vx), wy = hyf - FOps<F>::abs(vy), wz = hzf - FOps<F>::abs(vz);
-                            F tt = FOps<F>::fma(wx, wx, -Tg);
-                            tt = FOps<F>::fma(wy, wy, tt);
-                            tt = FOps<F>::fma(wz, wz, tt);
-                            if (k == 0) m0 = __funnelshift_l(FOps<F>::signword(tt), m0, 1);    // first jj ends at bit 31
-                            else        m1 = __funnelshift_l(FOps<F>::signword(tt), m1, 1);
+                            for (int k = 0; k < kIPT; ++k) {
+                                const FS dx = sx - cx[k], dy = sy - cy[k], dz = sz - cz[k];
+                                const FS vx = FOps<FS>::abs(dx) - hxf, vy = FOps<FS>::abs(dy) - hyf, vz = FOps<FS>::abs(dz) - hzf;
+                                const FS wx = hxf - FOps<FS>::abs(vx), wy = hyf - FOps<FS>::abs(vy), wz = hzf - FOps<FS>::abs(vz);
+                                FS tt = FOps<FS>::fma(wx, wx, -Tg);
+                                tt = FOps<FS>::fma(wy, wy, tt);
+                                tt = FOps<FS>::fma(wz, wz, tt);
+                                if (k == 0) m0 = __funnelshift_l(FOps<FS>::signword(tt), m0, 1);    // first jj ends at bit 31
+                                else        m1 = __funnelshift_l(FOps<FS>::signword(tt), m1, 1);
+                            }
                         }
                     }
                     // ---- publish survivors into this warp's ring (one packed scan for both core slots) ----
@@ -781,7 +849,7 @@ static pair_fn_t pick_fn(const PairConfig& c)
     return nf == 12 ? pick_shape<F, 12, 4>(c.hist_mode, weights, allm) : pick_shape<F, 8, 4>(c.hist_mode, weights, allm);
 }
 
-static pair_fn_t pick(const PairConfig& c) { return c.filter_fp64 ? pick_fn<double>(c) : pick_fn<float>(c); }
+static pair_fn_t pick(const PairConfig& c) { return c.filter_fp64 == 1 ? pick_fn<double>(c) : (c.filter_fp64 == 2 ? pick_fn<__half>(c) : pick_fn<float>(c)); }
 
 int tile_i(const PairConfig& cfg) { return (cfg.warps - cfg.drain_warps) * 32 * kIPT; }
 
@@ -792,7 +860,7 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
     int max_smem = 0, sms = 0;
     if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    cfg->filter_fp64 = (flags & GFN_FLAG_FILTER_FP64) ? 1 : 0;
+    cfg->filter_fp64 = (flags & GFN_FLAG_FILTER_FP64) ? 1 : ((flags & GFN_FLAG_FILTER_FP16) ? 2 : 0);
     cfg->nslot = (mode_sel == 1) ? 1 : 8;
     cfg->all_modes = (mode_sel == 127) ? 1 : 0;
     cfg->nrep = 1;

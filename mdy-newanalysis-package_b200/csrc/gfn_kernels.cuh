@@ -28,7 +28,7 @@ constexpr int kPadTo   = 1024;   // selections are padded to a multiple of this 
 constexpr int kDrainILP = 2;     // survivors evaluated per drain lane per batch
 constexpr int kRingCap = 2048;   // survivor ring entries (16 bit) per filter warp: one push (<= 32*32) always fits behind < 64 unread ones
 constexpr int kCtrlBytes = 640;  // shared-memory control block
-constexpr int kCounters = 8;     // 0 overflow, 1 zerodiv flag, 2 survivors, 3 in-range pairs
+constexpr int kCounters = 8;     // 0 overflow, 1 error flags (bit 0 zero-norm dipole, bit 1 fp16 filter range), 2 survivors, 3 in-range pairs
 
 struct PairParams {
     const Site* siteA;  const float* maxA;   // selection 1 (core)
@@ -50,7 +50,7 @@ struct PairParams {
 };
 
 struct PairConfig {
-    int filter_fp64;   // 0 fp32 pre-filter, 1 fp64 pre-test
+    int filter_fp64;   // 0 fp32 pre-filter, 1 fp64 pre-test, 2 fp16x2 pre-filter
     int hist_mode;     // 0 shared-memory warp replicas, 1 global atomics, 2 per-particle global atomics
     int warps;         // warps per CTA: filter warps (12 or 8) + drain warps
     int drain_warps;   // 4, or 8 working in pairs on 4 replicas
@@ -69,7 +69,8 @@ cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t
 
 // Converts nframes frames of one selection into Site records and the per-frame max |coordinate|.
 cudaError_t prep_launch(const double* xyz, long long stride_xyz, const double* dip, long long stride_dip,
-                        Site* site, float* maxabs, int n, int n_pad, int nframes, cudaStream_t s);
+                        Site* site, float* maxabs, int n, int n_pad, int nframes, const double* box, int half_filter,
+                        unsigned long long* counters, cudaStream_t s);
 
 // partials[grid][histo_n*nslot] -> gacc, blocks summed in ascending order (deterministic).
 cudaError_t finalize_launch(const double* partials, int grid, int histo_n, int nslot, double* gacc, cudaStream_t s);

@@ -88,7 +88,7 @@ cdef extern from "gfn.h":
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
 
 
-_FLAG_NAMES = {"x_atomics": 256, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
+_FLAG_NAMES = {"fp16": 16, "filter_fp16": 16, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
 
 
 def _parse_flags(spec):
@@ -175,9 +175,11 @@ cdef class DeviceArray:
     cdef readonly int device
     cdef readonly tuple shape
     cdef readonly unsigned long long nbytes
+    cdef public object absmax      # max |value| of the last upload (None when produced on the device)
 
     def __cinit__(self):
         self.ptr = NULL
+        self.absmax = None
 
     def __dealloc__(self):
         if self.ptr != NULL:
@@ -191,6 +193,7 @@ cdef class DeviceArray:
         cdef int rc = gfn_dev_upload(self.device, self.ptr, <const void *> flat.data, self.nbytes)
         if rc:
             _raise(rc, NULL)
+        self.absmax = float(np.abs(flat).max()) if flat.shape[0] else 0.0
 
     @property
     def address(self):
@@ -474,7 +477,7 @@ cdef class _Backend:
         self.check(gfn_stats(self.h, &s))
         return dict(pair_evals=s.pair_evals, survivors=s.survivors, in_range=s.in_range, kernel_ms=s.kernel_ms,
                     kernel_launches=s.kernel_launches, pair_launches=s.pair_launches, frames=s.frames,
-                    h2d_bytes=s.h2d_bytes, overflow=s.overflow, filter="fp64" if s.filter_fp64 else "fp32",
+                    h2d_bytes=s.h2d_bytes, overflow=s.overflow, filter=("fp32", "fp64", "fp16x2")[s.filter_fp64],
                     hist_mode=("smem_warp_replicas", "global_atomics", "per_particle")[s.hist_mode],
                     warps_per_block=s.warps_per_block, blocks_per_sm=s.blocks_per_sm, grid=s.grid,
                     smem_bytes=s.smem_bytes, batch_frames=s.batch_frames, ndev=s.ndev, hist_replicas=s.hist_replicas)
@@ -544,13 +547,35 @@ class RDF(object):
 
         self.histogram_out = np.zeros(self.histo_n * 7, dtype=np.float64)   # :333
 
-        self._flags = _parse_flags(gfn_flags)
+        # filter choice: explicit flag, or "auto" (default): fp32 until the first host frame shows that the
+        # coordinates stay within a few box lengths, then the cheaper packed-fp16 pre-filter (results identical)
+        spec = gfn_flags if gfn_flags is not None else os.environ.get("NEWANALYSIS_GFN_FLAGS", "")
+        self._auto_filter = not isinstance(spec, int) and not any(tok in str(spec) for tok in ("fp16", "fp32", "fp64"))
+        if not isinstance(spec, int):
+            spec = ",".join(tok for tok in str(spec).replace(" ", "").split(",") if tok and tok != "fp32")
+        self._flags = _parse_flags(spec)
         self._devices = _parse_devices(devices)
         if gfn_device_count() < 1:
             raise RuntimeError("newanalysis.gfunction (B200 backend): no CUDA device available and there is no CPU fallback")
+        self._open_backend()
+
+    def _open_backend(self):
         self._be = _Backend()
         self._be.open(int(self.n1), int(self.n2), int(self.histo_n), self.histo_min, self.histo_max,
-                      float(self.histo_inv_dr), mode_sel, self.box_dim, self._devices, self._flags)
+                      float(self.histo_inv_dr), int(self.mode_sel), self.box_dim, self._devices, self._flags)
+
+    def _auto_pick_filter(self, c1, c2, absmax=None):
+        """First frame of an "auto" handle: switch to the fp16 pre-filter when every coordinate lies within two
+        box lengths of the origin (wrapped trajectories); far-away (unwrapped) coordinates keep fp32."""
+        self._auto_filter = False
+        if self._flags & (2 | 16):
+            return
+        lmax = float(max(self.box_dim[0], self.box_dim[1], self.box_dim[2]))
+        if absmax is None:
+            absmax = max(float(np.abs(c1).max()), float(np.abs(c2).max()))
+        if absmax <= 2.0 * lmax and float(self.histo_max) >= 0.04 * lmax:
+            self._flags |= 16
+            self._open_backend()          # nothing has been enqueued yet
 
     # ------------------------------------------------------------------ reference API
     def update_box(self, box_x, box_y, box_z):
@@ -602,6 +627,8 @@ class RDF(object):
             else:
                 self.oneistwo = False
 
+        if self._auto_filter and self.ctr == 0:
+            self._auto_pick_filter(coor_sel1, coor_sel2)
         self.ctr += 1                                        # :424
         self.volume_list.append(self.volume)                 # :427
 
@@ -753,6 +780,8 @@ class RDF(object):
             vols = list(b3[:, 0] * b3[:, 1] * b3[:, 2])
         else:
             vols = [self.volume] * nf
+        if self._auto_filter and self.ctr == 0:
+            self._auto_pick_filter(c1[0], c2[0])
         self.ctr += nf
         self.volume_list.extend(vols)
         cdef _Backend be = self._be
@@ -767,6 +796,11 @@ class RDF(object):
         """Frames already resident in HBM (`DeviceArray`s of shape (>=first+nframes,n,3)); no host->device copy."""
         if self.oneistwo is None:
             self.oneistwo = bool(c1 is c2 and self.nmol1 == self.nmol2)
+        if self._auto_filter and self.ctr == 0:
+            if c1.absmax is not None and c2.absmax is not None:
+                self._auto_pick_filter(None, None, max(c1.absmax, c2.absmax))
+            else:
+                self._auto_filter = False
         self.ctr += nframes
         self.volume_list.extend([self.volume] * nframes)
         self._be.enqueue_device(nframes, c1, c2, d1, d2, boxes, first)

@@ -17,7 +17,7 @@ import oracle as O
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-12
-VARIANTS = ["", "fp64", "global", "fp64,global", "per_particle"]
+VARIANTS = ["", "fp32", "fp64", "fp16", "fp32,global", "fp64,global", "fp16,global", "per_particle"]
 
 
 def RDF(*a, **k):
@@ -100,7 +100,7 @@ def _random_frame(rng, n, L, dip=True):
     return np.ascontiguousarray(rng.random((n, 3)) * L), (np.ascontiguousarray(rng.standard_normal((n, 3))) if dip else None)
 
 
-@pytest.mark.parametrize("flags", ["", "fp64"])
+@pytest.mark.parametrize("flags", ["fp32", "fp64", "fp16"])
 @pytest.mark.parametrize("n,L", [(8192, 62.58), (32768, 99.33)])
 def test_cfg3_shape_against_oracle(n, L, flags):
     """BASELINE configs[2] shape (water, self, all modes, 0-15/0.05); n=32768 is the full size."""
@@ -166,8 +166,8 @@ def test_threshold_edges_exact():
     pts = np.array(pts)
     origin = np.array([[39.7, 0.2, 20.0]])
     c2 = np.ascontiguousarray((origin + pts) % L)
-    for flags in ("", "fp64"):
-        g = RDF(["000"], 0.0, 15.0, 0.05, 1, len(c2), 1, len(c2), L, gfn_flags=flags + ",per_particle" if flags else "per_particle")
+    for flags in ("fp32", "fp64", "fp16"):
+        g = RDF(["000"], 0.0, 15.0, 0.05, 1, len(c2), 1, len(c2), L, gfn_flags=flags + ",per_particle")
         o = O.OracleRDF(["000"], 0.0, 15.0, 0.05, 1, len(c2), 1, len(c2), L)
         o.histogram = np.zeros(2 * 300 * 7)          # spare row so the Q3 spill stays inspectable
         g.calcFrame(origin, c2); o.calcFrame(origin, c2)
@@ -407,3 +407,25 @@ def test_cfg5_row_block_against_oracle():
     assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 1000
     scale = np.maximum(np.abs(ref), np.tile(ref[:300], 7))
     assert np.all(np.abs(got - ref) <= 2 * RTOL * scale)
+
+
+def test_filter_auto_selection_and_fp16_range_guard():
+    """Default handles pick the packed-fp16 pre-filter for in-box coordinates and keep fp32 for far-away
+    (unwrapped) ones; an explicit fp16 handle refuses coordinates it cannot represent instead of losing pairs."""
+    n, L = 300, 30.0
+    rng = np.random.default_rng(77)
+    c = rng.random((n, 3)) * L; d = rng.standard_normal((n, 3))
+    a = RDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L); a.calcFrame(c, c, d, d)
+    assert a.stats()["filter"] == "fp16x2"
+    far = c + 100 * L
+    b = RDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L); b.calcFrame(far, far, d, d)
+    assert b.stats()["filter"] == "fp32"
+    o = O.OracleRDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L); o.calcFrame(far, far, d, d)
+    assert np.array_equal(b.raw_histogram()[:280], o.raw_sum()[:280])
+    # fp16 forced on data 100 box lengths away: still exact (the guard band widens with max|x|)
+    e = RDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L, gfn_flags="fp16"); e.calcFrame(far, far, d, d)
+    assert np.array_equal(e.raw_histogram()[:280], o.raw_sum()[:280])
+    # ... and refused beyond what fp16 can hold
+    g = RDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L, gfn_flags="fp16"); g.calcFrame(c + 1e6 * L, c + 1e6 * L, d, d)
+    with pytest.raises(ValueError, match="fp16"):
+        g.sync()
