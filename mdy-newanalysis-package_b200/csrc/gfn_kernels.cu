@@ -433,8 +433,12 @@ pair_kernel(const PairParams P)
                     if (P.tri && j0 + jbase + 31 < my_i_min) continue;         // chunk entirely below this warp's rows
                     unsigned m0 = 0u, m1 = 0u;
                     if (kH16) {
-                        // 9 HADD2 (with |.| modifiers) + 3 HFMA2 + 3 shifts per TWO pairs
-#pragma unroll 16
+                        // 9 HADD2 (with |.| modifiers) + 3 HFMA2 + SHF + LOP3 per TWO pairs.  The two sign bits of a
+                        // result (bit 15: core site 0, bit 31: core site 1) are shifted right by jj and OR-ed into an
+                        // accumulator that covers 16 surround sites; the two accumulators of a chunk are re-packed
+                        // into the usual masks (bit 31-jj = surround site jj) with two PRMTs.
+                        unsigned acc[2] = {0u, 0u};
+#pragma unroll
                         for (int jj = 0; jj < 32; ++jj) {
                             const uint4 s4 = *reinterpret_cast<const uint4*>(&js[jbase + jj].fx);
                             const __half2 sx = *reinterpret_cast<const __half2*>(&s4.x), sy = *reinterpret_cast<const __half2*>(&s4.y), sz = *reinterpret_cast<const __half2*>(&s4.z);
@@ -444,9 +448,10 @@ pair_kernel(const PairParams P)
                             const __half2 wz = __hsub2(hhz, __habs2(__hsub2(__habs2(dz), hhz)));
                             const __half2 tt = __hfma2(wz, wz, __hfma2(wy, wy, __hfma2(wx, wx, hTg)));
                             const unsigned tb = *reinterpret_cast<const unsigned*>(&tt);
-                            m0 = __funnelshift_l(tb << 16, m0, 1);      // sign of the low half: core site k = 0
-                            m1 = __funnelshift_l(tb, m1, 1);            // sign of the high half: core site k = 1
+                            acc[jj >> 4] |= (tb >> (jj & 15)) & (0x80008000u >> (jj & 15));
                         }
+                        m0 = __byte_perm(acc[1], acc[0], 0x5410);      // low halves: core site k = 0, sites 0-15 on top
+                        m1 = __byte_perm(acc[1], acc[0], 0x7632);      // high halves: core site k = 1
                     } else {
 #pragma unroll 16
                         for (int jj = 0; jj < 32; ++jj) {
