@@ -510,7 +510,15 @@ int gfn_enqueue_frames(gfn_t* h, int nframes,
         }
         memcpy(b->h_box + 6ll * b->nframes, box_dims ? box_dims + 6ll * f : h->box, sizeof(double) * 6);
         b->nframes++;
-        if (b->nframes == h->batch_frames) {
+        bool go = b->nframes == h->batch_frames;
+        if (!go && b->nframes >= (h->batch_frames + 3) / 4) {
+            // the device is idle (e.g. right after a readout): do not make it wait for a full batch
+            go = true;
+            for (Batch& o : d.ring)
+                if (o.inflight && cudaEventQuery(o.done) == cudaErrorNotReady) { go = false; break; }
+            cudaGetLastError();
+        }
+        if (go) {
             int rc = submit(h, d);
             if (rc) return rc;
             h->next_dev = (h->next_dev + 1) % (int)h->devs.size();
