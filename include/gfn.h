@@ -49,6 +49,8 @@ extern "C" {
 #define GFN_FLAG_DISCARD_OVERFLOW  4u  /* pos >= histo_n (quirk Q3) is dropped instead of spilling into
                                           bin pos-histo_n of the next row like the reference does */
 #define GFN_FLAG_HIST_GLOBAL       8u
+#define GFN_FLAG_NO_TRIANGLE       32u  /* evaluate all n1 x n2 pairs with weight 1 even when n1 == n2 (calcHistoTS,
+                                          gfunction.pyx:168-192, has no j >= i shortcut) */
 #define GFN_FLAG_FILTER_FP16       16u  /* range pre-filter in packed fp16 (two core sites per instruction, coordinates in box
                                           units, wider guard band); results identical, see DESIGN.md */  /* force the global-atomic histogram path (default: per-warp shared-memory
                                           replicas whenever they fit) */

@@ -191,7 +191,7 @@ int wait_batch(gfn_t* h, Dev& d, Batch& b)
 void fill_params(gfn_t* h, Dev& d, PairParams& p)
 {
     memset(&p, 0, sizeof(p));
-    p.n1 = h->n1; p.n2 = h->n2; p.tri = (h->n1 == h->n2);
+    p.n1 = h->n1; p.n2 = h->n2; p.tri = (h->n1 == h->n2) && !(h->flags & GFN_FLAG_NO_TRIANGLE);
     p.histo_n = h->histo_n; p.mode_sel = h->mode_sel;
     p.hmin = (double)h->hmin_f; p.hmax = (double)h->hmax_f; p.invdx = h->inv_dr;
     p.n_itiles = h->n_itiles; p.n_jtiles = h->n_jtiles; p.tiles_per_frame = h->tiles_per_frame;
@@ -234,7 +234,8 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
         CU(finalize_launch(d.partials, d.cfg.grid, h->histo_n, d.cfg.nslot, d.gacc, s));
         h->st_launches += 1;
     }
-    const double per = (h->n1 == h->n2) ? 0.5 * (double)h->n1 * ((double)h->n1 + 1.0) : (double)h->n1 * (double)h->n2;
+    const bool tri = (h->n1 == h->n2) && !(h->flags & GFN_FLAG_NO_TRIANGLE);
+    const double per = tri ? 0.5 * (double)h->n1 * ((double)h->n1 + 1.0) : (double)h->n1 * (double)h->n2;
     h->st_pairs += per * nframes;
     h->st_frames += nframes;
     return GFN_OK;
@@ -385,7 +386,8 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
     h->frame_doubles = h->off_d2 + (h->need2 ? 3ll * n2 : 0);
 
     // batch size: ~2^33 pair evaluations or 64 MB of frames per batch, whichever is smaller
-    const double per = (n1 == n2) ? 0.5 * (double)n1 * ((double)n1 + 1.0) : (double)n1 * (double)n2;
+    const bool tri_create = (n1 == n2) && !(flags & GFN_FLAG_NO_TRIANGLE);
+    const double per = tri_create ? 0.5 * (double)n1 * ((double)n1 + 1.0) : (double)n1 * (double)n2;
     long long bf = (long long)(8589934592.0 / per);
     const long long by_bytes = (64ll << 20) / (h->frame_doubles * 8);
     if (bf > by_bytes) bf = by_bytes;
@@ -410,7 +412,7 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
         // prefix of surround-tile visits per core tile (the triangle starts at the tile holding the diagonal)
         std::vector<int> start(h->n_itiles + 1, 0);
         for (int t = 0; t < h->n_itiles; ++t) {
-            const int first = (n1 == n2) ? (t * TI) / kTJ : 0;
+            const int first = tri_create ? (t * TI) / kTJ : 0;
             const int tiles = h->n_jtiles - first;
             start[t + 1] = start[t] + (tiles > 0 ? tiles : 0);
         }

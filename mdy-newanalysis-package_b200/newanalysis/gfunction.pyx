@@ -88,7 +88,7 @@ cdef extern from "gfn.h":
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
 
 
-_FLAG_NAMES = {"fp16": 16, "filter_fp16": 16, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
+_FLAG_NAMES = {"no_triangle": 32, "fp16": 16, "filter_fp16": 16, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
 
 
 def _parse_flags(spec):
@@ -481,6 +481,44 @@ cdef class _Backend:
                     hist_mode=("smem_warp_replicas", "global_atomics", "per_particle")[s.hist_mode],
                     warps_per_block=s.warps_per_block, blocks_per_sm=s.blocks_per_sm, grid=s.grid,
                     smem_bytes=s.smem_bytes, batch_frames=s.batch_frames, ndev=s.ndev, hist_replicas=s.hist_replicas)
+
+
+_ts_cache = {}
+
+
+def calcHistoTS(core_xyz, surr_xyz, np.ndarray[np.float64_t, ndim=3] result, double boxl, int t,
+                float histo_min, float histo_max, double invdx):
+    """RDF time series on the GPU: result[t, i, pos] += 1 for every surround site within range of core site i
+    (reference: def calcHistoTS, gfunction.pyx:168-192; cubic box, all n1 x n2 pairs, no dipoles).
+
+    Same signature and result as the reference for in-range bins.  A pair with pos >= nbins (quirk Q3) lands in
+    result[t, i+1, pos-nbins] like the reference's flat index does, except for the last core row, where the
+    reference writes into the next frame's slab (or past the array) and this version drops the pair."""
+    c1 = np.ascontiguousarray(core_xyz, dtype=np.float64)
+    c2 = c1 if surr_xyz is core_xyz else np.ascontiguousarray(surr_xyz, dtype=np.float64)
+    cdef int n1 = c1.shape[0], n2 = c2.shape[0], nb = result.shape[2]
+    if result.shape[1] != n1:
+        raise ValueError("result must have shape (nframes, %d, nbins)" % n1)
+    if t < 0 or t >= result.shape[0]:
+        raise IndexError("frame index out of range")
+    key = (n1, n2, nb, float(np.float32(histo_min)), float(np.float32(histo_max)), float(invdx), float(boxl))
+    be = _ts_cache.get(key)
+    if be is None:
+        if gfn_device_count() < 1:
+            raise RuntimeError("newanalysis.gfunction (B200 backend): no CUDA device available and there is no CPU fallback")
+        if len(_ts_cache) > 8:
+            _ts_cache.clear()
+        be = _Backend()
+        box = np.array([boxl, boxl, boxl, boxl / 2.0, boxl / 2.0, boxl / 2.0], dtype=np.float64)
+        be.open(n1, n2, nb, histo_min, histo_max, invdx, 1, box, [0], 1 | 32)      # per-particle, no triangle
+        _ts_cache[key] = be
+    cdef _Backend b = be
+    b.reset()
+    cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a1 = c1
+    cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a2 = c2
+    b.enqueue(<const double *> a1.data, <const double *> a2.data, NULL, NULL)
+    rows = b.readout_per_particle()[:n1 * nb].reshape(n1, nb)
+    result[t] += rows
 
 
 class RDF(object):

@@ -429,3 +429,22 @@ def test_filter_auto_selection_and_fp16_range_guard():
     g = RDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L, gfn_flags="fp16"); g.calcFrame(c + 1e6 * L, c + 1e6 * L, d, d)
     with pytest.raises(ValueError, match="fp16"):
         g.sync()
+
+
+# ---- N3: RDF time series ------------------------------------------------------------------------------------
+def test_calc_histo_ts_matches_oracle():
+    """calcHistoTS (gfunction.pyx:168-192): per-frame, per-core-site g000 rows; counts are exact."""
+    from newanalysis.gfunction import calcHistoTS
+    n1, n2, nb, L, nf = 150, 400, 240, 30.0, 3
+    rng = np.random.default_rng(41)
+    res = np.zeros((nf, n1, nb)); ref = np.zeros((nf, n1, nb))
+    for t in range(nf):
+        c1 = rng.random((n1, 3)) * L; c2 = rng.random((n2, 3)) * L
+        calcHistoTS(c1, c2, res, L, t, 0.0, 12.0, 20.0)
+        O.calc_histo_ts_c(c1, c2, ref[t], L, 0.0, 12.0, 20.0)
+    assert np.array_equal(res, ref) and ref.sum() > 1000
+    # same selection on both sides: every ordered pair counts once, i == j is rejected by the first-bin rule
+    c = rng.random((200, 3)) * L
+    r2 = np.zeros((1, 200, nb)); o2 = np.zeros((1, 200, nb))
+    calcHistoTS(c, c, r2, L, 0, 0.0, 12.0, 20.0); O.calc_histo_ts_c(c, c, o2[0], L, 0.0, 12.0, 20.0)
+    assert np.array_equal(r2, o2)
