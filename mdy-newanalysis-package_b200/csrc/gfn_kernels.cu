@@ -791,8 +791,18 @@ __global__ void finalize_kernel(const double* __restrict__ partials, int grid, i
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;    // over hn*nslot, layout [bin][slot]
     if (idx >= hn * nslot) return;
     const int bin = idx / nslot, slot = idx - bin * nslot;
+    // blocks are added in ascending order (fixed summation order); loads are issued eight at a time
     double s = 0.0;
-    for (int b = 0; b < grid; ++b) s += partials[(size_t)b * hn * nslot + idx];
+    const size_t stride = (size_t)hn * nslot;
+    int b = 0;
+    for (; b + 8 <= grid; b += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = partials[(size_t)(b + k) * stride + idx];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[k];
+    }
+    for (; b < grid; ++b) s += partials[(size_t)b * stride + idx];
     if (nslot == 1) {                       // g000-only kernels: slot 0 is both g000 and the pair weight
         gacc[bin] += s;
         gacc[7ll * hn + bin] += s;
