@@ -607,6 +607,7 @@ class RDF(object):
         box lengths of the origin (wrapped trajectories); far-away (unwrapped) coordinates keep fp32."""
         self._auto_filter = False
         if self._flags & (2 | 16):
+            self._finish_comm()
             return
         lmax = float(max(self.box_dim[0], self.box_dim[1], self.box_dim[2]))
         if absmax is None:
@@ -614,6 +615,7 @@ class RDF(object):
         if absmax <= 2.0 * lmax and float(self.histo_max) >= 0.04 * lmax:
             self._flags |= 16
             self._open_backend()          # nothing has been enqueued yet
+        self._finish_comm()
 
     # ------------------------------------------------------------------ reference API
     def update_box(self, box_x, box_y, box_z):
@@ -784,6 +786,9 @@ class RDF(object):
 
     def raw_histogram(self):
         """Un-normalised [mode][bin] sums accumulated since the last resetArrays (7*histo_n float64)."""
+        if self._auto_filter and self.ctr == 0:
+            self._auto_filter = False
+        self._finish_comm()
         hist, pw, ovf = self._be.readout()
         self.pair_weight = pw
         self.overflow = ovf
@@ -839,6 +844,7 @@ class RDF(object):
                 self._auto_pick_filter(None, None, max(c1.absmax, c2.absmax))
             else:
                 self._auto_filter = False
+                self._finish_comm()
         self.ctr += nframes
         self.volume_list.extend([self.volume] * nframes)
         self._be.enqueue_device(nframes, c1, c2, d1, d2, boxes, first)
@@ -861,5 +867,16 @@ class RDF(object):
         return self._be.mark_elapsed_ms()
 
     def attach_comm(self, uid, nranks, rank):
-        """One process per GPU: join an NCCL communicator; readout then sums the histograms of all ranks."""
-        self._be.attach_comm(uid, nranks, rank)
+        """One process per GPU: join an NCCL communicator; readout then sums the histograms of all ranks.
+        (A unique id makes exactly one communicator, so while the pre-filter choice is still open - "auto", no
+        frame seen yet - joining is postponed until the backend is final.)"""
+        if self._auto_filter and self.ctr == 0:
+            self._pending_comm = (uid, nranks, rank)
+        else:
+            self._be.attach_comm(uid, nranks, rank)
+
+    def _finish_comm(self):
+        pc = getattr(self, "_pending_comm", None)
+        if pc is not None:
+            self._pending_comm = None
+            self._be.attach_comm(*pc)
