@@ -498,7 +498,7 @@ pair_kernel(const PairParams P)
                         }
                         unsigned m = k == 0 ? m0 : m1;
                         unsigned at = tail + ((excl >> (16 * k)) & 0xffffu);
-                        const unsigned tag = (unsigned)(k * 32 + lane) << 7;
+                        const unsigned tag = ((unsigned)st << 13) | ((unsigned)(k * 32 + lane) << 7);     // stage | core slot | (site below)
                         while (m) {
                             const int jj = __clz(m);
                             m &= ~(0x80000000u >> jj);
@@ -549,38 +549,10 @@ pair_kernel(const PairParams P)
             mbar_wait(&ctrl->ifull, icount & 1);
             ++icount;
 
-            for (int t = 0; t < it.ntiles; ++t) {
-                const unsigned g = tcount + t;
-                const int st = g % S;
-                const int j0 = (it.jt_begin + t) * TJ;
-                mbar_wait(&ctrl->full[st], (g / S) & 1);
-                const Site* js = jsite + st * TJ;
+            int j0s0 = 0, j0s1 = 0, j0s2 = 0;          // first surround index of the tile currently held by stage 0 / 1 / 2
 
-#pragma unroll 1
-                for (int fw = dw; fw < NF; fw += ND) {      // this warp's rings, in this fixed order
-                    const unsigned short* q = rings + fw * kRingCap;
-                    unsigned head = ctrl->head[fw];         // this warp is its only writer
-                    for (;;) {
-                        const bool fin = ctrl->tdone[fw] > g;
-                        __threadfence_block();
-                        const unsigned limit = fin ? ctrl->tend[fw][g & 3] : ctrl->tail[fw];
-                        const unsigned avail = limit - head;
-                        // full batches of 32*kU; the partial one only when the producer has finished the tile, so the
-                        // grouping (and with it the summation order) does not depend on timing.  The ring holds
-                        // kRingCap >= 32*kU-1 + 32*32 entries, so a blocked producer always sees space again.
-                        if (avail < 32u * kU && !(fin && avail > 0u)) {
-                            if (fin) break;
-                            // a ring fills at a few entries per microsecond: sleep long enough that polling does not
-                            // steal issue slots from the filter warps of this sub-partition
-                            // (one nanosleep returns after well under 100 ns on B200 whatever its argument, and a poll
-                            // is ~15 instructions with three shared-memory reads: chain several sleeps per poll)
-#pragma unroll 1
-                            for (int z = P.poll_reps; z > 0; --z) __nanosleep(P.poll_ns);
-                            continue;
-                        }
-                        __threadfence_block();
-                        const int n = (int)min(avail, 32u * kU);
-
+            // ---- one batch: n <= 32*kU entries of ring fw starting at ring position head ------------------------
+            auto process_batch = [&](const unsigned short* q, const int fw, const unsigned head, const int n) {
                         // ---- exact evaluation: kU survivors per lane, branch-free so that ptxas interleaves
                         //      the dependent fp64 chains of all of them ---------------------------------------
                         bool ok[kU]; int pos[kU], gi[kU]; double w[kU], v[kU][6];
@@ -592,8 +564,10 @@ pair_kernel(const PairParams P)
                             const int idx = lane + 32 * u;
                             const bool have = idx < n;
                             const unsigned e = have ? q[(head + idx) & RMASK] : 0u;
-                            const int il = fw * (32 * kIPT) + (int)(e >> 7), jl = e & 127;
-                            const int i = it.i0 + il, j = j0 + jl;
+                            const int il = fw * (32 * kIPT) + (int)((e >> 7) & 63u), jl = e & 127;
+                            const int stg = (int)(e >> 13);
+                            const Site* js = jsite + stg * TJ;
+                            const int i = it.i0 + il, j = (stg == 0 ? j0s0 : (stg == 1 ? j0s1 : j0s2)) + jl;
                             gi[u] = i;
                             self_pair[u] = (i == j);
                             ok[u] = have && i < P.n1 && j < P.n2 && !(P.tri && j < i);
@@ -680,8 +654,7 @@ pair_kernel(const PairParams P)
                                 for (int k = 0; k < 6; ++k) v[u][k] = 0.0;
                         }
                         __syncwarp();
-                        head += (unsigned)n;
-                        if (lane == 0) ctrl->head[fw] = head;       // entries are in registers: the producer may reuse them
+                        if (lane == 0) ctrl->head[fw] = head + (unsigned)n;     // entries are in registers: the producer may reuse them
 
                         // ---- accumulate ----------------------------------------------------------------------
 #pragma unroll
@@ -739,9 +712,84 @@ pair_kernel(const PairParams P)
                                 }
                             }
                         }
+            };
+
+            if (ND == 8) {
+                // ---- one ring per drain warp: batches may span tile boundaries (entries carry their stage), so the
+                //      only partial batches are the ones needed to let a stage go.  Tile t_rel is released once all
+                //      its entries are evaluated; it must be flushed when the filter has finished the tile after it
+                //      (it will soon need the stage) or the run is over. ------------------------------------------------
+                const int fw = dw;
+                const unsigned short* q = rings + fw * kRingCap;
+                unsigned head = ctrl->head[fw];
+                int t_wait = 0, t_rel = 0;
+                for (;;) {
+                    int td = (int)(ctrl->tdone[fw] - tcount);           // tiles of this run the filter has finished
+                    td = td < 0 ? 0 : (td > it.ntiles ? it.ntiles : td);
+                    __threadfence_block();
+                    const unsigned tail_now = ctrl->tail[fw];
+                    const unsigned avail = tail_now - head;
+                    // stage data of every tile that may have entries in the ring: finished ones and the one in progress
+                    // (never beyond t_rel + S - 1: a later tile is only loaded after this warp has released t_rel)
+                    while (t_wait < it.ntiles && t_wait <= td && t_wait < t_rel + S) {
+                        const unsigned g = tcount + t_wait;
+                        mbar_wait(&ctrl->full[g % S], (g / S) & 1);
+                        const int j0 = (it.jt_begin + t_wait) * TJ;
+                        if (g % S == 0) j0s0 = j0; else if (g % S == 1) j0s1 = j0; else j0s2 = j0;
+                        ++t_wait;
                     }
+                    bool flush = false;
+                    if (t_rel < it.ntiles && td > t_rel && (td >= t_rel + 2 || td == it.ntiles))
+                        flush = (int)(ctrl->tend[fw][(tcount + t_rel) & 3] - head) > 0;
+                    if (avail >= 32u * kU || (flush && avail > 0u)) {
+                        __threadfence_block();
+                        const int n = (int)min(avail, 32u * kU);
+                        process_batch(q, fw, head, n);
+                        head += (unsigned)n;
+                    } else if (!(t_rel < it.ntiles && td > t_rel && (int)(head - ctrl->tend[fw][(tcount + t_rel) & 3]) >= 0)) {
+                        if (t_rel == it.ntiles) break;
+#pragma unroll 1
+                        for (int z = P.poll_reps; z > 0; --z) __nanosleep(P.poll_ns);
+                        continue;
+                    }
+                    while (t_rel < it.ntiles && td > t_rel && (int)(head - ctrl->tend[fw][(tcount + t_rel) & 3]) >= 0) {
+                        release_stage(ctrl, jsite, siteB, (int)((tcount + t_rel) % S), NW, t_rel, it.ntiles, it.jt_begin, lane);
+                        ++t_rel;
+                    }
+                    if (t_rel == it.ntiles) break;
                 }
-                release_stage(ctrl, jsite, siteB, st, NW, t, it.ntiles, it.jt_begin, lane);
+            } else {
+                // ---- several rings per drain warp: tile by tile, ring after ring, the rest of a ring's tile as a
+                //      partial batch (fixed grouping, no carry-over) ------------------------------------------------
+                for (int t = 0; t < it.ntiles; ++t) {
+                    const unsigned g = tcount + t;
+                    const int st = g % S;
+                    mbar_wait(&ctrl->full[st], (g / S) & 1);
+                    const int j0 = (it.jt_begin + t) * TJ;
+                    if (st == 0) j0s0 = j0; else if (st == 1) j0s1 = j0; else j0s2 = j0;
+#pragma unroll 1
+                    for (int fw = dw; fw < NF; fw += ND) {      // this warp's rings, in this fixed order
+                        const unsigned short* q = rings + fw * kRingCap;
+                        unsigned head = ctrl->head[fw];         // this warp is its only writer
+                        for (;;) {
+                            const bool fin = ctrl->tdone[fw] > g;
+                            __threadfence_block();
+                            const unsigned limit = fin ? ctrl->tend[fw][g & 3] : ctrl->tail[fw];
+                            const unsigned avail = limit - head;
+                            if (avail < 32u * kU && !(fin && avail > 0u)) {
+                                if (fin) break;
+#pragma unroll 1
+                                for (int z = P.poll_reps; z > 0; --z) __nanosleep(P.poll_ns);
+                                continue;
+                            }
+                            __threadfence_block();
+                            const int n = (int)min(avail, 32u * kU);
+                            process_batch(q, fw, head, n);
+                            head += (unsigned)n;
+                        }
+                    }
+                    release_stage(ctrl, jsite, siteB, st, NW, t, it.ntiles, it.jt_begin, lane);
+                }
             }
             tcount += it.ntiles;
         }
