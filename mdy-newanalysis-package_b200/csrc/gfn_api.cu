@@ -199,7 +199,7 @@ void fill_params(gfn_t* h, Dev& d, PairParams& p)
     p.partials = d.partials; p.gacc = d.gacc; p.gpp = d.gpp; p.counters = d.counters;
     p.flags = h->flags;
     p.nrep = d.cfg.nrep;
-    p.poll_ns = 400; p.poll_reps = 1;
+    p.poll_ns = 120; p.poll_reps = 1;
     if (const char* e = getenv("GFN_POLL_NS")) p.poll_ns = (unsigned)atoi(e);
     if (const char* e = getenv("GFN_POLL_REPS")) p.poll_reps = atoi(e);
     p.strideA = h->n1_pad; p.strideB = h->n2_pad;

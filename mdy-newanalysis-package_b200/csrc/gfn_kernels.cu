@@ -385,21 +385,22 @@ pair_kernel(const PairParams P)
             typedef typename std::conditional<kH16, float, F>::type FS;          // scalar type of the non-half paths
             FS Tg = 0, hxf = 0, hyf = 0, hzf = 0;
             FS cx[kIPT], cy[kIPT], cz[kIPT];
-            __half2 hTg, hhx, hhy, hhz, hcx, hcy, hcz;
+            __half2 hTg, hLx, hLy, hLz, hcx, hcy, hcz;
             if (kH16) {
                 const double S = fmax(b[0], fmax(b[1], b[2])), invS = 1.0 / S;
                 const double u = FOps<__half>::kU;
-                // component error of the fp16 fold for pairs near the cut-off (tight form):
-                //   e_w <= u (2 M' + 5 h' + 3 hmax') + O(u^2)   (primes: in units of S; M' enters only through the
-                //   rounding of the two coordinates because an in-range pair has |dx'| <= 2h' + hmax')
+                // component error of the fp16 fold min(|d|, L - |d|) for pairs near the cut-off:
+                //   e_w <= u (2 M' + 4 h' + 2 hmax') + O(u^2)   (primes: in units of S; 2M': rounding of the two
+                //   coordinates; 2h' + hmax' >= |d'| of an in-range pair: rounding of d; 2h': rounding of L';
+                //   hmax': rounding of L - |d| when it is not exact)
                 const double hm = P.hmax * invS;
-                const double ew = u * (2.1 * M * invS + 5.2 * fmax(b[3], fmax(b[4], b[5])) * invS + 3.2 * hm);
+                const double ew = u * (2.1 * M * invS + 4.2 * fmax(b[3], fmax(b[4], b[5])) * invS + 2.2 * hm);
                 const double T = (hm * hm * (1.0 + 1e-12) + 3.5 * ew * hm + 3.0 * ew * ew + 4.0 * 5.9604644775390625e-08) * (1.0 + 8.0 * u);
                 __half th = __double2half(T);
                 if (__half2float(th) <= (float)T) th = __ushort_as_half((unsigned short)(__half_as_ushort(th) + 1));   // round up
                 hTg = __halves2half2(__hneg(th), __hneg(th));
-                const __half a = __double2half(b[3] * invS), bq = __double2half(b[4] * invS), cq = __double2half(b[5] * invS);
-                hhx = __halves2half2(a, a); hhy = __halves2half2(bq, bq); hhz = __halves2half2(cq, cq);
+                const __half a = __double2half(b[0] * invS), bq = __double2half(b[1] * invS), cq = __double2half(b[2] * invS);
+                hLx = __halves2half2(a, a); hLy = __halves2half2(bq, bq); hLz = __halves2half2(cq, cq);
                 const Site* c0 = siteA + it.i0 + warp * (32 * kIPT) + lane;
                 const Site* c1 = c0 + 32;
                 const unsigned x0 = __float_as_uint(c0->fx), y0 = __float_as_uint(c0->fy), z0 = __float_as_uint(c0->fz);
@@ -443,9 +444,13 @@ pair_kernel(const PairParams P)
                             const uint4 s4 = *reinterpret_cast<const uint4*>(&js[jbase + jj].fx);
                             const __half2 sx = *reinterpret_cast<const __half2*>(&s4.x), sy = *reinterpret_cast<const __half2*>(&s4.y), sz = *reinterpret_cast<const __half2*>(&s4.z);
                             const __half2 dx = __hsub2(sx, hcx), dy = __hsub2(sy, hcy), dz = __hsub2(sz, hcz);
-                            const __half2 wx = __hsub2(hhx, __habs2(__hsub2(__habs2(dx), hhx)));
-                            const __half2 wy = __hsub2(hhy, __habs2(__hsub2(__habs2(dy), hhy)));
-                            const __half2 wz = __hsub2(hhz, __habs2(__hsub2(__habs2(dz), hhz)));
+                            // |w| = min(|d|, L - |d|) squared equals the single-shift minimum image squared for every d
+                            // (L - |d| < 0 beyond one box length, where the reference leaves |d| - L); L - |d| is exact
+                            // whenever it is small (Sterbenz).  The min runs on the ALU pipe, off the fp16 pipe.
+                            const __half2 ax = __habs2(dx), ay = __habs2(dy), az = __habs2(dz);
+                            const __half2 wx = __hmin2(ax, __hsub2(hLx, ax));
+                            const __half2 wy = __hmin2(ay, __hsub2(hLy, ay));
+                            const __half2 wz = __hmin2(az, __hsub2(hLz, az));
                             const __half2 tt = __hfma2(wz, wz, __hfma2(wy, wy, __hfma2(wx, wx, hTg)));
                             const unsigned tb = *reinterpret_cast<const unsigned*>(&tt);
                             acc[jj >> 4] |= (tb >> (jj & 15)) & (0x80008000u >> (jj & 15));
@@ -723,8 +728,17 @@ pair_kernel(const PairParams P)
                 const unsigned short* q = rings + fw * kRingCap;
                 unsigned head = ctrl->head[fw];
                 int t_wait = 0, t_rel = 0;
+                unsigned seen_td = 0xffffffffu;     // tdone at which the full check below last found nothing to do
                 for (;;) {
-                    int td = (int)(ctrl->tdone[fw] - tcount);           // tiles of this run the filter has finished
+                    const unsigned td_raw = ctrl->tdone[fw];
+                    if (td_raw == seen_td) {
+                        // fast poll: with tdone and head unchanged, only a full batch can give this warp work.
+                        // The back-off follows the deficit (survivors arrive every few tens of ns).
+                        const unsigned a = ctrl->tail[fw] - head;
+                        if (a < 32u * kU) { __nanosleep(min((32u * kU - a) * P.poll_ns, 4000u)); continue; }
+                    }
+                    seen_td = 0xffffffffu;
+                    int td = (int)(td_raw - tcount);                    // tiles of this run the filter has finished
                     td = td < 0 ? 0 : (td > it.ntiles ? it.ntiles : td);
                     __threadfence_block();
                     const unsigned tail_now = ctrl->tail[fw];
@@ -748,8 +762,8 @@ pair_kernel(const PairParams P)
                         head += (unsigned)n;
                     } else if (!(t_rel < it.ntiles && td > t_rel && (int)(head - ctrl->tend[fw][(tcount + t_rel) & 3]) >= 0)) {
                         if (t_rel == it.ntiles) break;
-#pragma unroll 1
-                        for (int z = P.poll_reps; z > 0; --z) __nanosleep(P.poll_ns);
+                        seen_td = td_raw;
+                        __nanosleep(min((32u * kU - min(avail, 32u * kU - 1u)) * P.poll_ns, 4000u));
                         continue;
                     }
                     while (t_rel < it.ntiles && td > t_rel && (int)(head - ctrl->tend[fw][(tcount + t_rel) & 3]) >= 0) {
@@ -779,7 +793,7 @@ pair_kernel(const PairParams P)
                             if (avail < 32u * kU && !(fin && avail > 0u)) {
                                 if (fin) break;
 #pragma unroll 1
-                                for (int z = P.poll_reps; z > 0; --z) __nanosleep(P.poll_ns);
+                                for (int z = P.poll_reps; z > 0; --z) __nanosleep(P.poll_ns * 10u);
                                 continue;
                             }
                             __threadfence_block();
