@@ -482,36 +482,47 @@ pair_kernel(const PairParams P)
                             }
                         }
                     }
-                    // ---- publish survivors into this warp's ring (one packed scan for both core slots) ----
+                    // ---- publish survivors into this warp's ring: warp-uniform rounds, one survivor per lane and
+                    //      core slot per round, compacted with ballots (no scan, no divergent loops).  Ring order:
+                    //      round, core slot, lane - fixed, so the summation order stays deterministic. ----
                     if (!__any_sync(0xffffffffu, (m0 | m1) != 0u)) continue;
-                    const unsigned cnt2 = (unsigned)__popc(m0) | ((unsigned)__popc(m1) << 16);
-                    unsigned incl = cnt2;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += up;
-                    }
-                    const unsigned tot2 = __shfl_sync(0xffffffffu, incl, 31);
-                    const unsigned excl = incl - cnt2;
-#pragma unroll
-                    for (int k = 0; k < kIPT; ++k) {
-                        const unsigned total = (tot2 >> (16 * k)) & 0xffffu;
-                        if (total == 0) continue;
-                        while (tail + total - head_seen > (unsigned)kRingCap) {      // ring full: wait for the drain warp
-                            head_seen = ctrl->head[warp];
-                            if (tail + total - head_seen > (unsigned)kRingCap) __nanosleep(64);
+                    {
+                        unsigned total = __reduce_add_sync(0xffffffffu, (unsigned)(__popc(m0) + __popc(m1)));
+                        unsigned hold1 = 0u;
+                        // a push must fit behind a partial batch the drain warp is still waiting to fill (< 32*kU unread
+                        // entries): at most half the ring at once, so a dense chunk goes in two pushes
+                        if (total > (unsigned)kRingCap / 2u) { hold1 = m1; m1 = 0u; total = __reduce_add_sync(0xffffffffu, (unsigned)__popc(m0)); }
+                        const unsigned lt = (1u << lane) - 1u;
+                        const unsigned tag0 = ((unsigned)st << 13) | ((unsigned)lane << 7) | (unsigned)jbase;   // stage | core slot | site
+                        const unsigned tag1 = tag0 | (32u << 7);
+                        for (;;) {
+                            while (tail + total - head_seen > (unsigned)kRingCap) {      // ring full: wait for the drain warp
+                                head_seen = ctrl->head[warp];
+                                if (tail + total - head_seen > (unsigned)kRingCap) __nanosleep(64);
+                            }
+                            for (;;) {
+                                const unsigned b0 = __ballot_sync(0xffffffffu, m0 != 0u);
+                                const unsigned b1 = __ballot_sync(0xffffffffu, m1 != 0u);
+                                if ((b0 | b1) == 0u) break;
+                                if (m0) {
+                                    const int jj = __clz(m0);
+                                    m0 &= ~(0x80000000u >> jj);
+                                    q[(tail + __popc(b0 & lt)) & RMASK] = (unsigned short)(tag0 + (unsigned)jj);
+                                }
+                                tail += __popc(b0);
+                                if (m1) {
+                                    const int jj = __clz(m1);
+                                    m1 &= ~(0x80000000u >> jj);
+                                    q[(tail + __popc(b1 & lt)) & RMASK] = (unsigned short)(tag1 + (unsigned)jj);
+                                }
+                                tail += __popc(b1);
+                            }
+                            __syncwarp();
+                            if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
+                            if (!__any_sync(0xffffffffu, hold1 != 0u)) break;
+                            m1 = hold1; hold1 = 0u;
+                            total = __reduce_add_sync(0xffffffffu, (unsigned)__popc(m1));
                         }
-                        unsigned m = k == 0 ? m0 : m1;
-                        unsigned at = tail + ((excl >> (16 * k)) & 0xffffu);
-                        const unsigned tag = ((unsigned)st << 13) | ((unsigned)(k * 32 + lane) << 7);     // stage | core slot | (site below)
-                        while (m) {
-                            const int jj = __clz(m);
-                            m &= ~(0x80000000u >> jj);
-                            q[(at++) & RMASK] = (unsigned short)(tag | (unsigned)(jbase + jj));
-                        }
-                        tail += total;
-                        __syncwarp();
-                        if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
                     }
                 }
                 // ---- tile finished: tell the drain warp where it ends, release the stage ----------------
