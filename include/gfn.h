@@ -122,6 +122,35 @@ int gfn_enqueue_device_frames(gfn_t *h, int nframes,
                               const double *box_dims);
 
 /* Submit a partially filled batch (asynchronous). */
+/* ---- N2: shell-resolved g-functions -------------------------------------------------
+ * Replaces cdef void calcHistoVoronoi / calcHistoVoronoiNonSelf (gfunction.pyx:570-664, :667-761; call site
+ * RDF_voronoi.calcFrame :1009-1021) and def calcHistoTSVoro (:195-224).  The pair loop is the one of calcHisto;
+ * each in-range pair additionally reads its shell from an int32 matrix that travels with the frame, and the
+ * histogram rows hold histo_n * nshells bins.
+ *   layout 1 (RDF_voronoi):     bin = pos*nshells + shell, shell = map[(i/apr_core)*map_ld + j/apr_surround] - 1,
+ *                               values outside [0, nshells) go to the last shell (:602-605); the reference passes
+ *                               map_ld = nsurround (:602, "Correctly shaped?")
+ *   layout 2 (calcHistoTSVoro): bin = shell*histo_n + pos, shell = min(map[i*map_ld + j], nshells) - 1, a negative
+ *                               index wraps once like Cython's wraparound indexing (:219-224)
+ * map_elems is the number of ints of one frame's matrix; it must cover the largest index the loop can form,
+ * (ceil(n1/apr_core)-1)*map_ld + ceil(n2/apr_surround) (the reference would read out of bounds otherwise).
+ * Handles created here take frames only through gfn_enqueue_frames_shells; readout sizes use
+ * histo_n*nshells bins per row.  exclude_self != 0 skips pairs with i/apr_core == j/apr_surround (:700). */
+typedef struct gfn_shell_cfg {
+    int nshells, layout;
+    int apr_core, apr_surround;
+    int map_ld;
+    long long map_elems;
+    int exclude_self;
+} gfn_shell_cfg;
+int gfn_create_shells(gfn_t **out, int n1, int n2, int histo_n, float histo_min, float histo_max,
+                      double inv_dr, int mode_sel, const double box_dim[6], const int *devices, int ndev,
+                      unsigned flags, const gfn_shell_cfg *cfg);
+int gfn_enqueue_frames_shells(gfn_t *h, int nframes,
+                              const double *c1, long long s_c1, const double *c2, long long s_c2,
+                              const double *d1, long long s_d1, const double *d2, long long s_d2,
+                              const double *box_dims, const int *shell_map, long long s_map);
+
 int gfn_flush(gfn_t *h);
 /* Flush and wait for every submitted frame; reports deferred GFN_EZERODIV. */
 int gfn_sync(gfn_t *h);

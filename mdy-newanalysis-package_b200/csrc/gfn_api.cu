@@ -123,7 +123,10 @@ struct Dev {
 }  // namespace
 
 struct gfn_handle {
-    int n1, n2, histo_n, mode_sel;
+    int n1, n2, histo_n, mode_sel;   // histo_n: bins per histogram row (radial bins x shells)
+    int histo_nr = 0;                // radial bins
+    gfn_shell_cfg shells = {0, 0, 1, 1, 0, 0, 0};   // layout 0: plain g-functions
+    long long off_map = 0;           // offset (doubles) of the shell matrix inside a frame
     float hmin_f, hmax_f;
     double inv_dr;
     double box[6];
@@ -203,6 +206,8 @@ void fill_params(gfn_t* h, Dev& d, PairParams& p)
     if (const char* e = getenv("GFN_POLL_NS")) p.poll_ns = (unsigned)atoi(e);
     if (const char* e = getenv("GFN_POLL_REPS")) p.poll_reps = atoi(e);
     p.strideA = h->n1_pad; p.strideB = h->n2_pad;
+    p.shell_mode = h->shells.layout; p.nshells = h->shells.nshells; p.histo_nr = h->histo_nr;
+    p.apr1 = h->shells.apr_core; p.apr2 = h->shells.apr_surround; p.map_ld = h->shells.map_ld; p.excl_self = h->shells.exclude_self;
 }
 
 // prep + pair + finalize for nframes frames whose raw arrays are on the device
@@ -210,7 +215,7 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
                   const double* c1, long long s_c1, const double* d1, long long s_d1,
                   const double* c2, long long s_c2, const double* d2, long long s_d2, bool aliased,
                   Site* siteA, Site* siteB, float* maxab, const double* d_box,
-                  cudaEvent_t k0, cudaEvent_t k1)
+                  cudaEvent_t k0, cudaEvent_t k1, const int* d_map = nullptr, long long s_map = 0)
 {
     cudaStream_t s = d.comp;
     CU(cudaMemsetAsync(maxab, 0, sizeof(float) * 2 * nframes, s));
@@ -226,6 +231,7 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
     p.siteA = siteA; p.maxA = maxab;
     p.siteB = aliased ? siteA : siteB; p.maxB = aliased ? maxab : maxab + nframes;
     p.box = d_box; p.nframes = nframes;
+    p.shell_map = d_map; p.stride_map = s_map;
     CU(cudaEventRecord(k0, s));
     CU(pair_launch(d.cfg, p, s));
     CU(cudaEventRecord(k1, s));
@@ -256,7 +262,8 @@ int submit(gfn_t* h, Dev& d)
     int rc = launch_frames(h, d, b.nframes,
                            b.d_raw + h->off_c1, fd, b.d_raw + h->off_d1, fd,
                            b.d_raw + h->off_c2, fd, b.d_raw + h->off_d2, fd, b.aliased,
-                           b.siteA, b.siteB, b.maxab, b.d_box, b.k0, b.k1);
+                           b.siteA, b.siteB, b.maxab, b.d_box, b.k0, b.k1,
+                           h->shells.layout ? reinterpret_cast<const int*>(b.d_raw + h->off_map) : nullptr, 2 * fd);
     if (rc) return rc;
     b.timed = true;
     CU(cudaEventRecord(b.done, d.comp));
@@ -341,10 +348,23 @@ int gfn_device_count(void)
 
 const char* gfn_last_error(const gfn_t* h) { return h ? h->err : g_create_err; }
 
-int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float histo_max,
-               double inv_dr, int mode_sel, const double box_dim[6], const int* devices, int ndev, unsigned flags)
+static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_min, float histo_max,
+                       double inv_dr, int mode_sel, const double box_dim[6], const int* devices, int ndev, unsigned flags,
+                       const gfn_shell_cfg* sc)
 {
     gfn_t* h = nullptr;
+    int histo_n = histo_nr;
+    if (sc) {
+        if (sc->layout != 1 && sc->layout != 2) return fail(h, GFN_EINVAL, "shell layout must be 1 ([bin][shell]) or 2 ([shell][bin])");
+        if (sc->nshells < 1) return fail(h, GFN_EINVAL, "nshells must be >= 1 (got %d)", sc->nshells);
+        if (sc->apr_core < 1 || sc->apr_surround < 1)
+            return fail(h, GFN_EINVAL, "sites per molecule must be >= 1 (got %d, %d): more molecules than sites", sc->apr_core, sc->apr_surround);
+        if (histo_nr >= 1 && (long long)histo_nr * sc->nshells > 2000000000ll / 8) return fail(h, GFN_EINVAL, "histo_n * nshells too large");
+        const long long need = (long long)((n1 + sc->apr_core - 1) / sc->apr_core - 1) * sc->map_ld + (n2 + sc->apr_surround - 1) / sc->apr_surround;
+        if (sc->map_ld < 1 || sc->map_elems < need)
+            return fail(h, GFN_EINVAL, "shell matrix too small: the pair loop indexes up to element %lld (row stride %d), the matrix has %lld", need - 1, sc->map_ld, sc->map_elems);
+        histo_n = histo_nr * sc->nshells;
+    }
     if (!out) return fail(h, GFN_EINVAL, "out is NULL");
     *out = nullptr;
     if (n1 < 1 || n2 < 1) return fail(h, GFN_EINVAL, "selection sizes must be >= 1 (got %d, %d)", n1, n2);
@@ -375,6 +395,8 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
     h->n1 = n1; h->n2 = n2; h->histo_n = histo_n; h->mode_sel = mode_sel;
     h->hmin_f = histo_min; h->hmax_f = histo_max; h->inv_dr = inv_dr; h->flags = flags;
     memcpy(h->box, box_dim, sizeof(h->box));
+    h->histo_nr = histo_nr;
+    if (sc) h->shells = *sc;
     h->need1 = mode_sel & (2 | 4 | 16 | 32);       // gfunction.pyx:121 / :411
     h->need2 = mode_sel & (2 | 8 | 16 | 64);       // gfunction.pyx:135 / :414
     h->n1_pad = (n1 + kPadTo - 1) / kPadTo * kPadTo;
@@ -384,6 +406,7 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
     h->off_c2 = h->off_d1 + (h->need1 ? 3ll * n1 : 0);
     h->off_d2 = h->off_c2 + 3ll * n2;
     h->frame_doubles = h->off_d2 + (h->need2 ? 3ll * n2 : 0);
+    if (sc) { h->off_map = h->frame_doubles; h->frame_doubles += (sc->map_elems + 1) / 2; }
 
     // batch size: ~2^33 pair evaluations or 64 MB of frames per batch, whichever is smaller
     const bool tri_create = (n1 == n2) && !(flags & GFN_FLAG_NO_TRIANGLE);
@@ -466,6 +489,20 @@ int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float 
     return GFN_OK;
 }
 
+int gfn_create(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float histo_max,
+               double inv_dr, int mode_sel, const double box_dim[6], const int* devices, int ndev, unsigned flags)
+{
+    return create_impl(out, n1, n2, histo_n, histo_min, histo_max, inv_dr, mode_sel, box_dim, devices, ndev, flags, nullptr);
+}
+
+int gfn_create_shells(gfn_t** out, int n1, int n2, int histo_n, float histo_min, float histo_max,
+                      double inv_dr, int mode_sel, const double box_dim[6], const int* devices, int ndev, unsigned flags,
+                      const gfn_shell_cfg* cfg)
+{
+    if (!cfg) return fail(nullptr, GFN_EINVAL, "cfg is NULL");
+    return create_impl(out, n1, n2, histo_n, histo_min, histo_max, inv_dr, mode_sel, box_dim, devices, ndev, flags, cfg);
+}
+
 int gfn_update_box(gfn_t* h, const double box_dim[6])
 {
     if (!h || !box_dim) return fail(h, GFN_EINVAL, "NULL argument");
@@ -475,16 +512,19 @@ int gfn_update_box(gfn_t* h, const double box_dim[6])
     return GFN_OK;
 }
 
-int gfn_enqueue_frames(gfn_t* h, int nframes,
+static int enqueue_impl(gfn_t* h, int nframes,
                        const double* c1, long long s_c1, const double* c2, long long s_c2,
-                       const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims)
+                       const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims,
+                       const int* shell_map, long long s_map)
 {
     if (!h) return GFN_EINVAL;
+    if (h->shells.layout && !shell_map) return fail(h, GFN_EINVAL, "this handle resolves shells: frames need a shell matrix (gfn_enqueue_frames_shells)");
+    if (!h->shells.layout && shell_map) return fail(h, GFN_EINVAL, "this handle was not created with gfn_create_shells");
     if (nframes < 0) return fail(h, GFN_EINVAL, "nframes < 0");
     if (!c1 || !c2) return fail(h, GFN_EINVAL, "coordinate array is NULL");
     if (h->need1 && !d1) return fail(h, GFN_EINVAL, "No dipole moment array for the first selection was passed, although the requested gfunctions need it");
     if (h->need2 && !d2) return fail(h, GFN_EINVAL, "No dipole moment array for the second selection was passed, although the requested gfunctions need it");
-    const bool aliased = (c2 == c1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || d2 == d1) && (!h->need2 || h->need1);
+    const bool aliased = !h->shells.layout && (c2 == c1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || d2 == d1) && (!h->need2 || h->need1);
     for (int f = 0; f < nframes; ++f) {
         Dev& d = h->devs[h->next_dev];
         Batch* b = &d.ring[d.cur];
@@ -510,6 +550,7 @@ int gfn_enqueue_frames(gfn_t* h, int nframes,
             memcpy(dst + h->off_c2, c2 + s_c2 * f, sizeof(double) * 3 * h->n2);
             if (h->need2) memcpy(dst + h->off_d2, d2 + s_d2 * f, sizeof(double) * 3 * h->n2);
         }
+        if (shell_map) memcpy(dst + h->off_map, shell_map + s_map * f, sizeof(int) * (size_t)h->shells.map_elems);
         memcpy(b->h_box + 6ll * b->nframes, box_dims ? box_dims + 6ll * f : h->box, sizeof(double) * 6);
         b->nframes++;
         bool go = b->nframes == h->batch_frames;
@@ -529,6 +570,22 @@ int gfn_enqueue_frames(gfn_t* h, int nframes,
     return GFN_OK;
 }
 
+int gfn_enqueue_frames(gfn_t* h, int nframes,
+                       const double* c1, long long s_c1, const double* c2, long long s_c2,
+                       const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims)
+{
+    return enqueue_impl(h, nframes, c1, s_c1, c2, s_c2, d1, s_d1, d2, s_d2, box_dims, nullptr, 0);
+}
+
+int gfn_enqueue_frames_shells(gfn_t* h, int nframes,
+                              const double* c1, long long s_c1, const double* c2, long long s_c2,
+                              const double* d1, long long s_d1, const double* d2, long long s_d2,
+                              const double* box_dims, const int* shell_map, long long s_map)
+{
+    if (h && !shell_map) return fail(h, GFN_EINVAL, "shell matrix is NULL");
+    return enqueue_impl(h, nframes, c1, s_c1, c2, s_c2, d1, s_d1, d2, s_d2, box_dims, shell_map, s_map);
+}
+
 int gfn_enqueue_frame(gfn_t* h, const double* c1, const double* c2, const double* d1, const double* d2)
 {
     return gfn_enqueue_frames(h, 1, c1, 0, c2, 0, d1, 0, d2, 0, nullptr);
@@ -543,6 +600,7 @@ int gfn_enqueue_device_frames(gfn_t* h, int nframes,
     if (!dc1 || !dc2) return fail(h, GFN_EINVAL, "coordinate array is NULL");
     if (h->need1 && !dd1) return fail(h, GFN_EINVAL, "dipoles of the first selection are required by mode_sel");
     if (h->need2 && !dd2) return fail(h, GFN_EINVAL, "dipoles of the second selection are required by mode_sel");
+    if (h->shells.layout) return fail(h, GFN_EINVAL, "shell-resolved handles take host frames (gfn_enqueue_frames_shells)");
     Dev& d = h->devs[0];
     CU(cudaSetDevice(d.dev));
     const bool aliased = (dc2 == dc1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || dd2 == dd1) && (!h->need2 || h->need1);

@@ -571,7 +571,7 @@ pair_kernel(const PairParams P)
             auto process_batch = [&](const unsigned short* q, const int fw, const unsigned head, const int n) {
                         // ---- exact evaluation: kU survivors per lane, branch-free so that ptxas interleaves
                         //      the dependent fp64 chains of all of them ---------------------------------------
-                        bool ok[kU]; int pos[kU], gi[kU]; double w[kU], v[kU][6];
+                        bool ok[kU]; int pos[kU], gi[kU], gj[kU]; double w[kU], v[kU][6];
                         double dxa[kU], dya[kU], dza[kU], d2[kU], dist[kU];
                         double apx[kU], apy[kU], apz[kU], an[kU], bpx[kU], bpy[kU], bpz[kU], bn[kU];
                         bool self_pair[kU];
@@ -584,7 +584,7 @@ pair_kernel(const PairParams P)
                             const int stg = (int)(e >> 13);
                             const Site* js = jsite + stg * TJ;
                             const int i = it.i0 + il, j = (stg == 0 ? j0s0 : (stg == 1 ? j0s1 : j0s2)) + jl;
-                            gi[u] = i;
+                            gi[u] = i; gj[u] = j;
                             self_pair[u] = (i == j);
                             ok[u] = have && i < P.n1 && j < P.n2 && !(P.tri && j < i);
                             const double2* ap = reinterpret_cast<const double2*>(isite + il);
@@ -623,8 +623,29 @@ pair_kernel(const PairParams P)
                             ok[u] = ok[u] && dist[u] >= P.hmin && !(dist[u] > P.hmax) && !(DMUL(dist[u], P.invdx) < 1.0);
                             pos[u] = __double2int_rd(DMUL(DSUB(dist[u], P.hmin), P.invdx));
                             w[u] = (P.tri && !self_pair[u]) ? 2.0 : 1.0;
-                            n_inr += ok[u] ? 1u : 0u;
                         }
+                        if (P.shell_mode) {
+                            // shell-resolved rows: the bin index gains the shell read from this frame's matrix
+                            const int* map = P.shell_map + (long long)it.f * P.stride_map;
+#pragma unroll
+                            for (int u = 0; u < kU; ++u) {
+                                const int r = gi[u] / P.apr1, c = gj[u] / P.apr2;
+                                if (P.excl_self && r == c) ok[u] = false;                                  // :700
+                                int sh = ok[u] ? __ldg(map + (long long)r * P.map_ld + c) : 1;             // :602
+                                if (P.shell_mode == 1) {
+                                    sh -= 1;                                                               // :603
+                                    if (sh < 0 || sh >= P.nshells) sh = P.nshells - 1;                     // :604-605
+                                    pos[u] = pos[u] * P.nshells + sh;                                      // :648-651
+                                } else {
+                                    sh = (sh > P.nshells ? P.nshells : sh) - 1;                            // :220-222
+                                    if (sh < 0) sh += P.nshells;                                           // negative index wraps (Cython wraparound)
+                                    if (sh < 0) { ok[u] = false; sh = 0; }
+                                    pos[u] = sh * P.histo_nr + pos[u];                                     // :224
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) n_inr += ok[u] ? 1u : 0u;
                         if (WEIGHTS) {
                             // --- orientation weights :154-165, all three cosines (unselected ones are masked below)
                             double den[kU][3], num[kU][3], c[kU][3];

@@ -47,6 +47,16 @@ struct PairParams {
     unsigned flags;                 // GFN_FLAG_DISCARD_OVERFLOW
     int nrep;                       // histogram replicas in shared memory
     unsigned poll_ns; int poll_reps; // drain-warp back-off while its ring holds less than a batch
+    // shell-resolved histograms (N2: RDF_voronoi gfunction.pyx:570-1148, calcHistoTSVoro :195-224); shell_mode 0 = off.
+    // histo_n above counts ALL bins of a row (radial bins x shells); histo_nr is the number of radial bins.
+    const int* shell_map;           // [nframes][...] int32 shell matrix of each frame (Delaunay distance)
+    long long stride_map;           // ints between the matrices of consecutive frames
+    int shell_mode;                 // 1: bin = pos*nshells + shell, shell = map-1 clamped to the last (:602-605)
+                                    // 2: bin = shell*histo_nr + pos, shell = min(map, nshells)-1, negative wraps (:219-224)
+    int nshells, histo_nr;
+    int apr1, apr2;                 // sites per molecule: matrix row = i / apr1, column = j / apr2 (:582-583, :601)
+    int map_ld;                     // row stride of the matrix as the reference indexes it (:602 uses nsurround)
+    int excl_self;                  // skip pairs of the same molecule (calcHistoVoronoiNonSelf :700)
 };
 
 struct PairConfig {

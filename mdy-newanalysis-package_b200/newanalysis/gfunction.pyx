@@ -60,6 +60,20 @@ cdef extern from "gfn.h":
                            const double *d1, long long s3, const double *d2, long long s4, const double *boxes) nogil
     int gfn_enqueue_device_frames(gfn_t *h, int nframes, const double *c1, long long s1, const double *c2, long long s2,
                                   const double *d1, long long s3, const double *d2, long long s4, const double *boxes) nogil
+    ctypedef struct gfn_shell_cfg:
+        int nshells
+        int layout
+        int apr_core
+        int apr_surround
+        int map_ld
+        long long map_elems
+        int exclude_self
+    int gfn_create_shells(gfn_t **out, int n1, int n2, int histo_n, float histo_min, float histo_max,
+                          double inv_dr, int mode_sel, const double *box_dim, const int *devices, int ndev,
+                          unsigned flags, const gfn_shell_cfg *cfg) nogil
+    int gfn_enqueue_frames_shells(gfn_t *h, int nframes, const double *c1, long long s1, const double *c2, long long s2,
+                                  const double *d1, long long s3, const double *d2, long long s4, const double *boxes,
+                                  const int *shell_map, long long s_map) nogil
     int gfn_flush(gfn_t *h) nogil
     int gfn_sync(gfn_t *h) nogil
     int gfn_readout(gfn_t *h, double *hist, double *pairw, unsigned long long *overflow) nogil
@@ -377,6 +391,30 @@ cdef class _Backend:
         self.n1 = n1
         self.n2 = n2
 
+    def open_shells(self, int n1, int n2, int histo_n, float hmin, float hmax, double inv_dr, int mode_sel,
+                    np.ndarray[np.float64_t, ndim=1, mode="c"] box_dim, devices, unsigned flags,
+                    int nshells, int layout, int apr_core, int apr_surround, int map_ld, long long map_elems, bint exclude_self):
+        """Shell-resolved handle (gfn_create_shells); histogram rows hold histo_n*nshells bins."""
+        cdef np.ndarray[np.int32_t, ndim=1, mode="c"] devs = np.ascontiguousarray(devices, dtype=np.int32)
+        cdef gfn_shell_cfg cfg
+        cfg.nshells = nshells; cfg.layout = layout; cfg.apr_core = apr_core; cfg.apr_surround = apr_surround
+        cfg.map_ld = map_ld; cfg.map_elems = map_elems; cfg.exclude_self = 1 if exclude_self else 0
+        cdef int ndev = devs.shape[0]
+        cdef int rc = gfn_create_shells(&self.h, n1, n2, histo_n, hmin, hmax, inv_dr, mode_sel, <const double *> box_dim.data,
+                                        <const int *> devs.data, ndev, flags, &cfg)
+        if rc != GFN_OK:
+            self.h = NULL
+            _raise(rc, NULL)
+        self.histo_n = histo_n * nshells
+        self.n1 = n1
+        self.n2 = n2
+
+    cdef int enqueue_shells(self, const double *c1, const double *c2, const double *d1, const double *d2, const int *shell_map) except -1:
+        cdef int rc
+        with nogil:
+            rc = gfn_enqueue_frames_shells(self.h, 1, c1, 0, c2, 0, d1, 0, d2, 0, NULL, shell_map, 0)
+        return self.check(rc)
+
     def update_box(self, np.ndarray[np.float64_t, ndim=1, mode="c"] box_dim):
         self.check(gfn_update_box(self.h, <const double *> box_dim.data))
 
@@ -518,6 +556,45 @@ def calcHistoTS(core_xyz, surr_xyz, np.ndarray[np.float64_t, ndim=3] result, dou
     cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a2 = c2
     b.enqueue(<const double *> a1.data, <const double *> a2.data, NULL, NULL)
     rows = b.readout_per_particle()[:n1 * nb].reshape(n1, nb)
+    result[t] += rows
+
+
+def calcHistoTSVoro(core_xyz, surr_xyz, np.ndarray[np.float64_t, ndim=4] result, ds, int maxshell,
+                    double boxl, int t, float histo_min, float histo_max, double invdx):
+    """Shell-resolved RDF time series on the GPU: result[t, i, shell-1, pos] += 1 with shell = min(ds[t, i, j], maxshell)
+    (reference: def calcHistoTSVoro, gfunction.pyx:195-224; ds is the char Delaunay-distance array [frame][core][surround]).
+
+    Same signature and result as the reference.  ds[t, i, j] == 0 addresses the last shell (index -1 wraps in the
+    reference); a pair past the last radial bin lands where the reference's flat index points, except beyond the
+    frame's slab, where the reference writes into the next frame (or past the array) and this version drops it."""
+    c1 = np.ascontiguousarray(core_xyz, dtype=np.float64)
+    c2 = c1 if surr_xyz is core_xyz else np.ascontiguousarray(surr_xyz, dtype=np.float64)
+    cdef int n1 = c1.shape[0], n2 = c2.shape[0], nb = result.shape[3]
+    if result.shape[1] != n1 or result.shape[2] != maxshell:
+        raise ValueError("result must have shape (nframes, %d, %d, nbins)" % (n1, maxshell))
+    if t < 0 or t >= result.shape[0]:
+        raise IndexError("frame index out of range")
+    cdef np.ndarray[np.int32_t, ndim=2, mode="c"] shells = np.ascontiguousarray(np.asarray(ds[t]), dtype=np.int32)
+    if shells.shape[0] != n1 or shells.shape[1] != n2:
+        raise ValueError("ds[t] must have shape (%d, %d)" % (n1, n2))
+    key = ("voro", n1, n2, nb, maxshell, float(np.float32(histo_min)), float(np.float32(histo_max)), float(invdx), float(boxl))
+    be = _ts_cache.get(key)
+    if be is None:
+        if gfn_device_count() < 1:
+            raise RuntimeError("newanalysis.gfunction (B200 backend): no CUDA device available and there is no CPU fallback")
+        if len(_ts_cache) > 8:
+            _ts_cache.clear()
+        be = _Backend()
+        box = np.array([boxl, boxl, boxl, boxl / 2.0, boxl / 2.0, boxl / 2.0], dtype=np.float64)
+        be.open_shells(n1, n2, nb, histo_min, histo_max, invdx, 1, box, [0], 1 | 32,       # per-particle, no triangle
+                       maxshell, 2, 1, 1, n2, <long long> n1 * n2, False)
+        _ts_cache[key] = be
+    cdef _Backend b = be
+    b.reset()
+    cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a1 = c1
+    cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a2 = c2
+    b.enqueue_shells(<const double *> a1.data, <const double *> a2.data, NULL, NULL, <const int *> shells.data)
+    rows = b.readout_per_particle()[:<long long> n1 * maxshell * nb].reshape(n1, maxshell, nb)
     result[t] += rows
 
 
@@ -880,3 +957,208 @@ class RDF(object):
         if pc is not None:
             self._pending_comm = None
             self._be.attach_comm(*pc)
+
+
+class RDF_voronoi(RDF):
+    """
+    class RDF_voronoi
+
+    Shell-resolved g-functions (B200 backend): drop-in for the reference's RDF_voronoi (gfunction.pyx:764-1148).
+    Every in-range pair is filed under the Delaunay shell of its two molecules, read from the int32 matrix passed to
+    calcFrame; histogram_out has the reference layout [mode][bin][shell].
+    """
+
+    def __init__(self, modes, histo_min, histo_max, histo_dr, sel1_n, sel2_n, sel1_nmol, sel2_nmol, box_x, nshells, box_y=None, box_z=None, use_cuda=False, norm_volume=None, exclude_self_mol=False, gfn_flags=None, devices=None):
+        """
+        Same arguments as the reference (gfunction.pyx:771).  use_cuda is accepted and ignored; gfn_flags / devices
+        are optional extensions.  The device handle is created by the first calcFrame, when the size of the
+        Delaunay matrix is known.
+        """
+        self.nshells = np.int32(nshells)                     # :842
+        self.exclude_self_mol = exclude_self_mol             # :843
+        self._map_shape = None
+        RDF.__init__(self, modes, histo_min, histo_max, histo_dr, sel1_n, sel2_n, sel1_nmol, sel2_nmol, box_x,
+                     box_y, box_z, use_cuda, norm_volume, gfn_flags, devices)
+        if int(self.nshells) < 1:
+            raise ValueError("nshells must be >= 1")
+        self.histogram_out = np.zeros(self.nshells * self.histo_n * 7, dtype=np.float64)    # :882
+
+    def _open_backend(self):
+        if self._map_shape is None:          # first frame not seen yet
+            self._be = None
+            return
+        cdef int n1 = self.n1, n2 = self.n2
+        if int(self.nmol1) < 1 or int(self.nmol2) < 1 or n1 // int(self.nmol1) < 1 or n2 // int(self.nmol2) < 1:
+            raise ValueError("sel*_nmol must be between 1 and the number of sites (apr = n // nmol, gfunction.pyx:582-583)")
+        self._be = _Backend()
+        self._be.open_shells(n1, n2, int(self.histo_n), self.histo_min, self.histo_max, float(self.histo_inv_dr),
+                             int(self.mode_sel), self.box_dim, self._devices, self._flags,
+                             int(self.nshells), 1, n1 // int(self.nmol1), n2 // int(self.nmol2), n2,
+                             <long long> self._map_shape[0] * self._map_shape[1], bool(self.exclude_self_mol))
+
+    def update_box(self, box_x, box_y, box_z):
+        """
+        update_box(box_x,box_y,box_z)
+
+        Update the box dimensions (:916-935).  Like the reference, self.volume is NOT refreshed here (the
+        assignment sits inside a string literal in the reference).
+        """
+        self.box_dim[0] = box_x
+        self.box_dim[3] = box_x / 2.0
+        self.box_dim[1] = box_y
+        self.box_dim[4] = box_y / 2.0
+        self.box_dim[2] = box_z
+        self.box_dim[5] = box_z / 2.0
+        if self._be is not None:
+            self._be.update_box(self.box_dim)
+
+    def calcFrame(self,
+                  np.ndarray[np.float64_t, ndim=2, mode="c"] coor_sel1,
+                  np.ndarray[np.float64_t, ndim=2, mode="c"] coor_sel2,
+                  np.ndarray[np.int32_t, ndim=2, mode="c"] delaunay_matrix,
+                  np.ndarray[np.float64_t, ndim=2, mode="c"] dip_sel1 = None,
+                  np.ndarray[np.float64_t, ndim=2, mode="c"] dip_sel2 = None,
+                  pre_coor_sel1_gpu=None, pre_coor_sel2_gpu=None,
+                  pre_dip_sel1_gpu=None, pre_dip_sel2_gpu=None):
+        """
+        calcFrame(coor_sel1, coor_sel2, delaunay_matrix, dip_sel1=None, dip_sel2=None, ...)
+
+        Pass the data of the current frame (:937-1021).  delaunay_matrix[a, b] is the Delaunay distance between
+        molecule a of the first and molecule b of the second selection; the reference indexes it as
+        flat[(i // apr_core) * sel2_n + j // apr_surround] (:602), so it must hold at least that many elements
+        (ValueError otherwise; the reference would read out of bounds).  pre_*_gpu are ignored like in the reference.
+        """
+        cdef int m = <int> self.mode_sel
+        if dip_sel1 is None and (m & 2 or m & 4 or m & 16 or m & 32):
+            raise TypeError("No dipole moment array for the first selection was passed, although the requested gfunctions need it!")
+        if dip_sel2 is None and (m & 2 or m & 8 or m & 16 or m & 64):
+            raise TypeError("No dipole moment array for the second selection was passed, although the requested gfunctions need it!")
+        if coor_sel1.shape[0] != self.n1 or coor_sel1.shape[1] != 3 or coor_sel2.shape[0] != self.n2 or coor_sel2.shape[1] != 3:
+            raise ValueError("coordinate arrays must have shapes (%d,3) and (%d,3)" % (self.n1, self.n2))
+        if dip_sel1 is not None and (dip_sel1.shape[0] != self.n1 or dip_sel1.shape[1] != 3):
+            raise ValueError("dip_sel1 must have shape (%d,3)" % self.n1)
+        if dip_sel2 is not None and (dip_sel2.shape[0] != self.n2 or dip_sel2.shape[1] != 3):
+            raise ValueError("dip_sel2 must have shape (%d,3)" % self.n2)
+
+        if self.oneistwo is None:                            # :972-976
+            if (coor_sel1[0] == coor_sel2[0]).all() and self.nmol1 == self.nmol2:
+                self.oneistwo = True
+            else:
+                self.oneistwo = False
+
+        shape = (delaunay_matrix.shape[0], delaunay_matrix.shape[1])
+        if self._map_shape is None:
+            self._map_shape = shape
+            if self._auto_filter:
+                self._auto_filter = False
+                lmax = float(max(self.box_dim[0], self.box_dim[1], self.box_dim[2]))
+                absmax = max(float(np.abs(coor_sel1).max()), float(np.abs(coor_sel2).max()))
+                if not (self._flags & (2 | 16)) and absmax <= 2.0 * lmax and float(self.histo_max) >= 0.04 * lmax:
+                    self._flags |= 16
+            self._open_backend()
+        elif shape != self._map_shape:
+            raise ValueError("delaunay_matrix changed shape from %r to %r" % (self._map_shape, shape))
+
+        self.ctr += 1                                        # :979
+        self.volume_list.append(self.volume)                 # :982
+        cdef _Backend be = self._be
+        be.enqueue_shells(<const double *> coor_sel1.data, <const double *> coor_sel2.data,
+                          <const double *> dip_sel1.data if dip_sel1 is not None else NULL,
+                          <const double *> dip_sel2.data if dip_sel2 is not None else NULL,
+                          <const int *> delaunay_matrix.data)
+
+    def _addHisto(self, np.ndarray[np.float64_t, ndim=1] histo_out, np.ndarray[np.float64_t, ndim=1] histo):
+        """
+        Add the histograms of all core particles (:1023-1047).  `histo` may be the per-particle array
+        (7*n1*histo_n*nshells) or the already summed [mode][bin][shell] array this backend keeps.
+        """
+        cdef long long row = <long long> self.histo_n * self.nshells
+        cdef long long n1 = self.n1
+        if histo.shape[0] == 7 * row:
+            histo_out += histo
+        elif histo.shape[0] == 7 * n1 * row:
+            histo_out += histo.reshape(7, n1, row).sum(axis=1).reshape(-1)
+        else:
+            raise ValueError("histogram has %d elements, expected %d or %d" % (histo.shape[0], 7 * row, 7 * n1 * row))
+
+    def _normHisto(self):
+        """
+        Normalize the histogram (:1049-1089); host code, same arithmetic as the reference.
+        """
+        if self.norm_volume:
+            volume = self.norm_volume
+        else:
+            volume = 0.0
+            for v in self.volume_list:
+                volume += v
+            volume /= len(self.volume_list)
+
+        PI = 3.14159265358979323846
+        if self.oneistwo:
+            rho = float(self.nmol1 * (self.nmol1 - 1)) / volume
+        else:
+            rho = float(self.nmol1 * self.nmol2) / volume
+
+        cdef int i, j, shell
+        for shell in range(self.nshells):
+            for i in range(self.histo_n):
+                r = self.histo_min + float(i) * self.histo_dr
+                r_out = r + self.histo_dr
+                slice_vol = 4.0 / 3.0 * PI * (r_out**3 - r**3)
+                norm = rho * slice_vol * float(self.ctr)
+                for j in range(7):
+                    self.histogram_out[j * self.histo_n * self.nshells + i * self.nshells + shell] /= norm
+
+    def scale(self, value):
+        """:1091-1093"""
+        self.histogram_out[:] *= value
+        if self._be is not None:
+            self._be.scale(float(value))
+
+    def write(self, filename="rdf"):
+        """
+        RDF_voronoi.write(filename="rdf")
+
+        Norm the calculated histograms and write them to <filename>_shell<n>_g000.dat ... (:1095-1133).
+        """
+        self._addHisto(self.histogram_out, self.raw_histogram())
+        self._normHisto()
+
+        names = ("000", "110", "101", "011", "220", "202", "022")
+        for shell in range(self.nshells):
+            files = {}
+            for k in range(7):
+                if self.mode_sel & (1 << k):
+                    files[k] = open(filename + "_shell" + str(shell + 1) + "_g" + names[k] + ".dat", 'w')
+            for i in range(self.histo_n):
+                r = self.histo_min + i * self.histo_dr + self.histo_dr * 0.5
+                for k in files:
+                    files[k].write("%5.5f\t%5.5f\n" % (r, self.histogram_out[k * self.histo_n * self.nshells + i * self.nshells + shell]))
+            for k in files:
+                files[k].close()
+
+    def resetArrays(self):
+        """
+        Reset histogram arrays to zero (:1135-1140)
+        """
+        self.histogram_out[:] = 0.0
+        if self._be is not None:
+            self._be.reset()
+
+    def raw_histogram(self):
+        """Un-normalised [mode][bin][shell] sums accumulated since the last resetArrays (7*histo_n*nshells float64)."""
+        if self._be is None:
+            return np.zeros(7 * int(self.histo_n) * int(self.nshells), dtype=np.float64)
+        hist, pw, ovf = self._be.readout()
+        self.pair_weight = pw
+        self.overflow = ovf
+        return hist
+
+    def calcFrames(self, *args, **kwargs):
+        raise NotImplementedError("RDF_voronoi takes one frame per call (calcFrame)")
+
+    def calcFramesDevice(self, *args, **kwargs):
+        raise NotImplementedError("RDF_voronoi takes host frames (calcFrame)")
+
+    def attach_comm(self, uid, nranks, rank):
+        raise NotImplementedError("RDF_voronoi: multi-process readout is not wired up; shard frames with devices=[...]")

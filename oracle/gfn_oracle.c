@@ -19,6 +19,9 @@
  *   gfn_oracle_calc_histo   <- cdef void calcHisto               :110-165
  *   gfn_oracle_add_histo    <- RDF._addHisto                     :466-480
  *   gfn_oracle_calc_histo_ts<- def calcHistoTS                   :168-192   (next-row N3)
+ *   gfn_oracle_calc_histo_shells <- cdef void calcHistoVoronoi / calcHistoVoronoiNonSelf :570-664, :667-761 (next-row N2)
+ *   gfn_oracle_add_histo_shells  <- RDF_voronoi._addHisto       :1023-1047
+ *   gfn_oracle_calc_histo_ts_voro<- def calcHistoTSVoro          :195-224
  *   gfn_oracle_com_by_residue / gfn_oracle_dip_by_residue <- newanalysis/helpers/helpers.pyx:71-98, :101-123 (next-row N1)
  */
 #include <math.h>
@@ -281,4 +284,147 @@ void gfn_oracle_dip_by_residue(const double *coor, const double *charges, int nr
         }
         for (k = 0; k < 3; k++) dip[3 * (long long)i + k] = s[k];
     }
+}
+
+
+/* ---- N2: shell-resolved pair loop ------------------------------------------------------------------------
+ * calcHistoVoronoi (gfunction.pyx:570-664) and calcHistoVoronoiNonSelf (:667-761, exclude_self != 0).
+ * Same pair arithmetic as calcHisto; every in-range pair also looks up the Delaunay shell of its two
+ * molecules, shell = delaunay[(i / apr_core) * nsurround + j / apr_surround] - 1 with values outside
+ * [0, nshells) sent to the last shell (:601-605; the row stride IS nsurround in the reference), and the
+ * row layout becomes [bin][shell]: flat index k*nshells*ncore*histo_n + i*nshells*histo_n + pos*nshells + shell
+ * (:574, :589, :648-651).  delaunay_elems bounds the lookup (the reference does not check); an index past
+ * it returns 2 (nothing written).  Returns 1 on a zero-norm division like gfn_oracle_calc_histo. */
+int gfn_oracle_calc_histo_shells(const double *core_xyz, const double *surr_xyz,
+                                 const double *core_dip, const double *surr_dip,
+                                 double *dest, const double *box_dim,
+                                 int ncore, int nsurround,
+                                 float histo_min, float histo_max, int histo_n,
+                                 double invdx, int mode_sel, int nm_core, int nm_surround, int nshells,
+                                 const int *delaunay, long long delaunay_elems, int exclude_self, long long *oob)
+{
+    const long long row = (long long)nshells * histo_n;
+    const long long ix1 = row * ncore;                                  /* :574 */
+    const long long total = 7 * ix1;
+    const int apr_core = ncore / nm_core, apr_surround = nsurround / nm_surround;   /* :582-583 */
+    const int need_c = (mode_sel & 2) || (mode_sel & 4) || (mode_sel & 16) || (mode_sel & 32);
+    const int need_s = (mode_sel & 2) || (mode_sel & 8) || (mode_sel & 16) || (mode_sel & 64);
+    int status = 0;
+    long long n_oob = 0;
+    int i;
+    if (apr_core < 1 || apr_surround < 1) return 2;
+    if ((long long)((ncore - 1) / apr_core) * nsurround + (nsurround - 1) / apr_surround >= delaunay_elems) return 2;
+
+#pragma omp parallel for schedule(static) reduction(|:status) reduction(+:n_oob)
+    for (i = 0; i < ncore; i++) {                                       /* :588 */
+        const long long ix2 = (long long)i * row;                       /* :590 */
+        const int mol_i = i / apr_core;                                 /* :591 */
+        double cpx = 0, cpy = 0, cpz = 0, clen = 0, spx = 0, spy = 0, spz = 0, slen = 0;
+        long long lost = 0;
+        int j, stop = 0;
+        if (need_c) {                                                   /* :593-597 */
+            cpx = core_dip[i * 3]; cpy = core_dip[i * 3 + 1]; cpz = core_dip[i * 3 + 2];
+            clen = sqrt(cpx * cpx + cpy * cpy + cpz * cpz);
+        }
+        for (j = (ncore == nsurround) ? i : 0; j < nsurround && !stop; j++) {   /* :598-602 */
+            const int mol_j = j / apr_surround;                         /* :601 */
+            const double w = (ncore == nsurround && i != j) ? 2.0 : 1.0;        /* :607-610 */
+            double dx, dy, dz, dist, c;
+            long long at;
+            int shell, pos, k;
+            if (exclude_self && mol_i == mol_j) continue;               /* :700 */
+            shell = delaunay[(long long)mol_i * nsurround + mol_j] - 1; /* :602-603 */
+            if (shell < 0 || shell >= nshells) shell = nshells - 1;     /* :604-605 */
+            if (need_s) {                                               /* :611-615 */
+                spx = surr_dip[j * 3]; spy = surr_dip[j * 3 + 1]; spz = surr_dip[j * 3 + 2];
+                slen = sqrt(spx * spx + spy * spy + spz * spz);
+            }
+            dx = surr_xyz[j * 3]     - core_xyz[i * 3];                 /* :617-619 */
+            dy = surr_xyz[j * 3 + 1] - core_xyz[i * 3 + 1];
+            dz = surr_xyz[j * 3 + 2] - core_xyz[i * 3 + 2];
+            if (fabs(dx) > box_dim[3]) dx = dx - ((0.0 < dx) - (dx < 0.0)) * box_dim[0];   /* :621-623 */
+            if (fabs(dy) > box_dim[4]) dy = dy - ((0.0 < dy) - (dy < 0.0)) * box_dim[1];
+            if (fabs(dz) > box_dim[5]) dz = dz - ((0.0 < dz) - (dz < 0.0)) * box_dim[2];
+            dist = sqrt(dx * dx + dy * dy + dz * dz);                   /* :624 */
+            if (dist < histo_min || dist > histo_max || floor(dist * invdx) == 0) continue;   /* :625 */
+            pos = (int)floor((dist - histo_min) * invdx);               /* :626 */
+            at = ix2 + (long long)pos * nshells + shell;                /* :648-649 */
+            for (k = 0; k < 3 && !stop; k++) {
+                /* k = 0: core.surr dipoles (:653-656), 1: core dipole.distance (:657-660), 2: surr dipole.distance (:661-664) */
+                const int lin = k == 0 ? 2 : (k == 1 ? 4 : 8), quad = lin << 3;
+                double den, num;
+                if (k == 0 && (mode_sel & 1)) {                         /* :651 */
+                    if (at < total) dest[at] += 1.0 * w; else lost++;
+                }
+                if (!(mode_sel & lin) && !(mode_sel & quad)) continue;
+                if (k == 0)      { den = clen * slen; num = cpx * spx + cpy * spy + cpz * spz; }
+                else if (k == 1) { den = clen * dist; num = cpx * dx + cpy * dy + cpz * dz; }
+                else             { den = slen * dist; num = spx * dx + spy * dy + spz * dz; }
+                if (den == 0) { status = 1; stop = 1; break; }
+                c = num / den;
+                if (mode_sel & lin)  { long long a = (long long)(k + 1) * ix1 + at; if (a < total) dest[a] += c * w; else lost++; }
+                if (mode_sel & quad) { long long a = (long long)(k + 4) * ix1 + at; if (a < total) dest[a] += (1.5 * c * c - 0.5) * w; else lost++; }
+            }
+        }
+        n_oob += lost;
+    }
+    if (oob) *oob += n_oob;
+    return status;
+}
+
+/* RDF_voronoi._addHisto, gfunction.pyx:1023-1047: out[k][bin][shell] += sum_i histogram[k][i][bin][shell],
+ * rows in ascending i.  Accumulates into out. */
+void gfn_oracle_add_histo_shells(double *out, const double *histogram, int n1, int histo_n, int nshells)
+{
+    const long long row = (long long)nshells * histo_n, ix2 = row * n1;
+    long long e;
+#pragma omp parallel for schedule(static)
+    for (e = 0; e < row; e++) {                                         /* :1043-1044: (bin, shell) pairs */
+        int j, k;
+        for (j = 0; j < n1; j++)                                        /* :1045 */
+            for (k = 0; k < 7; k++)                                     /* :1047 */
+                out[k * row + e] += histogram[k * ix2 + row * j + e];
+    }
+}
+
+/* calcHistoTSVoro, gfunction.pyx:195-224: result[t][i][shell-1][pos] += 1 with shell = min(ds[t][i][j], maxshell);
+ * result_t is the [ncore][maxshell][nbins] slab of frame t, ds_t the [ncore][nsurr] char matrix of frame t.
+ * A negative first index wraps once (Cython wraparound=True, boundscheck=False); pos >= nbins lands where
+ * the flat index points (next shell / next core row) and is dropped past the end of the slab.
+ * Returns the number of dropped pairs. */
+long long gfn_oracle_calc_histo_ts_voro(const double *core_xyz, const double *surr_xyz, double *result_t,
+                                        const signed char *ds_t, int maxshell,
+                                        int ncore, int nsurr, int nbins, double boxl,
+                                        float histo_min, float histo_max, double invdx)
+{
+    const double boxl2 = boxl / 2.0;                                    /* :203 */
+    const long long total = (long long)ncore * maxshell * nbins;
+    long long dropped = 0;
+    int i;
+#pragma omp parallel for schedule(static) reduction(+:dropped)
+    for (i = 0; i < ncore; i++) {
+        int j;
+        for (j = 0; j < nsurr; j++) {
+            double dx = surr_xyz[j * 3]     - core_xyz[i * 3];
+            double dy = surr_xyz[j * 3 + 1] - core_xyz[i * 3 + 1];
+            double dz = surr_xyz[j * 3 + 2] - core_xyz[i * 3 + 2];
+            double dist;
+            long long at;
+            int pos, shell;
+            if (fabs(dx) > boxl2) dx = dx - ((0.0 < dx) - (dx < 0.0)) * boxl;
+            if (fabs(dy) > boxl2) dy = dy - ((0.0 < dy) - (dy < 0.0)) * boxl;
+            if (fabs(dz) > boxl2) dz = dz - ((0.0 < dz) - (dz < 0.0)) * boxl;
+            dist = sqrt(dx * dx + dy * dy + dz * dz);
+            if (dist < histo_min || dist > histo_max || floor(dist * invdx) == 0) continue;
+            pos = (int)floor((dist - histo_min) * invdx);
+            shell = ds_t[(long long)i * nsurr + j];                     /* :219 */
+            if (shell > maxshell) shell = maxshell;                     /* :220-221 */
+            shell -= 1;
+            if (shell < 0) shell += maxshell;                           /* wraparound of index shell-1 */
+            if (shell < 0) { dropped++; continue; }
+            at = ((long long)i * maxshell + shell) * nbins + pos;       /* :224 */
+            if (at < total) result_t[at] += 1.0; else dropped++;
+        }
+    }
+    return dropped;
 }

@@ -64,6 +64,18 @@ def load_c():
                                                ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                                ctypes.c_float, ctypes.c_int, ctypes.c_double,
                                                ctypes.c_int, llp]
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.gfn_oracle_calc_histo_shells.restype = ctypes.c_int
+    lib.gfn_oracle_calc_histo_shells.argtypes = [dp, dp, dp, dp, dp, dp, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                 ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ip, ctypes.c_longlong, ctypes.c_int, llp]
+    lib.gfn_oracle_add_histo_shells.restype = None
+    lib.gfn_oracle_add_histo_shells.argtypes = [dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.gfn_oracle_calc_histo_ts_voro.restype = ctypes.c_longlong
+    lib.gfn_oracle_calc_histo_ts_voro.argtypes = [dp, dp, dp, ctypes.POINTER(ctypes.c_byte), ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                  ctypes.c_float, ctypes.c_float, ctypes.c_double]
     _c = lib
     return lib
 
@@ -169,6 +181,35 @@ def calc_histo_ts_c(core, surr, result_t, boxl, hmin, hmax, invdx):
     return lib.gfn_oracle_calc_histo_ts(_dptr(core), _dptr(surr), _dptr(result_t), core.shape[0],
                                         surr.shape[0], result_t.shape[1], float(boxl),
                                         np.float32(hmin), np.float32(hmax), float(invdx))
+
+
+def calc_histo_shells_c(c1, c2, d1, d2, dest, box_dim, hmin, hmax, histo_n, invdx, mode_sel,
+                        nm_core, nm_surround, nshells, delaunay, exclude_self=False):
+    """calcHistoVoronoi / calcHistoVoronoiNonSelf (gfunction.pyx:570-761) on the C restatement.
+    Returns (status, out_of_bounds)."""
+    lib = load_c()
+    c1 = _c64(c1); c2 = _c64(c2)
+    d1 = _c64(d1) if d1 is not None else None
+    d2 = _c64(d2) if d2 is not None else None
+    dl = np.ascontiguousarray(delaunay, dtype=np.int32)
+    oob = ctypes.c_longlong(0)
+    rc = lib.gfn_oracle_calc_histo_shells(
+        _dptr(c1), _dptr(c2), _dptr(d1) if d1 is not None else None, _dptr(d2) if d2 is not None else None,
+        _dptr(dest), _dptr(box_dim), c1.shape[0], c2.shape[0], float(hmin), float(hmax), int(histo_n),
+        float(invdx), int(mode_sel), int(nm_core), int(nm_surround), int(nshells),
+        dl.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), dl.size, 1 if exclude_self else 0, ctypes.byref(oob))
+    return rc, oob.value
+
+
+def calc_histo_ts_voro_c(core, surr, result_t, ds_t, maxshell, boxl, hmin, hmax, invdx):
+    """calcHistoTSVoro (gfunction.pyx:195-224) for one frame: result_t is result[t] ([ncore][maxshell][nbins]),
+    ds_t is ds[t] ([ncore][nsurr] int8)."""
+    core = _c64(core); surr = _c64(surr)
+    ds_t = np.ascontiguousarray(ds_t, dtype=np.int8)
+    assert result_t.flags.c_contiguous and result_t.dtype == np.float64
+    return load_c().gfn_oracle_calc_histo_ts_voro(
+        _dptr(core), _dptr(surr), _dptr(result_t), ds_t.ctypes.data_as(ctypes.POINTER(ctypes.c_byte)), int(maxshell),
+        core.shape[0], surr.shape[0], result_t.shape[-1], float(boxl), float(hmin), float(hmax), float(invdx))
 
 
 def calc_histo_numpy(c1, c2, d1, d2, dest, box_dim, hmin, hmax, histo_n, invdx, mode_sel):
@@ -333,6 +374,85 @@ class OracleRDF(object):
         """sum_i histogram[k][i][b] in the reference order (what _addHisto adds) - the quantity the
         GPU path is compared against, before normalisation."""
         out = np.zeros(7 * int(self.histo_n))
+        self._addHisto(out, self.histogram)
+        return out
+
+
+class OracleRDFVoronoi(OracleRDF):
+    """Host-logic restatement of the reference RDF_voronoi class (gfunction.pyx:764-1148), CPU path."""
+
+    def __init__(self, modes, histo_min, histo_max, histo_dr, sel1_n, sel2_n, sel1_nmol, sel2_nmol,
+                 box_x, nshells, box_y=None, box_z=None, use_cuda=False, norm_volume=None, exclude_self_mol=False):
+        OracleRDF.__init__(self, modes, histo_min, histo_max, histo_dr, sel1_n, sel2_n, sel1_nmol, sel2_nmol,
+                           box_x, box_y, box_z, use_cuda, norm_volume)
+        self.nshells = np.int32(nshells)                                    # :842
+        self.exclude_self_mol = exclude_self_mol                            # :843
+        self.histogram = np.zeros(int(self.nshells) * int(self.n1) * int(self.histo_n) * 7, dtype=self.dtype)   # :881
+        self.histogram_out = np.zeros(int(self.nshells) * int(self.histo_n) * 7, dtype=np.float64)              # :882
+
+    def update_box(self, box_x, box_y, box_z):                              # :916-935: self.volume is NOT refreshed
+        self.box_dim[0] = box_x; self.box_dim[3] = box_x / 2.0              #   (the assignment sits inside a string literal)
+        self.box_dim[1] = box_y; self.box_dim[4] = box_y / 2.0
+        self.box_dim[2] = box_z; self.box_dim[5] = box_z / 2.0
+
+    def calcFrame(self, coor_sel1, coor_sel2, delaunay_matrix, dip_sel1=None, dip_sel2=None):   # :937-1021
+        m = int(self.mode_sel)
+        if dip_sel1 is None and m & (2 | 4 | 16 | 32):
+            raise TypeError("No dipole moment array for the first selection was passed, although the requested gfunctions need it!")
+        if dip_sel2 is None and m & (2 | 8 | 16 | 64):
+            raise TypeError("No dipole moment array for the second selection was passed, although the requested gfunctions need it!")
+        if self.oneistwo is None:
+            self.oneistwo = bool((coor_sel1[0] == coor_sel2[0]).all() and self.nmol1 == self.nmol2)
+        self.ctr += 1
+        self.volume_list.append(self.volume)
+        rc, _ = calc_histo_shells_c(coor_sel1, coor_sel2, dip_sel1, dip_sel2, self.histogram, self.box_dim,
+                                    self.histo_min, self.histo_max, self.histo_n, self.histo_inv_dr, m,
+                                    self.nmol1, self.nmol2, self.nshells, delaunay_matrix, self.exclude_self_mol)
+        if rc == 1:
+            raise ZeroDivisionError("float division")
+        if rc:
+            raise ValueError("delaunay matrix too small for the reference's indexing")
+
+    def _addHisto(self, histo_out, histo):                                  # :1023-1047
+        load_c().gfn_oracle_add_histo_shells(_dptr(histo_out), _dptr(histo), int(self.n1), int(self.histo_n), int(self.nshells))
+
+    def _normHisto(self):                                                   # :1049-1089
+        if self.norm_volume:
+            volume = self.norm_volume
+        else:
+            volume = 0.0
+            for v in self.volume_list:
+                volume += v
+            volume /= len(self.volume_list)
+        PI = 3.14159265358979323846
+        if self.oneistwo:
+            rho = float(self.nmol1 * (self.nmol1 - 1)) / volume
+        else:
+            rho = float(self.nmol1 * self.nmol2) / volume
+        ns = int(self.nshells)
+        for shell in range(ns):
+            for i in range(self.histo_n):
+                r = self.histo_min + float(i) * self.histo_dr
+                r_out = r + self.histo_dr
+                slice_vol = 4.0 / 3.0 * PI * (r_out ** 3 - r ** 3)
+                norm = rho * slice_vol * float(self.ctr)
+                for j in range(7):
+                    self.histogram_out[j * self.histo_n * ns + i * ns + shell] /= norm
+
+    def write(self, filename="rdf"):                                        # :1095-1133
+        self._addHisto(self.histogram_out, self.histogram.astype(np.float64))
+        self._normHisto()
+        ns = int(self.nshells)
+        for shell in range(ns):
+            for k, name in enumerate(MODE_ORDER):
+                if int(self.mode_sel) & MODE_BITS[name]:
+                    with open(filename + "_shell" + str(shell + 1) + "_g" + name + ".dat", "w") as fh:
+                        for i in range(self.histo_n):
+                            r = self.histo_min + i * self.histo_dr + self.histo_dr * 0.5
+                            fh.write("%5.5f\t%5.5f\n" % (r, self.histogram_out[k * self.histo_n * ns + i * ns + shell]))
+
+    def raw_sum(self):
+        out = np.zeros(7 * int(self.histo_n) * int(self.nshells))
         self._addHisto(out, self.histogram)
         return out
 

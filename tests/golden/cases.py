@@ -112,3 +112,81 @@ def build_residues(case):
     masses = np.ascontiguousarray(1.0 + 15.0 * rng.random(natoms))
     charges = np.ascontiguousarray(rng.standard_normal(natoms))
     return coor, masses, charges, apr, rfa
+
+
+# N2 shell-resolved g-functions (RDF_voronoi, gfunction.pyx:764-1148) and calcHistoTSVoro (:195-224).
+# nmol*: molecules per selection (sites per molecule = n // nmol); the Delaunay matrix has shape (nmol1, n2) because
+# the reference indexes it with row stride n2 (:602); entries are drawn from [-1, nshells + 2] so that the clamping
+# of 0, negative and too large values is exercised.
+VORO_CASES = {
+    "voro_self":      dict(n1=600, n2=600, nmol1=200, nmol2=200, box=(28.0, None, None), modes=["all"], hmin=0.0, hmax=13.0, dr=0.1, nshells=3, frames=2, same=True, seed=31),
+    "voro_self_excl": dict(n1=600, n2=600, nmol1=200, nmol2=200, box=(28.0, None, None), modes=["all"], hmin=0.0, hmax=13.0, dr=0.1, nshells=3, frames=2, same=True, seed=32, exclude_self=True),
+    "voro_rect":      dict(n1=150, n2=420, nmol1=50, nmol2=210, box=(30.0, 33.0, 36.0), modes=["000", "110", "202", "022"], hmin=1.0, hmax=14.0, dr=0.05, nshells=4, frames=3, same=False, seed=33, npt=True),
+    "voro_mol":       dict(n1=500, n2=500, nmol1=500, nmol2=500, box=(31.04, None, None), modes=["all"], hmin=0.0, hmax=15.0, dr=0.05, nshells=2, frames=2, same=False, seed=34, exclude_self=True),
+    "voro_g000":      dict(n1=256, n2=128, nmol1=256, nmol2=64, box=(24.0, None, None), modes=["000"], hmin=0.0, hmax=12.0, dr=0.05, nshells=1, frames=2, same=False, seed=35, nodip=True),
+    "voro_many":      dict(n1=2048, n2=2048, nmol1=2048, nmol2=2048, box=(39.42, None, None), modes=["all"], hmin=0.0, hmax=15.0, dr=0.05, nshells=5, frames=1, same=True, seed=36),
+}
+
+
+def build_voro_inputs(case, frame):
+    """-> (c1, c2, d1, d2, newbox, delaunay int32 (nmol1, n2))."""
+    c1, c2, d1, d2, newbox = build_inputs(case, frame)
+    rng = np.random.default_rng(700001 * case["seed"] + frame)
+    dl = rng.integers(-1, case["nshells"] + 3, size=(case["nmol1"], case["n2"])).astype(np.int32)
+    return c1, c2, d1, d2, newbox, np.ascontiguousarray(dl)
+
+
+def voro_digest(case):
+    h = hashlib.sha256()
+    for f in range(case["frames"]):
+        for a in build_voro_inputs(case, f):
+            if isinstance(a, np.ndarray):
+                h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def make_voro(cls, case, **kw):
+    bx, by, bz = case["box"]
+    return cls(case["modes"], case["hmin"], case["hmax"], case["dr"], case["n1"], case["n2"], case["nmol1"], case["nmol2"],
+               bx, case["nshells"], by, bz, exclude_self_mol=bool(case.get("exclude_self")), **kw)
+
+
+def drive_voro(rdf, case):
+    for f in range(case["frames"]):
+        c1, c2, d1, d2, newbox, dl = build_voro_inputs(case, f)
+        if newbox is not None:
+            rdf.update_box(*newbox)
+        if d1 is None:
+            rdf.calcFrame(c1, c2, dl)
+        else:
+            rdf.calcFrame(c1, c2, dl, d1, d2)
+    return rdf
+
+
+TSVORO_CASES = {
+    "tsvoro_small": dict(n1=40, n2=90, box=22.0, hmin=0.0, hmax=10.0, dr=0.1, maxshell=3, frames=3, seed=41),
+    "tsvoro_self":  dict(n1=300, n2=300, box=26.0, hmin=0.5, hmax=12.0, dr=0.05, maxshell=4, frames=2, seed=42, same=True),
+}
+
+
+def build_tsvoro_inputs(case, frame):
+    """-> (core, surr, ds_t int8 (n1, n2)); shells drawn from [0, maxshell + 2] (0 wraps to the last shell)."""
+    rng = np.random.default_rng(800001 * case["seed"] + frame)
+    core = np.ascontiguousarray(rng.random((case["n1"], 3)) * case["box"])
+    surr = core if case.get("same") else np.ascontiguousarray(rng.random((case["n2"], 3)) * case["box"])
+    ds_t = rng.integers(0, case["maxshell"] + 3, size=(case["n1"], case["n2"])).astype(np.int8)
+    return core, surr, ds_t
+
+
+def drive_tsvoro(fn, case):
+    """fn(core, surr, result, ds, maxshell, boxl, t, hmin, hmax, invdx) for every frame -> result (frames, n1, maxshell, nbins)."""
+    nb = int(round((case["hmax"] - case["hmin"]) / case["dr"]))
+    T = case["frames"]
+    result = np.zeros((T, case["n1"], case["maxshell"], nb))
+    ds = np.zeros((T, case["n1"], case["n2"]), dtype=np.int8)
+    frames = [build_tsvoro_inputs(case, t) for t in range(T)]
+    for t in range(T):
+        ds[t] = frames[t][2]
+    for t in range(T):
+        fn(frames[t][0], frames[t][1], result, ds, case["maxshell"], case["box"], t, case["hmin"], case["hmax"], 1.0 / case["dr"])
+    return result

@@ -78,5 +78,34 @@ def main():
     np.savez_compressed(os.path.join(HERE, "residues.npz"), **out)
 
 
+def main_shells():
+    """N2: RDF_voronoi and calcHistoTSVoro fixtures from the unmodified reference module."""
+    ref = O.load_ref()
+    if ref is None:
+        sys.exit("oracle/_ref is not built; run python oracle/build_ref.py first")
+    for name, case in C.VORO_CASES.items():
+        rdf = C.drive_voro(C.make_voro(ref.RDF_voronoi, case), case)
+        ns, hn = int(rdf.nshells), int(rdf.histo_n)
+        raw = np.zeros(7 * hn * ns)
+        rdf._addHisto(raw, rdf.histogram)
+        with tempfile.TemporaryDirectory() as tmp:
+            rdf.write(os.path.join(tmp, "g"))
+            dat = {"%d_%s" % (sh + 1, m): open(os.path.join(tmp, "g_shell%d_g%s.dat" % (sh + 1, m))).read()
+                   for sh in range(ns) for m in O.MODE_ORDER if int(rdf.mode_sel) & O.MODE_BITS[m]}
+        meta = dict(histo_n=hn, nshells=ns, mode_sel=int(rdf.mode_sel), ctr=int(rdf.ctr), oneistwo=bool(rdf.oneistwo),
+                    volume=float(rdf.volume), digest=C.voro_digest(case), dat=dat)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), raw=raw, out=rdf.histogram_out, meta=np.array(json.dumps(meta)))
+        print("%-16s histo_n=%d nshells=%d g000 per shell=%s" % (name, hn, ns, raw[:hn * ns].reshape(hn, ns).sum(0)))
+    out = {}
+    for name, case in C.TSVORO_CASES.items():
+        out[name] = C.drive_tsvoro(ref.calcHistoTSVoro, case)
+        print("%-16s counts per shell=%s" % (name, out[name].sum(axis=(0, 1, 3))))
+    np.savez_compressed(os.path.join(HERE, "tsvoro.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "shells":
+        main_shells()
+    else:
+        main()
+        main_shells()

@@ -448,3 +448,94 @@ def test_calc_histo_ts_matches_oracle():
     r2 = np.zeros((1, 200, nb)); o2 = np.zeros((1, 200, nb))
     calcHistoTS(c, c, r2, L, 0, 0.0, 12.0, 20.0); O.calc_histo_ts_c(c, c, o2[0], L, 0.0, 12.0, 20.0)
     assert np.array_equal(r2, o2)
+
+
+# ---- N2: shell-resolved g-functions (RDF_voronoi gfunction.pyx:764-1148, calcHistoTSVoro :195-224) --------------
+def assert_shell_hist_close(got, ref, rows, pairw):
+    """rows = histo_n*nshells bins per mode; same bars as assert_hist_close."""
+    scale = np.maximum(np.abs(ref), np.tile(np.abs(pairw), 7))
+    err = np.abs(np.asarray(got) - np.asarray(ref))
+    bad = err > RTOL * scale
+    assert not bad.any(), "max err/scale = %g at %s" % (np.max(err / np.maximum(scale, 1e-300)), np.flatnonzero(bad)[:5])
+
+
+@pytest.mark.parametrize("flags", ["", "fp32", "fp64", "fp16,global", "per_particle"])
+@pytest.mark.parametrize("name", sorted(C.VORO_CASES))
+def test_voronoi_golden(golden_dir, name, flags, tmp_path):
+    from newanalysis.gfunction import RDF_voronoi
+    raw, out, meta = load_golden(golden_dir, name)
+    case = C.VORO_CASES[name]
+    if flags == "per_particle" and case["n1"] > 1000:
+        pytest.skip("per-particle layout only on the small cases")
+    rdf = C.drive_voro(C.make_voro(RDF_voronoi, case, gfn_flags=flags), case)
+    hn, ns = meta["histo_n"], meta["nshells"]
+    rows = hn * ns
+    assert int(rdf.histo_n) == hn and int(rdf.nshells) == ns and rdf.ctr == meta["ctr"]
+    assert bool(rdf.oneistwo) == meta["oneistwo"] and float(rdf.volume) == meta["volume"]
+    got = rdf.raw_histogram()
+    assert got.shape == (7 * rows,)
+    if meta["mode_sel"] & 1:
+        assert np.array_equal(got[:rows], raw[:rows]), "g000 not bit-exact"
+    assert_shell_hist_close(got, raw, rows, np.maximum(rdf.pair_weight, raw[:rows]))
+    if flags == "per_particle":
+        pp = rdf.histogram
+        assert pp.shape == (7 * case["n1"] * rows,)
+        assert_shell_hist_close(pp.reshape(7, case["n1"], rows).sum(1).reshape(-1), raw, rows, np.maximum(rdf.pair_weight, raw[:rows]))
+    rdf.write(str(tmp_path / "g"))
+    if meta["mode_sel"] & 1:
+        assert np.array_equal(rdf.histogram_out[:rows], out[:rows])
+    for key, text in meta["dat"].items():
+        sh, mode = key.split("_")
+        a = np.loadtxt(str(tmp_path / ("g_shell%s_g%s.dat" % (sh, mode))))
+        b = np.array([[float(v) for v in ln.split()] for ln in text.strip().splitlines()])
+        assert a.shape == b.shape and np.allclose(a, b, rtol=0, atol=2e-5)
+        if mode == "000":
+            assert (tmp_path / ("g_shell%s_g000.dat" % sh)).read_text() == text
+
+
+def test_voronoi_against_oracle_larger():
+    """2048 molecules of 2 sites, 3 shells, self: counts exact per shell, weights within 1e-12."""
+    from newanalysis.gfunction import RDF_voronoi
+    case = dict(n1=4096, n2=4096, nmol1=2048, nmol2=2048, box=(49.67, None, None), modes=["all"], hmin=0.0, hmax=15.0, dr=0.05,
+                nshells=3, frames=2, same=True, seed=91, exclude_self=True)
+    gpu = C.drive_voro(C.make_voro(RDF_voronoi, case), case)
+    got = gpu.raw_histogram()
+    rows = 300 * 3
+    ref = np.zeros(7 * rows)
+    o = C.make_voro(O.OracleRDFVoronoi, dict(case, n1=1, n2=1, nmol1=1, nmol2=1))     # host parameters only
+    for f in range(case["frames"]):
+        c1, c2, d1, d2, _, dl = C.build_voro_inputs(case, f)
+        big = np.zeros(7 * case["n1"] * rows)
+        rc, oob = O.calc_histo_shells_c(c1, c2, d1, d2, big, o.box_dim, o.histo_min, o.histo_max, 300, o.histo_inv_dr, 127,
+                                        case["nmol1"], case["nmol2"], 3, dl, True)
+        assert rc == 0 and oob == 0
+        ref += big.reshape(7, case["n1"], rows).sum(1).reshape(-1)
+    assert np.array_equal(got[:rows], ref[:rows])
+    assert_shell_hist_close(got, ref, rows, np.maximum(gpu.pair_weight, ref[:rows]))
+
+
+def test_voronoi_argument_errors():
+    from newanalysis.gfunction import RDF_voronoi
+    n = 64
+    c = np.random.default_rng(1).random((n, 3)) * 20.0
+    d = np.ones((n, 3))
+    r = RDF_voronoi(["all"], 0.0, 8.0, 0.1, n, n, 16, 16, 20.0, 2)
+    with pytest.raises(TypeError, match="first selection"):
+        r.calcFrame(c, c, np.ones((16, n), dtype=np.int32))
+    with pytest.raises(ValueError):                       # matrix smaller than the reference's indexing needs
+        r.calcFrame(c, c, np.ones((16, 16), dtype=np.int32), d, d)
+    r2 = RDF_voronoi(["000"], 0.0, 8.0, 0.1, n, n, 16, 16, 20.0, 2)
+    r2.calcFrame(c, c, np.ones((16, n), dtype=np.int32))
+    with pytest.raises(ValueError, match="changed shape"):
+        r2.calcFrame(c, c, np.ones((17, n), dtype=np.int32))
+    assert r2.raw_histogram().reshape(7, 80, 2)[0, :, 0].sum() > 0
+    with pytest.raises(ValueError):
+        RDF_voronoi(["000"], 0.0, 8.0, 0.1, n, n, 128, 16, 20.0, 2).calcFrame(c, c, np.ones((128, n), dtype=np.int32))
+
+
+@pytest.mark.parametrize("name", sorted(C.TSVORO_CASES))
+def test_calc_histo_ts_voro_golden(golden_dir, name):
+    from newanalysis.gfunction import calcHistoTSVoro
+    want = np.load(os.path.join(golden_dir, "tsvoro.npz"))[name]
+    got = C.drive_tsvoro(calcHistoTSVoro, C.TSVORO_CASES[name])
+    assert np.array_equal(got, want)

@@ -150,3 +150,41 @@ def test_residue_oracle_matches_reference_module_when_present():
     assert np.array_equal(com, O.com_by_residue_c(coor, masses, apr, rfa))
     assert np.array_equal(H.dipByResidue(coor, charges, masses, apr.shape[0], apr, rfa, com),
                           O.dip_by_residue_c(coor, charges, apr, rfa, com))
+
+
+# ---- N2: shell-resolved g-functions (RDF_voronoi gfunction.pyx:764-1148, calcHistoTSVoro :195-224) --------------
+@pytest.mark.parametrize("name", sorted(C.VORO_CASES))
+def test_voronoi_oracle_matches_golden(golden_dir, name, tmp_path):
+    raw, out, meta = load_golden(golden_dir, name)
+    case = C.VORO_CASES[name]
+    assert C.voro_digest(case) == meta["digest"]
+    rdf = C.drive_voro(C.make_voro(O.OracleRDFVoronoi, case), case)
+    assert int(rdf.histo_n) == meta["histo_n"] and int(rdf.nshells) == meta["nshells"]
+    assert bool(rdf.oneistwo) == meta["oneistwo"] and rdf.ctr == meta["ctr"]
+    assert float(rdf.volume) == meta["volume"]            # update_box leaves the volume alone (reference quirk)
+    assert np.array_equal(rdf.raw_sum(), raw)             # bit-exact, all modes and shells
+    rdf.write(str(tmp_path / "g"))
+    assert np.array_equal(rdf.histogram_out, out)
+    for key, text in meta["dat"].items():
+        sh, mode = key.split("_")
+        assert (tmp_path / ("g_shell%s_g%s.dat" % (sh, mode))).read_text() == text
+
+
+@pytest.mark.parametrize("name", sorted(C.TSVORO_CASES))
+def test_tsvoro_oracle_matches_golden(golden_dir, name):
+    want = np.load(os.path.join(golden_dir, "tsvoro.npz"))[name]
+
+    def fn(core, surr, result, ds, maxshell, boxl, t, hmin, hmax, invdx):
+        O.calc_histo_ts_voro_c(core, surr, result[t], ds[t], maxshell, boxl, hmin, hmax, invdx)
+    assert np.array_equal(C.drive_tsvoro(fn, C.TSVORO_CASES[name]), want)
+
+
+def test_voronoi_oracle_matches_reference_module():
+    ref = O.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    case = dict(n1=90, n2=60, nmol1=30, nmol2=20, box=(18.0, None, None), modes=["all"], hmin=0.0, hmax=9.0, dr=0.1,
+                nshells=3, frames=2, same=False, seed=77, exclude_self=True)
+    a = C.drive_voro(C.make_voro(ref.RDF_voronoi, case), case)
+    b = C.drive_voro(C.make_voro(O.OracleRDFVoronoi, case), case)
+    assert np.array_equal(a.histogram, b.histogram)
