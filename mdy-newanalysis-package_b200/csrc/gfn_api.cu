@@ -205,6 +205,7 @@ void fill_params(gfn_t* h, Dev& d, PairParams& p)
     p.poll_ns = 120; p.poll_reps = 1;
     if (const char* e = getenv("GFN_POLL_NS")) p.poll_ns = (unsigned)atoi(e);
     if (const char* e = getenv("GFN_POLL_REPS")) p.poll_reps = atoi(e);
+    if (const char* e = getenv("GFN_DEBUG")) p.debug = atoi(e);
     p.strideA = h->n1_pad; p.strideB = h->n2_pad;
     p.shell_mode = h->shells.layout; p.nshells = h->shells.nshells; p.histo_nr = h->histo_nr;
     p.apr1 = h->shells.apr_core; p.apr2 = h->shells.apr_surround; p.map_ld = h->shells.map_ld; p.excl_self = h->shells.exclude_self;
@@ -424,7 +425,7 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
     for (size_t i = 0; i < devs.size(); ++i) h->devs[i].dev = devs[i];
     for (Dev& d : h->devs) {
         CUC(cudaSetDevice(d.dev));
-        CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, &d.cfg));
+        CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, &d.cfg));
     }
     // work decomposition (identical on all devices)
     {

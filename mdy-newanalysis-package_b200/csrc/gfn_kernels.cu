@@ -79,7 +79,7 @@ prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* 
         } else {
             r.px = r.py = r.pz = 0.0; r.norm = 0.0;
         }
-        r.spare = 0.0;
+        r.spare = __drcp_rn(r.norm);       // 1/norm for the cosines (inf for a zero dipole: such sites take the exact division path)
         if (half_filter) {
             // fp16 filter: coordinates in units of the longest box edge, each duplicated into both halves of a
             // half2 so that one broadcast LDS.128 feeds the two core sites a filter thread keeps in one register
@@ -229,6 +229,23 @@ __device__ __forceinline__ double sqrt_inrange(double x)
     return fma(d, h, g);
 }
 
+// same sequence, also handing back the refined reciprocal root y ~ 1/sqrt(x) (relative error ~2^-52): 1/dist for
+// the orientation cosines comes for free with the distance
+__device__ __forceinline__ double sqrt_rsqrt_inrange(double x, double& rinv)
+{
+    double y = rsq64h(x);
+    const double t = __dmul_rn(y, y);
+    const double e = fma(x, -t, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    const double u = __dmul_rn(y, e);
+    y = fma(p, u, y);
+    rinv = y;
+    const double g = __dmul_rn(x, y);
+    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));   // y / 2
+    const double d = fma(g, -g, x);
+    return fma(d, h, g);
+}
+
 // |x| in [2^-300, 2^300]: far inside the range where the sequences above are exact (no intermediate can
 // overflow, underflow or lose bits to subnormals)
 __device__ __forceinline__ bool mid_range(double x)
@@ -306,7 +323,7 @@ __device__ __forceinline__ void release_stage(Ctrl* c, Site* jsite, const Site* 
 // Warps [NF,NF+4) are DRAIN warps (one per SM sub-partition): they consume the rings of filter warps
 // w = d, d+4, d+8 in that fixed order, evaluate two survivors per lane exactly in fp64 and add them
 // into their private histogram replica.  Registers are re-balanced with setmaxnreg.
-template <typename F, int NF, int ND, bool WEIGHTS, int HIST, bool ALLM>
+template <typename F, int NF, int ND, bool WEIGHTS, int HIST, bool ALLM, bool SHELLS>
 __global__ void __launch_bounds__((NF + ND) * 32, 1)
 pair_kernel(const PairParams P)
 {
@@ -356,7 +373,7 @@ pair_kernel(const PairParams P)
         // =========================================== FILTER ===========================================
         if (ND == 8)   asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
         else if (kF32 || kH16) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        else           asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        else           asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         unsigned short* q = rings + warp * kRingCap;
         unsigned tail = 0, head_seen = 0;
 
@@ -428,6 +445,7 @@ pair_kernel(const PairParams P)
                 mbar_wait(&ctrl->full[st], (g / S) & 1);
                 const Site* js = jsite + st * TJ;
 
+                unsigned mk0 = 0u, mk1 = 0u, mk2 = 0u, mk3 = 0u, mk4 = 0u, mk5 = 0u, mk6 = 0u, mk7 = 0u;   // masks of the tile: [chunk][core slot]
                 for (int jc = 0; jc < TJ / 32; ++jc) {
                     const int jbase = jc * 32;
                     if (j0 + jbase >= P.n2) break;                              // padding only
@@ -482,46 +500,82 @@ pair_kernel(const PairParams P)
                             }
                         }
                     }
-                    // ---- publish survivors into this warp's ring: warp-uniform rounds, one survivor per lane and
-                    //      core slot per round, compacted with ballots (no scan, no divergent loops).  Ring order:
-                    //      round, core slot, lane - fixed, so the summation order stays deterministic. ----
-                    if (!__any_sync(0xffffffffu, (m0 | m1) != 0u)) continue;
-                    {
-                        unsigned total = __reduce_add_sync(0xffffffffu, (unsigned)(__popc(m0) + __popc(m1)));
-                        unsigned hold1 = 0u;
-                        // a push must fit behind a partial batch the drain warp is still waiting to fill (< 32*kU unread
-                        // entries): at most half the ring at once, so a dense chunk goes in two pushes
-                        if (total > (unsigned)kRingCap / 2u) { hold1 = m1; m1 = 0u; total = __reduce_add_sync(0xffffffffu, (unsigned)__popc(m0)); }
-                        const unsigned lt = (1u << lane) - 1u;
-                        const unsigned tag0 = ((unsigned)st << 13) | ((unsigned)lane << 7) | (unsigned)jbase;   // stage | core slot | site
-                        const unsigned tag1 = tag0 | (32u << 7);
-                        for (;;) {
-                            while (tail + total - head_seen > (unsigned)kRingCap) {      // ring full: wait for the drain warp
+                    if (jc == 0) { mk0 = m0; mk1 = m1; } else if (jc == 1) { mk2 = m0; mk3 = m1; }
+                    else if (jc == 2) { mk4 = m0; mk5 = m1; } else { mk6 = m0; mk7 = m1; }
+                }
+                // ---- publish the tile's survivors into this warp's ring, once per tile: one scan over the lanes' counts,
+                //      then every lane writes its own entries (lane-major, then chunk, core slot, site: a fixed order, so
+                //      the summation order stays deterministic).  Two branch-free extraction steps per mask cover almost
+                //      every lane (0.5 survivors per mask and lane at cfg3); the rest loops. ----
+                if (!(P.debug & 2)) {
+                    static_assert(TJ / 32 == 4, "eight masks per tile");
+                    const unsigned c0 = __popc(mk0), c1 = __popc(mk1), c2 = __popc(mk2), c3 = __popc(mk3);
+                    const unsigned c4 = __popc(mk4), c5 = __popc(mk5), c6 = __popc(mk6), c7 = __popc(mk7);
+                    const unsigned cnt = ((c0 + c1) + (c2 + c3)) + ((c4 + c5) + (c6 + c7));
+                    unsigned incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += up;
+                    }
+                    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+                    const unsigned tagl = ((unsigned)st << 13) | ((unsigned)lane << 7);     // stage | core slot | (site below)
+                    // one mask: entries from ring position `at` on
+                    auto emit = [&](unsigned m, unsigned tag, unsigned at) {
+#pragma unroll
+                        for (int s2 = 0; s2 < 2; ++s2) {
+                            const bool hv = m != 0u;
+                            const int jj = __clz(m);
+                            if (hv) q[at & RMASK] = (unsigned short)(tag + (unsigned)jj);
+                            m = hv ? (m & ~(0x80000000u >> (jj & 31))) : 0u;
+                            at += hv ? 1u : 0u;
+                        }
+                        while (__any_sync(0xffffffffu, m != 0u)) {
+                            if (m) {
+                                const int jj = __clz(m);
+                                q[at & RMASK] = (unsigned short)(tag + (unsigned)jj);
+                                m &= ~(0x80000000u >> jj);
+                                ++at;
+                            }
+                        }
+                    };
+                    if (total != 0u && total <= (unsigned)kRingCap / 2u) {
+                        // a push must fit behind a partial batch the drain warp is still waiting to fill: at most half the ring
+                        while (tail + total - head_seen > (unsigned)kRingCap) {      // ring full: wait for the drain warp
+                            head_seen = ctrl->head[warp];
+                            if (tail + total - head_seen > (unsigned)kRingCap) __nanosleep(64);
+                        }
+                        const unsigned a0 = tail + (incl - cnt);
+                        const unsigned a1 = a0 + c0, a2 = a1 + c1, a3 = a2 + c2, a4 = a3 + c3, a5 = a4 + c4, a6 = a5 + c5, a7 = a6 + c6;
+                        emit(mk0, tagl, a0);               emit(mk1, tagl + (32u << 7), a1);
+                        emit(mk2, tagl + 32u, a2);         emit(mk3, tagl + (32u << 7) + 32u, a3);
+                        emit(mk4, tagl + 64u, a4);         emit(mk5, tagl + (32u << 7) + 64u, a5);
+                        emit(mk6, tagl + 96u, a6);         emit(mk7, tagl + (32u << 7) + 96u, a7);
+                        tail += total;
+                        __syncwarp();
+                        if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
+                    } else if (total != 0u) {
+                        // dense tile: mask by mask (<= 32*32 entries each), each with its own scan
+#pragma unroll 1
+                        for (int i = 0; i < 8; ++i) {
+                            const unsigned m = i == 0 ? mk0 : i == 1 ? mk1 : i == 2 ? mk2 : i == 3 ? mk3 : i == 4 ? mk4 : i == 5 ? mk5 : i == 6 ? mk6 : mk7;
+                            const unsigned ci = __popc(m);
+                            unsigned inc = ci;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const unsigned up = __shfl_up_sync(0xffffffffu, inc, d);
+                                if (lane >= d) inc += up;
+                            }
+                            const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
+                            if (tot == 0u) continue;
+                            while (tail + tot - head_seen > (unsigned)kRingCap) {
                                 head_seen = ctrl->head[warp];
-                                if (tail + total - head_seen > (unsigned)kRingCap) __nanosleep(64);
+                                if (tail + tot - head_seen > (unsigned)kRingCap) __nanosleep(64);
                             }
-                            for (;;) {
-                                const unsigned b0 = __ballot_sync(0xffffffffu, m0 != 0u);
-                                const unsigned b1 = __ballot_sync(0xffffffffu, m1 != 0u);
-                                if ((b0 | b1) == 0u) break;
-                                if (m0) {
-                                    const int jj = __clz(m0);
-                                    m0 &= ~(0x80000000u >> jj);
-                                    q[(tail + __popc(b0 & lt)) & RMASK] = (unsigned short)(tag0 + (unsigned)jj);
-                                }
-                                tail += __popc(b0);
-                                if (m1) {
-                                    const int jj = __clz(m1);
-                                    m1 &= ~(0x80000000u >> jj);
-                                    q[(tail + __popc(b1 & lt)) & RMASK] = (unsigned short)(tag1 + (unsigned)jj);
-                                }
-                                tail += __popc(b1);
-                            }
+                            emit(m, tagl + ((unsigned)(i & 1) << 12) + (unsigned)(i >> 1) * 32u, tail + (inc - ci));
+                            tail += tot;
                             __syncwarp();
                             if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
-                            if (!__any_sync(0xffffffffu, hold1 != 0u)) break;
-                            m1 = hold1; hold1 = 0u;
-                            total = __reduce_add_sync(0xffffffffu, (unsigned)__popc(m1));
                         }
                     }
                 }
@@ -571,9 +625,10 @@ pair_kernel(const PairParams P)
             auto process_batch = [&](const unsigned short* q, const int fw, const unsigned head, const int n) {
                         // ---- exact evaluation: kU survivors per lane, branch-free so that ptxas interleaves
                         //      the dependent fp64 chains of all of them ---------------------------------------
+                        if (P.debug & 1) { __syncwarp(); if (lane == 0) ctrl->head[fw] = head + (unsigned)n; return; }
                         bool ok[kU]; int pos[kU], gi[kU], gj[kU]; double w[kU], v[kU][6];
                         double dxa[kU], dya[kU], dza[kU], d2[kU], dist[kU];
-                        double apx[kU], apy[kU], apz[kU], an[kU], bpx[kU], bpy[kU], bpz[kU], bn[kU];
+                        double apx[kU], apy[kU], apz[kU], an[kU], bpx[kU], bpy[kU], bpz[kU], bn[kU], ian[kU], ibn[kU], idist[kU];
                         bool self_pair[kU];
 #pragma unroll
                         for (int u = 0; u < kU; ++u) {
@@ -584,15 +639,15 @@ pair_kernel(const PairParams P)
                             const int stg = (int)(e >> 13);
                             const Site* js = jsite + stg * TJ;
                             const int i = it.i0 + il, j = (stg == 0 ? j0s0 : (stg == 1 ? j0s1 : j0s2)) + jl;
-                            gi[u] = i; gj[u] = j;
+                            gi[u] = i; if (SHELLS) gj[u] = j;
                             self_pair[u] = (i == j);
                             ok[u] = have && i < P.n1 && j < P.n2 && !(P.tri && j < i);
                             const double2* ap = reinterpret_cast<const double2*>(isite + il);
                             const double2* bp = reinterpret_cast<const double2*>(js + jl);
                             const double2 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];   // x y | z px | py pz | norm -
                             const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-                            apx[u] = a1.y; apy[u] = a2.x; apz[u] = a2.y; an[u] = a3.x;
-                            bpx[u] = b1.y; bpy[u] = b2.x; bpz[u] = b2.y; bn[u] = b3.x;
+                            apx[u] = a1.y; apy[u] = a2.x; apz[u] = a2.y; an[u] = a3.x; ian[u] = a3.y;
+                            bpx[u] = b1.y; bpy[u] = b2.x; bpz[u] = b2.y; bn[u] = b3.x; ibn[u] = b3.y;
                             dxa[u] = min_image(DSUB(b0.x, a0.x), bx.Lx, bx.hx);                     // :141-147
                             dya[u] = min_image(DSUB(b0.y, a0.y), bx.Ly, bx.hy);
                             dza[u] = min_image(DSUB(b1.x, a1.x), bx.Lz, bx.hz);
@@ -611,10 +666,10 @@ pair_kernel(const PairParams P)
                         for (int u = 0; u < kU; ++u) { if (!ok[u]) d2[u] = 1.0; rng = rng && mid_range(d2[u]); }
                         if (__all_sync(0xffffffffu, rng)) {
 #pragma unroll
-                            for (int u = 0; u < kU; ++u) dist[u] = sqrt_inrange(d2[u]);
+                            for (int u = 0; u < kU; ++u) dist[u] = sqrt_rsqrt_inrange(d2[u], idist[u]);
                         } else {
 #pragma unroll
-                            for (int u = 0; u < kU; ++u) dist[u] = __dsqrt_rn(d2[u]);
+                            for (int u = 0; u < kU; ++u) { dist[u] = __dsqrt_rn(d2[u]); idist[u] = __drcp_rn(dist[u]); }
                         }
                         // --- range test :149, bin :150, weight :131-134
 #pragma unroll
@@ -624,7 +679,7 @@ pair_kernel(const PairParams P)
                             pos[u] = __double2int_rd(DMUL(DSUB(dist[u], P.hmin), P.invdx));
                             w[u] = (P.tri && !self_pair[u]) ? 2.0 : 1.0;
                         }
-                        if (P.shell_mode) {
+                        if (SHELLS) {
                             // shell-resolved rows: the bin index gains the shell read from this frame's matrix
                             const int* map = P.shell_map + (long long)it.f * P.stride_map;
 #pragma unroll
@@ -646,10 +701,42 @@ pair_kernel(const PairParams P)
                         }
 #pragma unroll
                         for (int u = 0; u < kU; ++u) n_inr += ok[u] ? 1u : 0u;
+                        // shared-memory replicas: lanes that hit the same bin will take turns in lane order (deterministic,
+                        // no fp64 atomics).  The ranking is started here so that MATCH/REDUX overlap the weight arithmetic.
+                        bool addf[kU]; int rnk[kU], mxr[kU];
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            addf[u] = ok[u] && pos[u] < hn;            // pos >= hn: quirk Q3, handled below
+                            rnk[u] = 0; mxr[u] = 0;
+                            if (HIST == 0 && WEIGHTS) {
+                                const unsigned key = addf[u] ? (unsigned)pos[u] : (0x40000000u | lane);
+                                const unsigned grp = __match_any_sync(0xffffffffu, key);
+                                rnk[u] = __popc(grp & ((1u << lane) - 1u));
+                                mxr[u] = (int)__reduce_max_sync(0xffffffffu, addf[u] ? (unsigned)rnk[u] : 0u);
+                            }
+                        }
                         if (WEIGHTS) {
-                            // --- orientation weights :154-165, all three cosines (unselected ones are masked below)
-                            double den[kU][3], num[kU][3], c[kU][3];
-                            bool drng = true;
+                            // --- orientation weights :154-165, all three cosines (unselected ones are never added)
+                            double c[kU][3];
+                            // Usual case: every needed norm of the warp's in-range pairs lies in [2^-300, 2^300].  Then no
+                            // denominator clen*slen, clen*dist, slen*dist can be zero or leave the normal range (quirk Q5
+                            // cannot fire), and the cosines are formed with the reciprocals 1/norm (prep_kernel) and 1/dist
+                            // (by-product of the root): 2 multiplications each, relative error < 4 ulp - far inside the
+                            // 1e-12 bar for the weighted rows; bins never depend on them.
+                            bool nrm = true;
+#pragma unroll
+                            for (int u = 0; u < kU; ++u)
+                                nrm = nrm && (!ok[u] || ((!(m_cs || m_cd) || mid_range(an[u])) && (!(m_cs || m_sd) || mid_range(bn[u]))));
+                            if (__all_sync(0xffffffffu, nrm)) {
+#pragma unroll
+                                for (int u = 0; u < kU; ++u) {
+                                    c[u][0] = DMUL(DOT3(apx[u], apy[u], apz[u], bpx[u], bpy[u], bpz[u]), DMUL(ian[u], ibn[u]));
+                                    c[u][1] = DMUL(DOT3(apx[u], apy[u], apz[u], dxa[u], dya[u], dza[u]), DMUL(ian[u], idist[u]));
+                                    c[u][2] = DMUL(DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]), DMUL(ibn[u], idist[u]));
+                                }
+                            } else {
+                            // rare: IEEE divisions with the reference's zero-denominator semantics
+                            double den[kU][3], num[kU][3];
 #pragma unroll
                             for (int u = 0; u < kU; ++u) {
                                 den[u][0] = DMUL(an[u], bn[u]);
@@ -663,19 +750,9 @@ pair_kernel(const PairParams P)
                                     const bool sel = k == 0 ? m_cs : (k == 1 ? m_cd : m_sd);
                                     if (ok[u] && sel && den[u][k] == 0.0) zerodiv = true;          // quirk Q5
                                     if (!ok[u] || !sel || den[u][k] == 0.0) { den[u][k] = 1.0; num[u][k] = 0.0; }
-                                    drng = drng && mid_range(den[u][k]);
+                                    c[u][k] = DDIV(num[u][k], den[u][k]);
                                 }
                             }
-                            if (__all_sync(0xffffffffu, drng)) {
-#pragma unroll
-                                for (int u = 0; u < kU; ++u)
-#pragma unroll
-                                    for (int k = 0; k < 3; ++k) c[u][k] = div_inrange(num[u][k], den[u][k]);
-                            } else {
-#pragma unroll
-                                for (int u = 0; u < kU; ++u)
-#pragma unroll
-                                    for (int k = 0; k < 3; ++k) c[u][k] = DDIV(num[u][k], den[u][k]);
                             }
 #pragma unroll
                             for (int u = 0; u < kU; ++u)
@@ -694,42 +771,46 @@ pair_kernel(const PairParams P)
                         if (lane == 0) ctrl->head[fw] = head + (unsigned)n;     // entries are in registers: the producer may reuse them
 
                         // ---- accumulate ----------------------------------------------------------------------
+                        bool slow = false;
 #pragma unroll
-                        for (int u = 0; u < kU; ++u) {
-                            const bool spill = ok[u] && pos[u] >= hn;          // quirk Q3
-                            if ((HIST != 0 && ok[u]) || spill) {
-                                const double v0 = (mode_sel & 1) ? w[u] : 0.0;                                // :152
-                                if (spill) ++n_ovf;
-                                if (!(spill && (P.flags & GFN_FLAG_DISCARD_OVERFLOW))) {
-                                    const int hm = HIST == 0 ? 1 : HIST;
-                                    if (mode_sel & 1)  global_add(P, hm, 0, gi[u], pos[u], v0);
-                                    if (mode_sel & 2)  global_add(P, hm, 1, gi[u], pos[u], v[u][0]);
-                                    if (mode_sel & 4)  global_add(P, hm, 2, gi[u], pos[u], v[u][1]);
-                                    if (mode_sel & 8)  global_add(P, hm, 3, gi[u], pos[u], v[u][2]);
-                                    if (mode_sel & 16) global_add(P, hm, 4, gi[u], pos[u], v[u][3]);
-                                    if (mode_sel & 32) global_add(P, hm, 5, gi[u], pos[u], v[u][4]);
-                                    if (mode_sel & 64) global_add(P, hm, 6, gi[u], pos[u], v[u][5]);
-                                    if (!spill) atomicAdd(P.gacc + 7ll * hn + pos[u], w[u]);      // pair weight row
+                        for (int u = 0; u < kU; ++u) slow = slow || (ok[u] && (HIST != 0 || pos[u] >= hn));
+                        if (HIST != 0 || __any_sync(0xffffffffu, slow)) {
+                            // global accumulators: the per-particle / global-atomic variants, and quirk Q3 spills
+#pragma unroll
+                            for (int u = 0; u < kU; ++u) {
+                                const bool spill = ok[u] && pos[u] >= hn;
+                                if ((HIST != 0 && ok[u]) || spill) {
+                                    const double v0 = (mode_sel & 1) ? w[u] : 0.0;                                // :152
+                                    if (spill) ++n_ovf;
+                                    if (!(spill && (P.flags & GFN_FLAG_DISCARD_OVERFLOW))) {
+                                        const int hm = HIST == 0 ? 1 : HIST;
+                                        if (mode_sel & 1)  global_add(P, hm, 0, gi[u], pos[u], v0);
+                                        if (mode_sel & 2)  global_add(P, hm, 1, gi[u], pos[u], v[u][0]);
+                                        if (mode_sel & 4)  global_add(P, hm, 2, gi[u], pos[u], v[u][1]);
+                                        if (mode_sel & 8)  global_add(P, hm, 3, gi[u], pos[u], v[u][2]);
+                                        if (mode_sel & 16) global_add(P, hm, 4, gi[u], pos[u], v[u][3]);
+                                        if (mode_sel & 32) global_add(P, hm, 5, gi[u], pos[u], v[u][4]);
+                                        if (mode_sel & 64) global_add(P, hm, 6, gi[u], pos[u], v[u][5]);
+                                        if (!spill) atomicAdd(P.gacc + 7ll * hn + pos[u], w[u]);      // pair weight row
+                                    }
                                 }
                             }
-                            if (HIST == 0) {
-                                if (32 * u >= n) continue;                // warp-uniform: this part of the batch is empty
-                                const bool add = ok[u] && !spill;
-                                if (add) atomicAdd(cnt + pos[u], (P.tri && !self_pair[u]) ? 2u : 1u);   // :152 and the weight row
-                                if (WEIGHTS) {
-                                    // lanes that hit the same bin take turns in lane order (deterministic, no fp64 atomics)
-                                    const unsigned key = add ? (unsigned)pos[u] : (0x40000000u | lane);
-                                    const unsigned grp = __match_any_sync(0xffffffffu, key);
-                                    const int rank = __popc(grp & ((1u << lane) - 1u));
-                                    const int maxr = __reduce_max_sync(0xffffffffu, add ? (unsigned)rank : 0u);
-                                    if (use_lock) {
-                                        if (lane == 0) { while (atomicCAS(&ctrl->locks[rep], 0, 1) != 0) __nanosleep(40); }
-                                        __syncwarp();
-                                        __threadfence_block();
-                                    }
+                        }
+                        if (HIST == 0) {
+#pragma unroll
+                            for (int u = 0; u < kU; ++u)
+                                if (addf[u]) atomicAdd(cnt + pos[u], (P.tri && !self_pair[u]) ? 2u : 1u);   // :152 and the weight row
+                            if (WEIGHTS) {
+                                if (use_lock) {
+                                    if (lane == 0) { while (atomicCAS(&ctrl->locks[rep], 0, 1) != 0) __nanosleep(40); }
+                                    __syncwarp();
+                                    __threadfence_block();
+                                }
+#pragma unroll
+                                for (int u = 0; u < kU; ++u) {
                                     double2* hp = reinterpret_cast<double2*>(wsum + (size_t)pos[u] * 6);
-                                    for (int rr = 0; rr <= maxr; ++rr) {
-                                        if (add && rank == rr) {
+                                    for (int rr = 0; rr <= mxr[u]; ++rr) {
+                                        if (addf[u] && rnk[u] == rr) {
                                             double2 h0 = hp[0], h1 = hp[1], h2 = hp[2];
                                             if (ALLM || (mode_sel & 2))  h0.x += v[u][0];       // g110
                                             if (ALLM || (mode_sel & 4))  h0.y += v[u][1];       // g101
@@ -741,11 +822,11 @@ pair_kernel(const PairParams P)
                                         }
                                         __syncwarp();
                                     }
-                                    if (use_lock) {
-                                        __threadfence_block();
-                                        __syncwarp();
-                                        if (lane == 0) atomicExch(&ctrl->locks[rep], 0);
-                                    }
+                                }
+                                if (use_lock) {
+                                    __threadfence_block();
+                                    __syncwarp();
+                                    if (lane == 0) atomicExch(&ctrl->locks[rep], 0);
                                 }
                             }
                         }
@@ -939,31 +1020,35 @@ static size_t smem_fixed_bytes(int nf)
 
 typedef void (*pair_fn_t)(const PairParams);
 
-template <typename F, int NF, int ND>
+template <typename F, int NF, int ND, bool SHELLS>
 static pair_fn_t pick_shape(int hist_mode, bool weights, bool allm)
 {
     if (hist_mode == 0) {
-        if (!weights) return pair_kernel<F, NF, ND, false, 0, false>;
-        return allm ? pair_kernel<F, NF, ND, true, 0, true> : pair_kernel<F, NF, ND, true, 0, false>;
+        if (!weights) return pair_kernel<F, NF, ND, false, 0, false, SHELLS>;
+        return allm ? pair_kernel<F, NF, ND, true, 0, true, SHELLS> : pair_kernel<F, NF, ND, true, 0, false, SHELLS>;
     }
-    return hist_mode == 1 ? pair_kernel<F, NF, ND, true, 1, false> : pair_kernel<F, NF, ND, true, 2, false>;
+    return hist_mode == 1 ? pair_kernel<F, NF, ND, true, 1, false, SHELLS> : pair_kernel<F, NF, ND, true, 2, false, SHELLS>;
 }
 
 template <typename F>
 static pair_fn_t pick_fn(const PairConfig& c)
 {
-    const int nf = c.warps - c.drain_warps;
     const bool weights = c.nslot == 8, allm = c.all_modes != 0;
-    if (c.drain_warps == 8) return pick_shape<F, 8, 8>(c.hist_mode, weights, allm);
-    return nf == 12 ? pick_shape<F, 12, 4>(c.hist_mode, weights, allm) : pick_shape<F, 8, 4>(c.hist_mode, weights, allm);
+    if (c.shells) return c.drain_warps == 8 ? pick_shape<F, 8, 8, true>(c.hist_mode, weights, allm) : pick_shape<F, 8, 4, true>(c.hist_mode, weights, allm);
+    return c.drain_warps == 8 ? pick_shape<F, 8, 8, false>(c.hist_mode, weights, allm) : pick_shape<F, 8, 4, false>(c.hist_mode, weights, allm);
 }
 
+#ifdef GFN_EXP_ONLY_H16      // experiment builds (profiles/exp.sh): one instantiation, seconds to compile; cfg3 fp16 shape only
+static pair_fn_t pick(const PairConfig& c) { return pair_kernel<__half, 8, 8, true, 0, true, false>; }
+#else
 static pair_fn_t pick(const PairConfig& c) { return c.filter_fp64 == 1 ? pick_fn<double>(c) : (c.filter_fp64 == 2 ? pick_fn<__half>(c) : pick_fn<float>(c)); }
+#endif
 
 int tile_i(const PairConfig& cfg) { return (cfg.warps - cfg.drain_warps) * 32 * kIPT; }
 
-cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, PairConfig* cfg)
+cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, int shells, PairConfig* cfg)
 {
+    cfg->shells = shells ? 1 : 0;
     static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block does not fit");
     cudaError_t e;
     int max_smem = 0, sms = 0;
@@ -973,12 +1058,11 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
     cfg->nslot = (mode_sel == 1) ? 1 : 8;
     cfg->all_modes = (mode_sel == 127) ? 1 : 0;
     cfg->nrep = 1;
-    // CTA shapes in order of preference: 8 filter + 8 drain warps, 12 + 4, 8 + 4
-    const int shapes[3][2] = {{8, 8}, {12, 4}, {8, 4}};
+    // CTA shapes in order of preference: 8 filter + 8 drain warps, 8 + 4 (fewer histogram replicas to fit)
+    const int shapes[2][2] = {{8, 8}, {8, 4}};
     int force_nf = 0, force_nd = 0;
     if (const char* env = getenv("GFN_FILTER_WARPS")) force_nf = atoi(env);
     if (const char* env = getenv("GFN_DRAIN_WARPS")) force_nd = atoi(env);
-    const double waste12 = (double)((n1 + 767) / 768 * 768) / n1, waste8 = (double)((n1 + 511) / 512 * 512) / n1;
     int nf = 8, nd = 8;
     if (flags & GFN_FLAG_PER_PARTICLE) { cfg->hist_mode = 2; cfg->nslot = 8; }
     else if (flags & GFN_FLAG_HIST_GLOBAL) { cfg->hist_mode = 1; cfg->nslot = 8; }
@@ -986,10 +1070,9 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
         const long long rb = (long long)replica_bytes(histo_n, cfg->nslot == 8);
         cfg->hist_mode = 0;
         int best = -1; long long best_fit = 0;
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 2; ++k) {
             const int f = shapes[k][0], d = shapes[k][1];
             if ((force_nf && force_nf != f) || (force_nd && force_nd != d)) continue;
-            if (f == 12 && waste8 < waste12 * 0.97) continue;            // 768-site core tiles would be mostly padding
             const long long fit = ((long long)max_smem - (long long)smem_fixed_bytes(f)) / rb;
             if (fit >= d) { best = k; best_fit = d; break; }              // a private replica per drain warp
             if (best < 0 && fit >= 1) { best = k; best_fit = fit >= 4 ? 4 : (fit >= 2 ? 2 : 1); }   // shared under a lock
@@ -1001,9 +1084,7 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
             if (cfg->hist_mode == 0 && r >= 1 && r <= cfg->nrep) cfg->nrep = r;
         }
     }
-    if (cfg->hist_mode != 0) {
-        if (force_nf == 12 || force_nd == 4) { nf = force_nf == 8 ? 8 : 12; nd = 4; }
-    }
+    if (cfg->hist_mode != 0 && force_nd == 4) { nf = 8; nd = 4; }
     cfg->drain_warps = nd;
     cfg->warps = nf + nd;
     const bool sh = cfg->hist_mode == 0;

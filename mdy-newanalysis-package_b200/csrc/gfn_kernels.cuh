@@ -47,6 +47,7 @@ struct PairParams {
     unsigned flags;                 // GFN_FLAG_DISCARD_OVERFLOW
     int nrep;                       // histogram replicas in shared memory
     unsigned poll_ns; int poll_reps; // drain-warp back-off while its ring holds less than a batch
+    int debug;                      // GFN_DEBUG ablations (timing experiments only, results wrong): 1 drain discards, 2 filter does not publish
     // shell-resolved histograms (N2: RDF_voronoi gfunction.pyx:570-1148, calcHistoTSVoro :195-224); shell_mode 0 = off.
     // histo_n above counts ALL bins of a row (radial bins x shells); histo_nr is the number of radial bins.
     const int* shell_map;           // [nframes][...] int32 shell matrix of each frame (Delaunay distance)
@@ -67,6 +68,7 @@ struct PairConfig {
     int nrep;          // shared-memory histogram replicas per CTA (drain warps sharing one take a lock)
     int nslot;         // 1 (g000 only) or 8
     int all_modes;     // mode_sel == 127: the kernel variant without mode masks
+    int shells;        // shell-resolved rows (gfn_create_shells): the kernel variant with the shell lookup
     int blocks_per_sm;
     int grid;
     int smem_bytes;
@@ -74,7 +76,7 @@ struct PairConfig {
 
 // Chooses kernel variant, grid and shared-memory size for a histogram of histo_n bins; sets the
 // function attributes.  Returns cudaSuccess or the failing error.
-cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, PairConfig* cfg);
+cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, int shells, PairConfig* cfg);
 cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
 
 // Converts nframes frames of one selection into Site records and the per-frame max |coordinate|.
