@@ -371,7 +371,11 @@ pair_kernel(const PairParams P)
 
     if (warp < NF) {
         // =========================================== FILTER ===========================================
-        if (ND == 8)   asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+#ifndef GFN_REGS_F
+#define GFN_REGS_F "104"
+#define GFN_REGS_D "152"
+#endif
+        if (ND == 8)   asm volatile("setmaxnreg.dec.sync.aligned.u32 " GFN_REGS_F ";");
         else if (kF32 || kH16) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         else           asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         unsigned short* q = rings + warp * kRingCap;
@@ -521,7 +525,9 @@ pair_kernel(const PairParams P)
                     const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
                     const unsigned tagl = ((unsigned)st << 13) | ((unsigned)lane << 7);     // stage | core slot | (site below)
                     // one mask: entries from ring position `at` on
-                    auto emit = [&](unsigned m, unsigned tag, unsigned at) {
+                    // (the first two survivors of a mask go out branch-free; `rest` collects what is left for emit_rest)
+                    unsigned rest = 0u;
+                    auto emit = [&](unsigned& m, unsigned tag, unsigned& at) {
 #pragma unroll
                         for (int s2 = 0; s2 < 2; ++s2) {
                             const bool hv = m != 0u;
@@ -530,13 +536,14 @@ pair_kernel(const PairParams P)
                             m = hv ? (m & ~(0x80000000u >> (jj & 31))) : 0u;
                             at += hv ? 1u : 0u;
                         }
-                        while (__any_sync(0xffffffffu, m != 0u)) {
-                            if (m) {
-                                const int jj = __clz(m);
-                                q[at & RMASK] = (unsigned short)(tag + (unsigned)jj);
-                                m &= ~(0x80000000u >> jj);
-                                ++at;
-                            }
+                        rest |= m;
+                    };
+                    auto emit_rest = [&](unsigned m, unsigned tag, unsigned at) {
+                        while (m) {
+                            const int jj = __clz(m);
+                            q[at & RMASK] = (unsigned short)(tag + (unsigned)jj);
+                            m &= ~(0x80000000u >> jj);
+                            ++at;
                         }
                     };
                     if (total != 0u && total <= (unsigned)kRingCap / 2u) {
@@ -545,12 +552,18 @@ pair_kernel(const PairParams P)
                             head_seen = ctrl->head[warp];
                             if (tail + total - head_seen > (unsigned)kRingCap) __nanosleep(64);
                         }
-                        const unsigned a0 = tail + (incl - cnt);
-                        const unsigned a1 = a0 + c0, a2 = a1 + c1, a3 = a2 + c2, a4 = a3 + c3, a5 = a4 + c4, a6 = a5 + c5, a7 = a6 + c6;
+                        unsigned a0 = tail + (incl - cnt);
+                        unsigned a1 = a0 + c0, a2 = a1 + c1, a3 = a2 + c2, a4 = a3 + c3, a5 = a4 + c4, a6 = a5 + c5, a7 = a6 + c6;
                         emit(mk0, tagl, a0);               emit(mk1, tagl + (32u << 7), a1);
                         emit(mk2, tagl + 32u, a2);         emit(mk3, tagl + (32u << 7) + 32u, a3);
                         emit(mk4, tagl + 64u, a4);         emit(mk5, tagl + (32u << 7) + 64u, a5);
                         emit(mk6, tagl + 96u, a6);         emit(mk7, tagl + (32u << 7) + 96u, a7);
+                        if (__any_sync(0xffffffffu, rest != 0u)) {       // some lane holds three or more survivors of one mask
+                            emit_rest(mk0, tagl, a0);               emit_rest(mk1, tagl + (32u << 7), a1);
+                            emit_rest(mk2, tagl + 32u, a2);         emit_rest(mk3, tagl + (32u << 7) + 32u, a3);
+                            emit_rest(mk4, tagl + 64u, a4);         emit_rest(mk5, tagl + (32u << 7) + 64u, a5);
+                            emit_rest(mk6, tagl + 96u, a6);         emit_rest(mk7, tagl + (32u << 7) + 96u, a7);
+                        }
                         tail += total;
                         __syncwarp();
                         if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
@@ -572,7 +585,7 @@ pair_kernel(const PairParams P)
                                 head_seen = ctrl->head[warp];
                                 if (tail + tot - head_seen > (unsigned)kRingCap) __nanosleep(64);
                             }
-                            emit(m, tagl + ((unsigned)(i & 1) << 12) + (unsigned)(i >> 1) * 32u, tail + (inc - ci));
+                            emit_rest(m, tagl + ((unsigned)(i & 1) << 12) + (unsigned)(i >> 1) * 32u, tail + (inc - ci));
                             tail += tot;
                             __syncwarp();
                             if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
@@ -592,7 +605,7 @@ pair_kernel(const PairParams P)
         }
     } else {
         // =========================================== DRAIN ============================================
-        if (ND == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        if (ND == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 " GFN_REGS_D ";");
         else         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int dw = warp - NF;                   // drain warp: serves the rings of filter warps dw, dw+ND, ...
         const int rep = dw % nrep;

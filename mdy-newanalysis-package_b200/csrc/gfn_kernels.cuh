@@ -25,7 +25,10 @@ constexpr int kTJ      = 128;    // surround sites per shared-memory stage
 constexpr int kStages  = 3;      // surround stages in flight
 constexpr int kIPT     = 2;      // core sites held in registers per thread
 constexpr int kPadTo   = 1024;   // selections are padded to a multiple of this many sites on the device
-constexpr int kDrainILP = 2;     // survivors evaluated per drain lane per batch
+#ifndef GFN_DRAIN_ILP
+#define GFN_DRAIN_ILP 2
+#endif
+constexpr int kDrainILP = GFN_DRAIN_ILP;     // survivors evaluated per drain lane per batch
 constexpr int kRingCap = 2048;   // survivor ring entries (16 bit) per filter warp: one push (<= 32*32) always fits behind < 64 unread ones
 constexpr int kCtrlBytes = 640;  // shared-memory control block
 constexpr int kCounters = 8;     // 0 overflow, 1 error flags (bit 0 zero-norm dipole, bit 1 fp16 filter range), 2 survivors, 3 in-range pairs
