@@ -302,7 +302,9 @@ def run_ours(args, rank, world, local_rank):
                    "filter": st1["filter"], "hist": st1["hist_mode"], "batch_frames": st1["batch_frames"], "grid": st1["grid"],
                    "warps_per_block": st1["warps_per_block"], "smem_bytes": st1["smem_bytes"]},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": (achieved / fp64_peak) if achieved else None, "traffic": None,
+                     "frac": (achieved / fp64_peak) if achieved else None, "traffic": ncu_traffic()[0],
+                     "traffic_unit": "bytes of DRAM read+write per pair_kernel launch (ncu --set full capture, %s); algorithmic: %d"
+                                     % (ncu_traffic()[1], st1["batch_frames"] * ((n + 1023) // 1024 * 1024) * 80),
                      "peak_source": "measured in this run: dependent-free DFMA loop (gfn_measure_peaks); nominal %.1f" % NOMINAL_FP64_TFLOPS,
                      "frac_of_nominal": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None,
                      "flops_per_eval": flops_eval, "in_range_fraction": f_in, "survivor_fraction": f_surv,
@@ -322,6 +324,24 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one pair_kernel launch, from the committed summary of the
+    latest `ncu --set full` capture of this very command (profiles/<round>/pair_kernel_raw_selected.txt); None if absent."""
+    import glob
+    import re
+    hits = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*", "pair_kernel_raw_selected.txt")),
+                  key=lambda f: [int(v) for v in re.findall(r"\d+", os.path.basename(os.path.dirname(f)))])
+    if not hits:
+        return None, "no capture"
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for ln in open(hits[-1]):
+        t = ln.split()
+        if len(t) == 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(t[2]) * mult.get(t[1], 1.0)
+    return tot, os.path.relpath(hits[-1], os.path.dirname(os.path.abspath(__file__)))
 
 
 def main():
