@@ -33,6 +33,11 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, printed to stdout) goes to stderr instead
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "mdy-newanalysis-package_b200")
 for p in (PKG, os.path.join(ROOT, "oracle")):
@@ -67,8 +72,10 @@ def make_pool(c, nframes, rank):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms by one nvidia-smi process per rank that is started early
+    (its start-up takes longer than a short timed region, above all on an 8-GPU box); window(t0, t1) reduces the samples
+    whose time stamps fall into a timed region (wall-clock seconds, time.time())."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -85,36 +92,50 @@ class ClockSampler(object):
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def window(self, t0, t1):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.12)           # let the sample that covers the end of the region land in the file
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
+        try:
+            for ln in open(self.path):
+                parts = [x.strip() for x in ln.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(parts[1]), float(parts[2]), [nm for nm, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
+                except ValueError:
+                    continue
+        except OSError:
+            return out
+        inside = [r for r in rows if t0 <= r[0] <= t1 + 0.05]
+        if not inside and rows:     # region shorter than the sampling period: the sample closest to it
+            mid = 0.5 * (t0 + t1)
+            near = min(rows, key=lambda r: abs(r[0] - mid))
+            if abs(near[0] - mid) < 0.5:
+                inside = [near]
+                out["note"] = "nearest sample, %.0f ms from the region" % (1e3 * abs(near[0] - mid))
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)), samples=len(inside))
+            out["reasons"] = sorted(set(nm for r in inside for nm in r[3]))
+        return out
+
+    def stop(self):
+        if self.proc is None:
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
-            for ln in open(self.path):
-                parts = [x.strip() for x in ln.split(",")]
-                if len(parts) < 7:
-                    continue
-                try:
-                    sm.append(float(parts[0])); mx.append(float(parts[1]))
-                except ValueError:
-                    continue
-                for nm, v in zip(names, parts[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
-        out["reasons"] = sorted(reasons)
-        return out
 
 
 def host_threads():
@@ -209,6 +230,8 @@ def run_ours(args, rank, world, local_rank):
 
     uid = sharding.broadcast_unique_id(dist, G.comm_unique_id, device="cuda") if world > 1 else None
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     pool_c, pool_d = make_pool(c, POOL_FRAMES, rank)
     fp64_peak, fp32_peak = G.measure_peaks(local_rank)
 
@@ -227,16 +250,16 @@ def run_ours(args, rank, world, local_rank):
     r.sync()
     st0 = r.stats()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    tw0 = time.time()
     r.mark(0)
     for s in range(K):
         dev_step(W + s)
     r.mark(1)
     r.sync()
+    tw1 = time.time()
     ms = allmax(r.mark_elapsed_ms())
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.window(tw0, tw1)
     st1 = r.stats()
     hist = r.raw_histogram()                     # includes the NCCL all-reduce over ranks when world > 1
     hn = 300
@@ -268,15 +291,16 @@ def run_ours(args, rank, world, local_rank):
     e.sync()
     se0 = e.stats()
     barrier()
-    sampler2 = ClockSampler(local_rank)
-    sampler2.start()
+    tw0 = time.time()
     t0 = time.perf_counter()
     for s in range(K):
         host_step(W + s)
     e.sync()
     dt = allmax(time.perf_counter() - t0)
+    tw1 = time.time()
     barrier()
-    clocks_e2e = sampler2.stop()
+    clocks_e2e = sampler.window(tw0, tw1)
+    sampler.stop()
     se1 = e.stats()
     e2e_value = world * K * F * per / dt / 1e9
     h2d = (se1["h2d_bytes"] - se0["h2d_bytes"]) / K

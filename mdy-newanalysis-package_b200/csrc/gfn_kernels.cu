@@ -422,8 +422,13 @@ pair_kernel(const PairParams P)
                 hTg = __halves2half2(__hneg(th), __hneg(th));
                 const __half a = __double2half(b[0] * invS), bq = __double2half(b[1] * invS), cq = __double2half(b[2] * invS);
                 hLx = __halves2half2(a, a); hLy = __halves2half2(bq, bq); hLz = __halves2half2(cq, cq);
+#ifdef GFN_EXP_SLOT_OLD
                 const Site* c0 = siteA + it.i0 + warp * (32 * kIPT) + lane;
                 const Site* c1 = c0 + 32;
+#else
+                const Site* c0 = siteA + it.i0 + warp * (32 * kIPT) + 2 * lane;     // core slots 2*lane, 2*lane + 1: adjacent records
+                const Site* c1 = c0 + 1;
+#endif
                 const unsigned x0 = __float_as_uint(c0->fx), y0 = __float_as_uint(c0->fy), z0 = __float_as_uint(c0->fz);
                 const unsigned x1 = __float_as_uint(c1->fx), y1 = __float_as_uint(c1->fy), z1 = __float_as_uint(c1->fz);
                 const unsigned px = __byte_perm(x0, x1, 0x5410), py = __byte_perm(y0, y1, 0x5410), pz = __byte_perm(z0, z1, 0x5410);
@@ -433,7 +438,11 @@ pair_kernel(const PairParams P)
                 hxf = (FS)b[3]; hyf = (FS)b[4]; hzf = (FS)b[5];
 #pragma unroll
                 for (int k = 0; k < kIPT; ++k) {
+#ifdef GFN_EXP_SLOT_OLD
                     const int il = warp * (32 * kIPT) + k * 32 + lane;
+#else
+                    const int il = warp * (32 * kIPT) + 2 * lane + k;
+#endif
                     const Site* c = siteA + it.i0 + il;
                     if (kF32) { cx[k] = (FS)c->fx; cy[k] = (FS)c->fy; cz[k] = (FS)c->fz; }
                     else if (it.i0 + il < P.n1) { cx[k] = (FS)c->x; cy[k] = (FS)c->y; cz[k] = (FS)c->z; }
@@ -523,7 +532,15 @@ pair_kernel(const PairParams P)
                         if (lane >= d) incl += up;
                     }
                     const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+#ifdef GFN_EXP_SLOT_OLD
+                    constexpr unsigned kSlot1 = 32u << 7;
                     const unsigned tagl = ((unsigned)st << 13) | ((unsigned)lane << 7);     // stage | core slot | (site below)
+#else
+                    // core slot of mask k of this lane: 2*lane + k.  Consecutive ring entries then address adjacent core
+                    // records, which the 80-byte stride spreads over distinct bank groups
+                    constexpr unsigned kSlot1 = 1u << 7;
+                    const unsigned tagl = ((unsigned)st << 13) | ((unsigned)(2 * lane) << 7);     // stage | core slot | (site below)
+#endif
                     // one mask: entries from ring position `at` on
                     // (the first two survivors of a mask go out branch-free; `rest` collects what is left for emit_rest)
                     unsigned rest = 0u;
@@ -554,15 +571,15 @@ pair_kernel(const PairParams P)
                         }
                         unsigned a0 = tail + (incl - cnt);
                         unsigned a1 = a0 + c0, a2 = a1 + c1, a3 = a2 + c2, a4 = a3 + c3, a5 = a4 + c4, a6 = a5 + c5, a7 = a6 + c6;
-                        emit(mk0, tagl, a0);               emit(mk1, tagl + (32u << 7), a1);
-                        emit(mk2, tagl + 32u, a2);         emit(mk3, tagl + (32u << 7) + 32u, a3);
-                        emit(mk4, tagl + 64u, a4);         emit(mk5, tagl + (32u << 7) + 64u, a5);
-                        emit(mk6, tagl + 96u, a6);         emit(mk7, tagl + (32u << 7) + 96u, a7);
+                        emit(mk0, tagl, a0);               emit(mk1, tagl + kSlot1, a1);
+                        emit(mk2, tagl + 32u, a2);         emit(mk3, tagl + kSlot1 + 32u, a3);
+                        emit(mk4, tagl + 64u, a4);         emit(mk5, tagl + kSlot1 + 64u, a5);
+                        emit(mk6, tagl + 96u, a6);         emit(mk7, tagl + kSlot1 + 96u, a7);
                         if (__any_sync(0xffffffffu, rest != 0u)) {       // some lane holds three or more survivors of one mask
-                            emit_rest(mk0, tagl, a0);               emit_rest(mk1, tagl + (32u << 7), a1);
-                            emit_rest(mk2, tagl + 32u, a2);         emit_rest(mk3, tagl + (32u << 7) + 32u, a3);
-                            emit_rest(mk4, tagl + 64u, a4);         emit_rest(mk5, tagl + (32u << 7) + 64u, a5);
-                            emit_rest(mk6, tagl + 96u, a6);         emit_rest(mk7, tagl + (32u << 7) + 96u, a7);
+                            emit_rest(mk0, tagl, a0);               emit_rest(mk1, tagl + kSlot1, a1);
+                            emit_rest(mk2, tagl + 32u, a2);         emit_rest(mk3, tagl + kSlot1 + 32u, a3);
+                            emit_rest(mk4, tagl + 64u, a4);         emit_rest(mk5, tagl + kSlot1 + 64u, a5);
+                            emit_rest(mk6, tagl + 96u, a6);         emit_rest(mk7, tagl + kSlot1 + 96u, a7);
                         }
                         tail += total;
                         __syncwarp();
@@ -585,7 +602,7 @@ pair_kernel(const PairParams P)
                                 head_seen = ctrl->head[warp];
                                 if (tail + tot - head_seen > (unsigned)kRingCap) __nanosleep(64);
                             }
-                            emit_rest(m, tagl + ((unsigned)(i & 1) << 12) + (unsigned)(i >> 1) * 32u, tail + (inc - ci));
+                            emit_rest(m, tagl + ((unsigned)(i & 1) * kSlot1) + (unsigned)(i >> 1) * 32u, tail + (inc - ci));
                             tail += tot;
                             __syncwarp();
                             if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
