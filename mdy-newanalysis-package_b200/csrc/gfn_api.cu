@@ -134,6 +134,7 @@ struct gfn_handle {
     bool need1, need2;
     int n1_pad, n2_pad;
     int batch_frames;
+    int idle_frames;              // frames worth sending on their own when the device has nothing to do
     long long frame_doubles;      // worst case (not aliased)
     long long off_c1, off_d1, off_c2, off_d2;   // offsets (doubles) inside a non-aliased frame
     int n_itiles, n_jtiles, tiles_per_frame;
@@ -419,6 +420,14 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
     if (bf < 1) bf = 1;
     if (const char* e = getenv("GFN_BATCH_FRAMES")) { long long v = atoll(e); if (v >= 1 && v <= 65535) bf = v; }
     h->batch_frames = (int)bf;
+    // an idle device (first frames of a run, right after a readout) should not wait for a full batch: a quarter of
+    // one, or ~2^28 pair evaluations (0.2 ms of kernel time) if that is less
+    {
+        long long idle = (long long)(268435456.0 / per) + 1;
+        const long long quarter = (bf + 3) / 4;
+        h->idle_frames = (int)(idle < quarter ? idle : quarter);
+        if (h->idle_frames < 1) h->idle_frames = 1;
+    }
 
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(nullptr, GFN_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); for (Dev& dd : h->devs) free_dev(dd); delete h; return GFN_ECUDA; } } while (0)
     h->devs.resize(devs.size());
@@ -555,7 +564,7 @@ static int enqueue_impl(gfn_t* h, int nframes,
         memcpy(b->h_box + 6ll * b->nframes, box_dims ? box_dims + 6ll * f : h->box, sizeof(double) * 6);
         b->nframes++;
         bool go = b->nframes == h->batch_frames;
-        if (!go && b->nframes >= (h->batch_frames + 3) / 4) {
+        if (!go && b->nframes >= h->idle_frames) {
             // the device is idle (e.g. right after a readout): do not make it wait for a full batch
             go = true;
             for (Batch& o : d.ring)
