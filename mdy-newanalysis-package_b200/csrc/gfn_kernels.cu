@@ -1068,7 +1068,9 @@ static pair_fn_t pick_fn(const PairConfig& c)
     return c.drain_warps == 8 ? pick_shape<F, 8, 8, false>(c.hist_mode, weights, allm) : pick_shape<F, 8, 4, false>(c.hist_mode, weights, allm);
 }
 
-#ifdef GFN_EXP_ONLY_H16      // experiment builds (profiles/exp.sh): one instantiation, seconds to compile; cfg3 fp16 shape only
+#ifdef GFN_EXP_ONLY_F32
+static pair_fn_t pick(const PairConfig& c) { return pair_kernel<float, 8, 8, true, 0, true, false>; }
+#elif defined(GFN_EXP_ONLY_H16)      // experiment builds (profiles/exp.sh): one instantiation, seconds to compile; cfg3 fp16 shape only
 static pair_fn_t pick(const PairConfig& c) { return pair_kernel<__half, 8, 8, true, 0, true, false>; }
 #else
 static pair_fn_t pick(const PairConfig& c) { return c.filter_fp64 == 1 ? pick_fn<double>(c) : (c.filter_fp64 == 2 ? pick_fn<__half>(c) : pick_fn<float>(c)); }

@@ -7,5 +7,5 @@ for spec in "$@"; do
   name=${spec%%:*}; envs=""; [ "$spec" != "$name" ] && envs=${spec#*:}
   cp $N/exp/libgfn_$name.so $N/libgfn.so
   echo "== $spec"
-  env $envs timeout 120 python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['frac'], d['e2e']['value'])"
+  env $envs timeout 120 python bench.py --steps 4 --warmup 3 --no-cpu-baseline $BENCH_ARGS 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['frac'], d['e2e']['value'])"
 done
