@@ -585,27 +585,39 @@ pair_kernel(const PairParams P)
                         __syncwarp();
                         if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
                     } else if (total != 0u) {
-                        // dense tile: mask by mask (<= 32*32 entries each), each with its own scan
+                        // dense tile: chunk by chunk (two masks, one scan); a chunk that would not fit behind a partial
+                        // batch the drain warp may still be waiting to fill goes mask by mask (<= 32*32 entries each)
 #pragma unroll 1
-                        for (int i = 0; i < 8; ++i) {
-                            const unsigned m = i == 0 ? mk0 : i == 1 ? mk1 : i == 2 ? mk2 : i == 3 ? mk3 : i == 4 ? mk4 : i == 5 ? mk5 : i == 6 ? mk6 : mk7;
-                            const unsigned ci = __popc(m);
-                            unsigned inc = ci;
+                        for (int c = 0; c < 4; ++c) {
+                            const unsigned ma = c == 0 ? mk0 : c == 1 ? mk2 : c == 2 ? mk4 : mk6;
+                            const unsigned mb = c == 0 ? mk1 : c == 1 ? mk3 : c == 2 ? mk5 : mk7;
+                            const unsigned ca = __popc(ma), cb = __popc(mb);
+                            const unsigned both = __reduce_add_sync(0xffffffffu, ca + cb);
+                            if (both == 0u) continue;
+                            const int npush = both <= (unsigned)kRingCap - 32u * kU ? 1 : 2;
+                            for (int ps = 0; ps < npush; ++ps) {
+                                const unsigned ci = npush == 1 ? ca + cb : (ps == 0 ? ca : cb);
+                                unsigned inc = ci;
 #pragma unroll
-                            for (int d = 1; d < 32; d <<= 1) {
-                                const unsigned up = __shfl_up_sync(0xffffffffu, inc, d);
-                                if (lane >= d) inc += up;
+                                for (int d = 1; d < 32; d <<= 1) {
+                                    const unsigned up = __shfl_up_sync(0xffffffffu, inc, d);
+                                    if (lane >= d) inc += up;
+                                }
+                                const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
+                                if (tot == 0u) continue;
+                                while (tail + tot - head_seen > (unsigned)kRingCap) {
+                                    head_seen = ctrl->head[warp];
+                                    if (tail + tot - head_seen > (unsigned)kRingCap) __nanosleep(64);
+                                }
+                                const unsigned at = tail + (inc - ci);
+                                const unsigned tg = tagl + (unsigned)c * 32u;
+                                if (npush == 1) { emit_rest(ma, tg, at); emit_rest(mb, tg + kSlot1, at + ca); }
+                                else if (ps == 0) emit_rest(ma, tg, at);
+                                else emit_rest(mb, tg + kSlot1, at);
+                                tail += tot;
+                                __syncwarp();
+                                if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
                             }
-                            const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
-                            if (tot == 0u) continue;
-                            while (tail + tot - head_seen > (unsigned)kRingCap) {
-                                head_seen = ctrl->head[warp];
-                                if (tail + tot - head_seen > (unsigned)kRingCap) __nanosleep(64);
-                            }
-                            emit_rest(m, tagl + ((unsigned)(i & 1) * kSlot1) + (unsigned)(i >> 1) * 32u, tail + (inc - ci));
-                            tail += tot;
-                            __syncwarp();
-                            if (lane == 0) { __threadfence_block(); ctrl->tail[warp] = tail; }
                         }
                     }
                 }
