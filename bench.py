@@ -300,8 +300,41 @@ def run_ours(args, rank, world, local_rank):
     tw1 = time.time()
     barrier()
     clocks_e2e = sampler.window(tw0, tw1)
-    sampler.stop()
     se1 = e.stats()
+
+    # ---------------- arm 3 (N=1 only): end to end from float32 ATOM positions (3-site water) ----------
+    # RDF.calcFrameAtoms: the frame crosses PCIe as the trajectory's native float32 positions, centres of mass and
+    # dipoles (helpers.comByResidue / dipByResidue of the reference workflow) are produced on the device
+    atoms = None
+    if world == 1:
+        rng = np.random.default_rng(4242)
+        off = (0.6 * rng.standard_normal((n, 3, 3))).astype(np.float32)
+        pool_a = np.ascontiguousarray((pool_c.astype(np.float32)[:, :, None, :] + off[None]).reshape(POOL_FRAMES, 3 * n, 3))
+        a = mk()
+        a.attach_topology(np.tile([15.999, 1.008, 1.008], n), np.full(n, 3, dtype=np.int32), (3 * np.arange(n)).astype(np.int32),
+                          np.tile([-0.8476, 0.4238, 0.4238], n))
+
+        def atom_step(s):
+            first = (s * F) % (POOL_FRAMES - F + 1) if POOL_FRAMES > F else 0
+            for f in range(first, first + F):
+                a.calcFrameAtoms(pool_a[f])
+            return a.raw_histogram()
+
+        for s in range(W):
+            atom_step(s)
+        a.sync()
+        sa0 = a.stats()
+        t0 = time.perf_counter()
+        for s in range(K):
+            atom_step(W + s)
+        a.sync()
+        dta = time.perf_counter() - t0
+        sa1 = a.stats()
+        atoms = {"value": K * F * per / dta / 1e9, "unit": UNIT, "h2d_bytes_per_step": (sa1["h2d_bytes"] - sa0["h2d_bytes"]) / K,
+                 "d2h_bytes_per_step": 8 * hn * 8 + 8 * 8, "ms_per_step": dta / K * 1e3,
+                 "gpu_launches": int(sa1["kernel_launches"] - sa0["kernel_launches"]),
+                 "api": "newanalysis.gfunction.RDF.calcFrameAtoms (host float32 positions, 3 atoms per site; COM + dipoles on the device) + readout per step"}
+    sampler.stop()
     e2e_value = world * K * F * per / dt / 1e9
     h2d = (se1["h2d_bytes"] - se0["h2d_bytes"]) / K
     d2h = 8 * hn * 8 + 8 * 8
@@ -345,6 +378,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if atoms is not None:
+        line["e2e_atoms"] = atoms
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -210,6 +210,22 @@ int gfn_residues_com_dip(gfn_residues_t *r, int nframes, const double *coor, con
 /* device arrays in and out (feed them to gfn_enqueue_device_frames); ddip may be NULL */
 int gfn_residues_com_dip_device(gfn_residues_t *r, int nframes, const double *dcoor, double *dcom, double *ddip);
 
+/* ---- N1 + N4: frames as raw float32 atom positions ------------------------------------------
+ * Replaces, per frame, the script-side chain  positions.astype(float64) -> helpers.comByResidue (helpers.pyx:71-98)
+ * -> helpers.dipByResidue (:101-123) -> RDF.calcFrame (gfunction.pyx:385-464): the ring carries the trajectory's
+ * native float32 positions (12 B/atom), centres of mass and dipoles are produced on the device, bit-identical to
+ * the reference chain (float32 widens exactly), and feed the pair kernel without touching the host again.
+ *   gfn_attach_topology: which = 0 / 1 selects selection 1 / 2; nres must equal n1 / n2.  Without a topology for
+ *     selection 2 (n1 == n2) the one of selection 1 serves both.  charges may be NULL when mode_sel does not need
+ *     that selection's dipoles.  The arrays are copied (to every device of the handle).
+ *   gfn_enqueue_atom_frames: a1 (nframes, natoms1, 3), a2 (nframes, natoms2, 3) float32, strides in floats;
+ *     a2 == NULL or a2 == a1: the self g-function (positions uploaded once).  Like gfn_enqueue_frames the arrays
+ *     are copied before the call returns; box_dims as there. */
+int gfn_attach_topology(gfn_t *h, int which, int natoms, int nres, const int *apr, const int *rfa,
+                        const double *masses, const double *charges);
+int gfn_enqueue_atom_frames(gfn_t *h, int nframes, const float *a1, long long stride_a1,
+                            const float *a2, long long stride_a2, const double *box_dims);
+
 /* Self-test of the kernel's straight-line fp64 division / square-root sequences against the IEEE
  * built-ins (__ddiv_rn, __dsqrt_rn) on n_operands random operand sets with exponents in the range the
  * kernel uses them for.  mismatches = {division, square root, near-tie cases}; all must be 0. */

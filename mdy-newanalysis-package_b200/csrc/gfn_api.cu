@@ -96,6 +96,9 @@ struct Batch {
     bool aliased = false;         // selection 2 is selection 1 (same pointer passed)
     bool inflight = false;
     bool timed = false;           // k0/k1 hold an un-harvested pair-kernel timing
+    float* h_atoms = nullptr;     // pinned [frame][atoms of selection 1 | atoms of selection 2][3] float32 (atom batches)
+    float* d_atoms = nullptr;
+    bool atoms = false;           // this batch holds atom positions; COM / dipoles are produced on the device
 };
 
 struct Dev {
@@ -118,15 +121,27 @@ struct Dev {
     XSlot xs[kXRing];
     int xcur = 0;
     cudaEvent_t mark[2] = {nullptr, nullptr};
+    gfn_residues_t* res[2] = {nullptr, nullptr};   // topology of selection 1 / 2 on this device (gfn_attach_topology)
 };
 
 }  // namespace
+
+struct gfn_residues {
+    int dev, natoms, nres;
+    int* apr = nullptr; int* rfa = nullptr;
+    double* masses = nullptr; double* charges = nullptr;
+    double* scratch = nullptr; size_t scratch_bytes = 0;     // staging for host-side calls
+    char err[256];
+};
 
 struct gfn_handle {
     int n1, n2, histo_n, mode_sel;   // histo_n: bins per histogram row (radial bins x shells)
     int histo_nr = 0;                // radial bins
     gfn_shell_cfg shells = {0, 0, 1, 1, 0, 0, 0};   // layout 0: plain g-functions
     long long off_map = 0;           // offset (doubles) of the shell matrix inside a frame
+    // atoms through the ring (N1 + N4): selections produced on the device from float32 atom positions
+    int na[2] = {0, 0};              // atoms of selection 1 / 2 (0: no topology attached)
+    long long atom_cap = 0;          // floats per frame the rings' atom buffers were sized for
     float hmin_f, hmax_f;
     double inv_dr;
     double box[6];
@@ -255,12 +270,35 @@ int submit(gfn_t* h, Dev& d)
     if (b.nframes == 0) return GFN_OK;
     CU(cudaSetDevice(d.dev));
     const long long fd = b.aliased ? (h->off_c2) : h->frame_doubles;    // aliased frames hold only c1|d1
-    const size_t bytes = (size_t)fd * b.nframes * sizeof(double);
-    CU(cudaMemcpyAsync(b.d_raw, b.h_pin, bytes, cudaMemcpyHostToDevice, d.copy));
+    size_t bytes = (size_t)fd * b.nframes * sizeof(double);
+    if (b.atoms) {
+        // the frame crosses PCIe as float32 atom positions; centres of mass and dipoles (helpers.pyx:71-123) are
+        // written by the residue kernels into the same [c1|d1|c2|d2] layout the host path uploads
+        const long long na1 = h->na[0], na2 = b.aliased ? 0 : (h->na[1] ? h->na[1] : h->na[0]);
+        const long long fa = 3 * (na1 + na2);
+        bytes = (size_t)fa * b.nframes * sizeof(float);
+        CU(cudaMemcpyAsync(b.d_atoms, b.h_atoms, bytes, cudaMemcpyHostToDevice, d.copy));
+    } else {
+        CU(cudaMemcpyAsync(b.d_raw, b.h_pin, bytes, cudaMemcpyHostToDevice, d.copy));
+    }
     CU(cudaMemcpyAsync(b.d_box, b.h_box, sizeof(double) * 6 * b.nframes, cudaMemcpyHostToDevice, d.copy));
     CU(cudaEventRecord(b.uploaded, d.copy));
     CU(cudaStreamWaitEvent(d.comp, b.uploaded, 0));
     h->st_h2d += (double)bytes + 48.0 * b.nframes;
+    if (b.atoms) {
+        const long long na1 = h->na[0], na2 = b.aliased ? 0 : (h->na[1] ? h->na[1] : h->na[0]);
+        const long long fa = 3 * (na1 + na2);
+        for (int k = 0; k < (b.aliased ? 1 : 2); ++k) {
+            const gfn_residues* r = (k == 1 && d.res[1]) ? d.res[1] : d.res[0];
+            const float* at = b.d_atoms + (k == 0 ? 0 : 3 * na1);
+            double* com = b.d_raw + (k == 0 ? h->off_c1 : h->off_c2);
+            double* dip = b.d_raw + (k == 0 ? h->off_d1 : h->off_d2);
+            const bool need = k == 0 ? h->need1 : h->need2;
+            CU(residue_com_launch_f32(at, fa, r->masses, r->apr, r->rfa, r->nres, b.nframes, com, fd, d.comp));
+            if (need) CU(residue_dip_launch_f32(at, fa, r->charges, r->apr, r->rfa, r->nres, b.nframes, com, dip, fd, d.comp));
+            h->st_launches += need ? 2 : 1;
+        }
+    }
     int rc = launch_frames(h, d, b.nframes,
                            b.d_raw + h->off_c1, fd, b.d_raw + h->off_d1, fd,
                            b.d_raw + h->off_c2, fd, b.d_raw + h->off_d2, fd, b.aliased,
@@ -314,6 +352,8 @@ void free_dev(Dev& d)
     for (Batch& b : d.ring) {
         if (b.h_pin) cudaFreeHost(b.h_pin);
         if (b.h_box) cudaFreeHost(b.h_box);
+        if (b.h_atoms) cudaFreeHost(b.h_atoms);
+        cudaFree(b.d_atoms);
         cudaFree(b.d_raw); cudaFree(b.d_box); cudaFree(b.siteA); cudaFree(b.siteB); cudaFree(b.maxab);
         if (b.uploaded) cudaEventDestroy(b.uploaded);
         if (b.done) cudaEventDestroy(b.done);
@@ -329,6 +369,7 @@ void free_dev(Dev& d)
         if (x.k1) cudaEventDestroy(x.k1);
     }
     for (cudaEvent_t e : d.mark) if (e) cudaEventDestroy(e);
+    for (gfn_residues_t*& r : d.res) { gfn_residues_destroy(r); r = nullptr; }
     if (d.comm && nccl().ok) nccl().CommDestroy(d.comm);
     if (d.copy) cudaStreamDestroy(d.copy);
     if (d.comp) cudaStreamDestroy(d.comp);
@@ -522,23 +563,21 @@ int gfn_update_box(gfn_t* h, const double box_dim[6])
     return GFN_OK;
 }
 
-static int enqueue_impl(gfn_t* h, int nframes,
-                       const double* c1, long long s_c1, const double* c2, long long s_c2,
-                       const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims,
-                       const int* shell_map, long long s_map)
+// one source of frames for the ring: host selections (coordinates / dipoles [/ shell matrix]) or float32 atom positions
+struct FrameSrc {
+    const double* c1 = nullptr; const double* c2 = nullptr; const double* d1 = nullptr; const double* d2 = nullptr;
+    long long s_c1 = 0, s_c2 = 0, s_d1 = 0, s_d2 = 0;
+    const int* shell_map = nullptr; long long s_map = 0;
+    const float* a1 = nullptr; const float* a2 = nullptr; long long s_a1 = 0, s_a2 = 0;
+};
+
+static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased, const double* box_dims)
 {
-    if (!h) return GFN_EINVAL;
-    if (h->shells.layout && !shell_map) return fail(h, GFN_EINVAL, "this handle resolves shells: frames need a shell matrix (gfn_enqueue_frames_shells)");
-    if (!h->shells.layout && shell_map) return fail(h, GFN_EINVAL, "this handle was not created with gfn_create_shells");
-    if (nframes < 0) return fail(h, GFN_EINVAL, "nframes < 0");
-    if (!c1 || !c2) return fail(h, GFN_EINVAL, "coordinate array is NULL");
-    if (h->need1 && !d1) return fail(h, GFN_EINVAL, "No dipole moment array for the first selection was passed, although the requested gfunctions need it");
-    if (h->need2 && !d2) return fail(h, GFN_EINVAL, "No dipole moment array for the second selection was passed, although the requested gfunctions need it");
-    const bool aliased = !h->shells.layout && (c2 == c1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || d2 == d1) && (!h->need2 || h->need1);
+    const bool atoms = src.a1 != nullptr;
     for (int f = 0; f < nframes; ++f) {
         Dev& d = h->devs[h->next_dev];
         Batch* b = &d.ring[d.cur];
-        if (b->nframes > 0 && b->aliased != aliased) {      // layout change: close the batch
+        if (b->nframes > 0 && (b->aliased != aliased || b->atoms != atoms)) {      // layout change: close the batch
             int rc = submit(h, d);
             if (rc) return rc;
             b = &d.ring[d.cur];
@@ -547,20 +586,28 @@ static int enqueue_impl(gfn_t* h, int nframes,
             int rc = wait_batch(h, d, *b);
             if (rc) return rc;
             b->aliased = aliased;
+            b->atoms = atoms;
         }
         if (box_dims) {
             int rc = validate_box(h, box_dims + 6ll * f);
             if (rc) return rc;
         }
-        const long long fd = aliased ? h->off_c2 : h->frame_doubles;
-        double* dst = b->h_pin + fd * b->nframes;
-        memcpy(dst + h->off_c1, c1 + s_c1 * f, sizeof(double) * 3 * h->n1);
-        if (h->need1) memcpy(dst + h->off_d1, d1 + s_d1 * f, sizeof(double) * 3 * h->n1);
-        if (!aliased) {
-            memcpy(dst + h->off_c2, c2 + s_c2 * f, sizeof(double) * 3 * h->n2);
-            if (h->need2) memcpy(dst + h->off_d2, d2 + s_d2 * f, sizeof(double) * 3 * h->n2);
+        if (atoms) {
+            const long long na1 = h->na[0], na2 = aliased ? 0 : (h->na[1] ? h->na[1] : h->na[0]);
+            float* dst = b->h_atoms + 3 * (na1 + na2) * b->nframes;
+            memcpy(dst, src.a1 + src.s_a1 * f, sizeof(float) * 3 * na1);
+            if (!aliased) memcpy(dst + 3 * na1, src.a2 + src.s_a2 * f, sizeof(float) * 3 * na2);
+        } else {
+            const long long fd = aliased ? h->off_c2 : h->frame_doubles;
+            double* dst = b->h_pin + fd * b->nframes;
+            memcpy(dst + h->off_c1, src.c1 + src.s_c1 * f, sizeof(double) * 3 * h->n1);
+            if (h->need1) memcpy(dst + h->off_d1, src.d1 + src.s_d1 * f, sizeof(double) * 3 * h->n1);
+            if (!aliased) {
+                memcpy(dst + h->off_c2, src.c2 + src.s_c2 * f, sizeof(double) * 3 * h->n2);
+                if (h->need2) memcpy(dst + h->off_d2, src.d2 + src.s_d2 * f, sizeof(double) * 3 * h->n2);
+            }
+            if (src.shell_map) memcpy(dst + h->off_map, src.shell_map + src.s_map * f, sizeof(int) * (size_t)h->shells.map_elems);
         }
-        if (shell_map) memcpy(dst + h->off_map, shell_map + s_map * f, sizeof(int) * (size_t)h->shells.map_elems);
         memcpy(b->h_box + 6ll * b->nframes, box_dims ? box_dims + 6ll * f : h->box, sizeof(double) * 6);
         b->nframes++;
         bool go = b->nframes == h->batch_frames;
@@ -578,6 +625,88 @@ static int enqueue_impl(gfn_t* h, int nframes,
         }
     }
     return GFN_OK;
+}
+
+static int enqueue_impl(gfn_t* h, int nframes,
+                       const double* c1, long long s_c1, const double* c2, long long s_c2,
+                       const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims,
+                       const int* shell_map, long long s_map)
+{
+    if (!h) return GFN_EINVAL;
+    if (h->shells.layout && !shell_map) return fail(h, GFN_EINVAL, "this handle resolves shells: frames need a shell matrix (gfn_enqueue_frames_shells)");
+    if (!h->shells.layout && shell_map) return fail(h, GFN_EINVAL, "this handle was not created with gfn_create_shells");
+    if (nframes < 0) return fail(h, GFN_EINVAL, "nframes < 0");
+    if (!c1 || !c2) return fail(h, GFN_EINVAL, "coordinate array is NULL");
+    if (h->need1 && !d1) return fail(h, GFN_EINVAL, "No dipole moment array for the first selection was passed, although the requested gfunctions need it");
+    if (h->need2 && !d2) return fail(h, GFN_EINVAL, "No dipole moment array for the second selection was passed, although the requested gfunctions need it");
+    const bool aliased = !h->shells.layout && (c2 == c1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || d2 == d1) && (!h->need2 || h->need1);
+    FrameSrc src;
+    src.c1 = c1; src.c2 = c2; src.d1 = d1; src.d2 = d2; src.s_c1 = s_c1; src.s_c2 = s_c2; src.s_d1 = s_d1; src.s_d2 = s_d2;
+    src.shell_map = shell_map; src.s_map = s_map;
+    return enqueue_loop(h, nframes, src, aliased, box_dims);
+}
+
+// ---- N1 + N4: atoms through the ring ---------------------------------------------------------------------
+int gfn_attach_topology(gfn_t* h, int which, int natoms, int nres, const int* apr, const int* rfa,
+                        const double* masses, const double* charges)
+{
+    if (!h) return GFN_EINVAL;
+    if (which < 0 || which > 1) return fail(h, GFN_EINVAL, "which must be 0 (selection 1) or 1 (selection 2)");
+    if (h->shells.layout) return fail(h, GFN_EINVAL, "shell-resolved handles take host frames (gfn_enqueue_frames_shells)");
+    if (which == 1 && !h->na[0]) return fail(h, GFN_EINVAL, "attach the topology of selection 1 first");
+    if (nres != (which == 0 ? h->n1 : h->n2))
+        return fail(h, GFN_EINVAL, "topology has %d residues, selection %d of this handle has %d sites", nres, which + 1, which == 0 ? h->n1 : h->n2);
+    int rc = gfn_flush(h);                       // batches filled so far were sized with the previous topology
+    if (rc) return rc;
+    for (Dev& d : h->devs) {
+        gfn_residues_t* r = nullptr;
+        rc = gfn_residues_create(&r, d.dev, natoms, nres, apr, rfa, masses, charges);
+        if (rc) return fail(h, rc, "%s", gfn_last_error(nullptr));
+        gfn_residues_destroy(d.res[which]);
+        d.res[which] = r;
+    }
+    h->na[which] = natoms;
+    const long long cap = 3ll * h->na[0] + 3ll * (h->na[1] ? h->na[1] : h->na[0]);
+    if (cap > h->atom_cap) {
+        for (Dev& d : h->devs) {
+            CU(cudaSetDevice(d.dev));
+            for (Batch& b : d.ring) {
+                int wrc = wait_batch(h, d, b);
+                if (wrc) return wrc;
+                if (b.h_atoms) { CU(cudaFreeHost(b.h_atoms)); b.h_atoms = nullptr; }
+                if (b.d_atoms) { CU(cudaFree(b.d_atoms)); b.d_atoms = nullptr; }
+                const size_t bytes = sizeof(float) * (size_t)cap * h->batch_frames;
+                CU(cudaHostAlloc(&b.h_atoms, bytes, cudaHostAllocDefault));
+                CU(cudaMalloc(&b.d_atoms, bytes));
+            }
+        }
+        h->atom_cap = cap;
+    }
+    return GFN_OK;
+}
+
+int gfn_enqueue_atom_frames(gfn_t* h, int nframes, const float* a1, long long stride_a1,
+                            const float* a2, long long stride_a2, const double* box_dims)
+{
+    if (!h) return GFN_EINVAL;
+    if (!h->na[0]) return fail(h, GFN_EINVAL, "no topology attached (gfn_attach_topology)");
+    if (nframes < 0) return fail(h, GFN_EINVAL, "nframes < 0");
+    if (!a1) return fail(h, GFN_EINVAL, "atom position array is NULL");
+    if (!a2) {
+        if (h->na[1] || h->n1 != h->n2) return fail(h, GFN_EINVAL, "atom positions of the second selection are NULL");
+        a2 = a1; stride_a2 = stride_a1;
+    }
+    {
+        const Dev& d0 = h->devs[0];
+        if (h->need1 && !d0.res[0]->charges)
+            return fail(h, GFN_EINVAL, "No charges for the first selection were attached, although the requested gfunctions need its dipole moments");
+        if (h->need2 && !(d0.res[1] ? d0.res[1] : d0.res[0])->charges)
+            return fail(h, GFN_EINVAL, "No charges for the second selection were attached, although the requested gfunctions need its dipole moments");
+    }
+    const bool aliased = (a2 == a1) && !h->na[1] && h->n1 == h->n2 && (!h->need2 || h->need1);
+    FrameSrc src;
+    src.a1 = a1; src.a2 = a2; src.s_a1 = stride_a1; src.s_a2 = stride_a2;
+    return enqueue_loop(h, nframes, src, aliased, box_dims);
 }
 
 int gfn_enqueue_frames(gfn_t* h, int nframes,
@@ -838,18 +967,6 @@ int gfn_measure_peaks(int dev, double* fp64_tflops, double* fp32_tflops)
 }
 
 // ---- N1: residue map (topology on the device) ----------------------------------------------------------
-}  // extern "C"
-
-struct gfn_residues {
-    int dev, natoms, nres;
-    int* apr = nullptr; int* rfa = nullptr;
-    double* masses = nullptr; double* charges = nullptr;
-    double* scratch = nullptr; size_t scratch_bytes = 0;     // staging for host-side calls
-    char err[256];
-};
-
-extern "C" {
-
 int gfn_residues_create(gfn_residues_t** out, int dev, int natoms, int nres, const int* apr, const int* rfa,
                         const double* masses, const double* charges)
 {

@@ -1158,36 +1158,38 @@ cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t
 // results are bit-identical to the reference.  velcomByResidue (helpers.pyx:41-68) is the same arithmetic
 // as comByResidue applied to velocities.
 // ------------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(128)
-residue_com_kernel(const double* __restrict__ coor, long long stride_coor, const double* __restrict__ masses,
+residue_com_kernel(const T* __restrict__ coor, long long stride_coor, const double* __restrict__ masses,
                    const int* __restrict__ apr, const int* __restrict__ rfa, int nres,
                    double* __restrict__ com, long long stride_out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nres) return;
-    const double* c = coor + (long long)blockIdx.y * stride_coor;
+    const T* c = coor + (long long)blockIdx.y * stride_coor;      // float positions widen exactly, like astype(float64)
     double sx = 0.0, sy = 0.0, sz = 0.0, tot = 0.0;
     const int first = rfa[i], n = apr[i];
     for (int j = 0; j < n; ++j) {
         const int a = first + j;
         const double m = masses[a];
-        sx = __dadd_rn(sx, __dmul_rn(c[3ll * a], m));
-        sy = __dadd_rn(sy, __dmul_rn(c[3ll * a + 1], m));
-        sz = __dadd_rn(sz, __dmul_rn(c[3ll * a + 2], m));
+        sx = __dadd_rn(sx, __dmul_rn((double)c[3ll * a], m));
+        sy = __dadd_rn(sy, __dmul_rn((double)c[3ll * a + 1], m));
+        sz = __dadd_rn(sz, __dmul_rn((double)c[3ll * a + 2], m));
         tot = __dadd_rn(tot, m);
     }
     double* o = com + (long long)blockIdx.y * stride_out + 3ll * i;
     o[0] = __ddiv_rn(sx, tot); o[1] = __ddiv_rn(sy, tot); o[2] = __ddiv_rn(sz, tot);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(128)
-residue_dip_kernel(const double* __restrict__ coor, long long stride_coor, const double* __restrict__ charges,
+residue_dip_kernel(const T* __restrict__ coor, long long stride_coor, const double* __restrict__ charges,
                    const int* __restrict__ apr, const int* __restrict__ rfa, int nres,
                    const double* __restrict__ com, double* __restrict__ dip, long long stride_out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nres) return;
-    const double* c = coor + (long long)blockIdx.y * stride_coor;
+    const T* c = coor + (long long)blockIdx.y * stride_coor;
     const double* cm = com + (long long)blockIdx.y * stride_out + 3ll * i;
     const double cx = cm[0], cy = cm[1], cz = cm[2];
     double dx = 0.0, dy = 0.0, dz = 0.0;
@@ -1195,36 +1197,64 @@ residue_dip_kernel(const double* __restrict__ coor, long long stride_coor, const
     for (int j = 0; j < n; ++j) {
         const int a = first + j;
         const double q = charges[a];
-        dx = __dadd_rn(dx, __dmul_rn(__dsub_rn(c[3ll * a], cx), q));
-        dy = __dadd_rn(dy, __dmul_rn(__dsub_rn(c[3ll * a + 1], cy), q));
-        dz = __dadd_rn(dz, __dmul_rn(__dsub_rn(c[3ll * a + 2], cz), q));
+        dx = __dadd_rn(dx, __dmul_rn(__dsub_rn((double)c[3ll * a], cx), q));
+        dy = __dadd_rn(dy, __dmul_rn(__dsub_rn((double)c[3ll * a + 1], cy), q));
+        dz = __dadd_rn(dz, __dmul_rn(__dsub_rn((double)c[3ll * a + 2], cz), q));
     }
     double* o = dip + (long long)blockIdx.y * stride_out + 3ll * i;
     o[0] = dx; o[1] = dy; o[2] = dz;
 }
 
-cudaError_t residue_com_launch(const double* coor, long long stride_coor, const double* masses, const int* apr, const int* rfa,
-                               int nres, int nframes, double* com, cudaStream_t s)
+// stride_out: doubles between the outputs of consecutive frames (3*nres when the output is a dense (nframes,nres,3) array)
+template <typename T>
+static cudaError_t residue_com_launch_t(const T* coor, long long stride_coor, const double* masses, const int* apr, const int* rfa,
+                                        int nres, int nframes, double* com, long long stride_out, cudaStream_t s)
 {
     for (int f0 = 0; f0 < nframes; f0 += 65535) {
         const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
         dim3 grid((nres + 127) / 128, nf);
-        residue_com_kernel<<<grid, 128, 0, s>>>(coor + (long long)f0 * stride_coor, stride_coor, masses, apr, rfa, nres,
-                                                com + (long long)f0 * 3 * nres, 3ll * nres);
+        residue_com_kernel<T><<<grid, 128, 0, s>>>(coor + (long long)f0 * stride_coor, stride_coor, masses, apr, rfa, nres,
+                                                   com + (long long)f0 * stride_out, stride_out);
     }
     return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t residue_dip_launch_t(const T* coor, long long stride_coor, const double* charges, const int* apr, const int* rfa,
+                                        int nres, int nframes, const double* com, double* dip, long long stride_out, cudaStream_t s)
+{
+    for (int f0 = 0; f0 < nframes; f0 += 65535) {
+        const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
+        dim3 grid((nres + 127) / 128, nf);
+        residue_dip_kernel<T><<<grid, 128, 0, s>>>(coor + (long long)f0 * stride_coor, stride_coor, charges, apr, rfa, nres,
+                                                   com + (long long)f0 * stride_out, dip + (long long)f0 * stride_out, stride_out);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t residue_com_launch(const double* coor, long long stride_coor, const double* masses, const int* apr, const int* rfa,
+                               int nres, int nframes, double* com, cudaStream_t s)
+{
+    return residue_com_launch_t<double>(coor, stride_coor, masses, apr, rfa, nres, nframes, com, 3ll * nres, s);
 }
 
 cudaError_t residue_dip_launch(const double* coor, long long stride_coor, const double* charges, const int* apr, const int* rfa,
                                int nres, int nframes, const double* com, double* dip, cudaStream_t s)
 {
-    for (int f0 = 0; f0 < nframes; f0 += 65535) {
-        const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
-        dim3 grid((nres + 127) / 128, nf);
-        residue_dip_kernel<<<grid, 128, 0, s>>>(coor + (long long)f0 * stride_coor, stride_coor, charges, apr, rfa, nres,
-                                                com + (long long)f0 * 3 * nres, dip + (long long)f0 * 3 * nres, 3ll * nres);
-    }
-    return cudaGetLastError();
+    return residue_dip_launch_t<double>(coor, stride_coor, charges, apr, rfa, nres, nframes, com, dip, 3ll * nres, s);
+}
+
+// float32 atom positions (trajectory-native) -> centres of mass / dipoles written straight into a frame batch
+cudaError_t residue_com_launch_f32(const float* coor, long long stride_coor, const double* masses, const int* apr, const int* rfa,
+                                   int nres, int nframes, double* com, long long stride_out, cudaStream_t s)
+{
+    return residue_com_launch_t<float>(coor, stride_coor, masses, apr, rfa, nres, nframes, com, stride_out, s);
+}
+
+cudaError_t residue_dip_launch_f32(const float* coor, long long stride_coor, const double* charges, const int* apr, const int* rfa,
+                                   int nres, int nframes, const double* com, double* dip, long long stride_out, cudaStream_t s)
+{
+    return residue_dip_launch_t<float>(coor, stride_coor, charges, apr, rfa, nres, nframes, com, dip, stride_out, s);
 }
 
 // ------------------------------------------------------------------------------------------------

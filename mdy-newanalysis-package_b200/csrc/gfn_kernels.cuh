@@ -98,6 +98,11 @@ cudaError_t residue_com_launch(const double* coor, long long stride_coor, const 
 cudaError_t residue_dip_launch(const double* coor, long long stride_coor, const double* charges, const int* apr, const int* rfa,
                                int nres, int nframes, const double* com, double* dip, cudaStream_t s);
 
+cudaError_t residue_com_launch_f32(const float* coor, long long stride_coor, const double* masses, const int* apr, const int* rfa,
+                                   int nres, int nframes, double* com, long long stride_out, cudaStream_t s);
+cudaError_t residue_dip_launch_f32(const float* coor, long long stride_coor, const double* charges, const int* apr, const int* rfa,
+                                   int nres, int nframes, const double* com, double* dip, long long stride_out, cudaStream_t s);
+
 cudaError_t peaks_measure(int dev, double* fp64_tflops, double* fp32_tflops);
 
 // Compares the kernel's in-range fp64 division / square-root sequences with the IEEE built-ins on

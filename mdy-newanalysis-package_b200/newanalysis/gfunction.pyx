@@ -97,6 +97,10 @@ cdef extern from "gfn.h":
     int gfn_residues_com_dip(gfn_residues_t *r, int nframes, const double *coor, const double *com_in,
                              double *com_out, double *dip_out) nogil
     int gfn_residues_com_dip_device(gfn_residues_t *r, int nframes, const double *dcoor, double *dcom, double *ddip) nogil
+    int gfn_attach_topology(gfn_t *h, int which, int natoms, int nres, const int *apr, const int *rfa,
+                            const double *masses, const double *charges) nogil
+    int gfn_enqueue_atom_frames(gfn_t *h, int nframes, const float *a1, long long s1, const float *a2, long long s2,
+                                const double *boxes) nogil
     int gfn_dev_alloc(int dev, void **dptr, unsigned long long nbytes) nogil
     int gfn_dev_free(int dev, void *dptr) nogil
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
@@ -451,6 +455,26 @@ cdef class _Backend:
         self.keepalive.append((c1, c2, d1, d2))
         self.check(rc)
 
+    def attach_topology(self, int which, masses, apr, rfa, charges=None):
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] m = np.ascontiguousarray(masses, dtype=np.float64)
+        cdef np.ndarray[np.int32_t, ndim=1, mode="c"] a = np.ascontiguousarray(apr, dtype=np.int32)
+        cdef np.ndarray[np.int32_t, ndim=1, mode="c"] f = np.ascontiguousarray(rfa, dtype=np.int32)
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] q = None
+        if a.shape[0] != f.shape[0]:
+            raise ValueError("apr and rfa must have one entry per residue")
+        if charges is not None:
+            q = np.ascontiguousarray(charges, dtype=np.float64)
+            if q.shape[0] != m.shape[0]:
+                raise ValueError("charges and masses must have one entry per atom")
+        self.check(gfn_attach_topology(self.h, which, <int> m.shape[0], <int> a.shape[0], <const int *> a.data, <const int *> f.data,
+                                       <const double *> m.data, <const double *> q.data if q is not None else NULL))
+
+    cdef int enqueue_atoms(self, int nframes, const float *a1, long long s1, const float *a2, long long s2, const double *boxes) except -1:
+        cdef int rc
+        with nogil:
+            rc = gfn_enqueue_atom_frames(self.h, nframes, a1, s1, a2, s2, boxes)
+        return self.check(rc)
+
     def flush(self):
         cdef int rc
         with nogil:
@@ -692,6 +716,11 @@ class RDF(object):
         if absmax <= 2.0 * lmax and float(self.histo_max) >= 0.04 * lmax:
             self._flags |= 16
             self._open_backend()          # nothing has been enqueued yet
+            topo = getattr(self, "_topology", None)
+            if topo is not None:
+                self._be.attach_topology(0, *topo[:4])
+                if topo[4] is not None:
+                    self._be.attach_topology(1, *topo[4:])
         self._finish_comm()
 
     # ------------------------------------------------------------------ reference API
@@ -926,6 +955,61 @@ class RDF(object):
         self.volume_list.extend([self.volume] * nframes)
         self._be.enqueue_device(nframes, c1, c2, d1, d2, boxes, first)
 
+    def attach_topology(self, masses, apr, rfa, charges=None, masses2=None, apr2=None, rfa2=None, charges2=None):
+        """Let the RDF object take raw atom positions (calcFrameAtoms / calcFramesAtoms): masses / charges per atom,
+        apr / rfa per residue (atoms per residue, first atom - the arrays the reference's helpers.comByResidue and
+        dipByResidue take, helpers.pyx:71-123).  The second set describes selection 2; without it selection 2 uses
+        the topology of selection 1 (sel1_n == sel2_n)."""
+        if self._auto_filter and self.ctr == 0:
+            self._topology = (masses, apr, rfa, charges, masses2, apr2, rfa2, charges2)     # re-applied if the backend is re-opened
+        self._be.attach_topology(0, masses, apr, rfa, charges)
+        if masses2 is not None:
+            self._be.attach_topology(1, masses2, apr2, rfa2, charges2)
+        self._natoms = (len(masses), len(masses2) if masses2 is not None else len(masses))
+        self._first_res = (int(np.asarray(apr)[0]), masses2 is None)
+
+    def calcFrameAtoms(self, pos_sel1, pos_sel2=None):
+        """One frame from atom positions (float32, (natoms,3), what MDAnalysis' AtomGroup.positions returns): the same
+        result, bit for bit, as  c = comByResidue(pos.astype(float64), ...); d = dipByResidue(..., c);
+        calcFrame(c1, c2, d1, d2)  of the reference workflow, with centres of mass and dipoles made on the device."""
+        p1 = np.ascontiguousarray(pos_sel1, dtype=np.float32)
+        p2 = p1 if (pos_sel2 is None or pos_sel2 is pos_sel1) else np.ascontiguousarray(pos_sel2, dtype=np.float32)
+        self.calcFramesAtoms(p1[None], p2[None] if p2 is not p1 else None)
+
+    def calcFramesAtoms(self, pos_sel1, pos_sel2=None, boxes=None):
+        """Many frames of atom positions: float32 (nframes,natoms,3); boxes (nframes,3) for NpT or None."""
+        if getattr(self, "_natoms", None) is None:
+            raise RuntimeError("attach_topology() must be called before atom positions can be passed")
+        cdef np.ndarray[np.float32_t, ndim=3, mode="c"] a1 = np.ascontiguousarray(pos_sel1, dtype=np.float32)
+        cdef np.ndarray[np.float32_t, ndim=3, mode="c"] a2 = a1 if (pos_sel2 is None or pos_sel2 is pos_sel1) else np.ascontiguousarray(pos_sel2, dtype=np.float32)
+        cdef np.ndarray[np.float64_t, ndim=2, mode="c"] bx = None
+        cdef int nf = a1.shape[0]
+        na1, na2 = self._natoms
+        if a1.shape[1] != na1 or a1.shape[2] != 3 or a2.shape[0] != nf or a2.shape[1] != na2 or a2.shape[2] != 3:
+            raise ValueError("position arrays must have shapes (nframes,%d,3) and (nframes,%d,3)" % (na1, na2))
+        if nf == 0:
+            return
+        if self.oneistwo is None:                            # :417-421 compares the first sites of the two selections
+            k, same_topology = self._first_res
+            self.oneistwo = bool(same_topology and (a2 is a1 or (a1[0, :k] == a2[0, :k]).all()) and self.nmol1 == self.nmol2)
+        if boxes is not None:
+            b3 = np.asarray(boxes, dtype=np.float64).reshape(nf, 3)
+            bx = np.ascontiguousarray(np.concatenate([b3, b3 / 2.0], axis=1))
+            vols = list(b3[:, 0] * b3[:, 1] * b3[:, 2])
+        else:
+            vols = [self.volume] * nf
+        if self._auto_filter and self.ctr == 0:
+            # a centre of mass lies inside the hull of its atoms, so max|position| bounds max|site coordinate|
+            self._auto_pick_filter(None, None, max(float(np.abs(a1[0]).max()), float(np.abs(a2[0]).max())))
+        self.ctr += nf
+        self.volume_list.extend(vols)
+        cdef _Backend be = self._be
+        be.enqueue_atoms(nf, <const float *> a1.data, 3 * <long long> a1.shape[1],
+                         <const float *> a2.data if a2 is not a1 else NULL, 3 * <long long> a2.shape[1],
+                         <const double *> bx.data if bx is not None else NULL)
+        if boxes is not None:
+            self.update_box(*[float(v) for v in b3[nf - 1]])
+
     def flush(self):
         self._be.flush()
 
@@ -1158,6 +1242,9 @@ class RDF_voronoi(RDF):
         raise NotImplementedError("RDF_voronoi takes one frame per call (calcFrame)")
 
     def calcFramesDevice(self, *args, **kwargs):
+        raise NotImplementedError("RDF_voronoi takes host frames (calcFrame)")
+
+    def attach_topology(self, *args, **kwargs):
         raise NotImplementedError("RDF_voronoi takes host frames (calcFrame)")
 
     def attach_comm(self, uid, nranks, rank):

@@ -391,6 +391,150 @@ def test_atoms_to_gfunction_on_device():
     assert_hist_close(got, ref, 300)
 
 
+# ---- N1 + N4: raw float32 atom positions through the upload ring --------------------------------------------
+def _water_box(nres, L, nf, seed):
+    rng = np.random.default_rng(seed)
+    apr = np.full(nres, 3, dtype=np.int32); rfa = (3 * np.arange(nres)).astype(np.int32)
+    masses = np.tile([15.999, 1.008, 1.008], nres); charges = np.tile([-0.8476, 0.4238, 0.4238], nres)
+    centre = rng.random((nf, nres, 1, 3)) * L
+    pos = (centre + rng.standard_normal((nf, nres, 3, 3)) * 0.6).reshape(nf, 3 * nres, 3).astype(np.float32)
+    return np.ascontiguousarray(pos), masses, charges, apr, rfa
+
+
+def _reference_chain(pos32, masses, charges, apr, rfa):
+    """What an analysis script does per frame before RDF.calcFrame: positions.astype(float64) -> comByResidue ->
+    dipByResidue (helpers.pyx:71-123), here through the oracle's C restatements."""
+    c64 = np.ascontiguousarray(pos32.astype(np.float64))
+    com = O.com_by_residue_c(c64, masses, apr, rfa)
+    return com, O.dip_by_residue_c(c64, charges, apr, rfa, com)
+
+
+@pytest.mark.parametrize("flags", ["", "fp32", "fp64"])
+def test_atom_frames_self_equal_reference_chain(flags):
+    nres, L, nf = 3000, 45.0, 5
+    pos, masses, charges, apr, rfa = _water_box(nres, L, nf, 41)
+    a = RDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L, gfn_flags=flags or None)
+    a.attach_topology(masses, apr, rfa, charges)
+    a.calcFrameAtoms(pos[0])                 # one frame per call ...
+    a.calcFramesAtoms(pos[1:])               # ... and the rest in one call
+    host = RDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L, gfn_flags=flags or None)
+    o = O.OracleRDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+    for f in range(nf):
+        com, dip = _reference_chain(pos[f], masses, charges, apr, rfa)
+        host.calcFrame(com, com, dip, dip)
+        o.calcFrame(com, com, dip, dip)
+    got, ref = a.raw_histogram(), o.raw_sum()
+    assert a.oneistwo is True and a.ctr == nf
+    assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 0
+    assert_hist_close(got, ref, 300)
+    # the device-made centres of mass / dipoles are bit-identical to the host-made ones, so the whole histogram is
+    assert np.array_equal(got, host.raw_histogram())
+    st = a.stats()
+    assert st["h2d_bytes"] == nf * (3 * nres * 3 * 4 + 48)      # float32 atoms once per frame + the box
+
+
+def test_atom_frames_two_selections_ragged_and_npt():
+    """Cations x anions with ragged residues (2..9 atoms; a single atom has a zero dipole, quirk Q5), a different topology per selection, per-frame boxes."""
+    rng = np.random.default_rng(43)
+    n1, n2, L, nf = 700, 500, 50.0, 4
+
+    def topo(n):
+        apr = rng.integers(2, 10, n).astype(np.int32)
+        rfa = np.concatenate([[0], np.cumsum(apr)[:-1]]).astype(np.int32)
+        na = int(apr.sum())
+        return apr, rfa, 1.0 + 15.0 * rng.random(na), rng.standard_normal(na), na
+    apr1, rfa1, m1, q1, na1 = topo(n1)
+    apr2, rfa2, m2, q2, na2 = topo(n2)
+
+    def frames(apr, na, n):
+        centre = np.repeat(rng.random((nf, n, 3)) * L, apr, axis=1)
+        return np.ascontiguousarray((centre + 0.8 * rng.standard_normal((nf, na, 3))).astype(np.float32))
+    p1, p2 = frames(apr1, na1, n1), frames(apr2, na2, n2)
+    boxes = L * (1.0 + 1e-3 * rng.standard_normal((nf, 3)))
+    modes = ["000", "110", "101", "011", "220"]
+    a = RDF(modes, 0.0, 20.0, 0.05, n1, n2, n1, n2, L)
+    a.attach_topology(m1, apr1, rfa1, q1, m2, apr2, rfa2, q2)
+    a.calcFramesAtoms(p1, p2, boxes=boxes)
+    o = O.OracleRDF(modes, 0.0, 20.0, 0.05, n1, n2, n1, n2, L)
+    for f in range(nf):
+        o.update_box(*boxes[f])
+        c1, d1 = _reference_chain(p1[f], m1, q1, apr1, rfa1)
+        c2, d2 = _reference_chain(p2[f], m2, q2, apr2, rfa2)
+        o.calcFrame(c1, c2, d1, d2)
+    got, ref = a.raw_histogram(), o.raw_sum()
+    assert a.oneistwo is False
+    assert np.array_equal(got[:400], ref[:400]) and ref[:400].sum() > 0
+    assert_hist_close(got, ref, 400)
+    assert a.volume_list == o.volume_list
+
+
+def test_atom_frames_mix_with_host_frames_and_small_batches(monkeypatch):
+    """Atom frames and host frames may alternate on one handle (a layout change closes the batch); tiny batches make the
+    ring recycle its atom buffers."""
+    monkeypatch.setenv("GFN_BATCH_FRAMES", "2")
+    nres, L, nf = 1200, 36.0, 9
+    pos, masses, charges, apr, rfa = _water_box(nres, L, nf, 47)
+    a = RDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+    a.attach_topology(masses, apr, rfa, charges)
+    o = O.OracleRDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+    for f in range(nf):
+        com, dip = _reference_chain(pos[f], masses, charges, apr, rfa)
+        o.calcFrame(com, com, dip, dip)
+        if f % 3 == 1:
+            a.calcFrame(com, com, dip, dip)
+        else:
+            a.calcFrameAtoms(pos[f])
+    got, ref = a.raw_histogram(), o.raw_sum()
+    assert np.array_equal(got[:300], ref[:300])
+    assert_hist_close(got, ref, 300)
+
+
+def test_atom_frames_g011_only_and_g000_without_charges():
+    """mode 011 needs only the dipoles of selection 2 (the frame is then not aliased); g000 needs no charges at all."""
+    nres, L, nf = 900, 33.0, 2
+    pos, masses, charges, apr, rfa = _water_box(nres, L, nf, 53)
+    for modes, q in ((["011"], charges), (["000"], None)):
+        a = RDF(modes, 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+        a.attach_topology(masses, apr, rfa, q)
+        a.calcFramesAtoms(pos)
+        o = O.OracleRDF(modes, 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+        for f in range(nf):
+            com, dip = _reference_chain(pos[f], masses, charges, apr, rfa)
+            o.calcFrame(com, com, dip, dip)
+        got, ref = a.raw_histogram(), o.raw_sum()
+        assert_hist_close(got, ref, 300, pairw=a.pair_weight)
+        assert np.array_equal(a.pair_weight, O_pair_weight(o, nres, L, pos, masses, charges, apr, rfa))
+
+
+def O_pair_weight(o, nres, L, pos, masses, charges, apr, rfa):
+    g = O.OracleRDF(["000"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+    for f in range(pos.shape[0]):
+        com, dip = _reference_chain(pos[f], masses, charges, apr, rfa)
+        g.calcFrame(com, com)
+    return g.raw_sum()[:300]
+
+
+def test_atom_frames_argument_errors():
+    nres, L = 300, 30.0
+    pos, masses, charges, apr, rfa = _water_box(nres, L, 1, 59)
+    a = RDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+    with pytest.raises(RuntimeError, match="attach_topology"):
+        a.calcFrameAtoms(pos[0])
+    with pytest.raises(ValueError, match="residues"):
+        a.attach_topology(masses[:-3], apr[:-1], rfa[:-1], charges[:-3])
+    a.attach_topology(masses, apr, rfa)                       # no charges, but "all" needs dipoles
+    with pytest.raises(ValueError, match="charges"):
+        a.calcFrameAtoms(pos[0])
+    a = RDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+    a.attach_topology(masses, apr, rfa, charges)
+    with pytest.raises(ValueError, match="shapes"):
+        a.calcFrameAtoms(pos[0, :-1])
+    b = RDF(["000"], 0.0, 15.0, 0.05, nres, nres + 1, nres, nres + 1, L)
+    b.attach_topology(masses, apr, rfa)
+    with pytest.raises(ValueError, match="second selection"):
+        b.calcFrameAtoms(pos[0])
+
+
 def test_cfg5_row_block_against_oracle():
     """BASELINE configs[4] shape (1M-site box, L = 315.4 A): a rectangular row block of 1,024 core sites
     against 262,144 surround sites (a quarter of the box population, same density region) vs the CPU oracle."""
