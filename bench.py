@@ -334,6 +334,39 @@ def run_ours(args, rank, world, local_rank):
                  "d2h_bytes_per_step": 8 * hn * 8 + 8 * 8, "ms_per_step": dta / K * 1e3,
                  "gpu_launches": int(sa1["kernel_launches"] - sa0["kernel_launches"]),
                  "api": "newanalysis.gfunction.RDF.calcFrameAtoms (host float32 positions, 3 atoms per site; COM + dipoles on the device) + readout per step"}
+
+        # ---------------- arm 4 (N=1 only): from a DCD file on disk (page cache) through reader threads -------------
+        import dcd as DCDORACLE                                  # only writes the synthetic input file
+        tmpd = tempfile.mkdtemp(prefix="gfn_bench_")
+        path = os.path.join(tmpd, "pool.dcd")
+        DCDORACLE.write_dcd(path, pool_a)
+        traj = G.DCDFile(path)
+        sel = np.arange(3 * n, dtype=np.int32)
+        t4 = mk()
+        t4.attach_topology(np.tile([15.999, 1.008, 1.008], n), np.full(n, 3, dtype=np.int32), (3 * np.arange(n)).astype(np.int32),
+                           np.tile([-0.8476, 0.4238, 0.4238], n))
+
+        def traj_step(s):
+            first = (s * F) % (POOL_FRAMES - F + 1) if POOL_FRAMES > F else 0
+            t4.calcTrajectory(traj, sel, first=first, last=first + F, threads=args.reader_threads)
+            return t4.raw_histogram()
+
+        for s in range(W):
+            traj_step(s)
+        t4.sync()
+        s40 = t4.stats()
+        t0 = time.perf_counter()
+        for s in range(K):
+            traj_step(W + s)
+        t4.sync()
+        dtt = time.perf_counter() - t0
+        s41 = t4.stats()
+        traj.close()
+        os.unlink(path); os.rmdir(tmpd)
+        atoms["from_dcd"] = {"value": K * F * per / dtt / 1e9, "unit": UNIT, "ms_per_step": dtt / K * 1e3,
+                             "file_bytes_per_step": F * (3 * (8 + 4 * 3 * n)), "h2d_bytes_per_step": (s41["h2d_bytes"] - s40["h2d_bytes"]) / K,
+                             "reader_threads": args.reader_threads,
+                             "api": "newanalysis.gfunction.RDF.calcTrajectory(DCDFile) + readout per step (file in the page cache)"}
     sampler.stop()
     e2e_value = world * K * F * per / dt / 1e9
     h2d = (se1["h2d_bytes"] - se0["h2d_bytes"]) / K
@@ -413,6 +446,7 @@ def main():
                     help="range pre-filter: auto = what the RDF class picks itself (fp16x2 for in-box coordinates)")
     ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reader-threads", type=int, default=2, help="decode threads of the DCD arm")
     ap.add_argument("--flags", default="", help="extra gfn flags (experiments)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -225,6 +225,32 @@ int gfn_attach_topology(gfn_t *h, int which, int natoms, int nres, const int *ap
                         const double *masses, const double *charges);
 int gfn_enqueue_atom_frames(gfn_t *h, int nframes, const float *a1, long long stride_a1,
                             const float *a2, long long stride_a2, const double *box_dims);
+/* atoms of the attached topologies (natoms2 = natoms1 when selection 2 shares the topology; 0, 0 before attaching) */
+int gfn_topology_natoms(gfn_t *h, int *natoms1, int *natoms2);
+
+/* ---- N4: trajectory decode overlapped with compute ------------------------------------------
+ * Replaces the script-side frame loop `for ts in u.trajectory[first:last:step]: ... sel.positions ...`
+ * (/root/reference/docs/notebooks/rdf.ipynb cells 10-18; MDAnalysis' DCD reader, a third-party dependency of the
+ * reference) for CHARMM / NAMD DCD files: both byte orders, optional unit-cell and fourth-dimension records; files
+ * with fixed atoms or 64-bit record markers are refused.  Host code, usable without a GPU.
+ *   gfn_traj_read: positions of the atoms idx[0..n) (idx == NULL: all atoms) of one frame as (n,3) float32 exactly as
+ *     stored; cell = A, B, C, alpha, beta, gamma (degrees; zeros when the file has no cell).  xyz / cell may be NULL.
+ *   gfn_enqueue_trajectory: frames first, first+step, ... (count of them) go through gfn_enqueue_atom_frames in
+ *     order; nthreads reader threads read, de-interleave and gather ahead while the calling thread fills the pinned
+ *     ring, so file decoding overlaps the uploads and kernels of earlier frames.  sel1 / sel2 are atom indices into
+ *     the trajectory (sel2 == NULL: self g-function) matching the attached topologies.  use_cell 0: the handle's
+ *     current box (gfn_update_box) for every frame; 1: each frame's own A, B, C as stored; 2: A, B, C rounded through
+ *     float32, what MDAnalysis' ts.dimensions hands to a script.  boxes_out: count x 3 lengths used (use_cell != 0), or NULL.
+ * Errors of these functions are reported by gfn_traj_last_error (t may be NULL: last gfn_traj_open_dcd failure). */
+typedef struct gfn_traj gfn_traj_t;
+int gfn_traj_open_dcd(gfn_traj_t **out, const char *path);
+void gfn_traj_close(gfn_traj_t *t);
+int gfn_traj_info(const gfn_traj_t *t, int *natoms, long long *nframes, int *has_cell);
+int gfn_traj_read(gfn_traj_t *t, long long frame, const int *idx, int n, float *xyz, double cell[6]);
+int gfn_enqueue_trajectory(gfn_t *h, gfn_traj_t *t, long long first, long long count, long long step,
+                           const int *sel1, int nsel1, const int *sel2, int nsel2, int use_cell,
+                           double *boxes_out, int nthreads);
+const char *gfn_traj_last_error(const gfn_traj_t *t);
 
 /* Self-test of the kernel's straight-line fp64 division / square-root sequences against the IEEE
  * built-ins (__ddiv_rn, __dsqrt_rn) on n_operands random operand sets with exponents in the range the

@@ -685,6 +685,14 @@ int gfn_attach_topology(gfn_t* h, int which, int natoms, int nres, const int* ap
     return GFN_OK;
 }
 
+int gfn_topology_natoms(gfn_t* h, int* natoms1, int* natoms2)
+{
+    if (!h) return GFN_EINVAL;
+    if (natoms1) *natoms1 = h->na[0];
+    if (natoms2) *natoms2 = h->na[1] ? h->na[1] : h->na[0];
+    return GFN_OK;
+}
+
 int gfn_enqueue_atom_frames(gfn_t* h, int nframes, const float* a1, long long stride_a1,
                             const float* a2, long long stride_a2, const double* box_dims)
 {

@@ -101,6 +101,17 @@ cdef extern from "gfn.h":
                             const double *masses, const double *charges) nogil
     int gfn_enqueue_atom_frames(gfn_t *h, int nframes, const float *a1, long long s1, const float *a2, long long s2,
                                 const double *boxes) nogil
+    int gfn_topology_natoms(gfn_t *h, int *natoms1, int *natoms2) nogil
+    ctypedef struct gfn_traj_t:
+        pass
+    int gfn_traj_open_dcd(gfn_traj_t **out, const char *path) nogil
+    void gfn_traj_close(gfn_traj_t *t) nogil
+    int gfn_traj_info(const gfn_traj_t *t, int *natoms, long long *nframes, int *has_cell) nogil
+    int gfn_traj_read(gfn_traj_t *t, long long frame, const int *idx, int n, float *xyz, double *cell) nogil
+    int gfn_enqueue_trajectory(gfn_t *h, gfn_traj_t *t, long long first, long long count, long long step,
+                               const int *sel1, int nsel1, const int *sel2, int nsel2, int use_cell,
+                               double *boxes_out, int nthreads) nogil
+    const char *gfn_traj_last_error(const gfn_traj_t *t) nogil
     int gfn_dev_alloc(int dev, void **dptr, unsigned long long nbytes) nogil
     int gfn_dev_free(int dev, void *dptr) nogil
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
@@ -362,6 +373,70 @@ def dipByResidue(coor, charges, masses, int nres, apr, rfa, com):
     return ResidueMap(masses, np.asarray(apr)[:nres], np.asarray(rfa)[:nres], charges).dip(np.asarray(coor, dtype=np.float64), com)
 
 
+cdef int _raise_traj(int rc, gfn_traj_t *t) except -1:
+    msg = gfn_traj_last_error(t).decode("utf-8", "replace")
+    if rc == GFN_EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+cdef class DCDFile:
+    """CHARMM / NAMD DCD trajectory read by libgfn.so (no MDAnalysis needed, no GPU needed): the frame source of
+    RDF.calcTrajectory.  n_atoms, n_frames, has_cell; read(frame, indices=None) -> (positions float32 (n,3) as stored,
+    cell = [A, B, C, alpha, beta, gamma] or None)."""
+    cdef gfn_traj_t *t
+    cdef readonly int n_atoms
+    cdef readonly long long n_frames
+    cdef readonly bint has_cell
+    cdef readonly str path
+
+    def __cinit__(self):
+        self.t = NULL
+
+    def __init__(self, path):
+        cdef bytes bp = os.fsencode(path)
+        cdef int rc = gfn_traj_open_dcd(&self.t, bp)
+        if rc:
+            self.t = NULL
+            _raise_traj(rc, NULL)
+        cdef int na = 0, hc = 0
+        cdef long long nf = 0
+        gfn_traj_info(self.t, &na, &nf, &hc)
+        self.n_atoms = na; self.n_frames = nf; self.has_cell = hc != 0
+        self.path = str(path)
+
+    def __dealloc__(self):
+        if self.t != NULL:
+            gfn_traj_close(self.t)
+            self.t = NULL
+
+    def close(self):
+        if self.t != NULL:
+            gfn_traj_close(self.t)
+            self.t = NULL
+
+    def __len__(self):
+        return self.n_frames
+
+    def read(self, long long frame, indices=None):
+        if self.t == NULL:
+            raise ValueError("trajectory is closed")
+        cdef np.ndarray[np.int32_t, ndim=1, mode="c"] idx = None
+        cdef int n = self.n_atoms
+        if indices is not None:
+            idx = np.ascontiguousarray(indices, dtype=np.int32)
+            n = idx.shape[0]
+        cdef np.ndarray[np.float32_t, ndim=2, mode="c"] xyz = np.empty((n, 3), dtype=np.float32)
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] cell = np.zeros(6)
+        cdef int rc
+        cdef const int *pi = <const int *> idx.data if idx is not None else NULL
+        with nogil:
+            rc = gfn_traj_read(self.t, frame, pi, n, <float *> xyz.data, <double *> cell.data)
+        if rc:
+            _raise_traj(rc, self.t)
+        return xyz, (cell if self.has_cell else None)
+
+
 cdef class _Backend:
     cdef gfn_t *h
     cdef int histo_n, n1, n2
@@ -474,6 +549,28 @@ cdef class _Backend:
         with nogil:
             rc = gfn_enqueue_atom_frames(self.h, nframes, a1, s1, a2, s2, boxes)
         return self.check(rc)
+
+    def enqueue_trajectory(self, DCDFile traj, long long first, long long count, long long step, sel1, sel2, int use_cell, int nthreads):
+        cdef np.ndarray[np.int32_t, ndim=1, mode="c"] s1 = np.ascontiguousarray(sel1, dtype=np.int32)
+        cdef np.ndarray[np.int32_t, ndim=1, mode="c"] s2 = None
+        cdef np.ndarray[np.float64_t, ndim=2, mode="c"] boxes = np.zeros((max(count, 1), 3))
+        if sel2 is not None:
+            s2 = np.ascontiguousarray(sel2, dtype=np.int32)
+        if traj.t == NULL:
+            raise ValueError("trajectory is closed")
+        cdef const int *p2 = <const int *> s2.data if s2 is not None else NULL
+        cdef int n1 = s1.shape[0]
+        cdef int n2 = s2.shape[0] if s2 is not None else 0
+        cdef int rc
+        with nogil:
+            rc = gfn_enqueue_trajectory(self.h, traj.t, first, count, step, <const int *> s1.data, n1, p2, n2,
+                                        use_cell, <double *> boxes.data, nthreads)
+        if rc:
+            msg = gfn_traj_last_error(traj.t).decode("utf-8", "replace")
+            if rc == GFN_EINVAL:
+                raise ValueError(msg)
+            raise RuntimeError(msg)
+        return boxes[:count]
 
     def flush(self):
         cdef int rc
@@ -1009,6 +1106,46 @@ class RDF(object):
                          <const double *> bx.data if bx is not None else NULL)
         if boxes is not None:
             self.update_box(*[float(v) for v in b3[nf - 1]])
+
+    def calcTrajectory(self, traj, sel1, sel2=None, first=0, last=None, step=1, use_cell=False, threads=2):
+        """Frames first, first+step, ... (< last) of a `DCDFile` straight into the histogram: replaces the script loop
+        `for ts in u.trajectory[first:last:step]: ...positions... comByResidue ... dipByResidue ... calcFrame`
+        (docs/notebooks/rdf.ipynb cell 18).  sel1 / sel2: atom indices into the trajectory (e.g. AtomGroup.indices) in
+        the order of the attached topology; sel2=None is the self g-function.  Reader threads decode ahead of the GPU.
+        use_cell: False - the box of the constructor / update_box for every frame; True - each frame's own A, B, C;
+        "float32" - A, B, C rounded through float32 (what MDAnalysis' ts.dimensions gives a script).
+        Returns the number of frames processed."""
+        if getattr(self, "_natoms", None) is None:
+            raise RuntimeError("attach_topology() must be called before atom positions can be passed")
+        cdef long long nfr = traj.n_frames
+        if last is None or last > nfr:
+            last = nfr
+        first = int(first); step = int(step)
+        if step < 1 or first < 0:
+            raise ValueError("first must be >= 0 and step >= 1")
+        cdef long long count = (last - first + step - 1) // step if last > first else 0
+        if count == 0:
+            return 0
+        s1 = np.ascontiguousarray(sel1, dtype=np.int32)
+        s2 = None if (sel2 is None or sel2 is sel1) else np.ascontiguousarray(sel2, dtype=np.int32)
+        cdef int uc = 2 if use_cell == "float32" else (1 if use_cell else 0)
+        if self.oneistwo is None:
+            k, same_topology = self._first_res
+            self.oneistwo = bool(same_topology and (s2 is None or np.array_equal(s1[:k], s2[:k])) and self.nmol1 == self.nmol2)
+        if self._auto_filter and self.ctr == 0:
+            p1, _ = traj.read(first, s1)
+            amax = float(np.abs(p1).max())
+            if s2 is not None:
+                amax = max(amax, float(np.abs(traj.read(first, s2)[0]).max()))
+            self._auto_pick_filter(None, None, amax)
+        boxes = self._be.enqueue_trajectory(traj, first, count, step, s1, s2, uc, int(threads))
+        self.ctr += count
+        if uc:
+            self.volume_list.extend(list(boxes[:, 0] * boxes[:, 1] * boxes[:, 2]))
+            self.update_box(*[float(v) for v in boxes[count - 1]])
+        else:
+            self.volume_list.extend([self.volume] * count)
+        return int(count)
 
     def flush(self):
         self._be.flush()

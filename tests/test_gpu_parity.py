@@ -535,6 +535,116 @@ def test_atom_frames_argument_errors():
         b.calcFrameAtoms(pos[0])
 
 
+# ---- N4: DCD trajectory -> reader threads -> upload ring ----------------------------------------------------
+def _solvated_system(nwat, nsol_atoms, L, nf, seed):
+    """A solute of nsol_atoms atoms followed by nwat 3-site waters; returns float32 positions (nf, natoms, 3)."""
+    rng = np.random.default_rng(seed)
+    wat, masses, charges, apr, rfa = _water_box(nwat, L, nf, seed + 1)
+    sol = (L / 2 + 2.0 * rng.standard_normal((nf, nsol_atoms, 3))).astype(np.float32)
+    pos = np.ascontiguousarray(np.concatenate([sol, wat], axis=1))
+    return pos, masses, charges, apr, rfa
+
+
+@pytest.mark.parametrize("big_endian,threads", [(False, 1), (True, 3)])
+def test_trajectory_self_npt_equals_atom_frames_and_oracle(tmp_path, big_endian, threads):
+    import dcd as D
+    from newanalysis.gfunction import DCDFile
+    nwat, nsol, L, nf = 2000, 17, 40.0, 23
+    pos, masses, charges, apr, rfa = _solvated_system(nwat, nsol, L, nf, 61)
+    rng = np.random.default_rng(62)
+    cells = np.concatenate([L * (1 + 1e-3 * rng.standard_normal((nf, 3))), np.full((nf, 3), 90.0)], axis=1)
+    path = str(tmp_path / "npt.dcd")
+    D.write_dcd(path, pos, cells, big_endian=big_endian)
+    sel = np.arange(nsol, nsol + 3 * nwat, dtype=np.int32)
+    first, last, step = 2, 21, 3
+    frames = list(range(first, last, step))
+
+    a = RDF(["all"], 0.0, 15.0, 0.05, nwat, nwat, nwat, nwat, L)
+    a.attach_topology(masses, apr, rfa, charges)
+    traj = DCDFile(path)
+    assert a.calcTrajectory(traj, sel, first=first, last=last, step=step, use_cell=True, threads=threads) == len(frames)
+
+    b = RDF(["all"], 0.0, 15.0, 0.05, nwat, nwat, nwat, nwat, L)
+    b.attach_topology(masses, apr, rfa, charges)
+    b.calcFramesAtoms(pos[frames][:, sel], boxes=cells[frames, :3])
+    o = O.OracleRDF(["all"], 0.0, 15.0, 0.05, nwat, nwat, nwat, nwat, L)
+    ora = D.DCD(path)
+    for f in frames:
+        xyz, cell = ora.read(f)
+        o.update_box(*cell[:3])
+        com, dip = _reference_chain(xyz[sel], masses, charges, apr, rfa)
+        o.calcFrame(com, com, dip, dip)
+    got, ref = a.raw_histogram(), o.raw_sum()
+    assert np.array_equal(got, b.raw_histogram())
+    assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 0
+    assert_hist_close(got, ref, 300)
+    assert a.ctr == len(frames) and a.oneistwo is True
+    assert a.volume_list == o.volume_list and a.volume == o.volume
+    assert np.array_equal(a.box_dim, o.box_dim)
+
+
+def test_trajectory_solute_solvent_fixed_box_and_float32_cells(tmp_path):
+    """rdf.ipynb's case: one solute molecule x all waters, box from the constructor; then the NpT variant with the
+    cell lengths rounded through float32 (what a script reading ts.dimensions would pass to update_box)."""
+    import dcd as D
+    from newanalysis.gfunction import DCDFile
+    nwat, nsol, L, nf = 1500, 24, 36.0, 12
+    pos, masses, charges, apr, rfa = _solvated_system(nwat, nsol, L, nf, 67)
+    rng = np.random.default_rng(68)
+    msol = 1.0 + 12.0 * rng.random(nsol); qsol = rng.standard_normal(nsol)
+    cells = np.concatenate([L * (1 + 1e-3 * rng.standard_normal((nf, 3))), np.full((nf, 3), 90.0)], axis=1)
+    path = str(tmp_path / "sol.dcd")
+    D.write_dcd(path, pos, cells)
+    s_sol = np.arange(nsol, dtype=np.int32); s_wat = np.arange(nsol, nsol + 3 * nwat, dtype=np.int32)
+    one = np.array([nsol], dtype=np.int32); zero = np.array([0], dtype=np.int32)
+    for use_cell in (False, "float32"):
+        a = RDF(["all"], 0.0, 15.0, 0.05, 1, nwat, 1, nwat, L)
+        a.attach_topology(msol, one, zero, qsol, masses, apr, rfa, charges)
+        a.calcTrajectory(DCDFile(path), s_sol, s_wat, use_cell=use_cell)
+        o = O.OracleRDF(["all"], 0.0, 15.0, 0.05, 1, nwat, 1, nwat, L)
+        for f in range(nf):
+            if use_cell:
+                o.update_box(*[float(np.float32(v)) for v in cells[f, :3]])
+            c1, d1 = _reference_chain(pos[f][s_sol], msol, qsol, one, zero)
+            c2, d2 = _reference_chain(pos[f][s_wat], masses, charges, apr, rfa)
+            o.calcFrame(c1, c2, d1, d2)
+        got, ref = a.raw_histogram(), o.raw_sum()
+        assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 0
+        assert_hist_close(got, ref, 300)
+        assert a.volume_list == o.volume_list and a.oneistwo is False
+
+
+def test_trajectory_argument_errors(tmp_path):
+    import dcd as D
+    from newanalysis.gfunction import DCDFile
+    nwat, L, nf = 200, 30.0, 3
+    pos, masses, charges, apr, rfa = _solvated_system(nwat, 5, L, nf, 71)
+    p_nocell, p_tric = str(tmp_path / "a.dcd"), str(tmp_path / "b.dcd")
+    D.write_dcd(p_nocell, pos)
+    D.write_dcd(p_tric, pos, np.tile([L, L, L, 90.0, 90.0, 120.0], (nf, 1)))
+    sel = np.arange(5, 5 + 3 * nwat, dtype=np.int32)
+    a = RDF(["all"], 0.0, 15.0, 0.05, nwat, nwat, nwat, nwat, L)
+    with pytest.raises(RuntimeError, match="attach_topology"):
+        a.calcTrajectory(DCDFile(p_nocell), sel)
+    a.attach_topology(masses, apr, rfa, charges)
+    with pytest.raises(ValueError, match="selection 1 has"):
+        a.calcTrajectory(DCDFile(p_nocell), sel[:-1])
+    bad = sel.copy(); bad[7] = 5 + 3 * nwat
+    with pytest.raises(ValueError, match="out of range"):
+        a.calcTrajectory(DCDFile(p_nocell), bad)
+    with pytest.raises(ValueError, match="no unit cell"):
+        a.calcTrajectory(DCDFile(p_nocell), sel, use_cell=True)
+    with pytest.raises(ValueError, match="orthorhombic"):
+        a.calcTrajectory(DCDFile(p_tric), sel, use_cell=True)
+    assert a.calcTrajectory(DCDFile(p_nocell), sel, first=5) == 0
+    # nothing of the failed calls may have reached the histogram except frames before the failing one (none here)
+    assert a.calcTrajectory(DCDFile(p_tric), sel) == nf            # cell ignored: fixed box
+    b = RDF(["all"], 0.0, 15.0, 0.05, nwat, nwat, nwat, nwat, L)
+    b.attach_topology(masses, apr, rfa, charges)
+    b.calcFramesAtoms(pos[:, sel])
+    assert np.array_equal(a.raw_histogram(), b.raw_histogram())
+
+
 def test_cfg5_row_block_against_oracle():
     """BASELINE configs[4] shape (1M-site box, L = 315.4 A): a rectangular row block of 1,024 core sites
     against 262,144 surround sites (a quarter of the box population, same density region) vs the CPU oracle."""
