@@ -48,12 +48,12 @@ extern "C" {
                                           results are identical, only the pipe that rejects far pairs changes */
 #define GFN_FLAG_DISCARD_OVERFLOW  4u  /* pos >= histo_n (quirk Q3) is dropped instead of spilling into
                                           bin pos-histo_n of the next row like the reference does */
-#define GFN_FLAG_HIST_GLOBAL       8u
-#define GFN_FLAG_NO_TRIANGLE       32u  /* evaluate all n1 x n2 pairs with weight 1 even when n1 == n2 (calcHistoTS,
-                                          gfunction.pyx:168-192, has no j >= i shortcut) */
-#define GFN_FLAG_FILTER_FP16       16u  /* range pre-filter in packed fp16 (two core sites per instruction, coordinates in box
-                                          units, wider guard band); results identical, see DESIGN.md */  /* force the global-atomic histogram path (default: per-warp shared-memory
+#define GFN_FLAG_HIST_GLOBAL       8u  /* force the global-atomic histogram path (default: per-warp shared-memory
                                           replicas whenever they fit) */
+#define GFN_FLAG_FILTER_FP16       16u /* range pre-filter in packed fp16 (two core sites per instruction, coordinates in box
+                                          units, wider guard band); results identical, see DESIGN.md section 4 */
+#define GFN_FLAG_NO_TRIANGLE       32u /* evaluate all n1 x n2 pairs with weight 1 even when n1 == n2 (calcHistoTS,
+                                          gfunction.pyx:168-192, has no j >= i shortcut) */
 
 /* bits of mode_sel, gfunction.pyx:274-288 */
 #define GFN_MODE_000 1
@@ -121,7 +121,6 @@ int gfn_enqueue_device_frames(gfn_t *h, int nframes,
                               const double *dd1, long long stride_d1, const double *dd2, long long stride_d2,
                               const double *box_dims);
 
-/* Submit a partially filled batch (asynchronous). */
 /* ---- N2: shell-resolved g-functions -------------------------------------------------
  * Replaces cdef void calcHistoVoronoi / calcHistoVoronoiNonSelf (gfunction.pyx:570-664, :667-761; call site
  * RDF_voronoi.calcFrame :1009-1021) and def calcHistoTSVoro (:195-224).  The pair loop is the one of calcHisto;
@@ -151,6 +150,7 @@ int gfn_enqueue_frames_shells(gfn_t *h, int nframes,
                               const double *d1, long long s_d1, const double *d2, long long s_d2,
                               const double *box_dims, const int *shell_map, long long s_map);
 
+/* Submit a partially filled batch (asynchronous). */
 int gfn_flush(gfn_t *h);
 /* Flush and wait for every submitted frame; reports deferred GFN_EZERODIV. */
 int gfn_sync(gfn_t *h);

@@ -7,6 +7,6 @@ name=$1; shift
 mkdir -p ../newanalysis/exp
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -warn-spills"
 $NV ${ONLY:--DGFN_EXP_ONLY_H16} "$@" -c -o /tmp/exp_$name.o gfn_kernels.cu
-[ -f gfn_api.o ] || make -s gfn_api.o
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../newanalysis/exp/libgfn_$name.so /tmp/exp_$name.o gfn_api.o -cudart static -ldl -lpthread
+make -s gfn_api.o gfn_traj.o
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../newanalysis/exp/libgfn_$name.so /tmp/exp_$name.o gfn_api.o gfn_traj.o -cudart static -ldl -lpthread
 echo built $name

@@ -79,3 +79,15 @@ def test_create_validates_arguments_before_touching_cuda():
     box = (ctypes.c_double * 6)(40, 40, 40, 20, 20, 20)
     assert lib.gfn_create(ctypes.byref(h), 0, 10, 300, ctypes.c_float(0), ctypes.c_float(15), ctypes.c_double(20.0), 127, box, None, 0, 0) == 1
     assert lib.gfn_create(ctypes.byref(h), 10, 10, 300, ctypes.c_float(0), ctypes.c_float(15), ctypes.c_double(20.0), 128, box, None, 0, 0) == 1
+
+
+def test_copy_helper_stress(tmp_path):
+    """The pinned-ring copy helper (csrc/copy_helper.h) alone: 16 caller/helper pairs on however many cores there are,
+    random sizes and alignments, helpers falling asleep every few jobs; every copy verified, no lost wake-up."""
+    import subprocess
+    exe = str(tmp_path / "stress")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-pthread", "-o", exe,
+                           os.path.join(ROOT, "tests", "stress_copy_helper.cpp")])
+    out = subprocess.run([exe, "16", "3000", "3"], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "bad 0" in out.stdout
