@@ -352,6 +352,35 @@ def test_single_process_two_devices_frame_sharding(monkeypatch):
     assert np.array_equal(one.raw_histogram()[:300], two.raw_histogram()[:300])
 
 
+@pytest.mark.skipif("_ngpu() < 2")
+def test_two_devices_atom_frames_and_trajectory(tmp_path, monkeypatch):
+    """The topology is copied to every device of the handle: atom frames and a DCD trajectory sharded over two GPUs give
+    the counts of the one-GPU run (weighted rows differ by the order of the final sum only)."""
+    import dcd as D
+    from newanalysis.gfunction import DCDFile
+    monkeypatch.setenv("GFN_BATCH_FRAMES", "2")
+    nres, L, nf = 1100, 36.0, 9
+    pos, masses, charges, apr, rfa = _water_box(nres, L, nf, 83)
+    path = str(tmp_path / "two.dcd")
+    D.write_dcd(path, pos)
+    sel = np.arange(3 * nres, dtype=np.int32)
+    one = RDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L)
+    one.attach_topology(masses, apr, rfa, charges)
+    one.calcFramesAtoms(pos)
+    ref = one.raw_histogram()
+    for feed in ("atoms", "dcd"):
+        two = RDF(["all"], 0.0, 15.0, 0.05, nres, nres, nres, nres, L, devices=[0, 1])
+        two.attach_topology(masses, apr, rfa, charges)
+        if feed == "atoms":
+            two.calcFramesAtoms(pos)
+        else:
+            assert two.calcTrajectory(DCDFile(path), sel) == nf
+        got = two.raw_histogram()
+        assert two.stats()["ndev"] == 2
+        assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 0
+        assert_hist_close(got, ref, 300)
+
+
 # ---- N1: centre of mass / dipole producers on the device ------------------------------------------------
 @pytest.mark.parametrize("name", sorted(C.RESIDUE_CASES))
 def test_residue_producers_bit_exact(golden_dir, name):
