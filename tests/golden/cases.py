@@ -190,3 +190,41 @@ def drive_tsvoro(fn, case):
     for t in range(T):
         fn(frames[t][0], frames[t][1], result, ds, case["maxshell"], case["box"], t, case["hmin"], case["hmax"], 1.0 / case["dr"])
     return result
+
+
+# N1 + N4 atom frames: float32 atom positions -> astype(float64) -> helpers.comByResidue / dipByResidue -> RDF.calcFrame,
+# all three steps by the UNMODIFIED reference modules (tests/golden/make_golden.py); fixture atoms.npz holds the raw sums.
+ATOM_CASES = {
+    "atoms_water_self": dict(n1=900, apr1=("const", 3), same=True, L=33.0, modes=["all"], hmax=15.0, frames=3, seed=31),
+    "atoms_ions_cross": dict(n1=160, apr1=("range", 2, 12), n2=210, apr2=("range", 2, 7), same=False, L=38.0,
+                             modes=["000", "110", "101", "011", "220"], hmax=19.0, frames=2, seed=32, npt=True),
+    "atoms_solute_water": dict(n1=1, apr1=("const", 24), n2=700, apr2=("const", 3), same=False, L=30.0, modes=["all"],
+                               hmax=15.0, frames=4, seed=33),
+}
+
+
+def build_atoms(case):
+    """-> dict(topo1=(masses, apr, rfa, charges), topo2=... or None, pos1 (frames, na1, 3) float32, pos2 or None,
+    boxes (frames, 3) or None)."""
+    rng = np.random.default_rng(700001 * case["seed"])
+    nf, L = case["frames"], case["L"]
+
+    def topo(n, kind):
+        apr = np.full(n, kind[1], dtype=np.int32) if kind[0] == "const" else rng.integers(kind[1], kind[2] + 1, n).astype(np.int32)
+        rfa = np.concatenate([[0], np.cumsum(apr)[:-1]]).astype(np.int32)
+        na = int(apr.sum())
+        return (np.ascontiguousarray(1.0 + 15.0 * rng.random(na)), apr, rfa, np.ascontiguousarray(rng.standard_normal(na)))
+
+    def frames(tp):
+        apr = tp[1]
+        centre = np.repeat(rng.random((nf, apr.shape[0], 3)) * L, apr, axis=1)
+        return np.ascontiguousarray((centre + 0.7 * rng.standard_normal(centre.shape)).astype(np.float32))
+
+    t1 = topo(case["n1"], case["apr1"])
+    p1 = frames(t1)
+    t2 = p2 = None
+    if not case["same"]:
+        t2 = topo(case["n2"], case["apr2"])
+        p2 = frames(t2)
+    boxes = L * (1.0 + 1e-3 * rng.standard_normal((nf, 3))) if case.get("npt") else None
+    return dict(topo1=t1, topo2=t2, pos1=p1, pos2=p2, boxes=boxes)

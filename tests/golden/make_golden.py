@@ -77,6 +77,34 @@ def main():
         print("residues %-10s nres=%d natoms=%d" % (name, nres, coor.shape[0]))
     np.savez_compressed(os.path.join(HERE, "residues.npz"), **out)
 
+    # N1 + N4 atom frames: the whole script-side chain with the unmodified reference modules
+    out = {}
+    for name in sorted(C.ATOM_CASES):
+        case = C.ATOM_CASES[name]
+        a = C.build_atoms(case)
+        n1 = case["n1"]; n2 = n1 if case["same"] else case["n2"]
+        rdf = ref.RDF(case["modes"], 0.0, case["hmax"], 0.05, n1, n2, n1, n2, case["L"])
+        for f in range(case["frames"]):
+            if a["boxes"] is not None:
+                rdf.update_box(*[float(v) for v in a["boxes"][f]])
+            sel = []
+            for tp, pos in ((a["topo1"], a["pos1"]), (a["topo2"], a["pos2"])):
+                if tp is None:
+                    sel.append(sel[0]); continue
+                masses, apr, rfa, charges = tp
+                coor = np.ascontiguousarray(pos[f], dtype="double")          # the notebook's np.ascontiguousarray(sel.positions, dtype='double')
+                com = H.comByResidue(coor, masses, apr.shape[0], apr, rfa)
+                dip = H.dipByResidue(coor, charges, masses, apr.shape[0], apr, rfa, com)
+                sel.append((com, dip))
+            rdf.calcFrame(sel[0][0], sel[1][0], sel[0][1], sel[1][1])
+        raw = np.zeros(7 * int(rdf.histo_n))
+        rdf._addHisto(raw, rdf.histogram)
+        out[name + "_raw"] = raw
+        out[name + "_volumes"] = np.array(rdf.volume_list)
+        out[name + "_oneistwo"] = np.array(bool(rdf.oneistwo))
+        print("atoms %-20s histo_n=%d in-range(g000 raw)=%.0f oneistwo=%s" % (name, rdf.histo_n, raw[:int(rdf.histo_n)].sum(), rdf.oneistwo))
+    np.savez_compressed(os.path.join(HERE, "atoms.npz"), **out)
+
 
 def main_shells():
     """N2: RDF_voronoi and calcHistoTSVoro fixtures from the unmodified reference module."""

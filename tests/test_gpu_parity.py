@@ -674,6 +674,43 @@ def test_trajectory_argument_errors(tmp_path):
     assert np.array_equal(a.raw_histogram(), b.raw_histogram())
 
 
+@pytest.mark.parametrize("feed", ["atoms", "dcd"])
+@pytest.mark.parametrize("name", sorted(C.ATOM_CASES))
+def test_atom_frames_golden(golden_dir, tmp_path, name, feed):
+    """Fixture tests/golden/atoms.npz: positions.astype(float64) -> helpers.comByResidue -> helpers.dipByResidue ->
+    RDF.calcFrame, all by the UNMODIFIED reference modules.  The GPU takes the float32 positions (or a DCD file
+    holding them) and must reproduce the reference's un-normalised sums: counts bit-exact, weighted rows within 1e-12."""
+    import dcd as D
+    from newanalysis.gfunction import DCDFile
+    case = C.ATOM_CASES[name]
+    z = np.load(os.path.join(golden_dir, "atoms.npz"))
+    a = C.build_atoms(case)
+    n1 = case["n1"]; n2 = n1 if case["same"] else case["n2"]
+    r = RDF(case["modes"], 0.0, case["hmax"], 0.05, n1, n2, n1, n2, case["L"])
+    hn = int(r.histo_n)
+    if a["topo2"] is None:
+        r.attach_topology(*a["topo1"])
+    else:
+        r.attach_topology(*a["topo1"], *a["topo2"])
+    if feed == "atoms":
+        r.calcFramesAtoms(a["pos1"], a["pos2"], boxes=a["boxes"])
+    else:
+        na1 = a["pos1"].shape[1]
+        pos = a["pos1"] if a["pos2"] is None else np.concatenate([a["pos1"], a["pos2"]], axis=1)
+        cells = None if a["boxes"] is None else np.concatenate([a["boxes"], np.full_like(a["boxes"], 90.0)], axis=1)
+        path = str(tmp_path / "g.dcd")
+        D.write_dcd(path, pos, cells)
+        s1 = np.arange(na1, dtype=np.int32)
+        s2 = None if a["pos2"] is None else np.arange(na1, pos.shape[1], dtype=np.int32)
+        r.calcTrajectory(DCDFile(path), s1, s2, use_cell=cells is not None)
+    got, ref = r.raw_histogram(), z[name + "_raw"]
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:hn], ref[:hn]) and ref[:hn].sum() > 0
+    assert_hist_close(got, ref, hn, pairw=np.maximum(r.pair_weight, ref[:hn]))
+    assert np.array_equal(np.array(r.volume_list), z[name + "_volumes"])
+    assert bool(r.oneistwo) == bool(z[name + "_oneistwo"])
+
+
 def test_cfg5_row_block_against_oracle():
     """BASELINE configs[4] shape (1M-site box, L = 315.4 A): a rectangular row block of 1,024 core sites
     against 262,144 surround sites (a quarter of the box population, same density region) vs the CPU oracle."""

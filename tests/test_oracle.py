@@ -188,3 +188,32 @@ def test_voronoi_oracle_matches_reference_module():
     a = C.drive_voro(C.make_voro(ref.RDF_voronoi, case), case)
     b = C.drive_voro(C.make_voro(O.OracleRDFVoronoi, case), case)
     assert np.array_equal(a.histogram, b.histogram)
+
+
+# ---- N1 + N4 atom frames: the oracle's chain against the fixture made by the unmodified reference modules ----------
+def atom_chain_oracle(case):
+    a = C.build_atoms(case)
+    n1 = case["n1"]; n2 = n1 if case["same"] else case["n2"]
+    o = O.OracleRDF(case["modes"], 0.0, case["hmax"], 0.05, n1, n2, n1, n2, case["L"])
+    for f in range(case["frames"]):
+        if a["boxes"] is not None:
+            o.update_box(*[float(v) for v in a["boxes"][f]])
+        sel = []
+        for tp, pos in ((a["topo1"], a["pos1"]), (a["topo2"], a["pos2"])):
+            if tp is None:
+                sel.append(sel[0]); continue
+            masses, apr, rfa, charges = tp
+            coor = np.ascontiguousarray(pos[f], dtype=np.float64)
+            com = O.com_by_residue_c(coor, masses, apr, rfa)
+            sel.append((com, O.dip_by_residue_c(coor, charges, apr, rfa, com)))
+        o.calcFrame(sel[0][0], sel[1][0], sel[0][1], sel[1][1])
+    return o
+
+
+@pytest.mark.parametrize("name", sorted(C.ATOM_CASES))
+def test_atom_chain_oracle_matches_golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "atoms.npz"))
+    o = atom_chain_oracle(C.ATOM_CASES[name])
+    assert np.array_equal(o.raw_sum(), z[name + "_raw"])
+    assert np.array_equal(np.array(o.volume_list), z[name + "_volumes"])
+    assert bool(o.oneistwo) == bool(z[name + "_oneistwo"])
