@@ -182,6 +182,10 @@ int gfn_stats(gfn_t *h, gfn_stats_t *out);
  * up their communicator internally (ncclCommInitAll). */
 int gfn_comm_unique_id(char out[128]);
 int gfn_comm_attach(gfn_t *h, const char unique_id[128], int nranks, int rank);
+/* Sum of n host doubles over the ranks of the attached communicator, in place (collective; no-op without
+ * gfn_comm_attach).  For what RDF._normHisto needs besides the histogram when frames are spread over processes: the
+ * number of frames (self.ctr, gfunction.pyx:424) and the sum of their volumes (self.volume_list, :427, :487-492). */
+int gfn_allreduce_host(gfn_t *h, double *vals, int n);
 
 /* Device-side stopwatch for benchmarks: gfn_mark records a CUDA event on the compute stream of the
  * handle's first device (after flushing pending frames), gfn_mark_elapsed_ms waits for mark 1 and

@@ -981,6 +981,25 @@ int gfn_comm_attach(gfn_t* h, const char unique_id[128], int nranks, int rank)
     return GFN_OK;
 }
 
+int gfn_allreduce_host(gfn_t* h, double* vals, int n)
+{
+    if (!h || !vals || n < 0) return fail(h, GFN_EINVAL, "bad argument");
+    if (!h->ext_comm || h->nranks == 1 || n == 0) return GFN_OK;      // the devices of one process share these host values
+    if (n > 8 * h->histo_n) return fail(h, GFN_EINVAL, "at most %d values", 8 * h->histo_n);
+    Nccl& nc = nccl();
+    if (!nc.ok) return fail(h, GFN_ENCCL, "%s", nc.err.c_str());
+    Dev& d = h->devs[0];
+    CU(cudaSetDevice(d.dev));
+    // gsum is free between readouts (gfn_readout waits for its all-reduce before it returns)
+    CU(cudaMemcpyAsync(d.gsum, vals, sizeof(double) * n, cudaMemcpyHostToDevice, d.comp));
+    const int nr = nc.AllReduce(d.gsum, d.gsum, (size_t)n, ncclFloat64, ncclSum, d.comm, d.comp);
+    if (nr != ncclSuccess) return fail(h, GFN_ENCCL, "ncclAllReduce: %s", nc.GetErrorString(nr));
+    CU(cudaMemcpyAsync(vals, d.gsum, sizeof(double) * n, cudaMemcpyDeviceToHost, d.comp));
+    CU(cudaStreamSynchronize(d.comp));
+    h->st_launches += 1;
+    return GFN_OK;
+}
+
 int gfn_mark(gfn_t* h, int which)
 {
     if (!h || which < 0 || which > 1) return fail(h, GFN_EINVAL, "gfn_mark: which must be 0 or 1");

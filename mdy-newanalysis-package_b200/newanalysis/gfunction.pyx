@@ -85,6 +85,7 @@ cdef extern from "gfn.h":
     int gfn_stats(gfn_t *h, gfn_stats_t *out) nogil
     int gfn_comm_unique_id(char *out) nogil
     int gfn_comm_attach(gfn_t *h, const char *uid, int nranks, int rank) nogil
+    int gfn_allreduce_host(gfn_t *h, double *vals, int n) nogil
     int gfn_measure_peaks(int dev, double *fp64, double *fp32) nogil
     int gfn_mark(gfn_t *h, int which) nogil
     int gfn_selftest_arith(int dev, unsigned long long seed, long long n, unsigned long long *mism) nogil
@@ -631,6 +632,16 @@ cdef class _Backend:
             rc = gfn_comm_attach(self.h, p, nranks, rank)
         self.check(rc)
 
+    def allreduce_host(self, values):
+        """Sum of a few host doubles over the ranks of the attached communicator (collective)."""
+        cdef np.ndarray[np.float64_t, ndim=1, mode="c"] v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        cdef int n = v.shape[0]
+        cdef int rc
+        with nogil:
+            rc = gfn_allreduce_host(self.h, <double *> v.data, n)
+        self.check(rc)
+        return v
+
     def stats(self):
         cdef gfn_stats_t s
         self.check(gfn_stats(self.h, &s))
@@ -916,7 +927,14 @@ class RDF(object):
         """
         Normalize the histogram (:483-511); host code, same arithmetic as the reference.
         """
-        if self.norm_volume:
+        ctr = self.ctr
+        if getattr(self, "_nranks", 1) > 1:
+            # frames are spread over processes: the histogram read out is the sum over all ranks, so the frame count and
+            # the mean volume must be taken over all ranks as well (collective, like the readout)
+            tot = self._be.allreduce_host([float(self.ctr), float(sum(self.volume_list))])
+            ctr = int(tot[0])
+            volume = self.norm_volume if self.norm_volume else tot[1] / tot[0]
+        elif self.norm_volume:
             volume = self.norm_volume
         else:
             volume = 0.0
@@ -935,7 +953,7 @@ class RDF(object):
             r = self.histo_min + float(i) * self.histo_dr
             r_out = r + self.histo_dr
             slice_vol = 4.0 / 3.0 * PI * (r_out**3 - r**3)
-            norm = rho * slice_vol * float(self.ctr)
+            norm = rho * slice_vol * float(ctr)
             for j in range(7):
                 self.histogram_out[j * self.histo_n + i] /= norm
 
@@ -1168,6 +1186,7 @@ class RDF(object):
         """One process per GPU: join an NCCL communicator; readout then sums the histograms of all ranks.
         (A unique id makes exactly one communicator, so while the pre-filter choice is still open - "auto", no
         frame seen yet - joining is postponed until the backend is final.)"""
+        self._nranks = int(nranks)
         if self._auto_filter and self.ctr == 0:
             self._pending_comm = (uid, nranks, rank)
         else:

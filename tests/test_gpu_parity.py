@@ -381,6 +381,32 @@ def test_two_devices_atom_frames_and_trajectory(tmp_path, monkeypatch):
         assert_hist_close(got, ref, 300)
 
 
+@pytest.mark.skipif("_ngpu() < 2")
+def test_multi_process_write_normalises_over_all_ranks(tmp_path):
+    """One process per GPU (torchrun, 2 ranks, NCCL): write() on every rank gives the g-functions of the whole run -
+    histogram summed by ncclAllReduce, frame count and mean volume summed with gfn_allreduce_host."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import mp_write_check as M
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                    "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(here, "mp_write_check.py"), str(tmp_path)],
+                   check=True, timeout=180)
+    n, L, nf = 1500, 40.0, 11
+    c, d, boxes = M.frames(nf, n, L)
+    o = O.OracleRDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
+    for f in range(nf):
+        o.update_box(*[float(v) for v in boxes[f]])
+        o.calcFrame(c[f], c[f], d[f], d[f])
+    o.write(str(tmp_path / "oracle"))
+    for rank in (0, 1):
+        got = np.load(str(tmp_path / ("rank%d_out.npy" % rank)))
+        assert np.allclose(got[:300], o.histogram_out[:300], rtol=1e-13, atol=0)         # counts exact; mean volume summed in another order
+        assert np.allclose(got, o.histogram_out, rtol=1e-9, atol=1e-10)
+        assert (tmp_path / ("rank%d_g000.dat" % rank)).read_text() == (tmp_path / "oracle_g000.dat").read_text()
+
+
 # ---- N1: centre of mass / dipole producers on the device ------------------------------------------------
 @pytest.mark.parametrize("name", sorted(C.RESIDUE_CASES))
 def test_residue_producers_bit_exact(golden_dir, name):
