@@ -10,11 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "mdy-newanalysis-package_b200"))
 
-import torch                                    # noqa: E402
-import torch.distributed as dist                # noqa: E402
-
-import newanalysis.gfunction as G               # noqa: E402
-from gfn_b200 import sharding                   # noqa: E402
+# torch is imported in main() only: the pytest process imports this module for frames() after libgfn has loaded the
+# system NCCL, and torch's own libtorch_cuda.so must not be resolved against that one
 
 
 def frames(nf, n, L, seed=97):
@@ -26,6 +23,10 @@ def frames(nf, n, L, seed=97):
 
 
 def main():
+    import torch
+    import torch.distributed as dist
+    import newanalysis.gfunction as G
+    from gfn_b200 import sharding
     out = sys.argv[1]
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
