@@ -7,7 +7,8 @@ and the frame loop.  The frame loop, the centres of mass, the dipoles and the pa
 the topology arrays come from wherever you have them (MDAnalysis, a PSF parser, ...).  Without arguments the script
 writes a small synthetic solvated system to a temporary DCD file first so that it runs anywhere with a B200.
 
-    python examples/rdf_from_dcd.py [trajectory.dcd topology.npz]      # npz: masses, charges, resid (per atom), solute_resid
+    python examples/rdf_from_dcd.py [trajectory.dcd topology.psf SOLUTE_RESNAME SOLVENT_RESNAME]
+e.g. the notebook's data:  python examples/rdf_from_dcd.py 1mq_swm4.dcd mqs0_swm4_1000.psf MQS0 SWM4
 """
 import os
 import sys
@@ -20,6 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "mdy-newanalysis-package_b200"))
 
 from newanalysis.gfunction import RDF, DCDFile  # noqa: E402
+from newanalysis.functions import atomsPerResidue, residueFirstAtom  # noqa: E402
+from newanalysis.psf import PSF  # noqa: E402
 
 
 def residues(resid):
@@ -46,28 +49,31 @@ def synthetic(path, nwat=4000, nsol=24, L=49.3, nframes=50, seed=5):
 
 
 def main():
-    if len(sys.argv) == 3:
+    tmp = None
+    if len(sys.argv) == 5:
         path = sys.argv[1]
-        z = np.load(sys.argv[2])
-        masses, charges, resid, solute = z["masses"], z["charges"], z["resid"], int(z["solute_resid"])
-        tmp = None
+        top = PSF(sys.argv[2])
+        s_sol, s_wat = top.select(resname=sys.argv[3]), top.select(resname=sys.argv[4])
+        sel_solute, sel_wat = s_sol.indices, s_wat.indices
+        apr_s, rfa_s, apr_w, rfa_w = atomsPerResidue(s_sol), residueFirstAtom(s_sol), atomsPerResidue(s_wat), residueFirstAtom(s_wat)
+        m_s, q_s, m_w, q_w = s_sol.masses, s_sol.charges, s_wat.masses, s_wat.charges
     else:
         tmp = tempfile.mkdtemp(prefix="gfn_example_")
         path = os.path.join(tmp, "demo.dcd")
         masses, charges, resid, solute = synthetic(path)
+        sel_solute = np.flatnonzero(resid == solute).astype(np.int32)
+        sel_wat = np.flatnonzero(resid != solute).astype(np.int32)
+        apr_s, rfa_s = residues(resid[sel_solute])
+        apr_w, rfa_w = residues(resid[sel_wat])
+        m_s, q_s, m_w, q_w = masses[sel_solute], charges[sel_solute], masses[sel_wat], charges[sel_wat]
 
     traj = DCDFile(path)
     _, cell = traj.read(0)
     boxl = np.float64(round(float(cell[0]), 4))                   # the notebook: round(u.coord.dimensions[0], 4)
-    sel_solute = np.flatnonzero(resid == solute).astype(np.int32)
-    sel_wat = np.flatnonzero(resid != solute).astype(np.int32)
-    apr_s, rfa_s = residues(resid[sel_solute])
-    apr_w, rfa_w = residues(resid[sel_wat])
     nsolute, nwat = apr_s.shape[0], apr_w.shape[0]
 
     sol_wat = RDF(["all"], 0.0, 20.0, 0.05, nsolute, nwat, nsolute, nwat, boxl)
-    sol_wat.attach_topology(masses[sel_solute], apr_s, rfa_s, charges[sel_solute],
-                            masses[sel_wat], apr_w, rfa_w, charges[sel_wat])
+    sol_wat.attach_topology(m_s, apr_s, rfa_s, q_s, m_w, apr_w, rfa_w, q_w)
     t0 = time.time()
     n = sol_wat.calcTrajectory(traj, sel_solute, sel_wat, step=1)
     out = os.path.join(tmp or ".", "rdf")

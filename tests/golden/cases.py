@@ -228,3 +228,43 @@ def build_atoms(case):
         p2 = frames(t2)
     boxes = L * (1.0 + 1e-3 * rng.standard_normal((nf, 3))) if case.get("npt") else None
     return dict(topo1=t1, topo2=t2, pos1=p1, pos2=p2, boxes=boxes)
+
+
+# Topology side (newanalysis.psf / newanalysis.functions): synthetic PSF files; fixture topology.npz holds what the
+# UNMODIFIED reference functions atomsPerResidue / residueFirstAtom (py_functions.py:64-89) return for the selections.
+PSF_CASES = {
+    "solvated": dict(ext=False, seed=51, blocks=[("SOLU", "MQS0", 1, 24), ("WAT", "SWM4", 300, 5)]),
+    "ionic":    dict(ext=True, seed=52, blocks=[("CAT", "C2MI", 40, 19), ("AN", "OTF", 40, 8), ("CAT", "C2MI", 3, 19)]),
+    "ragged":   dict(ext=False, seed=53, blocks=[("A", "LIG", 7, (1, 9)), ("A", "LIG2", 5, (2, 4)), ("B", "LIG", 7, (1, 9))],
+                     same_resid_across_segments=True),
+}
+PSF_SELECTIONS = {
+    "solvated": [dict(resname="SWM4"), dict(resname="MQS0"), dict()],
+    "ionic":    [dict(resname="C2MI"), dict(resname="OTF"), dict(segid="CAT"), dict(resname="C2MI OTF")],
+    "ragged":   [dict(resname="LIG"), dict(segid="B"), dict(), dict(resname="LIG2")],
+}
+
+
+def build_psf(case):
+    """-> (text of a PSF file, dict of per-atom arrays that were written)."""
+    rng = np.random.default_rng(800001 * case["seed"])
+    segs, resids, resnames, names, charges, masses = [], [], [], [], [], []
+    for seg, resname, nres, na in case["blocks"]:
+        first = 1 if case.get("same_resid_across_segments") else (int(resids[-1]) + 1 if resids else 1)
+        for r in range(nres):
+            n = na if isinstance(na, int) else int(rng.integers(na[0], na[1] + 1))
+            for a in range(n):
+                segs.append(seg); resids.append(str(first + r)); resnames.append(resname); names.append("A%d" % (a + 1))
+                charges.append(round(float(rng.standard_normal()), 6)); masses.append(round(1.0 + 15.0 * float(rng.random()), 4))
+    n = len(segs)
+    ext = case["ext"]
+    out = ["PSF EXT CMAP" if ext else "PSF CMAP", "", "%8d !NTITLE" % 2, "* synthetic topology (tests/golden/cases.py)", "* seed %d" % case["seed"], "",
+           ("%10d !NATOM" if ext else "%8d !NATOM") % n]
+    for k in range(n):
+        if ext:
+            out.append("%10d %-8s %-8s %-8s %-8s %-6s %14.6f%14.4f%8d" % (k + 1, segs[k], resids[k], resnames[k], names[k], "T%d" % (k % 7), charges[k], masses[k], 0))
+        else:
+            out.append("%8d %-4s %-4s %-4s %-4s %4d %14.6f%14.4f%8d" % (k + 1, segs[k], resids[k], resnames[k], names[k], k % 90, charges[k], masses[k], 0))
+    out += ["", ("%10d !NBOND: bonds" if ext else "%8d !NBOND: bonds") % 0, "", ""]
+    return "\n".join(out), dict(segids=np.array(segs), resids=np.array(resids), resnames=np.array(resnames), names=np.array(names),
+                                 charges=np.array(charges), masses=np.array(masses))

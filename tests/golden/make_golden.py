@@ -130,6 +130,34 @@ def main_shells():
         print("%-16s counts per shell=%s" % (name, out[name].sum(axis=(0, 1, 3))))
     np.savez_compressed(os.path.join(HERE, "tsvoro.npz"), **out)
 
+    # topology helpers: the reference's own atomsPerResidue / residueFirstAtom (py_functions.py:64-89, pure Python) run on the
+    # AtomGroup-like selections of newanalysis.psf
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_py_functions", "/root/reference/newanalysis/functions/py_functions.py")
+    RF = importlib.util.module_from_spec(spec); spec.loader.exec_module(RF)
+    sys.path.insert(0, os.path.join(ROOT, "mdy-newanalysis-package_b200", "newanalysis"))
+    import psf as PSFMOD                      # the module file alone: the package __init__ would load the CUDA extension
+
+    class RefView(object):                    # what the reference functions touch: n_atoms, n_residues, atoms[i].resid / .resname
+        def __init__(self, sel):
+            self.n_atoms, self.n_residues = sel.n_atoms, sel.n_residues
+            self.atoms = [type("A", (), dict(resid=sel.resids[i], resname=sel.resnames[i])) for i in range(sel.n_atoms)]
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in sorted(C.PSF_CASES):
+            text, _ = C.build_psf(C.PSF_CASES[name])
+            path = os.path.join(tmp, name + ".psf")
+            open(path, "w").write(text)
+            top = PSFMOD.PSF(path)
+            for k, crit in enumerate(C.PSF_SELECTIONS[name]):
+                sel = top.select(**crit)
+                rv = RefView(sel)
+                out["%s_%d_apr" % (name, k)] = RF.atomsPerResidue(rv)
+                out["%s_%d_rfa" % (name, k)] = RF.residueFirstAtom(rv)
+                out["%s_%d_n" % (name, k)] = np.array([sel.n_atoms, sel.n_residues])
+                print("topology %-10s sel %d: %d atoms, %d residues" % (name, k, sel.n_atoms, sel.n_residues))
+    np.savez_compressed(os.path.join(HERE, "topology.npz"), **out)
+
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "shells":

@@ -446,6 +446,26 @@ def test_atoms_to_gfunction_on_device():
     assert_hist_close(got, ref, 300)
 
 
+def test_function_wrappers_from_psf_selection(tmp_path):
+    """newanalysis.functions.centerOfMassByResidue / dipoleMomentByResidue (py_functions.py:91-150) on a selection of a
+    PSF topology, producers on the GPU: bit-identical to the oracle's restatement of helpers.pyx:71-123."""
+    from newanalysis import psf, functions as F
+    text, _ = C.build_psf(C.PSF_CASES["ionic"])
+    path = tmp_path / "i.psf"
+    path.write_text(text)
+    sel = psf.PSF(str(path)).select(resname="C2MI")
+    rng = np.random.default_rng(77)
+    sel.positions = (rng.random((sel.n_atoms, 3)) * 40).astype(np.float32)
+    apr, rfa = F.atomsPerResidue(sel), F.residueFirstAtom(sel)
+    coor = sel.positions.astype("float64")
+    com = F.centerOfMassByResidue(sel, apr=apr, rfa=rfa)
+    dip = F.dipoleMomentByResidue(sel, com=com, apr=apr, rfa=rfa)
+    ref_com = O.com_by_residue_c(coor, sel.masses, apr, rfa)
+    assert np.array_equal(com, ref_com)
+    assert np.array_equal(dip, O.dip_by_residue_c(coor, sel.charges, apr, rfa, ref_com))
+    assert np.array_equal(F.dipoleMomentByResidue(sel, apr=apr, rfa=rfa), dip)
+
+
 # ---- N1 + N4: raw float32 atom positions through the upload ring --------------------------------------------
 def _water_box(nres, L, nf, seed):
     rng = np.random.default_rng(seed)
