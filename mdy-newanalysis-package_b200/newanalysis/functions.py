@@ -48,61 +48,40 @@ def residueFirstAtom(sel):
     return rfa
 
 
+_SLOW = "Warning: %s is now calculated each timestep (very slow)! Give %s as an argument to speed up code"
+
+
+def _inputs(sel, kwargs, want):
+    """Keyword arguments of the reference wrappers with their defaults taken from the selection: coor (float64 copy of
+    sel.positions), masses / charges (contiguous), apr / rfa (recomputed, with the reference's warning, when absent)."""
+    out = {}
+    for key in want:
+        if key in kwargs:
+            out[key] = kwargs[key]
+        elif key == "coor":
+            out[key] = sel.positions.astype('float64')
+        elif key in ("masses", "charges"):
+            out[key] = numpy.ascontiguousarray(getattr(sel, key))
+        else:
+            print(_SLOW % (key, key))
+            out[key] = atomsPerResidue(sel) if key == "apr" else residueFirstAtom(sel)
+    return out
+
+
 def centerOfMassByResidue(sel, **kwargs):
-    """Returns an array of the centers of mass of all residues in the current AtomGroup (py_functions.py:91-114)."""
+    """Centres of mass of all residues of the AtomGroup-like `sel` (py_functions.py:91-114): optional keywords coor,
+    masses, apr, rfa; computed by helpers.comByResidue on the GPU, bit-identical to the reference's arrays."""
     from newanalysis.helpers import comByResidue
-    if "coor" not in kwargs:
-        coor = sel.positions.astype('float64')
-    else:
-        coor = kwargs["coor"]
-    if "masses" not in kwargs:
-        masses = numpy.ascontiguousarray(sel.masses)
-    else:
-        masses = kwargs["masses"]
-    if "apr" not in kwargs:
-        print("Warning: apr is now calculated each timestep (very slow)! Give apr as an argument to speed up code")
-        apr = atomsPerResidue(sel)
-    else:
-        apr = kwargs["apr"]
-    if "rfa" not in kwargs:
-        print("Warning: rfa is now calculated each timestep (very slow)! Give rfa as an argument to speed up code")
-        rfa = residueFirstAtom(sel)
-    else:
-        rfa = kwargs["rfa"]
-    numres = sel.n_residues
-    return comByResidue(coor, masses, numres, apr, rfa)
+    a = _inputs(sel, kwargs, ("coor", "masses", "apr", "rfa"))
+    return comByResidue(a["coor"], a["masses"], sel.n_residues, a["apr"], a["rfa"])
 
 
 def dipoleMomentByResidue(sel, **kwargs):
-    """Returns an array of the dipole moments of all residues in the current AtomGroup (py_functions.py:120-150)."""
+    """Dipole moments of all residues relative to `com` (default: their centres of mass) (py_functions.py:120-150):
+    optional keywords charges, masses, coor, com, apr, rfa; helpers.dipByResidue on the GPU."""
     from newanalysis.helpers import dipByResidue
-    if "charges" not in kwargs:
-        charges = numpy.ascontiguousarray(sel.charges)
-    else:
-        charges = kwargs["charges"]
-    if "masses" not in kwargs:
-        masses = numpy.ascontiguousarray(sel.masses)
-    else:
-        masses = kwargs["masses"]
-    if "coor" not in kwargs:
-        coor = sel.positions.astype('float64')
-    else:
-        coor = kwargs["coor"]
-    if "apr" not in kwargs:
-        print("Warning: apr is now calculated each timestep (very slow)! Give apr as an argument to speed up code")
-        apr = atomsPerResidue(sel)
-    else:
-        apr = kwargs["apr"]
-    if "rfa" not in kwargs:
-        print("Warning: rfa is now calculated each timestep (very slow)! Give rfa as an argument to speed up code")
-        rfa = residueFirstAtom(sel)
-    else:
-        rfa = kwargs["rfa"]
-    if "com" not in kwargs:
-        # the reference calls centerOfMassByResidue(sel, masses=masses, coor=coor) here, which recomputes apr / rfa
-        # (and prints its warnings) even when they were passed; the arrays are the same
-        com = centerOfMassByResidue(sel, masses=masses, coor=coor, apr=apr, rfa=rfa)
-    else:
-        com = kwargs["com"]
-    numres = sel.n_residues
-    return dipByResidue(coor, charges, masses, numres, apr, rfa, com)
+    a = _inputs(sel, kwargs, ("charges", "masses", "coor", "apr", "rfa"))
+    # (the reference computes a missing com with centerOfMassByResidue(sel, masses=masses, coor=coor), which derives
+    # apr / rfa once more and prints its warnings again; the arrays are the same)
+    com = kwargs["com"] if "com" in kwargs else centerOfMassByResidue(sel, **{k: a[k] for k in ("masses", "coor", "apr", "rfa")})
+    return dipByResidue(a["coor"], a["charges"], a["masses"], sel.n_residues, a["apr"], a["rfa"], com)
