@@ -336,10 +336,9 @@ def run_ours(args, rank, world, local_rank):
                  "api": "newanalysis.gfunction.RDF.calcFrameAtoms (host float32 positions, 3 atoms per site; COM + dipoles on the device) + readout per step"}
 
         # ---------------- arm 4 (N=1 only): from a DCD file on disk (page cache) through reader threads -------------
-        import dcd as DCDORACLE                                  # only writes the synthetic input file
         tmpd = tempfile.mkdtemp(prefix="gfn_bench_")
         path = os.path.join(tmpd, "pool.dcd")
-        DCDORACLE.write_dcd(path, pool_a)
+        synth.write_dcd(path, pool_a)
         traj = G.DCDFile(path)
         sel = np.arange(3 * n, dtype=np.int32)
         t4 = mk()

@@ -34,14 +34,13 @@ def residues(resid):
 
 
 def synthetic(path, nwat=4000, nsol=24, L=49.3, nframes=50, seed=5):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import dcd                                   # test infrastructure: only used to WRITE the demo file
+    from gfn_b200 import synth                   # synthetic-input helpers: writes the demo file
     rng = np.random.default_rng(seed)
     wat = rng.random((nframes, nwat, 1, 3)) * L + 0.6 * rng.standard_normal((nframes, nwat, 3, 3))
     sol = L / 2 + 2.0 * rng.standard_normal((nframes, nsol, 3))
     pos = np.concatenate([sol, wat.reshape(nframes, 3 * nwat, 3)], axis=1).astype(np.float32)
     cells = np.tile([L, L, L, 90.0, 90.0, 90.0], (nframes, 1))
-    dcd.write_dcd(path, pos, cells)
+    synth.write_dcd(path, pos, cells)
     masses = np.r_[1.0 + 12.0 * rng.random(nsol), np.tile([15.999, 1.008, 1.008], nwat)]
     charges = np.r_[rng.standard_normal(nsol), np.tile([-0.8476, 0.4238, 0.4238], nwat)]
     resid = np.r_[np.zeros(nsol, dtype=np.int64), 1 + np.repeat(np.arange(nwat), 3)]

@@ -74,3 +74,30 @@ def flops_per_eval(mode_sel, f_in):
 def in_range_fraction(hmax, L):
     import math
     return min(1.0, 4.0 * math.pi * hmax ** 3 / (3.0 * L ** 3))
+
+
+def write_dcd(path, positions, cells=None):
+    """Synthetic trajectory file for bench.py / examples: positions (nframes, natoms, 3) float32 -> little-endian CHARMM
+    DCD (optional per-frame cells A, B, C, alpha, beta, gamma in degrees).  Input generation only - the product reads
+    trajectories with libgfn.so (newanalysis.gfunction.DCDFile); the checker's independent writer / reader with all the
+    format variants lives in oracle/dcd.py and is not used outside tests/."""
+    import struct
+    pos = np.ascontiguousarray(positions, dtype="<f4")
+    nf, na = pos.shape[0], pos.shape[1]
+    icntrl = np.zeros(20, dtype="<i4")
+    icntrl[0], icntrl[2], icntrl[3] = nf, 1, nf
+    icntrl[10] = 1 if cells is not None else 0
+    icntrl[19] = 24
+    head = b"CORD" + icntrl.tobytes()
+    head = head[:40] + struct.pack("<f", 0.002) + head[44:]          # icntrl[9]: time step, float32 in CHARMM files
+    title = struct.pack("<i", 1) + b"synthetic trajectory (gfn_b200.synth.write_dcd)".ljust(80)
+    mark = struct.pack("<i", 4 * na)
+    with open(path, "wb") as f:
+        for payload in (head, title, struct.pack("<i", na)):
+            f.write(struct.pack("<i", len(payload)) + payload + struct.pack("<i", len(payload)))
+        for i in range(nf):
+            if cells is not None:
+                A, B, C, al, be, ga = [float(v) for v in cells[i]]
+                f.write(struct.pack("<i6di", 48, A, ga, B, be, al, C, 48))
+            for k in range(3):
+                f.write(mark); f.write(np.ascontiguousarray(pos[i, :, k]).tobytes()); f.write(mark)

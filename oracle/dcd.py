@@ -1,7 +1,8 @@
 """oracle/dcd.py - numpy writer and reader of CHARMM / NAMD DCD trajectories (checker for csrc/gfn_traj.cpp).
 
-TEST INFRASTRUCTURE.  Only tests/ and bench.py (to create its synthetic input file) may import this module; the
-product reads trajectories with libgfn.so (gfn_traj_open_dcd / gfn_traj_read / gfn_enqueue_trajectory).
+TEST INFRASTRUCTURE.  Only tests/ may import this module; the product reads trajectories with libgfn.so
+(gfn_traj_open_dcd / gfn_traj_read / gfn_enqueue_trajectory), bench.py and the examples write their synthetic input
+files with gfn_b200.synth.write_dcd.
 
 Parity status: UNPINNED.  The reference reads DCD files through MDAnalysis (docs/notebooks/rdf.ipynb cell 10:
 `MDAnalysis.Universe(psf, base + "1mq_swm4.dcd")`), a third-party dependency (unpinned in the reference's setup.py /

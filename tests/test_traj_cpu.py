@@ -105,3 +105,23 @@ def test_refused_files(tmp_path):
     with pytest.raises(ValueError, match="damaged"):
         t.read(1)
     del t0
+
+
+def test_synth_writer_is_read_back_by_both_readers(tmp_path):
+    """gfn_b200.synth.write_dcd (input generation for bench.py / examples) against the native reader and the oracle's."""
+    from gfn_b200 import synth
+    pos, cells = _frames(4, 257, 9)
+    for with_cell in (False, True):
+        p = str(tmp_path / ("s%d.dcd" % with_cell))
+        synth.write_dcd(p, pos, cells if with_cell else None)
+        t, ora = DCDFile(p), D.DCD(p)
+        assert (t.n_atoms, t.n_frames, t.has_cell) == (257, 4, with_cell) == (ora.n_atoms, ora.n_frames, ora.has_cell)
+        for f in range(4):
+            xyz, cell = t.read(f)
+            assert np.array_equal(xyz, pos[f]) and np.array_equal(ora.read(f)[0], pos[f])
+            if with_cell:
+                assert np.array_equal(cell, cells[f]) and np.array_equal(ora.read(f)[1], cells[f])
+        # the same bytes as the checker's writer produces for this simplest variant, apart from the title text
+        q = str(tmp_path / "o.dcd")
+        D.write_dcd(q, pos, cells if with_cell else None, titles=("synthetic trajectory (gfn_b200.synth.write_dcd)",))
+        assert open(p, "rb").read() == open(q, "rb").read()
