@@ -52,6 +52,8 @@ struct gfn_traj {
     // staging of gfn_enqueue_trajectory, kept between calls (fresh 1 MB buffers cost a page fault per 4 KB)
     std::vector<std::vector<float>> slot_atoms;
     std::vector<std::vector<unsigned char>> raws;
+    std::vector<unsigned char> read_raw;     // frame buffer of gfn_traj_read (kept: a fresh 1 MB vector costs more than the read)
+    std::mutex read_mu;
     char err[256];
 };
 
@@ -250,8 +252,10 @@ int gfn_traj_read(gfn_traj_t* t, long long frame, const int* idx, int n, float* 
     if (frame < 0 || frame >= t->nframes) return tfail(t, GFN_EINVAL, "frame %lld out of range (0..%lld)", frame, t->nframes - 1);
     if (idx) for (int k = 0; k < n; ++k) if (idx[k] < 0 || idx[k] >= t->natoms) return tfail(t, GFN_EINVAL, "atom index %d out of range (0..%d)", idx[k], t->natoms - 1);
     if (!idx) n = t->natoms;
-    std::vector<unsigned char> raw((size_t)t->frame_bytes);
-    if (!pread_all(t->fd, raw.data(), raw.size(), t->first_off + frame * t->frame_bytes)) return tfail(t, GFN_EINVAL, "frame %lld: read failed", frame);
+    std::lock_guard<std::mutex> lk(t->read_mu);
+    std::vector<unsigned char>& raw = t->read_raw;
+    if (raw.size() < (size_t)t->frame_bytes) raw.resize((size_t)t->frame_bytes);
+    if (!pread_all(t->fd, raw.data(), (size_t)t->frame_bytes, t->first_off + frame * t->frame_bytes)) return tfail(t, GFN_EINVAL, "frame %lld: read failed", frame);
     const unsigned char* cr; const unsigned char* b[3];
     int rc = locate(t, raw.data(), frame, &cr, b);
     if (rc) return rc;
