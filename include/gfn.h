@@ -20,9 +20,16 @@
  * their arrays every frame).  There is NO CPU fallback: without a usable sm_100 device gfn_create
  * fails with GFN_ENODEV.
  *
- * Arithmetic contract: bin assignment and all orientation weights are computed in IEEE fp64 with
- * exactly the reference's operation order (no fused multiply-add), see DESIGN.md.  The g000 row is
- * bit-exact; weighted rows differ from the reference only by summation order.
+ * Arithmetic contract (DESIGN.md sections 3 and 6):
+ *   - Distances and bins: IEEE fp64 with exactly the reference's operation order and one rounding per operation (no
+ *     fused multiply-add), so every pair lands in the reference's bin and the g000 row / pair counts are bit-exact.
+ *   - Orientation weights (gfunction.pyx:154-165): by default each cosine is formed as  dot * (1/|a| * 1/|b|)  with
+ *     separately rounded reciprocals (1/norm per site, 1/dist from the square-root iteration) instead of the
+ *     reference's  dot / (|a|*|b|):  a per-pair increment can differ from the reference's by up to 4 ulp (relative
+ *     4.5e-16), far inside the 1e-12 bar of the weighted rows; sums additionally differ by summation order.  A pair
+ *     whose needed norm is zero / outside [2^-300, 2^300] always takes the literal divisions (quirk Q5 semantics).
+ *   - GFN_FLAG_EXACT_DIV makes every pair take the literal IEEE divisions: per-pair increments are then bit-identical to
+ *     the reference's and the weighted rows differ from it by summation order only.
  */
 #ifndef GFN_H
 #define GFN_H
@@ -54,6 +61,9 @@ extern "C" {
                                           units, wider guard band); results identical, see DESIGN.md section 4 */
 #define GFN_FLAG_NO_TRIANGLE       32u /* evaluate all n1 x n2 pairs with weight 1 even when n1 == n2 (calcHistoTS,
                                           gfunction.pyx:168-192, has no j >= i shortcut) */
+#define GFN_FLAG_EXACT_DIV         64u /* orientation cosines by the reference's literal divisions dot/(|a|*|b|)
+                                          (gfunction.pyx:155,159,163) instead of reciprocal products: per-pair increments
+                                          bit-identical to the reference, see "Arithmetic contract" above */
 
 /* bits of mode_sel, gfunction.pyx:274-288 */
 #define GFN_MODE_000 1
@@ -76,7 +86,7 @@ typedef struct gfn_stats {
     double frames;            /* frames submitted */
     double h2d_bytes;         /* bytes copied host->device */
     double overflow;          /* pairs with pos >= histo_n (quirk Q3) */
-    int    filter_fp64;       /* 1 if the fp64 pre-test is active, 0 for the fp32 pre-filter */
+    int    filter_fp64;       /* range pre-filter in use: 0 fp32, 1 fp64 pre-test, 2 packed fp16 */
     int    hist_mode;         /* 0 shared-memory warp replicas, 1 global atomics, 2 per-particle global */
     int    warps_per_block, blocks_per_sm, grid, smem_bytes, batch_frames, ndev, hist_replicas;
 } gfn_stats_t;
@@ -113,9 +123,11 @@ int gfn_enqueue_frames(gfn_t *h, int nframes,
                        const double *d1, long long stride_d1, const double *d2, long long stride_d2,
                        const double *box_dims);
 
-/* Device-resident frames (inputs already in HBM on h's device 0; the legacy pre_*_gpu kwargs of
+/* Device-resident frames (inputs already in HBM on one of h's devices; the legacy pre_*_gpu kwargs of
  * calcFrame, gfunction.pyx:390-391,431-453, map here).  Pointers are DEVICE pointers with the same
- * layout as gfn_enqueue_frames; nothing is copied from the host except the boxes. */
+ * layout as gfn_enqueue_frames, all on the same device; the frames are processed on the device that
+ * holds them (a multi-device handle takes frames on each of its GPUs).  Nothing is copied from the host
+ * except the boxes. */
 int gfn_enqueue_device_frames(gfn_t *h, int nframes,
                               const double *dc1, long long stride_c1, const double *dc2, long long stride_c2,
                               const double *dd1, long long stride_d1, const double *dd2, long long stride_d2,
@@ -162,6 +174,9 @@ int gfn_sync(gfn_t *h);
  *             (OVERWRITES hist; the caller adds it to histogram_out like _addHisto does)
  *   pairw     histo_n doubles or NULL: total pair weight per bin (what g000 would hold) regardless of mode_sel
  *   overflow  1 value or NULL: number of pairs whose pos >= histo_n (quirk Q3)
+ * Everything is enqueued behind the last frame on the compute stream (status words, the all-reduce, the copy into
+ * pinned memory) and the host waits once.  Deferred errors (GFN_EZERODIV, the fp16 range GFN_EINVAL) are summed over
+ * the communicator together with the histogram: every rank returns the error if any rank hit it.
  */
 int gfn_readout(gfn_t *h, double *hist, double *pairw, unsigned long long *overflow);
 

@@ -89,6 +89,7 @@ Nccl& nccl()
 // ------------------------------------------------------------------------------------------------
 constexpr int kRing = 3;
 constexpr int kXRing = 4;
+constexpr int kStatusSlots = 2;   // behind the 8*histo_n accumulators: [0] ranks/devices that hit the fp16 range error, [1] ... a zero-norm dipole
 
 struct Batch {
     double* h_pin = nullptr;      // pinned staging: [frame][c1 | d1 | c2 | d2] (absent parts omitted)
@@ -112,8 +113,9 @@ struct Dev {
     cudaStream_t copy = nullptr, comp = nullptr;
     Batch ring[kRing];
     int cur = 0;
-    double* gacc = nullptr;               // [8][histo_n]
-    double* gsum = nullptr;               // all-reduce result
+    double* gacc = nullptr;               // [8][histo_n] + kStatusSlots status words (filled at readout, summed over ranks)
+    double* gsum = nullptr;               // all-reduce result, same layout
+    double* h_out = nullptr;              // pinned: readout lands here ([8][histo_n] + status, then kCounters u64)
     double* gpp = nullptr;                // per-particle
     double* partials = nullptr;
     unsigned long long* counters = nullptr;
@@ -368,6 +370,7 @@ void free_dev(Dev& d)
         if (b.k0) cudaEventDestroy(b.k0);
         if (b.k1) cudaEventDestroy(b.k1);
     }
+    if (d.h_out) cudaFreeHost(d.h_out);
     cudaFree(d.gacc); cudaFree(d.gsum); cudaFree(d.gpp); cudaFree(d.partials); cudaFree(d.counters); cudaFree(d.item_start);
     cudaFree(d.xsiteA); cudaFree(d.xsiteB); cudaFree(d.xmax);
     for (Dev::XSlot& x : d.xs) {
@@ -517,9 +520,10 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
         CUC(cudaSetDevice(d.dev));
         CUC(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
         CUC(cudaStreamCreateWithFlags(&d.comp, cudaStreamNonBlocking));
-        CUC(cudaMalloc(&d.gacc, sizeof(double) * 8 * histo_n));
-        CUC(cudaMalloc(&d.gsum, sizeof(double) * 8 * histo_n));
-        CUC(cudaMemset(d.gacc, 0, sizeof(double) * 8 * histo_n));
+        CUC(cudaMalloc(&d.gacc, sizeof(double) * (8 * (size_t)histo_n + kStatusSlots)));
+        CUC(cudaMalloc(&d.gsum, sizeof(double) * (8 * (size_t)histo_n + kStatusSlots)));
+        CUC(cudaMemset(d.gacc, 0, sizeof(double) * (8 * (size_t)histo_n + kStatusSlots)));
+        CUC(cudaHostAlloc(&d.h_out, sizeof(double) * (8 * (size_t)histo_n + kStatusSlots) + sizeof(unsigned long long) * kCounters, cudaHostAllocDefault));
         CUC(cudaMalloc(&d.counters, sizeof(unsigned long long) * kCounters));
         CUC(cudaMemset(d.counters, 0, sizeof(unsigned long long) * kCounters));
         if (d.cfg.hist_mode == 0) CUC(cudaMalloc(&d.partials, sizeof(double) * (size_t)d.cfg.grid * histo_n * d.cfg.nslot));
@@ -783,7 +787,28 @@ int gfn_enqueue_device_frames(gfn_t* h, int nframes,
     if (h->need1 && !dd1) return fail(h, GFN_EINVAL, "dipoles of the first selection are required by mode_sel");
     if (h->need2 && !dd2) return fail(h, GFN_EINVAL, "dipoles of the second selection are required by mode_sel");
     if (h->shells.layout) return fail(h, GFN_EINVAL, "shell-resolved handles take host frames (gfn_enqueue_frames_shells)");
-    Dev& d = h->devs[0];
+    // the frames run on the device that holds them: a multi-device handle takes device-resident frames on each of its GPUs
+    Dev* dp = &h->devs[0];
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, dc1) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            return fail(h, GFN_EINVAL, "dc1 is not a device pointer");
+        }
+        dp = nullptr;
+        for (Dev& cand : h->devs) if (cand.dev == at.device) dp = &cand;
+        if (!dp) return fail(h, GFN_EINVAL, "the frames live on device %d, which is not one of this handle's devices", at.device);
+        const double* others[3] = {dc2, dd1, dd2};
+        for (const double* q : others) {
+            if (!q) continue;
+            cudaPointerAttributes a2;
+            if (cudaPointerGetAttributes(&a2, q) != cudaSuccess || a2.type != cudaMemoryTypeDevice || a2.device != at.device) {
+                cudaGetLastError();
+                return fail(h, GFN_EINVAL, "all arrays of a device-resident frame must live on the same device (%d)", at.device);
+            }
+        }
+    }
+    Dev& d = *dp;
     CU(cudaSetDevice(d.dev));
     const bool aliased = (dc2 == dc1) && h->n1 == h->n2 && (!h->need2 || !h->need1 || dd2 == dd1) && (!h->need2 || h->need1);
     const int chunk = h->batch_frames;
@@ -845,44 +870,58 @@ int gfn_sync(gfn_t* h)
     return check_zerodiv(h);
 }
 
+// Everything of a readout is enqueued behind the last frame on each device's compute stream - status words, the
+// all-reduce, the copy into pinned memory - and the host waits ONCE per device (the collective is fused
+// into the tail of the last frame).  The two status words travel through the same all-reduce as the histogram, so every
+// rank of a multi-process job learns about an error any rank hit and all of them return it: no rank is left waiting
+// in a collective the failing rank never entered.
 int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overflow)
 {
     if (!h || !hist) return fail(h, GFN_EINVAL, "NULL argument");
-    int rc = gfn_sync(h);
-    if (rc && rc != GFN_EZERODIV) return rc;
-    const int zd = rc;
-    const size_t n8 = 8ull * h->histo_n;
+    int rc = gfn_flush(h);
+    if (rc) return rc;
+    const size_t n8 = 8ull * h->histo_n, nall = n8 + kStatusSlots;
     const bool collective = h->devs.size() > 1 || h->ext_comm;
+    if (collective && (rc = setup_comm(h))) return rc;
+    for (Dev& d : h->devs) {
+        CU(cudaSetDevice(d.dev));
+        CU(status_launch(d.counters, d.gacc + n8, d.comp));
+    }
+    h->st_launches += (double)h->devs.size();
     if (collective) {
-        if ((rc = setup_comm(h))) return rc;
         Nccl& n = nccl();
         if (h->devs.size() > 1) n.GroupStart();
         for (Dev& d : h->devs) {
             CU(cudaSetDevice(d.dev));
-            int nr = n.AllReduce(d.gacc, d.gsum, n8, ncclFloat64, ncclSum, d.comm, d.comp);
+            int nr = n.AllReduce(d.gacc, d.gsum, nall, ncclFloat64, ncclSum, d.comm, d.comp);
             if (nr != ncclSuccess) { if (h->devs.size() > 1) n.GroupEnd(); return fail(h, GFN_ENCCL, "ncclAllReduce: %s", n.GetErrorString(nr)); }
         }
         if (h->devs.size() > 1) { int nr = n.GroupEnd(); if (nr != ncclSuccess) return fail(h, GFN_ENCCL, "ncclGroupEnd: %s", n.GetErrorString(nr)); }
         h->st_launches += (double)h->devs.size();
-        for (Dev& d : h->devs) { CU(cudaSetDevice(d.dev)); CU(cudaStreamSynchronize(d.comp)); }
     }
-    Dev& d0 = h->devs[0];
-    CU(cudaSetDevice(d0.dev));
-    std::vector<double> tmp(n8);
-    CU(cudaMemcpy(tmp.data(), collective ? d0.gsum : d0.gacc, sizeof(double) * n8, cudaMemcpyDeviceToHost));
-    memcpy(hist, tmp.data(), sizeof(double) * 7 * h->histo_n);
-    if (pairw) memcpy(pairw, tmp.data() + 7ull * h->histo_n, sizeof(double) * h->histo_n);
-    if (overflow) {
-        unsigned long long tot = 0;
-        for (Dev& d : h->devs) {
-            unsigned long long c[kCounters];
-            CU(cudaSetDevice(d.dev));
-            CU(cudaMemcpy(c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
-            tot += c[0];
-        }
-        *overflow = tot;      // local devices only; ranks of an external communicator report their own
+    for (size_t i = 0; i < h->devs.size(); ++i) {
+        Dev& d = h->devs[i];
+        CU(cudaSetDevice(d.dev));
+        if (i == 0) CU(cudaMemcpyAsync(d.h_out, collective ? d.gsum : d.gacc, sizeof(double) * nall, cudaMemcpyDeviceToHost, d.comp));
+        CU(cudaMemcpyAsync(d.h_out + nall, d.counters, sizeof(unsigned long long) * kCounters, cudaMemcpyDeviceToHost, d.comp));
     }
-    return zd;
+    unsigned long long ovf = 0;
+    for (Dev& d : h->devs) {
+        CU(cudaSetDevice(d.dev));
+        CU(cudaStreamSynchronize(d.comp));       // the one wait: frames, all-reduce and copies are all behind it
+        for (Batch& b : d.ring) { b.inflight = false; harvest_timing(h, b); }
+        for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms; x.timed = false; }
+        ovf += reinterpret_cast<const unsigned long long*>(d.h_out + nall)[0];
+    }
+    const double* out = h->devs[0].h_out;
+    if (out[n8] != 0.0)
+        return fail(h, GFN_EINVAL, "coordinates lie more than 30000 box lengths from the origin: the fp16 pre-filter cannot represent them, create the handle without GFN_FLAG_FILTER_FP16%s",
+                    collective ? " (reported by at least one rank / device)" : "");
+    memcpy(hist, out, sizeof(double) * 7 * h->histo_n);
+    if (pairw) memcpy(pairw, out + 7ull * h->histo_n, sizeof(double) * h->histo_n);
+    if (overflow) *overflow = ovf;      // local devices only; ranks of an external communicator report their own
+    if (out[n8 + 1] != 0.0) return fail(h, GFN_EZERODIV, "float division");
+    return GFN_OK;
 }
 
 int gfn_readout_per_particle(gfn_t* h, double* hist)

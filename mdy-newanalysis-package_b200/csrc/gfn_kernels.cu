@@ -769,6 +769,7 @@ pair_kernel(const PairParams P)
 #pragma unroll
                             for (int u = 0; u < kU; ++u)
                                 nrm = nrm && (!ok[u] || ((!(m_cs || m_cd) || mid_range(an[u])) && (!(m_cs || m_sd) || mid_range(bn[u]))));
+                            if (P.flags & GFN_FLAG_EXACT_DIV) nrm = false;      // the caller asked for the literal divisions
                             if (__all_sync(0xffffffffu, nrm)) {
 #pragma unroll
                                 for (int u = 0; u < kU; ++u) {
@@ -1048,6 +1049,19 @@ cudaError_t scale_launch(double* a, long long n, double v, cudaStream_t s)
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     scale_kernel<<<(int)blocks, 256, 0, s>>>(a, n, v);
+    return cudaGetLastError();
+}
+
+__global__ void status_kernel(const unsigned long long* __restrict__ counters, double* __restrict__ status)
+{
+    const unsigned long long e = counters[1];
+    status[0] = (e & 2ull) ? 1.0 : 0.0;
+    status[1] = (e & 1ull) ? 1.0 : 0.0;
+}
+
+cudaError_t status_launch(const unsigned long long* counters, double* status, cudaStream_t s)
+{
+    status_kernel<<<1, 1, 0, s>>>(counters, status);
     return cudaGetLastError();
 }
 

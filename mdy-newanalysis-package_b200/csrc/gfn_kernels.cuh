@@ -92,6 +92,10 @@ cudaError_t finalize_launch(const double* partials, int grid, int histo_n, int n
 
 cudaError_t scale_launch(double* a, long long n, double v, cudaStream_t s);
 
+// status[0] = 1 if the fp16 range flag is set in counters[1], status[1] = 1 if a zero-norm dipole was hit (quirk Q5):
+// the two words ride behind the accumulators through the readout's all-reduce.
+cudaError_t status_launch(const unsigned long long* counters, double* status, cudaStream_t s);
+
 // N1 producers (helpers.pyx:71-123): nframes frames of natoms x 3 coordinates -> nres x 3 centres of mass / dipoles.
 cudaError_t residue_com_launch(const double* coor, long long stride_coor, const double* masses, const int* apr, const int* rfa,
                                int nres, int nframes, double* com, cudaStream_t s);

@@ -36,6 +36,7 @@
 
 #include <condition_variable>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -127,12 +128,12 @@ int locate(gfn_traj* t, const unsigned char* raw, long long frame, const unsigne
         *cell = p + 4;
         p += 56;
     }
-    const int32_t nb = 4 * t->natoms;
+    const long long nb = 4ll * t->natoms;        // fits an int32 marker: gfn_traj_open_dcd refuses natoms beyond that
     for (int k = 0; k < 3; ++k) {
-        if (rd_i32(p, t->swap) != nb || rd_i32(p + 4 + nb, t->swap) != nb)
+        if ((long long)rd_i32(p, t->swap) != nb || (long long)rd_i32(p + 4 + nb, t->swap) != nb)
             return tfail(t, GFN_EINVAL, "frame %lld: coordinate record %d is damaged", frame, k);
         xyz[k] = p + 4;
-        p += 8 + (long long)nb;
+        p += 8 + nb;
     }
     return GFN_OK;
 }
@@ -213,6 +214,16 @@ int gfn_traj_open_dcd(gfn_traj_t** out, const char* path)
     const int32_t natoms = rd_i32(na + 4, swap);
     if (natoms < 1) { close(fd); return tfail(t, GFN_EINVAL, "%s: %d atoms", path, natoms); }
     off += 12;
+    // natoms comes from the file: a coordinate record (4*natoms bytes behind an int32 marker) must fit the marker, and one
+    // whole frame must fit into what is left of the file - otherwise the header is damaged (or hostile)
+    {
+        const bool cell_ = ic[19] != 0 && ic[10] != 0, fourd_ = ic[19] != 0 && ic[11] != 0;
+        const long long fb = (cell_ ? 56 : 0) + (3 + (fourd_ ? 1 : 0)) * (8 + 4ll * natoms);
+        if (4ll * natoms > 2147483647ll || fb > (long long)st.st_size - off) {
+            close(fd);
+            return tfail(t, GFN_EINVAL, "%s: the header announces %d atoms, but the file holds less than one frame of that size", path, natoms);
+        }
+    }
 
     t = new gfn_traj();
     t->err[0] = 0;
@@ -254,7 +265,11 @@ int gfn_traj_read(gfn_traj_t* t, long long frame, const int* idx, int n, float* 
     if (!idx) n = t->natoms;
     std::lock_guard<std::mutex> lk(t->read_mu);
     std::vector<unsigned char>& raw = t->read_raw;
-    if (raw.size() < (size_t)t->frame_bytes) raw.resize((size_t)t->frame_bytes);
+    try {
+        if (raw.size() < (size_t)t->frame_bytes) raw.resize((size_t)t->frame_bytes);
+    } catch (const std::bad_alloc&) {
+        return tfail(t, GFN_ENOMEM, "out of memory for a frame buffer of %lld bytes", t->frame_bytes);
+    }
     if (!pread_all(t->fd, raw.data(), (size_t)t->frame_bytes, t->first_off + frame * t->frame_bytes)) return tfail(t, GFN_EINVAL, "frame %lld: read failed", frame);
     const unsigned char* cr; const unsigned char* b[3];
     int rc = locate(t, raw.data(), frame, &cr, b);
@@ -294,13 +309,18 @@ int gfn_enqueue_trajectory(gfn_t* h, gfn_traj_t* t, long long first, long long c
     const int nslots = 2 * nthreads + 2;
     std::vector<Slot> slots(nslots);
     const size_t per = 3 * ((size_t)nsel1 + (self ? 0 : (size_t)nsel2));
-    if ((int)t->slot_atoms.size() < nslots) t->slot_atoms.resize(nslots);
-    if ((int)t->raws.size() < nthreads) t->raws.resize(nthreads);
-    for (int k = 0; k < nslots; ++k) {
-        if (t->slot_atoms[k].size() < per) t->slot_atoms[k].resize(per);
-        slots[k].atoms = t->slot_atoms[k].data();
+    try {       // no C++ exception may cross the C ABI
+        if ((int)t->slot_atoms.size() < nslots) t->slot_atoms.resize(nslots);
+        if ((int)t->raws.size() < nthreads) t->raws.resize(nthreads);
+        for (int k = 0; k < nslots; ++k) {
+            if (t->slot_atoms[k].size() < per) t->slot_atoms[k].resize(per);
+            slots[k].atoms = t->slot_atoms[k].data();
+        }
+        for (int k = 0; k < nthreads; ++k) if (t->raws[k].size() < (size_t)t->frame_bytes) t->raws[k].resize((size_t)t->frame_bytes);
+    } catch (const std::bad_alloc&) {
+        return tfail(t, GFN_ENOMEM, "out of memory for the staging buffers (%d slots of %zu floats, %d frame buffers of %lld bytes)",
+                     nslots, per, nthreads, t->frame_bytes);
     }
-    for (int k = 0; k < nthreads; ++k) if (t->raws[k].size() < (size_t)t->frame_bytes) t->raws[k].resize((size_t)t->frame_bytes);
     std::mutex mu;
     std::condition_variable cv;
     long long consumed = 0;          // frames handed to the ring so far
@@ -363,7 +383,7 @@ int gfn_enqueue_trajectory(gfn_t* h, gfn_traj_t* t, long long first, long long c
             const float* a1 = s.atoms;
             const float* a2 = self ? nullptr : a1 + 3 * (size_t)nsel1;
             out_rc = gfn_enqueue_atom_frames(h, 1, a1, 0, a2, 0, use_cell ? s.box : nullptr);
-            if (out_rc) tfail(t, out_rc, "%s", gfn_last_error(h));
+            if (out_rc) { std::lock_guard<std::mutex> lk(mu); tfail(t, out_rc, "%s", gfn_last_error(h)); }    // err text is shared with the workers
             if (!out_rc && boxes_out && use_cell) memcpy(boxes_out + 3 * k, s.box, sizeof(double) * 3);
         }
         {

@@ -118,7 +118,7 @@ cdef extern from "gfn.h":
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
 
 
-_FLAG_NAMES = {"no_triangle": 32, "fp16": 16, "filter_fp16": 16, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
+_FLAG_NAMES = {"exact_div": 64, "no_triangle": 32, "fp16": 16, "filter_fp16": 16, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
 
 
 def _parse_flags(spec):
@@ -528,8 +528,14 @@ cdef class _Backend:
         cdef int rc
         with nogil:
             rc = gfn_enqueue_device_frames(self.h, nframes, p1, s1, p2, s2, q1, s1, q2, s2, pb)
-        self.keepalive.append((c1, c2, d1, d2))
+        # the arrays must outlive the kernels that read them.  A long run that never reads out would pile up one entry per
+        # call: beyond a few dozen, wait for the device once and let them go.
+        cdef Py_ssize_t nk = len(self.keepalive)
+        if nk == 0 or self.keepalive[nk - 1] != (c1, c2, d1, d2):
+            self.keepalive.append((c1, c2, d1, d2))
         self.check(rc)
+        if len(self.keepalive) > 64:
+            self.sync()
 
     def attach_topology(self, int which, masses, apr, rfa, charges=None):
         cdef np.ndarray[np.float64_t, ndim=1, mode="c"] m = np.ascontiguousarray(masses, dtype=np.float64)
@@ -661,9 +667,10 @@ def calcHistoTS(core_xyz, surr_xyz, np.ndarray[np.float64_t, ndim=3] result, dou
     """RDF time series on the GPU: result[t, i, pos] += 1 for every surround site within range of core site i
     (reference: def calcHistoTS, gfunction.pyx:168-192; cubic box, all n1 x n2 pairs, no dipoles).
 
-    Same signature and result as the reference for in-range bins.  A pair with pos >= nbins (quirk Q3) lands in
-    result[t, i+1, pos-nbins] like the reference's flat index does, except for the last core row, where the
-    reference writes into the next frame's slab (or past the array) and this version drops the pair."""
+    Same signature and result as the reference (pinned by tests/golden/ts.npz, generated by the unmodified reference
+    function).  A pair with pos >= nbins (quirk Q3) lands in result[t, i+1, pos-nbins] like the reference's unchecked
+    flat index does; for the last core row that is the first row of frame t+1 when `result` is C-contiguous and has such
+    a frame - beyond the array (where the reference writes out of bounds) the pair is dropped."""
     c1 = np.ascontiguousarray(core_xyz, dtype=np.float64)
     c2 = c1 if surr_xyz is core_xyz else np.ascontiguousarray(surr_xyz, dtype=np.float64)
     cdef int n1 = c1.shape[0], n2 = c2.shape[0], nb = result.shape[2]
@@ -687,8 +694,11 @@ def calcHistoTS(core_xyz, surr_xyz, np.ndarray[np.float64_t, ndim=3] result, dou
     cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a1 = c1
     cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a2 = c2
     b.enqueue(<const double *> a1.data, <const double *> a2.data, NULL, NULL)
-    rows = b.readout_per_particle()[:n1 * nb].reshape(n1, nb)
-    result[t] += rows
+    pp = b.readout_per_particle()
+    result[t] += pp[:n1 * nb].reshape(n1, nb)
+    # Q3 spill of the last core row: the device keeps it right behind the frame's slab (first row of the next mode)
+    if t + 1 < result.shape[0] and result.flags.c_contiguous:
+        result[t + 1, 0, :] += pp[n1 * nb:n1 * nb + nb]
 
 
 def calcHistoTSVoro(core_xyz, surr_xyz, np.ndarray[np.float64_t, ndim=4] result, ds, int maxshell,
@@ -888,26 +898,41 @@ class RDF(object):
 
         cdef _Backend be = self._be
         if pre_coor_sel1_gpu is not None or pre_coor_sel2_gpu is not None or pre_dip_sel1_gpu is not None or pre_dip_sel2_gpu is not None:
-            c1 = pre_coor_sel1_gpu if pre_coor_sel1_gpu is not None else to_device(coor_sel1, self._devices[0])
+            # arrays not shared by the caller are staged in per-object device buffers that are reused every frame
+            # (DeviceArray.upload waits for the frames that still read them), so a long run allocates nothing per frame
+            given = [a for a in (pre_coor_sel1_gpu, pre_coor_sel2_gpu, pre_dip_sel1_gpu, pre_dip_sel2_gpu) if a is not None]
+            dev = given[0].device
+            c1 = pre_coor_sel1_gpu if pre_coor_sel1_gpu is not None else self._stage(0, coor_sel1, dev)
             if pre_coor_sel2_gpu is not None:
                 c2 = pre_coor_sel2_gpu
             elif coor_sel2 is coor_sel1:
                 c2 = c1
             else:
-                c2 = to_device(coor_sel2, self._devices[0])
-            d1 = pre_dip_sel1_gpu if pre_dip_sel1_gpu is not None else (to_device(dip_sel1, self._devices[0]) if dip_sel1 is not None else None)
+                c2 = self._stage(1, coor_sel2, dev)
+            d1 = pre_dip_sel1_gpu if pre_dip_sel1_gpu is not None else (self._stage(2, dip_sel1, dev) if dip_sel1 is not None else None)
             if pre_dip_sel2_gpu is not None:
                 d2 = pre_dip_sel2_gpu
             elif dip_sel2 is dip_sel1:
                 d2 = d1
             else:
-                d2 = to_device(dip_sel2, self._devices[0]) if dip_sel2 is not None else None
+                d2 = self._stage(3, dip_sel2, dev) if dip_sel2 is not None else None
             be.enqueue_device(1, c1, c2, d1, d2, self.box_dim.reshape(1, 6))
             return
 
         be.enqueue(<const double *> coor_sel1.data, <const double *> coor_sel2.data,
                    <const double *> dip_sel1.data if dip_sel1 is not None else NULL,
                    <const double *> dip_sel2.data if dip_sel2 is not None else NULL)
+
+    def _stage(self, int slot, arr, int dev):
+        """Per-object staging buffer `slot` (0 c1, 1 c2, 2 d1, 3 d2) on device `dev`, refilled with arr."""
+        st = self.__dict__.setdefault("_staged", {})
+        cdef DeviceArray d = st.get((slot, dev))
+        if d is None or d.nbytes != <unsigned long long> arr.nbytes:
+            d = to_device(arr, dev)
+            st[(slot, dev)] = d
+        else:
+            d.upload(arr)
+        return d
 
     def _addHisto(self, np.ndarray[np.float64_t, ndim=1] histo_out, np.ndarray[np.float64_t, ndim=1] histo):
         """
@@ -1296,6 +1321,7 @@ class RDF_voronoi(RDF):
                 if not (self._flags & (2 | 16)) and absmax <= 2.0 * lmax and float(self.histo_max) >= 0.04 * lmax:
                     self._flags |= 16
             self._open_backend()
+            self._finish_comm()
         elif shape != self._map_shape:
             raise ValueError("delaunay_matrix changed shape from %r to %r" % (self._map_shape, shape))
 
@@ -1325,7 +1351,13 @@ class RDF_voronoi(RDF):
         """
         Normalize the histogram (:1049-1089); host code, same arithmetic as the reference.
         """
-        if self.norm_volume:
+        ctr = self.ctr
+        if getattr(self, "_nranks", 1) > 1 and self._be is not None:
+            # frames are spread over processes (attach_comm): frame count and mean volume over all ranks, like RDF._normHisto
+            tot = self._be.allreduce_host([float(self.ctr), float(sum(self.volume_list))])
+            ctr = int(tot[0])
+            volume = self.norm_volume if self.norm_volume else tot[1] / tot[0]
+        elif self.norm_volume:
             volume = self.norm_volume
         else:
             volume = 0.0
@@ -1345,7 +1377,7 @@ class RDF_voronoi(RDF):
                 r = self.histo_min + float(i) * self.histo_dr
                 r_out = r + self.histo_dr
                 slice_vol = 4.0 / 3.0 * PI * (r_out**3 - r**3)
-                norm = rho * slice_vol * float(self.ctr)
+                norm = rho * slice_vol * float(ctr)
                 for j in range(7):
                     self.histogram_out[j * self.histo_n * self.nshells + i * self.nshells + shell] /= norm
 
@@ -1387,21 +1419,80 @@ class RDF_voronoi(RDF):
 
     def raw_histogram(self):
         """Un-normalised [mode][bin][shell] sums accumulated since the last resetArrays (7*histo_n*nshells float64)."""
-        if self._be is None:
+        if not self._ensure_backend():
             return np.zeros(7 * int(self.histo_n) * int(self.nshells), dtype=np.float64)
         hist, pw, ovf = self._be.readout()
         self.pair_weight = pw
         self.overflow = ovf
         return hist
 
-    def calcFrames(self, *args, **kwargs):
-        raise NotImplementedError("RDF_voronoi takes one frame per call (calcFrame)")
+    def calcFrames(self, coor_sel1, coor_sel2, delaunay_matrices, dip_sel1=None, dip_sel2=None, boxes=None):
+        """Many frames per call: coordinates / dipoles (nframes, n, 3), delaunay_matrices (nframes, rows, cols) int32,
+        boxes (nframes, 3) for NpT or None (the volume used by _normHisto stays the constructor's, like update_box)."""
+        c1 = np.ascontiguousarray(coor_sel1, dtype=np.float64)
+        c2 = c1 if coor_sel2 is coor_sel1 else np.ascontiguousarray(coor_sel2, dtype=np.float64)
+        dm = np.ascontiguousarray(delaunay_matrices, dtype=np.int32)
+        d1 = None if dip_sel1 is None else np.ascontiguousarray(dip_sel1, dtype=np.float64)
+        d2 = None if dip_sel2 is None else (d1 if dip_sel2 is dip_sel1 else np.ascontiguousarray(dip_sel2, dtype=np.float64))
+        if c1.ndim != 3 or c2.ndim != 3 or dm.ndim != 3 or c2.shape[0] != c1.shape[0] or dm.shape[0] != c1.shape[0]:
+            raise ValueError("calcFrames takes arrays of shape (nframes, n, 3) and matrices of shape (nframes, rows, cols)")
+        for f in range(c1.shape[0]):
+            if boxes is not None:
+                self.update_box(*[float(v) for v in np.asarray(boxes, dtype=np.float64).reshape(-1, 3)[f]])
+            self.calcFrame(c1[f], c2[f], dm[f], None if d1 is None else d1[f], None if d2 is None else d2[f])
 
     def calcFramesDevice(self, *args, **kwargs):
-        raise NotImplementedError("RDF_voronoi takes host frames (calcFrame)")
+        raise TypeError("RDF_voronoi takes host frames: the Delaunay matrix travels with every frame (calcFrame / calcFrames)")
 
     def attach_topology(self, *args, **kwargs):
-        raise NotImplementedError("RDF_voronoi takes host frames (calcFrame)")
+        raise TypeError("RDF_voronoi takes host frames: the Delaunay matrix travels with every frame (calcFrame / calcFrames)")
+
+    def calcFrameAtoms(self, *args, **kwargs):
+        raise TypeError("RDF_voronoi takes host frames: the Delaunay matrix travels with every frame (calcFrame / calcFrames)")
+
+    calcFramesAtoms = calcFrameAtoms
+    calcTrajectory = calcFrameAtoms
 
     def attach_comm(self, uid, nranks, rank):
-        raise NotImplementedError("RDF_voronoi: multi-process readout is not wired up; shard frames with devices=[...]")
+        """One process per GPU: join an NCCL communicator; readout then sums the shell-resolved histograms of all ranks
+        (the device handle is created by the first calcFrame, so joining happens there or at the first readout)."""
+        self._nranks = int(nranks)
+        if self._be is None:
+            self._pending_comm = (uid, nranks, rank)
+        else:
+            self._be.attach_comm(uid, nranks, rank)
+
+    def _ensure_backend(self):
+        """A rank that saw no frame still has to take part in the collective readout: open the handle with the smallest
+        matrix the selections allow."""
+        if self._be is None:
+            if getattr(self, "_nranks", 1) <= 1:
+                return False
+            self._auto_filter = False
+            self._map_shape = (max(1, int(self.nmol1)), int(self.n2))
+            self._open_backend()
+        self._finish_comm()
+        return True
+
+    def sync(self):
+        if self._be is not None:
+            self._be.sync()
+
+    def flush(self):
+        if self._be is not None:
+            self._be.flush()
+
+    def stats(self):
+        if self._be is None:
+            raise RuntimeError("RDF_voronoi: the device handle is created by the first calcFrame")
+        return self._be.stats()
+
+    def mark(self, which):
+        if self._be is None:
+            raise RuntimeError("RDF_voronoi: the device handle is created by the first calcFrame")
+        self._be.mark(which)
+
+    def mark_elapsed_ms(self):
+        if self._be is None:
+            raise RuntimeError("RDF_voronoi: the device handle is created by the first calcFrame")
+        return self._be.mark_elapsed_ms()

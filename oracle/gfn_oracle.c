@@ -137,10 +137,26 @@ void gfn_oracle_add_histo(double *out, const double *histogram, int n1, int hist
 }
 
 /* calcHistoTS, gfunction.pyx:168-192: g000 time series, cubic box, result[t][i][pos] += 1.
- * result is the [ncore][nbins] slab of frame t.  pos >= nbins (Q3) is dropped and counted. */
+ * result_t is the [ncore][nbins] slab of frame t inside the C-contiguous result array; `room` doubles are addressable
+ * from result_t on (to the end of the whole array).  The reference indexes its memoryview without a bounds check
+ * (boundscheck(False), :167), so pos >= nbins (Q3) lands at flat offset i*nbins + pos: bin 0 of the next core row, or of
+ * the next frame's first row for the last core site.  Reproduced while it stays inside `room`; beyond it (where the
+ * reference writes past its array) the pair is dropped and counted in the return value. */
+long long gfn_oracle_calc_histo_ts_room(const double *core_xyz, const double *surr_xyz, double *result_t,
+                                        int ncore, int nsurr, int nbins, double boxl,
+                                        float histo_min, float histo_max, double invdx, long long room);
+
 long long gfn_oracle_calc_histo_ts(const double *core_xyz, const double *surr_xyz, double *result_t,
                                    int ncore, int nsurr, int nbins, double boxl,
                                    float histo_min, float histo_max, double invdx)
+{
+    return gfn_oracle_calc_histo_ts_room(core_xyz, surr_xyz, result_t, ncore, nsurr, nbins, boxl, histo_min, histo_max,
+                                         invdx, (long long)ncore * nbins);
+}
+
+long long gfn_oracle_calc_histo_ts_room(const double *core_xyz, const double *surr_xyz, double *result_t,
+                                        int ncore, int nsurr, int nbins, double boxl,
+                                        float histo_min, float histo_max, double invdx, long long room)
 {
     const double boxl2 = boxl / 2.0;                                /* :176 */
     long long dropped = 0;
@@ -160,7 +176,12 @@ long long gfn_oracle_calc_histo_ts(const double *core_xyz, const double *surr_xy
             dist = sqrt(dx * dx + dy * dy + dz * dz);
             if (dist < histo_min || dist > histo_max || floor(dist * invdx) == 0) continue;
             pos = (int)floor((dist - histo_min) * invdx);
-            if (pos < nbins) result_t[(long long)i * nbins + pos] += 1.0; else dropped++;
+            /* rows are thread-private except for the Q3 spill into the next row's first bins: atomic adds keep the
+             * (integer) counts exact whatever the interleaving */
+            if ((long long)i * nbins + pos < room) {
+#pragma omp atomic
+                result_t[(long long)i * nbins + pos] += 1.0;
+            } else dropped++;
         }
     }
     return dropped;

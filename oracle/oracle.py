@@ -176,11 +176,27 @@ def calc_histo_rows_c(c1, c2, d1, d2, out7, box_dim, hmin, hmax, histo_n, invdx,
 
 
 def calc_histo_ts_c(core, surr, result_t, boxl, hmin, hmax, invdx):
+    """calcHistoTS on the slab result_t = result[t] ([n1][nbins]); a Q3 pair of the last core row is dropped and counted."""
     lib = load_c()
     core = _c64(core); surr = _c64(surr)
     return lib.gfn_oracle_calc_histo_ts(_dptr(core), _dptr(surr), _dptr(result_t), core.shape[0],
                                         surr.shape[0], result_t.shape[1], float(boxl),
                                         np.float32(hmin), np.float32(hmax), float(invdx))
+
+
+def calc_histo_ts(core, surr, result, boxl, t, hmin, hmax, invdx):
+    """Same signature as the reference's calcHistoTS (gfunction.pyx:168-192) on the whole C-contiguous result array:
+    a Q3 pair (pos >= nbins) lands where the reference's unchecked flat index points, also across the frame boundary."""
+    lib = load_c()
+    core = _c64(core); surr = _c64(surr)
+    assert result.flags.c_contiguous and result.dtype == np.float64
+    slab = result[t]
+    room = (result.shape[0] - t) * result.shape[1] * result.shape[2]
+    lib.gfn_oracle_calc_histo_ts_room.restype = ctypes.c_longlong
+    return lib.gfn_oracle_calc_histo_ts_room(_dptr(core), _dptr(surr), _dptr(slab), ctypes.c_int(core.shape[0]),
+                                             ctypes.c_int(surr.shape[0]), ctypes.c_int(result.shape[2]), ctypes.c_double(boxl),
+                                             ctypes.c_float(np.float32(hmin)), ctypes.c_float(np.float32(hmax)),
+                                             ctypes.c_double(invdx), ctypes.c_longlong(room))
 
 
 def calc_histo_shells_c(c1, c2, d1, d2, dest, box_dim, hmin, hmax, histo_n, invdx, mode_sel,

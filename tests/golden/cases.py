@@ -192,6 +192,44 @@ def drive_tsvoro(fn, case):
     return result
 
 
+# N3 RDF time series (calcHistoTS, gfunction.pyx:168-192): result[t, i, pos] += 1 for all n1 x n2 pairs, cubic box.
+# The fixture ts.npz holds what the UNMODIFIED reference function wrote.  `edge` plants surround sites at exactly
+# histo_max from core sites (quirk Q3: pos == nbins, which the reference's unchecked index turns into bin 0 of the next
+# core row - or of the next frame's first row for the last core site); the result array therefore gets one spare frame.
+TS_CASES = {
+    "ts_rect":  dict(n1=150, n2=400, box=30.0, hmin=0.0, hmax=12.0, dr=0.05, frames=3, seed=61),
+    "ts_self":  dict(n1=220, n2=220, box=27.0, hmin=0.0, hmax=12.0, dr=0.05, frames=2, seed=62, same=True),
+    "ts_hmin":  dict(n1=64, n2=300, box=24.0, hmin=1.5, hmax=11.5, dr=0.1, frames=2, seed=63),
+    "ts_edge":  dict(n1=5, n2=40, box=40.0, hmin=0.0, hmax=15.0, dr=0.05, frames=2, seed=64, edge=True),
+}
+
+
+def build_ts_inputs(case, frame):
+    """-> (core (n1,3), surr (n2,3))."""
+    rng = np.random.default_rng(600001 * case["seed"] + frame)
+    core = np.ascontiguousarray(rng.random((case["n1"], 3)) * case["box"])
+    surr = core if case.get("same") else np.ascontiguousarray(rng.random((case["n2"], 3)) * case["box"])
+    if case.get("edge"):
+        # exact distances histo_max (15.0) along x from core sites 1 and n1-1 (the last row), straight and across the boundary
+        core[1] = (2.0, 3.0, 4.0); surr[0] = (17.0, 3.0, 4.0)
+        core[case["n1"] - 1] = (30.0, 8.0, 9.0); surr[1] = (5.0, 8.0, 9.0)       # 5 - 30 = -25 -> +40 = 15
+    return core, surr
+
+
+def ts_nbins(case):
+    return int(round((case["hmax"] - case["hmin"]) / case["dr"]))
+
+
+def drive_ts(fn, case, spare_frames=1):
+    """fn(core, surr, result, boxl, t, hmin, hmax, invdx) for every frame -> result (frames + spare, n1, nbins)."""
+    T = case["frames"]
+    result = np.zeros((T + spare_frames, case["n1"], ts_nbins(case)))
+    for t in range(T):
+        core, surr = build_ts_inputs(case, t)
+        fn(core, surr, result, case["box"], t, case["hmin"], case["hmax"], 1.0 / case["dr"])
+    return result
+
+
 # N1 + N4 atom frames: float32 atom positions -> astype(float64) -> helpers.comByResidue / dipByResidue -> RDF.calcFrame,
 # all three steps by the UNMODIFIED reference modules (tests/golden/make_golden.py); fixture atoms.npz holds the raw sums.
 ATOM_CASES = {

@@ -130,6 +130,14 @@ def main_shells():
         print("%-16s counts per shell=%s" % (name, out[name].sum(axis=(0, 1, 3))))
     np.savez_compressed(os.path.join(HERE, "tsvoro.npz"), **out)
 
+    # N3: calcHistoTS (gfunction.pyx:168-192) by the unmodified reference function, incl. the Q3 spill of the last core row
+    out = {}
+    for name, case in C.TS_CASES.items():
+        out[name] = C.drive_ts(ref.calcHistoTS, case)
+        T = case["frames"]
+        print("%-16s counts per frame=%s spare frame holds %.0f" % (name, out[name][:T].sum(axis=(1, 2)), out[name][T:].sum()))
+    np.savez_compressed(os.path.join(HERE, "ts.npz"), **out)
+
     # topology helpers: the reference's own atomsPerResidue / residueFirstAtom (py_functions.py:64-89, pure Python) run on the
     # AtomGroup-like selections of newanalysis.psf
     import importlib.util

@@ -96,6 +96,42 @@ def test_per_particle_matches_reference_layout():
     assert_hist_close(out, a.raw_sum(), hn)
 
 
+@pytest.mark.parametrize("filt", ["fp16", "fp32", "fp64"])
+def test_exact_div_flag_gives_reference_increments_bit_for_bit(filt):
+    """GFN_FLAG_EXACT_DIV: the cosines are the reference's literal divisions (gfunction.pyx:155,159,163), so a
+    per-particle histogram entry that received exactly ONE pair holds exactly the reference's increment - all seven
+    modes, bit for bit.  (Without the flag the reciprocal form may differ by a few ulp; checked to stay below 1e-14.)"""
+    case = C.CASES["rect_all"]
+    n1, n2 = case["n1"], case["n2"]
+    a = C.drive(C.make_rdf(O.OracleRDF, dict(case, frames=1)), dict(case, frames=1))
+    ref = a.histogram.reshape(7, n1, -1)
+    single = ref[0] == 1.0                      # rectangular case: weight 1 per pair
+    assert single.sum() > 5000
+    for flags, exact in ((filt + ",per_particle,exact_div", True), (filt + ",per_particle", False)):
+        b = RDF(case["modes"], case["hmin"], case["hmax"], case["dr"], n1, n2, n1, n2, case["box"][0], gfn_flags=flags)
+        C.drive(b, dict(case, frames=1))
+        got = b.histogram.reshape(7, n1, -1)
+        assert np.array_equal(got[0], ref[0])
+        for k in range(1, 7):
+            if exact:
+                assert np.array_equal(got[k][single], ref[k][single]), "mode row %d: increments differ from the reference's" % k
+            else:
+                assert np.max(np.abs(got[k][single] - ref[k][single])) < 1e-14
+
+
+def test_exact_div_flag_on_shared_replicas():
+    """The flag on the default (shared-memory replica) path: counts exact, sums within the usual bar, and closer to the
+    reference's than 1e-13 of the pair weight (summation order only)."""
+    case = C.CASES["cfg3_density"]
+    a = C.drive(C.make_rdf(O.OracleRDF, case), case)
+    b = C.drive(RDF(case["modes"], case["hmin"], case["hmax"], case["dr"], case["n1"], case["n2"], case["n1"], case["n2"],
+                    case["box"][0], gfn_flags="exact_div"), case)
+    got, ref = b.raw_histogram(), a.raw_sum()
+    assert np.array_equal(got[:300], ref[:300])
+    assert_hist_close(got, ref, 300)
+    assert np.max(np.abs(got - ref) / np.maximum(np.tile(ref[:300], 7), 1.0)) < 1e-13
+
+
 def _random_frame(rng, n, L, dip=True):
     return np.ascontiguousarray(rng.random((n, 3)) * L), (np.ascontiguousarray(rng.standard_normal((n, 3))) if dip else None)
 
@@ -350,6 +386,30 @@ def test_single_process_two_devices_frame_sharding(monkeypatch):
     assert_hist_close(b, a, 300)
     two.calcFrame(c[0], c[0], d[0], d[0]); one.calcFrame(c[0], c[0], d[0], d[0])     # accumulation continues after a readout
     assert np.array_equal(one.raw_histogram()[:300], two.raw_histogram()[:300])
+
+
+@pytest.mark.skipif("_ngpu() < 2")
+def test_two_devices_device_resident_frames():
+    """gfn_enqueue_device_frames runs the frames on the device that holds them: a two-device handle fed with frames
+    uploaded to GPU 0 and GPU 1 equals the one-GPU run."""
+    from newanalysis.gfunction import to_device
+    n, L, nf = 3000, 45.0, 8
+    rng = np.random.default_rng(92)
+    c = rng.random((nf, n, 3)) * L; d = rng.standard_normal((nf, n, 3))
+    one = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
+    one.calcFrames(c, c, d, d)
+    two = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L, devices=[0, 1])
+    h = nf // 2
+    c0, d0 = to_device(c[:h], 0), to_device(d[:h], 0)
+    c1, d1 = to_device(c[h:], 1), to_device(d[h:], 1)
+    two.calcFramesDevice(h, c0, c0, d0, d0)
+    two.calcFramesDevice(nf - h, c1, c1, d1, d1)
+    a, b = one.raw_histogram(), two.raw_histogram()
+    assert np.array_equal(a[:300], b[:300]) and a[:300].sum() > 0
+    assert_hist_close(b, a, 300)
+    # frames on a device the handle does not own are refused
+    with pytest.raises(ValueError, match="not one of this handle"):
+        one.calcFramesDevice(1, c1, c1, d1, d1)
 
 
 @pytest.mark.skipif("_ngpu() < 2")
@@ -757,10 +817,75 @@ def test_atom_frames_golden(golden_dir, tmp_path, name, feed):
     assert bool(r.oneistwo) == bool(z[name + "_oneistwo"])
 
 
+def _cfg4_box(rng, ns, nu, apu, L):
+    """A cfg4-shaped frame: ns solvent molecules (COM + dipole, and an O site each), nu solute molecules
+    (COM + dipole) of apu atoms each."""
+    solv_c, solv_d = _random_frame(rng, ns, L)
+    solv_o = np.ascontiguousarray(solv_c + 0.06 * rng.standard_normal((ns, 3)))
+    solu_c, solu_d = _random_frame(rng, nu, L)
+    solu_a = np.ascontiguousarray(np.repeat(solu_c, apu, axis=0) + 1.5 * rng.standard_normal((nu * apu, 3)))
+    return solv_c, solv_d, solv_o, solu_c, solu_d, solu_a
+
+
+def test_cfg4_four_objects_share_one_upload():
+    """BASELINE configs[3] as north_star states it: four RDF objects per frame on ONE shared upload of the frame's arrays
+    (the reference's pre_*_gpu kwargs, gfunction.pyx:390-391, 431-453): solute COM x solvent COM "all", solvent self
+    "all", solute atoms x solvent O "000", solute self "all" - reduced sizes, three frames, against OracleRDF."""
+    from newanalysis.gfunction import to_device
+    ns, nu, apu, L = 3000, 96, 4, 48.0
+    mk = lambda cls, **kw: [cls(["all"], 0.0, 15.0, 0.05, nu, ns, nu, ns, L, **kw),              # noqa: E731
+                            cls(["all"], 0.0, 15.0, 0.05, ns, ns, ns, ns, L, **kw),
+                            cls(["000"], 0.0, 15.0, 0.05, nu * apu, ns, nu, ns, L, **kw),
+                            cls(["all"], 0.0, 15.0, 0.05, nu, nu, nu, nu, L, **kw)]
+    gpu, cpu = mk(RDF), mk(O.OracleRDF)
+    rng = np.random.default_rng(4004)
+    for f in range(3):
+        solv_c, solv_d, solv_o, solu_c, solu_d, solu_a = _cfg4_box(rng, ns, nu, apu, L)
+        # one upload per array and frame, shared by the four objects
+        g_solv_c, g_solv_d, g_solv_o = to_device(solv_c), to_device(solv_d), to_device(solv_o)
+        g_solu_c, g_solu_d, g_solu_a = to_device(solu_c), to_device(solu_d), to_device(solu_a)
+        gpu[0].calcFrame(solu_c, solv_c, solu_d, solv_d, pre_coor_sel1_gpu=g_solu_c, pre_coor_sel2_gpu=g_solv_c,
+                         pre_dip_sel1_gpu=g_solu_d, pre_dip_sel2_gpu=g_solv_d)
+        gpu[1].calcFrame(solv_c, solv_c, solv_d, solv_d, pre_coor_sel1_gpu=g_solv_c, pre_coor_sel2_gpu=g_solv_c,
+                         pre_dip_sel1_gpu=g_solv_d, pre_dip_sel2_gpu=g_solv_d)
+        gpu[2].calcFrame(solu_a, solv_o, pre_coor_sel1_gpu=g_solu_a, pre_coor_sel2_gpu=g_solv_o)
+        gpu[3].calcFrame(solu_c, solu_c, solu_d, solu_d, pre_coor_sel1_gpu=g_solu_c, pre_coor_sel2_gpu=g_solu_c,
+                         pre_dip_sel1_gpu=g_solu_d, pre_dip_sel2_gpu=g_solu_d)
+        cpu[0].calcFrame(solu_c, solv_c, solu_d, solv_d)
+        cpu[1].calcFrame(solv_c, solv_c, solv_d, solv_d)
+        cpu[2].calcFrame(solu_a, solv_o)
+        cpu[3].calcFrame(solu_c, solu_c, solu_d, solu_d)
+    for k, (g, c) in enumerate(zip(gpu, cpu)):
+        got, ref = g.raw_histogram(), c.raw_sum()
+        assert bool(g.oneistwo) == bool(c.oneistwo) and g.ctr == c.ctr == 3, k
+        assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 100, "object %d: g000 not bit-exact" % k
+        assert_hist_close(got, ref, 300, pairw=np.maximum(g.pair_weight, ref[:300]))
+        assert g.stats()["h2d_bytes"] < 1000, "object %d copied frame data although every array was shared" % k
+
+
+def test_cfg4_solvent_self_full_size():
+    """BASELINE configs[3], the dominant object at its real size: 81,920 solvent molecules, self, all modes, L = 143.6 A
+    (3.36e9 pair evaluations) against the row-block CPU oracle."""
+    n, L = 81920, 143.6
+    rng = np.random.default_rng(4040)
+    c, d = _random_frame(rng, n, L)
+    rdf = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
+    rdf.calcFrame(c, c, d, d)
+    got = rdf.raw_histogram()
+    ref = np.zeros(7 * 300)
+    box = np.array([L, L, L, L / 2, L / 2, L / 2])
+    rc, oob = O.calc_histo_rows_c(c, c, d, d, ref, box, 0.0, 15.0, 300, 20.0, 127)
+    assert rc == 0 and oob == 0
+    assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 1e7
+    scale = np.maximum(np.abs(ref), np.tile(ref[:300], 7))
+    assert np.all(np.abs(got - ref) <= 2 * RTOL * scale)
+
+
 def test_cfg5_row_block_against_oracle():
-    """BASELINE configs[4] shape (1M-site box, L = 315.4 A): a rectangular row block of 1,024 core sites
-    against 262,144 surround sites (a quarter of the box population, same density region) vs the CPU oracle."""
-    n1, n2, L = 1024, 262144, 315.4
+    """BASELINE configs[4] shape (1M-site box, L = 315.4 A): the rectangular row block BASELINE.md section 3 names -
+    1,024 core sites against ALL 1,048,576 surround sites of the box (gfunction.pyx:126-130, rectangular path) - vs
+    the CPU oracle (1.07e9 pair evaluations)."""
+    n1, n2, L = 1024, 1048576, 315.4
     rng = np.random.default_rng(5005)
     c1, d1 = _random_frame(rng, n1, L); c2, d2 = _random_frame(rng, n2, L)
     rdf = RDF(["all"], 0.0, 15.0, 0.05, n1, n2, n1, n2, L)
@@ -814,6 +939,17 @@ def test_calc_histo_ts_matches_oracle():
     r2 = np.zeros((1, 200, nb)); o2 = np.zeros((1, 200, nb))
     calcHistoTS(c, c, r2, L, 0, 0.0, 12.0, 20.0); O.calc_histo_ts_c(c, c, o2[0], L, 0.0, 12.0, 20.0)
     assert np.array_equal(r2, o2)
+
+
+@pytest.mark.parametrize("name", sorted(C.TS_CASES))
+def test_calc_histo_ts_golden(golden_dir, name):
+    """calcHistoTS against what the UNMODIFIED reference function wrote (tests/golden/ts.npz), including the quirk-Q3
+    spill of a pair at exactly histo_max into the next core row / the next frame's first row (ts_edge)."""
+    from newanalysis.gfunction import calcHistoTS
+    want = np.load(os.path.join(golden_dir, "ts.npz"))[name]
+    got = C.drive_ts(calcHistoTS, C.TS_CASES[name])
+    assert got.shape == want.shape and want.sum() > 50
+    assert np.array_equal(got, want)
 
 
 # ---- N2: shell-resolved g-functions (RDF_voronoi gfunction.pyx:764-1148, calcHistoTSVoro :195-224) --------------
@@ -899,9 +1035,73 @@ def test_voronoi_argument_errors():
         RDF_voronoi(["000"], 0.0, 8.0, 0.1, n, n, 128, 16, 20.0, 2).calcFrame(c, c, np.ones((128, n), dtype=np.int32))
 
 
+def test_voronoi_before_first_frame_and_batch_call():
+    """RDF_voronoi creates its device handle with the first frame: the inherited helpers must not trip over that, and
+    calcFrames (many frames per call) equals frame-by-frame calls."""
+    from newanalysis.gfunction import RDF_voronoi
+    case = C.VORO_CASES["voro_rect"]
+    r = C.make_voro(RDF_voronoi, case)
+    r.sync(); r.flush(); r.scale(2.0); r.resetArrays()
+    assert not r.raw_histogram().any()
+    with pytest.raises(RuntimeError, match="first calcFrame"):
+        r.stats()
+    with pytest.raises(TypeError):
+        r.attach_topology(np.ones(3), [3], [0])
+    a = C.drive_voro(C.make_voro(RDF_voronoi, case), case)
+    fr = [C.build_voro_inputs(case, f) for f in range(case["frames"])]
+    r.calcFrames(np.stack([x[0] for x in fr]), np.stack([x[1] for x in fr]), np.stack([x[5] for x in fr]),
+                 np.stack([x[2] for x in fr]), np.stack([x[3] for x in fr]), boxes=np.array([x[4] for x in fr]))
+    assert np.array_equal(r.raw_histogram(), a.raw_histogram()) and r.ctr == a.ctr
+    assert r.stats()["frames"] == case["frames"]
+
+
 @pytest.mark.parametrize("name", sorted(C.TSVORO_CASES))
 def test_calc_histo_ts_voro_golden(golden_dir, name):
     from newanalysis.gfunction import calcHistoTSVoro
     want = np.load(os.path.join(golden_dir, "tsvoro.npz"))[name]
     got = C.drive_tsvoro(calcHistoTSVoro, C.TSVORO_CASES[name])
     assert np.array_equal(got, want)
+
+
+# ---- the C ABI itself, without the Cython shim ------------------------------------------------------------------
+def test_c_abi_through_ctypes_matches_golden(golden_dir):
+    """gfn_create -> gfn_enqueue_frame -> gfn_readout driven through raw ctypes (what a cgo / JNI / ctypes binding of
+    include/gfn.h would do) on the golden case rect_all: g000 bit-exact, weighted rows 1e-12."""
+    import ctypes
+    import newanalysis
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(newanalysis.__file__), "libgfn.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.gfn_create.restype = ctypes.c_int
+    lib.gfn_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                               ctypes.c_float, ctypes.c_double, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                               ctypes.c_uint]
+    lib.gfn_enqueue_frame.restype = ctypes.c_int
+    lib.gfn_enqueue_frame.argtypes = [ctypes.c_void_p, dp, dp, dp, dp]
+    lib.gfn_readout.restype = ctypes.c_int
+    lib.gfn_readout.argtypes = [ctypes.c_void_p, dp, dp, ctypes.POINTER(ctypes.c_ulonglong)]
+    lib.gfn_destroy.restype = None
+    lib.gfn_destroy.argtypes = [ctypes.c_void_p]
+    lib.gfn_last_error.restype = ctypes.c_char_p
+    lib.gfn_last_error.argtypes = [ctypes.c_void_p]
+
+    raw, _out, meta = load_golden(golden_dir, "rect_all")
+    case = C.CASES["rect_all"]
+    hn = meta["histo_n"]
+    L = case["box"][0]
+    box = (ctypes.c_double * 6)(L, L, L, L / 2, L / 2, L / 2)
+    h = ctypes.c_void_p()
+    # histo_min/max as C floats, inv_dr = 1/round(dr,5): what RDF.__init__ computes (gfunction.pyx:291-295)
+    rc = lib.gfn_create(ctypes.byref(h), case["n1"], case["n2"], hn, ctypes.c_float(case["hmin"]), ctypes.c_float(case["hmax"]),
+                        1.0 / np.round(case["dr"], 5), 127, box, None, 0, 0)
+    assert rc == 0, lib.gfn_last_error(None)
+    try:
+        for f in range(case["frames"]):
+            c1, c2, d1, d2, _ = C.build_inputs(case, f)
+            p = [a.ctypes.data_as(dp) for a in (c1, c2, d1, d2)]
+            assert lib.gfn_enqueue_frame(h, *p) == 0, lib.gfn_last_error(h)
+        hist = np.zeros(7 * hn); pw = np.zeros(hn); ovf = ctypes.c_ulonglong(0)
+        assert lib.gfn_readout(h, hist.ctypes.data_as(dp), pw.ctypes.data_as(dp), ctypes.byref(ovf)) == 0, lib.gfn_last_error(h)
+    finally:
+        lib.gfn_destroy(h)
+    assert np.array_equal(hist[:hn], raw[:hn]) and raw[:hn].sum() > 0
+    assert_hist_close(hist, raw, hn, pairw=np.maximum(pw, raw[:hn]))

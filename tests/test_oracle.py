@@ -179,6 +179,34 @@ def test_tsvoro_oracle_matches_golden(golden_dir, name):
     assert np.array_equal(C.drive_tsvoro(fn, C.TSVORO_CASES[name]), want)
 
 
+@pytest.mark.parametrize("name", sorted(C.TS_CASES))
+def test_ts_oracle_matches_golden(golden_dir, name):
+    """N3 pin: the C restatement of calcHistoTS (gfunction.pyx:168-192) equals what the unmodified reference function
+    wrote, including the quirk-Q3 spill across rows and frames (ts_edge)."""
+    want = np.load(os.path.join(golden_dir, "ts.npz"))[name]
+    got = C.drive_ts(O.calc_histo_ts, C.TS_CASES[name])
+    assert np.array_equal(got, want)
+    if name == "ts_edge":
+        T = C.TS_CASES[name]["frames"]
+        assert want[0, 2, 0] == 1 and want[1, 0, 0] == 1 and want[T, 0, 0] == 1       # next row, next frame, spare frame
+    # the slab-wise entry point (what the GPU test of larger cases uses) agrees wherever no pair leaves the slab
+    if not C.TS_CASES[name].get("edge"):
+        case = C.TS_CASES[name]
+        for t in range(case["frames"]):
+            slab = np.zeros_like(want[t])
+            core, surr = C.build_ts_inputs(case, t)
+            assert O.calc_histo_ts_c(core, surr, slab, case["box"], case["hmin"], case["hmax"], 1.0 / case["dr"]) == 0
+            assert np.array_equal(slab, want[t])
+
+
+def test_ts_oracle_matches_reference_module_when_present():
+    ref = O.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    for name, case in C.TS_CASES.items():
+        assert np.array_equal(C.drive_ts(ref.calcHistoTS, case), C.drive_ts(O.calc_histo_ts, case)), name
+
+
 def test_voronoi_oracle_matches_reference_module():
     ref = O.load_ref()
     if ref is None:

@@ -107,6 +107,24 @@ def test_refused_files(tmp_path):
     del t0
 
 
+@pytest.mark.parametrize("natoms", [2 ** 29 + 7, 2 ** 31 - 1, 50000])
+def test_header_atom_count_is_checked_against_the_file(tmp_path, natoms):
+    """natoms comes from the (untrusted) header: a count whose coordinate record would not fit an int32 marker, or
+    whose frame is larger than what is left of the file, is refused at open instead of wrapping / reading wild."""
+    import struct
+    pos, _ = _frames(2, 10, 9)
+    p = str(tmp_path / "t.dcd")
+    D.write_dcd(p, pos)
+    raw = bytearray(open(p, "rb").read())
+    # the atom-count record: int32 4 | natoms | int32 4, right before frame 0
+    off = len(raw) - 2 * 3 * (8 + 40) - 12
+    assert struct.unpack("<iii", raw[off:off + 12]) == (4, 10, 4)
+    raw[off + 4:off + 8] = struct.pack("<i", natoms)
+    open(p, "wb").write(bytes(raw))
+    with pytest.raises(ValueError, match="less than one frame"):
+        DCDFile(p)
+
+
 def test_synth_writer_is_read_back_by_both_readers(tmp_path):
     """gfn_b200.synth.write_dcd (input generation for bench.py / examples) against the native reader and the oracle's."""
     from gfn_b200 import synth
