@@ -61,6 +61,10 @@ extern "C" {
                                           units, wider guard band); results identical, see DESIGN.md section 4 */
 #define GFN_FLAG_NO_TRIANGLE       32u /* evaluate all n1 x n2 pairs with weight 1 even when n1 == n2 (calcHistoTS,
                                           gfunction.pyx:168-192, has no j >= i shortcut) */
+#define GFN_FLAG_DENSE             128u /* force the dense-neighbourhood kernel (every warp filters AND evaluates, core
+                                          sites in registers) where it supports the handle; default: chosen when the
+                                          share of in-range pairs expected from box and histo_max exceeds 10 % */
+#define GFN_FLAG_NO_DENSE          256u /* never use it (the warp-specialised ring kernel serves every handle) */
 #define GFN_FLAG_EXACT_DIV         64u /* orientation cosines by the reference's literal divisions dot/(|a|*|b|)
                                           (gfunction.pyx:155,159,163) instead of reciprocal products: per-pair increments
                                           bit-identical to the reference, see "Arithmetic contract" above */
@@ -89,6 +93,9 @@ typedef struct gfn_stats {
     int    filter_fp64;       /* range pre-filter in use: 0 fp32, 1 fp64 pre-test, 2 packed fp16 */
     int    hist_mode;         /* 0 shared-memory warp replicas, 1 global atomics, 2 per-particle global */
     int    warps_per_block, blocks_per_sm, grid, smem_bytes, batch_frames, ndev, hist_replicas;
+    int    dense;             /* 0 ring kernel, 1 dense-neighbourhood kernel, 2 g000 count kernel (fp32 classification) */
+    double exact_evals;       /* count kernel: pairs the fp32 classification could not decide, evaluated in fp64 */
+    double selfcheck_bad;     /* count kernel under GFN_DEBUG=8: pairs whose fp32 decision differs from the exact one (must be 0) */
 } gfn_stats_t;
 
 /* Number of CUDA devices visible (0 if none / no driver).  Never fails. */

@@ -97,7 +97,7 @@ struct Batch {
     double* h_box = nullptr;      // pinned [frames][6]
     double* d_box = nullptr;
     Site* siteA = nullptr; Site* siteB = nullptr;
-    float*  maxab = nullptr;      // [2][frames]
+    float*  maxab = nullptr;      // [4][frames]: max |coordinate| of selection 1, 2; dipole-norm flag words of selection 1, 2
     cudaEvent_t uploaded = nullptr, done = nullptr, k0 = nullptr, k1 = nullptr;
     int nframes = 0;
     bool aliased = false;         // selection 2 is selection 1 (same pointer passed)
@@ -120,6 +120,7 @@ struct Dev {
     double* partials = nullptr;
     unsigned long long* counters = nullptr;
     int* item_start = nullptr;
+    double* bin_thr = nullptr;            // dense kernel, g000-only handles: bin thresholds in d^2
     PairConfig cfg;
     ncclComm_t comm = nullptr;
     // device-frame scratch (gfn_enqueue_device_frames)
@@ -163,6 +164,7 @@ struct gfn_handle {
     long long frame_doubles;      // worst case (not aliased)
     long long off_c1, off_d1, off_c2, off_d2;   // offsets (doubles) inside a non-aliased frame
     int n_itiles, n_jtiles, tiles_per_frame;
+    double acc_lo = 0, acc_hi = 0; int pos_max = 0;      // dense kernel: acceptance interval of d^2, bin of its upper end
     std::vector<Dev> devs;
     int next_dev = 0;
     // external communicator (one process per GPU)
@@ -235,6 +237,58 @@ void fill_params(gfn_t* h, Dev& d, PairParams& p)
     p.strideA = h->n1_pad; p.strideB = h->n2_pad;
     p.shell_mode = h->shells.layout; p.nshells = h->shells.nshells; p.histo_nr = h->histo_nr;
     p.apr1 = h->shells.apr_core; p.apr2 = h->shells.apr_surround; p.map_ld = h->shells.map_ld; p.excl_self = h->shells.exclude_self;
+    p.bin_thr = d.bin_thr; p.acc_lo = h->acc_lo; p.acc_hi = h->acc_hi; p.pos_max = h->pos_max;
+}
+
+// ---- exact bin thresholds in d^2 (dense kernel, g000-only handles) ------------------------------------------------
+// The reference decides a pair's fate from dist = sqrt(d2) (gfunction.pyx:148-150):
+//   reject if dist < hmin or dist > hmax or floor(dist*invdx) == 0;   pos = floor((dist - hmin) * invdx)
+// sqrt, the subtraction, the multiplication (each correctly rounded) and floor are monotone non-decreasing, so both the
+// acceptance and the bin are step functions of d2: the steps are found by bisection over the (ordered) bit patterns of the
+// non-negative doubles, evaluating the reference's own expressions with the host's IEEE arithmetic (volatile: one rounding
+// per operation, no contraction).
+template <class Pred>
+double min_true(Pred pred, double hi)
+{
+    if (!pred(hi)) return INFINITY;
+    if (pred(0.0)) return 0.0;
+    unsigned long long lo = 0, hb;
+    memcpy(&hb, &hi, 8);
+    while (hb - lo > 1) {          // invariant: !pred(lo), pred(hb)
+        const unsigned long long mid = lo + (hb - lo) / 2;
+        double t;
+        memcpy(&t, &mid, 8);
+        if (pred(t)) hb = mid; else lo = mid;
+    }
+    double t;
+    memcpy(&t, &hb, 8);
+    return t;
+}
+
+// Fills thr[0 .. histo_n+3]; returns false if the handle's parameters do not suit the table (the caller then keeps the
+// ring kernel).
+bool bin_thresholds(double hmin, double hmax, double invdx, int histo_n, std::vector<double>& thr, double* acc_lo, double* acc_hi, int* pos_max)
+{
+    if (!(hmax > 0.0) || !(hmax < 1e15) || !(invdx < 1e15) || !(invdx > 1e-15) || hmin < 0.0 || !(hmin <= hmax)) return false;
+    auto dist_of = [](double t) { volatile double s = sqrt(t); return (double)s; };
+    auto bin_of = [&](double t) { volatile double s = sqrt(t); volatile double d = s - hmin; volatile double q = d * invdx; return floor((double)q); };
+    const double top = (hmax + 4.0 / invdx + 1.0) * (hmax + 4.0 / invdx + 1.0) * 4.0;
+    const double lo = min_true([&](double t) { volatile double q = dist_of(t) * invdx; return dist_of(t) >= hmin && !((double)q < 1.0); }, top);
+    const double above = min_true([&](double t) { return dist_of(t) > hmax; }, top);
+    if (!isfinite(lo) || !isfinite(above) || !(above > 0.0)) return false;
+    unsigned long long ab;
+    memcpy(&ab, &above, 8);
+    ab -= 1;
+    double hi;
+    memcpy(&hi, &ab, 8);
+    if (!(lo <= hi)) return false;                      // nothing can be in range: leave such handles to the ring kernel
+    const double pm = bin_of(hi);
+    if (!(pm >= 0.0) || pm > (double)histo_n + 1.0) return false;
+    *acc_lo = lo; *acc_hi = hi; *pos_max = (int)pm;
+    thr.assign((size_t)histo_n + 4, INFINITY);
+    for (int k = 0; k <= *pos_max + 1; ++k)
+        thr[k] = min_true([&](double t) { return dist_of(t) >= hmin && bin_of(t) >= (double)k; }, top);
+    return true;
 }
 
 // prep + pair + finalize for nframes frames whose raw arrays are on the device
@@ -245,18 +299,20 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
                   cudaEvent_t k0, cudaEvent_t k1, const int* d_map = nullptr, long long s_map = 0)
 {
     cudaStream_t s = d.comp;
-    CU(cudaMemsetAsync(maxab, 0, sizeof(float) * 2 * nframes, s));
+    CU(cudaMemsetAsync(maxab, 0, sizeof(float) * 4 * nframes, s));
+    unsigned* nflag = reinterpret_cast<unsigned*>(maxab + 2 * nframes);
     const int hf = d.cfg.filter_fp64 == 2;
-    CU(prep_launch(c1, s_c1, h->need1 ? d1 : nullptr, s_d1, siteA, maxab, h->n1, h->n1_pad, nframes, d_box, hf, d.counters, s));
+    CU(prep_launch(c1, s_c1, h->need1 ? d1 : nullptr, s_d1, siteA, maxab, nflag, h->n1, h->n1_pad, nframes, d_box, hf, d.counters, s));
     h->st_launches += 1;
     if (!aliased) {
-        CU(prep_launch(c2, s_c2, h->need2 ? d2 : nullptr, s_d2, siteB, maxab + nframes, h->n2, h->n2_pad, nframes, d_box, hf, d.counters, s));
+        CU(prep_launch(c2, s_c2, h->need2 ? d2 : nullptr, s_d2, siteB, maxab + nframes, nflag + nframes, h->n2, h->n2_pad, nframes, d_box, hf, d.counters, s));
         h->st_launches += 1;
     }
     PairParams p;
     fill_params(h, d, p);
     p.siteA = siteA; p.maxA = maxab;
     p.siteB = aliased ? siteA : siteB; p.maxB = aliased ? maxab : maxab + nframes;
+    p.nflagA = nflag; p.nflagB = aliased ? nflag : nflag + nframes;
     p.box = d_box; p.nframes = nframes;
     p.shell_map = d_map; p.stride_map = s_map;
     CU(cudaEventRecord(k0, s));
@@ -371,7 +427,7 @@ void free_dev(Dev& d)
         if (b.k1) cudaEventDestroy(b.k1);
     }
     if (d.h_out) cudaFreeHost(d.h_out);
-    cudaFree(d.gacc); cudaFree(d.gsum); cudaFree(d.gpp); cudaFree(d.partials); cudaFree(d.counters); cudaFree(d.item_start);
+    cudaFree(d.gacc); cudaFree(d.gsum); cudaFree(d.gpp); cudaFree(d.partials); cudaFree(d.counters); cudaFree(d.item_start); cudaFree(d.bin_thr);
     cudaFree(d.xsiteA); cudaFree(d.xsiteB); cudaFree(d.xmax);
     for (Dev::XSlot& x : d.xs) {
         if (x.h_box) cudaFreeHost(x.h_box);
@@ -494,7 +550,22 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
     for (size_t i = 0; i < devs.size(); ++i) h->devs[i].dev = devs[i];
     for (Dev& d : h->devs) {
         CUC(cudaSetDevice(d.dev));
-        CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, &d.cfg));
+        // expected share of in-range pairs in a uniform box: decides between the ring kernel and the dense kernel
+        const double vol = box_dim[0] * box_dim[1] * box_dim[2];
+        const double share = fmin(1.0, 4.18879020478639098 * (double)histo_max * (double)histo_max * (double)histo_max / vol);
+        const HandleGeom geom = {(double)(float)histo_max, inv_dr, fmax(box_dim[0], fmax(box_dim[1], box_dim[2]))};
+        CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, share, geom, &d.cfg));
+    }
+    std::vector<double> thr;
+    if (h->devs[0].cfg.dense &&
+        !bin_thresholds((double)histo_min, (double)histo_max, inv_dr, histo_n, thr, &h->acc_lo, &h->acc_hi, &h->pos_max)) {
+        // parameters the threshold table does not cover: the ring kernel serves the handle
+        flags |= GFN_FLAG_NO_DENSE; flags &= ~GFN_FLAG_DENSE;
+        h->flags = flags;
+        for (Dev& d : h->devs) {
+            CUC(cudaSetDevice(d.dev));
+            CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, 0.0, HandleGeom{0.0, 0.0, 0.0}, &d.cfg));
+        }
     }
     // work decomposition (identical on all devices)
     {
@@ -502,18 +573,36 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
         const int TI = tile_i(c);
         h->n_itiles = (n1 + TI - 1) / TI;
         h->n_jtiles = (n2 + kTJ - 1) / kTJ;
-        // prefix of surround-tile visits per core tile (the triangle starts at the tile holding the diagonal)
-        std::vector<int> start(h->n_itiles + 1, 0);
-        for (int t = 0; t < h->n_itiles; ++t) {
-            const int first = tri_create ? (t * TI) / kTJ : 0;
-            const int tiles = h->n_jtiles - first;
-            start[t + 1] = start[t] + (tiles > 0 ? tiles : 0);
+        std::vector<int> start;
+        if (c.dense) {
+            // dense kernels: units of 64 (count kernel: 128) core rows per surround tile; prefix of units per surround tile (a triangular frame
+            // needs only the row blocks that reach the tile's last column: rows <= 128 jt + 127)
+            start.assign(h->n_jtiles + 1, 0);
+            for (int jt = 0; jt < h->n_jtiles; ++jt) {
+                long long cnt = h->n_itiles;
+                if (tri_create && c.dense == 2 && jt + 1 < cnt) cnt = jt + 1;             // count kernel: 128-row blocks
+                if (tri_create && c.dense == 1 && 2ll * jt + 2 < cnt) cnt = 2ll * jt + 2;
+                start[jt + 1] = start[jt] + (int)cnt;
+            }
+            h->tiles_per_frame = start[h->n_jtiles];
+        } else {
+            // prefix of surround-tile visits per core tile (the triangle starts at the tile holding the diagonal)
+            start.assign(h->n_itiles + 1, 0);
+            for (int t = 0; t < h->n_itiles; ++t) {
+                const int first = tri_create ? (t * TI) / kTJ : 0;
+                const int tiles = h->n_jtiles - first;
+                start[t + 1] = start[t] + (tiles > 0 ? tiles : 0);
+            }
+            h->tiles_per_frame = start[h->n_itiles];
         }
-        h->tiles_per_frame = start[h->n_itiles];
         for (Dev& d : h->devs) {
             CUC(cudaSetDevice(d.dev));
             CUC(cudaMalloc(&d.item_start, sizeof(int) * start.size()));
             CUC(cudaMemcpy(d.item_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+            if (!thr.empty() && c.dense == 2) {
+                CUC(cudaMalloc(&d.bin_thr, sizeof(double) * thr.size()));
+                CUC(cudaMemcpy(d.bin_thr, thr.data(), sizeof(double) * thr.size(), cudaMemcpyHostToDevice));
+            }
         }
     }
     for (Dev& d : h->devs) {
@@ -548,7 +637,7 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
             CUC(cudaMalloc(&b.d_box, sizeof(double) * 6 * h->batch_frames));
             CUC(cudaMalloc(&b.siteA, sizeof(Site) * (size_t)h->n1_pad * h->batch_frames));
             CUC(cudaMalloc(&b.siteB, sizeof(Site) * (size_t)h->n2_pad * h->batch_frames));
-            CUC(cudaMalloc(&b.maxab, sizeof(float) * 2 * h->batch_frames));
+            CUC(cudaMalloc(&b.maxab, sizeof(float) * 4 * h->batch_frames));
             CUC(cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming));
             CUC(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
             CUC(cudaEventCreateWithFlags(&b.k0, cudaEventDefault));
@@ -815,7 +904,7 @@ int gfn_enqueue_device_frames(gfn_t* h, int nframes,
     if (d.xcap < chunk) {
         CU(cudaMalloc(&d.xsiteA, sizeof(Site) * (size_t)h->n1_pad * chunk));
         CU(cudaMalloc(&d.xsiteB, sizeof(Site) * (size_t)h->n2_pad * chunk));
-        CU(cudaMalloc(&d.xmax, sizeof(float) * 2 * chunk));
+        CU(cudaMalloc(&d.xmax, sizeof(float) * 4 * chunk));
         d.xcap = chunk;
     }
     for (int f0 = 0; f0 < nframes; f0 += chunk) {
@@ -984,11 +1073,12 @@ int gfn_stats(gfn_t* h, gfn_stats_t* out)
         CU(cudaSetDevice(d.dev));
         CU(cudaMemcpy(c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
         out->overflow += (double)c[0]; out->survivors += (double)c[2]; out->in_range += (double)c[3];
+        out->selfcheck_bad += (double)c[4]; out->exact_evals += (double)c[5];
     }
     const PairConfig& c = h->devs[0].cfg;
     out->filter_fp64 = c.filter_fp64; out->hist_mode = c.hist_mode; out->warps_per_block = c.warps; out->hist_replicas = c.nrep;
     out->blocks_per_sm = c.blocks_per_sm; out->grid = c.grid; out->smem_bytes = c.smem_bytes;
-    out->batch_frames = h->batch_frames; out->ndev = (int)h->devs.size();
+    out->batch_frames = h->batch_frames; out->ndev = (int)h->devs.size(); out->dense = c.dense;
     return GFN_OK;
 }
 

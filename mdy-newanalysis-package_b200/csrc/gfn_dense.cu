@@ -1,0 +1,535 @@
+// gfn_dense.cu - the pair kernel for DENSE neighbourhoods (a large share of all pairs lies inside histo_max:
+// BASELINE configs[0] SPC/E water at hmax ~ L/2, 47 % in range; configs[1] ionic liquid, 36 %).
+//
+// Same arithmetic as pair_kernel (gfn_kernels.cu) - it replaces the same reference loop, cdef void calcHisto,
+// gfunction.pyx:110-165 - but a different division of labour.  pair_kernel is built for sparse neighbourhoods (1.4 % in
+// range at cfg3): half of its warps run the cheap range pre-filter, the other half evaluates the few survivors handed
+// over through shared-memory rings.  When every second or third pair survives, the hand-off (per-survivor bit extraction
+// and ring stores in the filter warps, two record gathers per survivor in the drain warps) costs more than the filter
+// saves and the eight drain warps carry all the work.  Here every warp is the same:
+//
+//   * WORK UNIT = 64 core rows x one surround tile of 128 sites.  Units are enumerated (frame, surround tile, row
+//     block) - for a triangular (n1 == n2) frame only the blocks that reach the diagonal - and a CTA owns a contiguous
+//     range of them; its warps PULL units from a shared-memory counter, so warps never wait for each other and the
+//     triangle balances itself.  Surround tiles stream through a 3-stage TMA ring (cp.async.bulk + mbarrier); a stage is
+//     refilled by the warp that finishes the last unit of its tile.
+//   * a lane OWNS two adjacent core rows of the unit and keeps their fp64 records (coordinates, dipole, 1/norm) in
+//     REGISTERS, so the exact path never gathers a core record.
+//   * per unit the warp runs the packed-fp16 (or fp32) range pre-filter of pair_kernel - two core rows per instruction -
+//     and keeps the survivor masks in registers: 4 chunks x 2 rows x 32 bits.
+//   * then every lane WALKS ITS OWN masks, two survivors of one row per step (two independent fp64 chains): it gathers
+//     only the surround record, evaluates distance, bin and weights in the reference's arithmetic and adds into the warp's
+//     PRIVATE histogram replica.  Pair counts use native shared-memory integer atomics (2 clocks per warp instruction
+//     on B200, profiles/microbench/warp_ops.cu).  fp64 sums must not use atomics (CAS loops) and must not use match.any
+//     either (73 clocks per warp instruction and SM when the keys differ - it was the top stall of the first version):
+//     lanes that hit the same bin are serialised by a write-and-check on a per-warp tag array (every contender stores its
+//     id, the one that reads its own id back adds, the rest retry), on average 1.5 rounds.
+//   * the acceptance test :149 is taken on d^2: acc_lo <= d^2 <= acc_hi with the exact thresholds the host finds by
+//     bisection over the reference's own expressions (gfn_api.cu bin_thresholds), so rejected pairs never reach the
+//     square root.  g000-only handles are not served here: gfn_count.cu decides their bins in fp32.
+//
+// Results: bins bit-exact, weighted sums within the same bound as pair_kernel's.
+#include "gfn_device.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace gfn {
+
+constexpr int kDStages = 3;
+
+struct DCtrl {
+    uint64_t full[kDStages];     // TMA landed in stage s
+    int done[4];                 // units finished on the tile held by stage s (the last one refills the stage)
+    int next;                    // next unit of this CTA's range to hand out
+    int pad[3];
+};
+constexpr int kDCtrlBytes = 64;
+static_assert(sizeof(DCtrl) <= kDCtrlBytes, "control block");
+
+// weighted columns of a bin record for a compile-time mode set (MSEL = 0: chosen at run time, all six columns kept)
+__host__ __device__ constexpr int dense_ncol(int msel)
+{
+    return msel == 0 ? 6 : ((msel >> 1) & 1) + ((msel >> 2) & 1) + ((msel >> 3) & 1) + ((msel >> 4) & 1) + ((msel >> 5) & 1) + ((msel >> 6) & 1);
+}
+// column of mode bit k (1..6) inside the record, or -1
+__host__ __device__ constexpr int dense_col(int msel, int k)
+{
+    if (msel == 0) return k - 1;
+    if (!((msel >> k) & 1)) return -1;
+    int c = 0;
+    for (int b = 1; b < k; ++b) c += (msel >> b) & 1;
+    return c;
+}
+
+__host__ __device__ inline size_t pad16(size_t b) { return (b + 15) & ~(size_t)15; }
+// per-warp replica: [bin][NCOL] fp64 sums, [bin] u32 pair weights, [bin] u8 tags
+__host__ __device__ inline size_t dense_replica_bytes(int hn, int msel)
+{
+    return pad16((size_t)hn * dense_ncol(msel) * 8) + pad16((size_t)hn * 4) + pad16((size_t)hn);
+}
+
+template <typename F, int NW, int MSEL>
+__global__ void __launch_bounds__(NW * 32, 1)
+dense_kernel(const PairParams P)
+{
+    constexpr bool kH16 = std::is_same<F, __half>::value;
+    static_assert(MSEL != 1, "g000-only handles are served by gfn_count.cu");
+    constexpr int TJ = kTJ, S = kDStages;
+    constexpr int NCOL = dense_ncol(MSEL);
+    static_assert(TJ / 32 == 4, "four chunks per surround tile");
+    static_assert(std::is_same<F, __half>::value || std::is_same<F, float>::value, "fp16x2 or fp32 pre-filter");
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    Site* jsite = reinterpret_cast<Site*>(smem);                                           // [S][TJ]
+    DCtrl* ctrl = reinterpret_cast<DCtrl*>(jsite + S * TJ);
+    const int hn = P.histo_n;
+    unsigned char* hist = reinterpret_cast<unsigned char*>(ctrl) + kDCtrlBytes;                      // [NW] replicas
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t rbytes = dense_replica_bytes(hn, MSEL);
+    const int mode_sel = MSEL == 0 ? P.mode_sel : MSEL;
+    const bool m_cs = mode_sel & (2 | 16), m_cd = mode_sel & (4 | 32), m_sd = mode_sel & (8 | 64);
+
+    // this CTA's range of units and the surround tiles it touches (tile index gt = frame * n_jtiles + jt)
+    const int upf = P.tiles_per_frame;                        // units per frame
+    const long long total_units = (long long)upf * P.nframes;
+    const long long ubeg = total_units * blockIdx.x / gridDim.x;
+    const long long uend = total_units * (blockIdx.x + 1) / gridDim.x;
+    auto tile_of = [&](long long u, int& iu) -> long long {
+        const int f = (int)(u / upf);
+        const int r = (int)(u - (long long)f * upf);
+        int lo = 0, hi = P.n_jtiles;       // jt with tile_start[jt] <= r < tile_start[jt+1]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.tile_start[mid] <= r) lo = mid; else hi = mid; }
+        iu = r - P.tile_start[lo];
+        return (long long)f * P.n_jtiles + lo;
+    };
+    auto units_in_range = [&](long long gt) -> int {          // units of tile gt that belong to this CTA
+        const int f = (int)(gt / P.n_jtiles), jt = (int)(gt - (long long)f * P.n_jtiles);
+        long long b = (long long)f * upf + P.tile_start[jt], e = (long long)f * upf + P.tile_start[jt + 1];
+        if (b < ubeg) b = ubeg;
+        if (e > uend) e = uend;
+        return (int)(e - b);
+    };
+    auto load_tile = [&](long long gt, int st) {
+        const int f = (int)(gt / P.n_jtiles), jt = (int)(gt - (long long)f * P.n_jtiles);
+        mbar_expect_tx(&ctrl->full[st], TJ * (uint32_t)sizeof(Site));
+        bulk_g2s(jsite + st * TJ, P.siteB + (long long)f * P.strideB + (long long)jt * TJ, TJ * (uint32_t)sizeof(Site), &ctrl->full[st]);
+    };
+    int dummy_iu;
+    const long long gt_first = ubeg < uend ? tile_of(ubeg, dummy_iu) : 0;
+    const long long gt_last = ubeg < uend ? tile_of(uend - 1, dummy_iu) : -1;
+
+    {
+        unsigned* z = reinterpret_cast<unsigned*>(hist);
+        for (size_t k = tid; k < (size_t)NW * rbytes / 4; k += NW * 32) z[k] = 0u;
+    }
+    if (tid < 4) ctrl->done[tid] = 0;
+    if (tid == 0) {
+        ctrl->next = 0;
+        for (int k = 0; k < S; ++k) mbar_init(&ctrl->full[k], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) for (int k = 0; k < S && gt_first + k <= gt_last; ++k) load_tile(gt_first + k, k);
+
+    unsigned char* rep = hist + (size_t)warp * rbytes;
+    double* wsum = reinterpret_cast<double*>(rep);                                                            // [bin][NCOL]
+    unsigned* cnt = reinterpret_cast<unsigned*>(rep + pad16((size_t)hn * NCOL * 8));          // [bin]
+    unsigned char* tag = rep + pad16((size_t)hn * NCOL * 8) + pad16((size_t)hn * 4);          // [bin]
+
+    unsigned n_surv = 0, n_inr = 0, n_ovf = 0;
+    bool zerodiv = false;
+    const double acc_lo = P.acc_lo, acc_hi = P.acc_hi;
+    const bool dynamic = P.debug & 4;                        // experiments: units pulled from a counter (not reproducible)
+
+    // frame constants, refreshed when a unit belongs to another frame
+    int f_cur = -1;
+    bool exact_div = false;                                  // this frame: literal divisions (a norm is zero / out of range, or asked for)
+    Box bx; bx.Lx = bx.Ly = bx.Lz = bx.hx = bx.hy = bx.hz = 0.0;
+    float Tg = 0.f, hxf = 0.f, hyf = 0.f, hzf = 0.f;
+    __half2 hTg, hLx, hLy, hLz;
+    hTg = hLx = hLy = hLz = __halves2half2(__ushort_as_half(0), __ushort_as_half(0));
+
+    for (int iter = 0;; ++iter) {
+        // units of the range go round-robin over the warps (fixed assignment: the summation order, and with it every bit of
+        // the result, is reproducible); a surround tile's units are consecutive, so they spread evenly over the warps
+        int un = warp + NW * iter;
+        if (dynamic) {
+            if (lane == 0) un = atomicAdd(&ctrl->next, 1);
+            un = __shfl_sync(0xffffffffu, un, 0);
+        }
+        const long long u = ubeg + un;
+        if (u >= uend) break;
+        int iu;
+        const long long gt = tile_of(u, iu);
+        const int f = (int)(gt / P.n_jtiles), jt = (int)(gt - (long long)f * P.n_jtiles);
+        const long long k = gt - gt_first;                    // ordinal of the tile inside this CTA's range
+        const int st = (int)(k % S);
+        const int j0 = jt * TJ;
+        const Site* siteA = P.siteA + (long long)f * P.strideA;
+
+        if (f != f_cur) {
+            f_cur = f;
+            const double* b = P.box + 6ll * f;
+            bx.Lx = b[0]; bx.Ly = b[1]; bx.Lz = b[2]; bx.hx = b[3]; bx.hy = b[4]; bx.hz = b[5];
+            const double M = (double)fmaxf(P.maxA[f], P.maxB[f]) * (1.0 + 1.2e-7);
+            // a dipole norm of this frame that is zero or outside [2^-300, 2^300] (prep_kernel flags it): the whole frame
+            // takes the reference's literal divisions with the zero-denominator test of quirk Q5
+            exact_div = (P.flags & GFN_FLAG_EXACT_DIV) || ((m_cs || m_cd) && P.nflagA[f]) || ((m_cs || m_sd) && P.nflagB[f]);
+            // filter constants (same guard bands as pair_kernel)
+            if (kH16) {
+                const double Sb = fmax(b[0], fmax(b[1], b[2])), invS = 1.0 / Sb;
+                const double uu = FOps<__half>::kU;
+                const double hm = P.hmax * invS;
+                const double ew = uu * (2.1 * M * invS + 4.2 * fmax(b[3], fmax(b[4], b[5])) * invS + 2.2 * hm);
+                const double T = (hm * hm * (1.0 + 1e-12) + 3.5 * ew * hm + 3.0 * ew * ew + 4.0 * 5.9604644775390625e-08) * (1.0 + 8.0 * uu);
+                __half th = __double2half(T);
+                if (__half2float(th) <= (float)T) th = __ushort_as_half((unsigned short)(__half_as_ushort(th) + 1));   // round up
+                hTg = __halves2half2(__hneg(th), __hneg(th));
+                const __half a = __double2half(b[0] * invS), bq = __double2half(b[1] * invS), cq = __double2half(b[2] * invS);
+                hLx = __halves2half2(a, a); hLy = __halves2half2(bq, bq); hLz = __halves2half2(cq, cq);
+            } else {
+                Tg = guard_threshold<float>(P.hmax, M, fmax(b[3], fmax(b[4], b[5])));
+                hxf = (float)b[3]; hyf = (float)b[4]; hzf = (float)b[5];
+            }
+        }
+        // ---- this lane's two core rows -----------------------------------------------------------------------------
+        const int row0 = iu * 64 + 2 * lane;
+        double cx[2], cy[2], cz[2], cpx[2], cpy[2], cpz[2], cn[2], icn[2];
+        unsigned fxb[2], fyb[2], fzb[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const double2* rp = reinterpret_cast<const double2*>(siteA + row0 + r);
+            const double2 a0 = __ldg(rp), a1 = __ldg(rp + 1);
+            cx[r] = a0.x; cy[r] = a0.y; cz[r] = a1.x; cpx[r] = a1.y;
+            const double2 a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
+            cpy[r] = a2.x; cpz[r] = a2.y; cn[r] = a3.x; icn[r] = a3.y;
+            const uint4 f4 = __ldg(reinterpret_cast<const uint4*>(&siteA[row0 + r].fx));
+            fxb[r] = f4.x; fyb[r] = f4.y; fzb[r] = f4.z;
+        }
+        __half2 hcx, hcy, hcz;
+        float fcx[2], fcy[2], fcz[2];
+        {
+            const unsigned px = __byte_perm(fxb[0], fxb[1], 0x5410), py = __byte_perm(fyb[0], fyb[1], 0x5410), pz = __byte_perm(fzb[0], fzb[1], 0x5410);
+            hcx = *reinterpret_cast<const __half2*>(&px); hcy = *reinterpret_cast<const __half2*>(&py); hcz = *reinterpret_cast<const __half2*>(&pz);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) { fcx[r] = __uint_as_float(fxb[r]); fcy[r] = __uint_as_float(fyb[r]); fcz[r] = __uint_as_float(fzb[r]); }
+        }
+
+        mbar_wait(&ctrl->full[st], (unsigned)((k / S) & 1));
+        const Site* js = jsite + st * TJ;
+
+        // ---- range pre-filter: survivor masks of the unit, [chunk][row], bit 31-jj = surround site jj ---------------
+        unsigned mk[4][2];
+#pragma unroll
+        for (int jc = 0; jc < 4; ++jc) {
+            mk[jc][0] = 0u; mk[jc][1] = 0u;
+            const int jbase = jc * 32;
+            if (j0 + jbase >= P.n2) continue;                               // padding only
+            if (P.tri && j0 + jbase + 31 < iu * 64) continue;              // chunk entirely left of the diagonal
+            unsigned m0 = 0u, m1 = 0u;
+            if (kH16) {
+                // 9 HADD2 (with |.| modifiers) + 3 HFMA2 + SHF + LOP3 per TWO pairs, see pair_kernel
+                unsigned acc[2] = {0u, 0u};
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    const uint4 s4 = *reinterpret_cast<const uint4*>(&js[jbase + jj].fx);
+                    const __half2 sx = *reinterpret_cast<const __half2*>(&s4.x), sy = *reinterpret_cast<const __half2*>(&s4.y), sz = *reinterpret_cast<const __half2*>(&s4.z);
+                    const __half2 dx = __hsub2(sx, hcx), dy = __hsub2(sy, hcy), dz = __hsub2(sz, hcz);
+                    const __half2 ax = __habs2(dx), ay = __habs2(dy), az = __habs2(dz);
+                    const __half2 wx = __hmin2(ax, __hsub2(hLx, ax));
+                    const __half2 wy = __hmin2(ay, __hsub2(hLy, ay));
+                    const __half2 wz = __hmin2(az, __hsub2(hLz, az));
+                    const __half2 tt = __hfma2(wz, wz, __hfma2(wy, wy, __hfma2(wx, wx, hTg)));
+                    const unsigned tb = *reinterpret_cast<const unsigned*>(&tt);
+                    acc[jj >> 4] |= (tb >> (jj & 15)) & (0x80008000u >> (jj & 15));
+                }
+                m0 = __byte_perm(acc[1], acc[0], 0x5410);
+                m1 = __byte_perm(acc[1], acc[0], 0x7632);
+            } else {
+#pragma unroll 16
+                for (int jj = 0; jj < 32; ++jj) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(&js[jbase + jj].fx);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const float dx = s4.x - fcx[r], dy = s4.y - fcy[r], dz = s4.z - fcz[r];
+                        const float vx = fabsf(dx) - hxf, vy = fabsf(dy) - hyf, vz = fabsf(dz) - hzf;
+                        const float wx = hxf - fabsf(vx), wy = hyf - fabsf(vy), wz = hzf - fabsf(vz);
+                        float tt = fmaf(wx, wx, -Tg);
+                        tt = fmaf(wy, wy, tt);
+                        tt = fmaf(wz, wz, tt);
+                        if (r == 0) m0 = __funnelshift_l(__float_as_uint(tt), m0, 1);
+                        else        m1 = __funnelshift_l(__float_as_uint(tt), m1, 1);
+                    }
+                }
+            }
+            // rows beyond the selection; for a triangular frame everything left of the diagonal (j < i, :126-129)
+            if (row0 >= P.n1) m0 = 0u;
+            if (row0 + 1 >= P.n1) m1 = 0u;
+            if (P.tri) {
+                const int k0 = row0 - (j0 + jbase);                         // first allowed jj of row 0 (row 1: one more)
+                if (k0 > 0) m0 = k0 >= 32 ? 0u : (m0 & (0xffffffffu >> k0));
+                if (k0 + 1 > 0) m1 = k0 + 1 >= 32 ? 0u : (m1 & (0xffffffffu >> (k0 + 1)));
+            }
+            mk[jc][0] = m0; mk[jc][1] = m1;
+            n_surv += __popc(m0) + __popc(m1);
+        }
+
+        // ---- walk: per row and chunk, every lane pops two of its survivors per step -------------------------------
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = row0 + r;
+#pragma unroll 1
+            for (int jc = 0; jc < 4; ++jc) {
+                unsigned m = jc == 0 ? mk[0][r] : jc == 1 ? mk[1][r] : jc == 2 ? mk[2][r] : mk[3][r];
+                const int jbase = jc * 32;
+                while (__any_sync(0xffffffffu, m != 0u)) {
+                    bool ok[2]; int pos[2], jg[2];
+                    {
+                        // ======== weighted modes: the reference's arithmetic as in pair_kernel's drain warps
+                        bool self_pair[2]; double w[2], v[2][6];
+                        double dxa[2], dya[2], dza[2], d2[2], dist[2], idist[2];
+                        double bpx[2], bpy[2], bpz[2], bn[2], ibn[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int fl = 31 - __clz(m);                  // highest set bit = first surround site; -1: none left
+                            const bool have = fl >= 0;
+                            m &= ~(1u << (fl & 31));
+                            const int jl = jbase + 31 - fl;
+                            jg[u] = j0 + jl;
+                            self_pair[u] = (row == jg[u]);
+                            const double2* bp = reinterpret_cast<const double2*>(js + jl);
+                            const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];   // x y | z px | py pz | norm 1/norm
+                            bpx[u] = b1.y; bpy[u] = b2.x; bpz[u] = b2.y; bn[u] = b3.x; ibn[u] = b3.y;
+                            dxa[u] = wrap_signed(b0.x, cx[r], bx.hx, bx.Lx);                         // :141-147
+                            dya[u] = wrap_signed(b0.y, cy[r], bx.hy, bx.Ly);
+                            dza[u] = wrap_signed(b1.x, cz[r], bx.hz, bx.Lz);
+                            d2[u] = DOT3(dxa[u], dya[u], dza[u], dxa[u], dya[u], dza[u]);
+                            // :149 as an interval of d^2 (exact thresholds from the host; false for NaN).  Accepted values lie
+                            // far inside the range where the straight-line square root below is exact (gfn_create checks
+                            // histo_max and inv_dr), the others are replaced by 1.
+                            ok[u] = have && d2[u] >= acc_lo && d2[u] <= acc_hi;
+                            if (!ok[u]) d2[u] = 1.0;
+                        }
+                        // --- distance :148, bin :150, weight :131-134
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            dist[u] = sqrt_rsqrt_inrange(d2[u], idist[u]);
+                            pos[u] = __double2int_rd(DMUL(DSUB(dist[u], P.hmin), P.invdx));
+                            w[u] = (P.tri && !self_pair[u]) ? 2.0 : 1.0;
+                        }
+                        n_inr += (ok[0] ? 1u : 0u) + (ok[1] ? 1u : 0u);
+                        // --- orientation weights :154-165: reciprocal form (see pair_kernel) unless this frame holds a norm that
+                        //     is zero / out of range or the caller asked for the literal divisions
+                        double c[2][3];
+                        if (!exact_div) {
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                c[u][0] = DMUL(DOT3(cpx[r], cpy[r], cpz[r], bpx[u], bpy[u], bpz[u]), DMUL(icn[r], ibn[u]));
+                                c[u][1] = DMUL(DOT3(cpx[r], cpy[r], cpz[r], dxa[u], dya[u], dza[u]), DMUL(icn[r], idist[u]));
+                                c[u][2] = DMUL(DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]), DMUL(ibn[u], idist[u]));
+                            }
+                        } else {
+                            double den[2][3], num[2][3];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                den[u][0] = DMUL(cn[r], bn[u]);
+                                den[u][1] = DMUL(cn[r], dist[u]);
+                                den[u][2] = DMUL(bn[u], dist[u]);
+                                num[u][0] = DOT3(cpx[r], cpy[r], cpz[r], bpx[u], bpy[u], bpz[u]);
+                                num[u][1] = DOT3(cpx[r], cpy[r], cpz[r], dxa[u], dya[u], dza[u]);
+                                num[u][2] = DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]);
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) {
+                                    const bool sel = q == 0 ? m_cs : (q == 1 ? m_cd : m_sd);
+                                    if (ok[u] && sel && den[u][q] == 0.0) zerodiv = true;          // quirk Q5
+                                    if (!ok[u] || !sel || den[u][q] == 0.0) { den[u][q] = 1.0; num[u][q] = 0.0; }
+                                    c[u][q] = DDIV(num[u][q], den[u][q]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                v[u][q] = DMUL(c[u][q], w[u]);                                          // incr*off_diag
+                                v[u][3 + q] = DMUL(DSUB(DMUL(DMUL(1.5, c[u][q]), c[u][q]), 0.5), w[u]);   // (1.5*incr*incr-0.5)*off_diag
+                            }
+                        // ---- accumulate -------------------------------------------------------------------------------
+                        bool pend[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            pend[u] = ok[u] && pos[u] < hn;
+                            if (pend[u]) atomicAdd(cnt + pos[u], (P.tri && !self_pair[u]) ? 2u : 1u);     // :152 and the weight row
+                            if (ok[u] && pos[u] >= hn) {
+                                // quirk Q3: the reference's flat index runs into the next row / mode; global accumulators
+                                ++n_ovf;
+                                if (!(P.flags & GFN_FLAG_DISCARD_OVERFLOW)) {
+                                    if (mode_sel & 1)  global_add(P, 1, 0, row, pos[u], w[u]);
+                                    if (mode_sel & 2)  global_add(P, 1, 1, row, pos[u], v[u][0]);
+                                    if (mode_sel & 4)  global_add(P, 1, 2, row, pos[u], v[u][1]);
+                                    if (mode_sel & 8)  global_add(P, 1, 3, row, pos[u], v[u][2]);
+                                    if (mode_sel & 16) global_add(P, 1, 4, row, pos[u], v[u][3]);
+                                    if (mode_sel & 32) global_add(P, 1, 5, row, pos[u], v[u][4]);
+                                    if (mode_sel & 64) global_add(P, 1, 6, row, pos[u], v[u][5]);
+                                }
+                            }
+                        }
+                        // fp64 sums: contenders for a bin store their id into the bin's tag; whoever reads its own id back
+                        // owns the bin for this round (exactly one per bin), the others retry
+                        const unsigned char id0 = (unsigned char)(2 * lane), id1 = (unsigned char)(2 * lane + 1);
+                        while (__any_sync(0xffffffffu, pend[0] || pend[1])) {
+                            if (pend[0]) tag[pos[0]] = id0;
+                            if (pend[1]) tag[pos[1]] = id1;
+                            __syncwarp();
+                            const bool win0 = pend[0] && tag[pos[0]] == id0;
+                            const bool win1 = pend[1] && tag[pos[1]] == id1;
+                            __syncwarp();
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                if (u == 0 ? win0 : win1) {
+                                    // column c of the record holds mode bit q with dense_col(MSEL, q) == c (a compile-time
+                                    // map; MSEL == 0: all six columns, unselected ones are never added to)
+                                    double addv[NCOL];
+#pragma unroll
+                                    for (int q = 1; q <= 6; ++q) {
+                                        const int col = dense_col(MSEL, q);
+                                        if (col >= 0) addv[col] = (MSEL != 0 || (mode_sel & (1 << q))) ? v[u][q - 1] : 0.0;
+                                    }
+                                    static_assert(NCOL % 2 == 0, "bin records are read and written as double2");
+                                    double2* h2 = reinterpret_cast<double2*>(wsum + (size_t)pos[u] * NCOL);
+                                    double2 hv[NCOL / 2];
+#pragma unroll
+                                    for (int c2 = 0; c2 < NCOL / 2; ++c2) hv[c2] = h2[c2];
+#pragma unroll
+                                    for (int c2 = 0; c2 < NCOL / 2; ++c2) { hv[c2].x += addv[2 * c2]; hv[c2].y += addv[2 * c2 + 1]; }
+#pragma unroll
+                                    for (int c2 = 0; c2 < NCOL / 2; ++c2) h2[c2] = hv[c2];
+                                }
+                            }
+                            pend[0] = pend[0] && !win0;
+                            pend[1] = pend[1] && !win1;
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        }
+        // ---- unit finished; the warp that finishes the last unit of a tile refills its stage with the tile S ahead ---
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            const int d = atomicAdd(&ctrl->done[st], 1) + 1;
+            if (d == units_in_range(gt)) {
+                atomicExch(&ctrl->done[st], 0);
+                if (gt + S <= gt_last) load_tile(gt + S, st);
+            }
+        }
+    }
+
+    // counters: warp-reduce then one atomic per warp
+    for (int d = 16; d; d >>= 1) {
+        n_surv += __shfl_xor_sync(0xffffffffu, n_surv, d);
+        n_inr  += __shfl_xor_sync(0xffffffffu, n_inr, d);
+        n_ovf  += __shfl_xor_sync(0xffffffffu, n_ovf, d);
+    }
+    const bool anyz = __any_sync(0xffffffffu, zerodiv);
+    if (lane == 0) {
+        if (n_surv) atomicAdd(P.counters + 2, (unsigned long long)n_surv);
+        if (n_inr)  atomicAdd(P.counters + 3, (unsigned long long)n_inr);
+        if (n_ovf)  atomicAdd(P.counters + 0, (unsigned long long)n_ovf);
+        if (anyz)   atomicOr(P.counters + 1, 1ull);
+    }
+
+    // ---- flush: replicas summed in a fixed order -> this CTA's partial histogram (layout of pair_kernel) --------
+    __syncthreads();
+    {
+        constexpr int PS = 8;
+        double* out = P.partials + (size_t)blockIdx.x * hn * PS;
+        for (int k = tid; k < hn * PS; k += NW * 32) {
+            const int bin = k / PS, sl = k - bin * PS;
+            double s = 0.0;
+            int col = -1;
+            if (sl >= 1 && sl <= 6) col = MSEL == 0 ? sl - 1 : dense_col(MSEL, sl);
+            for (int r = 0; r < NW; ++r) {
+                const unsigned char* base = hist + (size_t)r * rbytes;
+                if (sl == 0 || sl == 7) {
+                    const unsigned c = reinterpret_cast<const unsigned*>(base + pad16((size_t)hn * NCOL * 8))[bin];
+                    if (sl == 7 || (mode_sel & 1)) s += (double)c;
+                } else if (col >= 0) {
+                    s += reinterpret_cast<const double*>(base)[(size_t)bin * NCOL + col];
+                }
+            }
+            out[k] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// variant selection
+// ------------------------------------------------------------------------------------------------
+typedef void (*pair_fn_t)(const PairParams);
+
+static size_t dense_smem(int nw, int hn, int msel)
+{
+    return (size_t)kDStages * kTJ * sizeof(Site) + kDCtrlBytes + (size_t)nw * dense_replica_bytes(hn, msel);
+}
+
+template <typename F, int MSEL>
+static pair_fn_t dense_pick_w(int nw)
+{
+    return nw == 16 ? dense_kernel<F, 16, MSEL> : (nw == 12 ? dense_kernel<F, 12, MSEL> : dense_kernel<F, 8, MSEL>);
+}
+
+template <typename F>
+static pair_fn_t dense_pick_t(int msel, int nw)
+{
+    switch (msel) {
+        case 127: return dense_pick_w<F, 127>(nw);
+        case 31:  return dense_pick_w<F, 31>(nw);
+        default:  return dense_pick_w<F, 0>(nw);
+    }
+}
+
+static pair_fn_t dense_pick(const PairConfig& c)
+{
+    return c.filter_fp64 == 2 ? dense_pick_t<__half>(c.dense_msel, c.warps) : dense_pick_t<float>(c.dense_msel, c.warps);
+}
+
+// Fills the dense fields of cfg (dense, dense_msel, warps, smem_bytes, nslot, grid) when the dense kernel can serve this
+// handle; returns false (cfg untouched) otherwise.
+bool dense_configure(int dev, int histo_n, int mode_sel, int max_smem, int sms, PairConfig* cfg, cudaError_t* err)
+{
+    *err = cudaSuccess;
+    if (cfg->filter_fp64 == 1 || cfg->shells || cfg->hist_mode != 0) return false;
+    if (mode_sel == 0 || mode_sel == 1) return false;     // g000 only: gfn_count.cu (or the ring kernel)
+    const int msel = mode_sel == 127 ? 127 : (mode_sel == 31 ? 31 : 0);
+    int nw = 0;
+    for (int cand : {12, 8}) if (!nw && dense_smem(cand, histo_n, msel) <= (size_t)max_smem) nw = cand;
+    // (16 warps leave the weighted path 128 registers per thread and spill ~100 bytes: experiments only)
+    if (const char* env = getenv("GFN_DENSE_WARPS")) {
+        const int v = atoi(env);
+        if ((v == 8 || v == 12 || v == 16) && dense_smem(v, histo_n, msel) <= (size_t)max_smem) nw = v;
+    }
+    if (!nw) return false;                            // the replicas do not fit: the ring kernel takes the handle
+    PairConfig c = *cfg;
+    c.dense = 1; c.dense_msel = msel;
+    c.warps = nw; c.drain_warps = 0; c.nrep = nw;
+    c.nslot = 8;
+    c.smem_bytes = (int)dense_smem(nw, histo_n, msel);
+    c.blocks_per_sm = 1; c.grid = sms;
+    pair_fn_t fn = dense_pick(c);
+    if ((*err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes)) != cudaSuccess) return false;
+    *cfg = c;
+    return true;
+}
+
+cudaError_t dense_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s)
+{
+    pair_fn_t fn = dense_pick(cfg);
+    fn<<<cfg.grid, cfg.warps * 32, cfg.smem_bytes, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace gfn

@@ -21,46 +21,19 @@
 //   ordered with match.any, so no atomics are needed and the result is deterministic.
 // Kernel K2 (finalize_kernel): block partials -> device accumulators in a fixed order.
 // Kernel K0 (prep_kernel): user layout (n,3) fp64 -> Rec64 + float4 records, dipole norms, max |x|.
-#include "gfn_kernels.cuh"
-#include "../../include/gfn.h"
+#include "gfn_device.cuh"
 
-#include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
-#include <type_traits>
 
 namespace gfn {
-
-// ------------------------------------------------------------------------------------------------
-// PTX helpers (TMA 1-D bulk copy + mbarrier)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // K0: prep
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* __restrict__ dip, long long stride_dip,
-            Site* __restrict__ site, float* __restrict__ maxabs, int n, int n_pad, const double* __restrict__ box, int half_filter,
+            Site* __restrict__ site, float* __restrict__ maxabs, unsigned* __restrict__ nflag, int n, int n_pad, const double* __restrict__ box, int half_filter,
             unsigned long long* __restrict__ counters)
 {
     const int f = blockIdx.y;
@@ -68,6 +41,7 @@ prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* 
     if (s >= n_pad) return;
     Site r;
     float m = 0.f;
+    bool odd_norm = false;      // a dipole norm the reciprocal form of the cosines cannot take (zero: quirk Q5; outside [2^-300, 2^300])
     if (s < n) {
         const double* c = xyz + (long long)f * stride_xyz + 3ll * s;
         r.x = c[0]; r.y = c[1]; r.z = c[2];
@@ -76,6 +50,7 @@ prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* 
             r.px = d[0]; r.py = d[1]; r.pz = d[2];
             // gfunction.pyx:125/:139  sqrt(px*px+py*py+pz*pz), left-to-right, un-fused
             r.norm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(r.px, r.px), __dmul_rn(r.py, r.py)), __dmul_rn(r.pz, r.pz)));
+            odd_norm = !mid_range(r.norm);
         } else {
             r.px = r.py = r.pz = 0.0; r.norm = 0.0;
         }
@@ -106,10 +81,11 @@ prep_kernel(const double* __restrict__ xyz, long long stride_xyz, const double* 
     site[(long long)f * n_pad + s] = r;
     unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like their bits
     if ((threadIdx.x & 31) == 0 && mb) atomicMax(reinterpret_cast<unsigned*>(maxabs) + f, mb);
+    if (__any_sync(0xffffffffu, odd_norm) && (threadIdx.x & 31) == 0) atomicOr(nflag + f, 1u);
 }
 
 cudaError_t prep_launch(const double* xyz, long long stride_xyz, const double* dip, long long stride_dip,
-                        Site* site, float* maxabs, int n, int n_pad, int nframes, const double* box, int half_filter,
+                        Site* site, float* maxabs, unsigned* nflag, int n, int n_pad, int nframes, const double* box, int half_filter,
                         unsigned long long* counters, cudaStream_t s)
 {
     for (int f0 = 0; f0 < nframes; f0 += 65535) {
@@ -117,7 +93,7 @@ cudaError_t prep_launch(const double* xyz, long long stride_xyz, const double* d
         dim3 grid((n_pad + 255) / 256, nf);
         prep_kernel<<<grid, 256, 0, s>>>(xyz + (long long)f0 * stride_xyz, stride_xyz,
                                          dip ? dip + (long long)f0 * stride_dip : nullptr, stride_dip,
-                                         site + (long long)f0 * n_pad, maxabs + f0, n, n_pad, box + 6ll * f0, half_filter, counters);
+                                         site + (long long)f0 * n_pad, maxabs + f0, nflag + f0, n, n_pad, box + 6ll * f0, half_filter, counters);
     }
     return cudaGetLastError();
 }
@@ -125,158 +101,6 @@ cudaError_t prep_launch(const double* xyz, long long stride_xyz, const double* d
 // ------------------------------------------------------------------------------------------------
 // K1: pair kernel
 // ------------------------------------------------------------------------------------------------
-template <typename F> struct FOps;
-template <> struct FOps<float> {
-    static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
-    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
-    static __device__ __forceinline__ unsigned signword(float a) { return __float_as_uint(a); }
-    static constexpr double kU = 5.9604644775390625e-08;   // 2^-24
-    static __device__ __forceinline__ float up(double t) { return __uint_as_float(__float_as_uint(__double2float_ru(t)) + 1u); }
-};
-template <> struct FOps<double> {
-    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
-    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
-    static __device__ __forceinline__ unsigned signword(double a) { return (unsigned)__double2hiint(a); }
-    static constexpr double kU = 1.1102230246251565e-16;   // 2^-53
-    static __device__ __forceinline__ double up(double t) { return t * (1.0 + 1e-15); }
-};
-
-template <> struct FOps<__half> {
-    static constexpr double kU = 4.8828125e-04;            // 2^-11
-};
-
-// Guard-banded squared cut-off of the pre-filter (see DESIGN.md "filter guard band" for the proof).
-//   M        bound on |coordinate| of both selections in this frame, halfmax = max half box length
-//   e_w      bound on the error of one filtered component  w  against the exact minimum-image component
-//   accept   <=  fma-chain(w) - Tg < 0   for every pair with  d2_ref <= hmax^2 * (1 + 1e-12)
-template <typename F>
-__device__ __forceinline__ F guard_threshold(double hmax, double M, double halfmax)
-{
-    const double u = FOps<F>::kU;
-    const double ew = u * (10.0 * M + 7.0 * halfmax);
-    const double T = (hmax * hmax * (1.0 + 1e-12) + 3.5 * ew * hmax + 3.0 * ew * ew) * (1.0 + 16.0 * u);
-    return FOps<F>::up(T);
-}
-
-struct Box { double Lx, Ly, Lz, hx, hy, hz; };
-
-#define DMUL(a, b) __dmul_rn((a), (b))
-#define DADD(a, b) __dadd_rn((a), (b))
-#define DSUB(a, b) __dsub_rn((a), (b))
-#define DDIV(a, b) __ddiv_rn((a), (b))
-#define DOT3(ax, ay, az, bx, by, bz) DADD(DADD(DMUL(ax, bx), DMUL(ay, by)), DMUL(az, bz))
-
-// Adds one value into the global accumulators, reproducing where the reference's flat index
-// ix_mode + i*histo_n + pos lands (quirk Q3: pos may reach past the row).
-__device__ __forceinline__ void global_add(const PairParams& P, int hist_mode, int k, int i, int pos, double v)
-{
-    const long long hn = P.histo_n;
-    if (hist_mode == 2) {   // per-particle: literal reference index, bounds-checked
-        const long long ix = (long long)k * P.n1 * hn + (long long)i * hn + pos;
-        if (ix < 7ll * P.n1 * hn) atomicAdd(P.gpp + ix, v);
-    }
-    // compact [mode][bin]: the sum over rows of wherever the reference wrote
-    const long long flat = (long long)i * hn + pos;
-    const int kk = flat >= (long long)P.n1 * hn ? k + 1 : k;
-    const int bin = pos >= hn ? (int)(pos - hn) : pos;
-    if (kk < 7 && bin < hn) atomicAdd(P.gacc + (long long)kk * hn + bin, v);
-}
-
-// reference minimum image, gfunction.pyx:145-147:  if fabs(d) > half: d = d - sign(d)*L
-// (|d| > half > 0 implies d != 0, so sign(d)*L == copysign(L, d) exactly; one rounding in the subtraction)
-__device__ __forceinline__ double min_image(double d, double L, double half)
-{
-    const double t = DSUB(d, copysign(L, d));
-    return fabs(d) > half ? t : d;
-}
-
-// ---- straight-line fp64 division / square root ---------------------------------------------------
-// The CUDA built-ins (__ddiv_rn, __dsqrt_rn) are a serial block each: a seed from the MUFU unit, a
-// Newton chain of dependent DFMAs and a branch to a subroutine for out-of-range operands.  Those
-// branches stop ptxas from interleaving the chains of several survivors, and the exact path then runs
-// at ~0.1 instructions per cycle.  The two functions below are the built-ins' own in-range sequences
-// (read off the SASS nvcc 12.9 emits for sm_100a) without the branch; they return the correctly rounded
-// IEEE result for operands inside the ranges checked by div_in_range / sqrt_in_range (verified against the
-// built-ins on 2^32 random operands by gfn_selftest_arith, tests/test_gpu_parity.py).  A warp whose
-// operands are not all in range takes the built-in path instead.
-__device__ __forceinline__ double rcp64h(double b) { double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b)); return y; }
-__device__ __forceinline__ double rsq64h(double x) { double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
-
-__device__ __forceinline__ double div_inrange(double a, double b)
-{
-    double y = rcp64h(b);
-    double e = fma(-b, y, 1.0);
-    e = fma(e, e, e);
-    y = fma(y, e, y);
-    e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
-    const double q = __dmul_rn(a, y);
-    const double r = fma(-b, q, a);
-    return fma(y, r, q);
-}
-
-__device__ __forceinline__ double sqrt_inrange(double x)
-{
-    double y = rsq64h(x);
-    const double t = __dmul_rn(y, y);
-    const double e = fma(x, -t, 1.0);
-    const double p = fma(e, 0.375, 0.5);
-    const double u = __dmul_rn(y, e);
-    y = fma(p, u, y);
-    const double g = __dmul_rn(x, y);
-    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));   // y / 2
-    const double d = fma(g, -g, x);
-    return fma(d, h, g);
-}
-
-// same sequence, also handing back the refined reciprocal root y ~ 1/sqrt(x) (relative error ~2^-52): 1/dist for
-// the orientation cosines comes for free with the distance
-__device__ __forceinline__ double sqrt_rsqrt_inrange(double x, double& rinv)
-{
-    double y = rsq64h(x);
-    const double t = __dmul_rn(y, y);
-    const double e = fma(x, -t, 1.0);
-    const double p = fma(e, 0.375, 0.5);
-    const double u = __dmul_rn(y, e);
-    y = fma(p, u, y);
-    rinv = y;
-    const double g = __dmul_rn(x, y);
-    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));   // y / 2
-    const double d = fma(g, -g, x);
-    return fma(d, h, g);
-}
-
-// |x| in [2^-300, 2^300]: far inside the range where the sequences above are exact (no intermediate can
-// overflow, underflow or lose bits to subnormals)
-__device__ __forceinline__ bool mid_range(double x)
-{
-    const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
-    return ex - 723u <= 600u;       // biased exponent in [723, 1323]
-}
-
-// Work decomposition: all surround-tile visits of a launch form one flat sequence ordered by
-// (frame, core tile, surround tile); CTA c owns the contiguous slice [T*c/grid, T*(c+1)/grid), so every
-// CTA gets the same number of tiles (+-1) whatever the triangle looks like, and the assignment is static
-// (deterministic summation).  A "run" is the part of a slice that stays inside one (frame, core tile).
-struct Item { int f, i0, jt_begin, ntiles; };
-
-__device__ __forceinline__ Item decode_run(const PairParams& P, long long cur, long long end, int TI)
-{
-    Item it;
-    it.f = (int)(cur / P.tiles_per_frame);
-    const int r = (int)(cur - (long long)it.f * P.tiles_per_frame);
-    int lo = 0, hi = P.n_itiles;      // core tile ti with tile_start[ti] <= r < tile_start[ti+1]
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.tile_start[mid] <= r) lo = mid; else hi = mid; }
-    const int off = r - P.tile_start[lo];
-    const int row = P.tile_start[lo + 1] - P.tile_start[lo];
-    it.i0 = lo * TI;
-    const int jt_first = P.tri ? (it.i0 / kTJ) : 0;
-    it.jt_begin = jt_first + off;
-    const long long left = end - cur;
-    it.ntiles = (long long)(row - off) < left ? row - off : (int)left;
-    return it;
-}
-
 // Shared-memory control block of one CTA (after the data arrays).
 struct Ctrl {
     uint64_t full[kStages];      // TMA landed in stage s
@@ -1102,11 +926,12 @@ static pair_fn_t pick(const PairConfig& c) { return pair_kernel<__half, 8, 8, tr
 static pair_fn_t pick(const PairConfig& c) { return c.filter_fp64 == 1 ? pick_fn<double>(c) : (c.filter_fp64 == 2 ? pick_fn<__half>(c) : pick_fn<float>(c)); }
 #endif
 
-int tile_i(const PairConfig& cfg) { return (cfg.warps - cfg.drain_warps) * 32 * kIPT; }
+int tile_i(const PairConfig& cfg) { return cfg.dense == 2 ? 128 : (cfg.dense ? 64 : (cfg.warps - cfg.drain_warps) * 32 * kIPT); }
 
-cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, int shells, PairConfig* cfg)
+cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, int shells, double in_range_hint, const HandleGeom& geom, PairConfig* cfg)
 {
     cfg->shells = shells ? 1 : 0;
+    cfg->dense = 0; cfg->dense_msel = 0;
     static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block does not fit");
     cudaError_t e;
     int max_smem = 0, sms = 0;
@@ -1151,11 +976,22 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
     if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes)) != cudaSuccess) return e;
     cfg->blocks_per_sm = 1;
     cfg->grid = sms;
+    // dense neighbourhoods: the symmetric kernel, when it supports the handle
+    const bool want_dense = (flags & GFN_FLAG_DENSE) || (!(flags & GFN_FLAG_NO_DENSE) && in_range_hint > kDenseShare);
+    if (want_dense) {
+        cudaError_t de = cudaSuccess;
+        // g000 only: the count kernel (fp32 classification, fp64 for the ambiguous pairs), else the dense walk kernel
+        if (count_configure(dev, histo_n, mode_sel, geom.invdx, geom.hmax, geom.box_max, max_smem, sms, cfg, &de)) return cudaSuccess;
+        if (de != cudaSuccess) return de;
+        if (!dense_configure(dev, histo_n, mode_sel, max_smem, sms, cfg, &de) && de != cudaSuccess) return de;
+    }
     return cudaSuccess;
 }
 
 cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s)
 {
+    if (cfg.dense == 2) return count_launch(cfg, p, s);
+    if (cfg.dense) return dense_launch(cfg, p, s);
     pair_fn_t fn = pick(cfg);
     long long tiles = (long long)p.tiles_per_frame * p.nframes;
     int grid = cfg.grid;

@@ -31,11 +31,13 @@ constexpr int kPadTo   = 1024;   // selections are padded to a multiple of this 
 constexpr int kDrainILP = GFN_DRAIN_ILP;     // survivors evaluated per drain lane per batch
 constexpr int kRingCap = 2048;   // survivor ring entries (16 bit) per filter warp: one push (<= 32*32) always fits behind < 64 unread ones
 constexpr int kCtrlBytes = 640;  // shared-memory control block
-constexpr int kCounters = 8;     // 0 overflow, 1 error flags (bit 0 zero-norm dipole, bit 1 fp16 filter range), 2 survivors, 3 in-range pairs
+constexpr int kCounters = 8;     // 0 overflow, 1 error flags (bit 0 zero-norm dipole, bit 1 fp16 filter range), 2 survivors, 3 in-range pairs,
+                                 // 4 count kernel self-check mismatches (GFN_DEBUG=8), 5 count kernel: pairs evaluated in fp64
 
 struct PairParams {
     const Site* siteA;  const float* maxA;   // selection 1 (core)
     const Site* siteB;  const float* maxB;   // selection 2 (surround)
+    const unsigned* nflagA; const unsigned* nflagB;   // [nframes] != 0: a dipole norm of the frame is zero or outside [2^-300, 2^300]
     const double* box;              // [nframes][6] lengths, half lengths
     long long strideA, strideB;     // padded sites per frame
     int n1, n2, nframes, tri;       // tri: n1 == n2 (reference keys the triangle on sizes, quirk Q1)
@@ -61,6 +63,10 @@ struct PairParams {
     int apr1, apr2;                 // sites per molecule: matrix row = i / apr1, column = j / apr2 (:582-583, :601)
     int map_ld;                     // row stride of the matrix as the reference indexes it (:602 uses nsurround)
     int excl_self;                  // skip pairs of the same molecule (calcHistoVoronoiNonSelf :700)
+    // dense kernel, g000-only handles: the bin of a pair from d^2 without a square root (gfn_dense.cu)
+    const double* bin_thr;          // [histo_n + 4]  T[k] = min { t : sqrt(t) >= hmin and floor((sqrt(t) - hmin) * invdx) >= k }
+    double acc_lo, acc_hi;          // a pair passes gfunction.pyx:149  <=>  acc_lo <= d^2 <= acc_hi
+    int pos_max;                    // bin of d^2 = acc_hi (histo_n when dist == hmax lands on the edge, quirk Q3)
 };
 
 struct PairConfig {
@@ -75,16 +81,26 @@ struct PairConfig {
     int blocks_per_sm;
     int grid;
     int smem_bytes;
+    int dense;         // 1: the symmetric dense-neighbourhood kernel (gfn_dense.cu) serves this handle, 2: the g000 count kernel (gfn_count.cu)
+    int dense_msel;    // its compile-time mode set (1, 31, 127) or 0 = run-time modes
 };
 
 // Chooses kernel variant, grid and shared-memory size for a histogram of histo_n bins; sets the
 // function attributes.  Returns cudaSuccess or the failing error.
-cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, int shells, PairConfig* cfg);
+//   in_range_hint: expected share of pairs inside histo_max, (4/3) pi hmax^3 / V of the handle's box: above kDenseShare
+//   the dense kernel is chosen when it supports the handle (GFN_FLAG_DENSE / GFN_FLAG_NO_DENSE override the hint).
+constexpr double kDenseShare = 0.10;
+struct HandleGeom { double hmax, invdx, box_max; };    // what the kernel choice looks at besides the in-range share
+cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, int shells, double in_range_hint, const HandleGeom& geom, PairConfig* cfg);
+bool count_configure(int dev, int histo_n, int mode_sel, double invdx, double hmax, double box_max, int max_smem, int sms, PairConfig* cfg, cudaError_t* err);
+cudaError_t count_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
+bool dense_configure(int dev, int histo_n, int mode_sel, int max_smem, int sms, PairConfig* cfg, cudaError_t* err);
+cudaError_t dense_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
 cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
 
 // Converts nframes frames of one selection into Site records and the per-frame max |coordinate|.
 cudaError_t prep_launch(const double* xyz, long long stride_xyz, const double* dip, long long stride_dip,
-                        Site* site, float* maxabs, int n, int n_pad, int nframes, const double* box, int half_filter,
+                        Site* site, float* maxabs, unsigned* nflag, int n, int n_pad, int nframes, const double* box, int half_filter,
                         unsigned long long* counters, cudaStream_t s);
 
 // partials[grid][histo_n*nslot] -> gacc, blocks summed in ascending order (deterministic).

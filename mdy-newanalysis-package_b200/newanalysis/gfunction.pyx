@@ -48,6 +48,9 @@ cdef extern from "gfn.h":
         int batch_frames
         int ndev
         int hist_replicas
+        int dense
+        double exact_evals
+        double selfcheck_bad
     int GFN_OK, GFN_EINVAL, GFN_ECUDA, GFN_ENCCL, GFN_EZERODIV, GFN_ENOMEM, GFN_ENODEV
     unsigned GFN_FLAG_PER_PARTICLE, GFN_FLAG_FILTER_FP64, GFN_FLAG_DISCARD_OVERFLOW, GFN_FLAG_HIST_GLOBAL
     int gfn_device_count() nogil
@@ -118,7 +121,7 @@ cdef extern from "gfn.h":
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
 
 
-_FLAG_NAMES = {"exact_div": 64, "no_triangle": 32, "fp16": 16, "filter_fp16": 16, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
+_FLAG_NAMES = {"dense": 128, "nodense": 256, "exact_div": 64, "no_triangle": 32, "fp16": 16, "filter_fp16": 16, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
 
 
 def _parse_flags(spec):
@@ -656,7 +659,8 @@ cdef class _Backend:
                     h2d_bytes=s.h2d_bytes, overflow=s.overflow, filter=("fp32", "fp64", "fp16x2")[s.filter_fp64],
                     hist_mode=("smem_warp_replicas", "global_atomics", "per_particle")[s.hist_mode],
                     warps_per_block=s.warps_per_block, blocks_per_sm=s.blocks_per_sm, grid=s.grid,
-                    smem_bytes=s.smem_bytes, batch_frames=s.batch_frames, ndev=s.ndev, hist_replicas=s.hist_replicas)
+                    smem_bytes=s.smem_bytes, batch_frames=s.batch_frames, ndev=s.ndev, hist_replicas=s.hist_replicas,
+                    kernel=("ring", "dense", "count")[s.dense], exact_evals=s.exact_evals, selfcheck_bad=s.selfcheck_bad)
 
 
 _ts_cache = {}

@@ -14,7 +14,8 @@ import newanalysis.gfunction as G          # noqa: E402
 from gfn_b200 import synth                 # noqa: E402
 
 
-def run(name, n1, n2, L, modes, hmax, nframes, reps, self_pairs, flags=""):
+def run(name, n1, n2, L, modes, hmax, nframes, reps, self_pairs, flags="", env=None):
+    os.environ.update(env or {})
     rng = np.random.default_rng(5)
     c1 = rng.random((nframes, n1, 3)) * L; d1 = rng.standard_normal((nframes, n1, 3))
     r = G.RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags)
@@ -36,13 +37,24 @@ def run(name, n1, n2, L, modes, hmax, nframes, reps, self_pairs, flags=""):
     f_in = (st["in_range"] - st0["in_range"]) / evals
     out = dict(config=name, n1=n1, n2=n2, modes=modes, frames=nframes * reps, gpair_per_s=evals / ms / 1e6,
                in_range_fraction=f_in, kernel_ms=st["kernel_ms"] - st0["kernel_ms"], wall_ms=ms, hist=st["hist_mode"],
-               warps=st["warps_per_block"], replicas=st["hist_replicas"], batch_frames=st["batch_frames"], filter=st["filter"])
+               warps=st["warps_per_block"], replicas=st["hist_replicas"], batch_frames=st["batch_frames"], filter=st["filter"],
+               kernel=st["kernel"], flags=flags, survivor_fraction=(st["survivors"] - st0["survivors"]) / evals,
+               exact_fraction=(st["exact_evals"] - st0["exact_evals"]) / evals)
+    for k in (env or {}):
+        os.environ.pop(k, None)
     print(json.dumps(out), flush=True)
 
 
 CONFIGS = {
-    "cfg1": lambda: run("cfg1 SPC/E 1000 O-O g000", 1000, 1000, 31.04, ["000"], 15.0, 100, 20, True),
-    "cfg2": lambda: run("cfg2 [C2mim][OTf] 1000x1000 5 modes 600 bins", 1000, 1000, 67.7, ["000", "110", "101", "011", "220"], 30.0, 500, 4, False),
+    "cfg1": lambda: run("cfg1 SPC/E 1000 O-O g000", 1000, 1000, 31.04, ["000"], 15.0, 1398, 3, True),
+    "cfg1_small_batches": lambda: run("cfg1, 100 frames per call", 1000, 1000, 31.04, ["000"], 15.0, 100, 20, True),
+    "cfg2": lambda: run("cfg2 [C2mim][OTf] 1000x1000 5 modes 600 bins", 1000, 1000, 67.7, ["000", "110", "101", "011", "220"], 30.0, 699, 3, False),
+    "cfg3_g000_count": lambda: run("cfg3 shape, g000 only (count kernel forced)", 32768, 32768, 99.33, ["000"], 15.0, 15, 2, True, "dense"),
+    "cfg1_ring": lambda: run("cfg1 SPC/E 1000 O-O g000 (ring kernel)", 1000, 1000, 31.04, ["000"], 15.0, 100, 20, True, "nodense"),
+    "cfg2_ring": lambda: run("cfg2 (ring kernel)", 1000, 1000, 67.7, ["000", "110", "101", "011", "220"], 30.0, 500, 4, False, "nodense"),
+    "cfg1_all": lambda: run("cfg1 shape, all modes", 1000, 1000, 31.04, ["all"], 15.0, 100, 20, True),
+    "cfg1_all_ring": lambda: run("cfg1 shape, all modes (ring kernel)", 1000, 1000, 31.04, ["all"], 15.0, 100, 20, True, "nodense"),
+    "cfg3_dense": lambda: run("cfg3 water 32768 all modes (dense kernel forced)", 32768, 32768, 99.33, ["all"], 15.0, 15, 2, True, "dense"),
     "cfg3": lambda: run("cfg3 water 32768 all modes", 32768, 32768, 99.33, ["all"], 15.0, 15, 4, True),
     "cfg3_g000": lambda: run("cfg3 shape, g000 only", 32768, 32768, 99.33, ["000"], 15.0, 15, 4, True),
     "cfg4a": lambda: run("cfg4 solute COM 1024 x solvent 81920 all", 1024, 81920, 143.6, ["all"], 15.0, 16, 4, False),

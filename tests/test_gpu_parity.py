@@ -17,7 +17,10 @@ import oracle as O
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-12
-VARIANTS = ["", "fp32", "fp64", "fp16", "fp32,global", "fp64,global", "fp16,global", "per_particle"]
+# "" / fp16 / fp32: the library picks the kernel itself - the dense-neighbourhood kernel for most of the small golden boxes
+# (expected in-range share > 10 %), the warp-specialised ring kernel otherwise; "dense" / "nodense" force one of them
+VARIANTS = ["", "fp32", "fp64", "fp16", "fp32,global", "fp64,global", "fp16,global", "per_particle",
+            "fp16,dense", "fp32,dense", "fp16,nodense", "fp32,nodense"]
 
 
 def RDF(*a, **k):
@@ -67,6 +70,28 @@ def test_golden(golden_dir, name, flags, tmp_path):
         a = np.loadtxt(str(tmp_path / ("g_g%s.dat" % mode)))
         b = np.array([[float(v) for v in ln.split()] for ln in text.strip().splitlines()])
         assert a.shape == b.shape and np.allclose(a, b, rtol=0, atol=2e-5)
+
+
+def test_kernel_choice_follows_the_expected_in_range_share():
+    """Dense boxes (BASELINE configs[0] / [1] shapes) get the dense kernel, sparse ones (cfg3 density) the ring kernel;
+    flags override; handles the dense kernel does not support fall back to the ring kernel."""
+    mk = lambda L, hmax, modes, n=256, **kw: RDF(modes, 0.0, hmax, 0.05, n, n, n, n, L, **kw)      # noqa: E731
+    assert mk(31.04, 15.0, ["000"]).stats()["kernel"] == "count"            # g000 only: fp32 classification + exact pass
+    assert mk(31.04, 15.0, ["000"], gfn_flags="fp16").stats()["kernel"] == "count"
+    assert mk(31.04, 15.0, ["000"], gfn_flags="fp64").stats()["kernel"] == "ring"
+    assert mk(99.33, 15.0, ["000"]).stats()["kernel"] == "ring"
+    assert mk(67.7, 30.0, ["000", "110", "101", "011", "220"]).stats()["kernel"] == "dense"
+    assert mk(99.33, 15.0, ["all"]).stats()["kernel"] == "ring"
+    assert mk(99.33, 15.0, ["all"], gfn_flags="dense").stats()["kernel"] == "dense"
+    assert mk(31.04, 15.0, ["all"], gfn_flags="nodense").stats()["kernel"] == "ring"
+    assert mk(31.04, 15.0, ["all"], gfn_flags="fp64").stats()["kernel"] == "ring"
+    assert mk(31.04, 15.0, ["all"], gfn_flags="global").stats()["kernel"] == "ring"
+    st = mk(31.04, 15.0, ["000"]).stats()
+    assert st["warps_per_block"] == 16 and st["hist_replicas"] == 16
+    st = mk(31.04, 15.0, ["all"]).stats()
+    assert st["warps_per_block"] == 12 and st["hist_replicas"] == 12
+    st = RDF(["000", "110", "101", "011", "220"], 0.0, 30.0, 0.05, 256, 256, 256, 256, 67.7).stats()     # 600 bins, 4 weighted columns
+    assert st["kernel"] == "dense" and st["warps_per_block"] == 8
 
 
 def test_micro_cases(golden_dir):
@@ -212,6 +237,84 @@ def test_threshold_edges_exact():
         assert hp[:300].sum() > 50
 
 
+@pytest.mark.parametrize("hmin,hmax,dr,L", [(0.0, 15.0, 0.05, 40.0), (2.0, 12.0, 0.1, 32.0), (0.0, 30.0, 0.05, 67.7), (0.0, 15.02, 0.05, 40.0)])
+@pytest.mark.parametrize("filt,kernel", [("fp16", "count"), ("fp32", "count")])
+def test_dense_threshold_table_at_every_bin_edge(hmin, hmax, dr, L, filt, kernel):
+    """The exact pass of the g000 count kernel takes the bin from a table of exact d^2 thresholds instead of the square root:
+    pairs placed within +-4 ulp of EVERY bin edge (and of histo_min, histo_max and the first-bin rule) along all three
+    axes, straight and across the periodic boundary, must land in the reference's bins - also the quirk-Q3 spill count.
+    (For the count kernel all of these pairs are ambiguous in fp32 and go through its exact pass.)"""
+    nb = int(np.int32((hmax - hmin) / dr + 0.5))
+    edges = [np.float64(np.float32(hmin)) + k * np.round(dr, 5) for k in range(nb + 2)] + [1.0 / (1.0 / np.round(dr, 5)), float(np.float32(hmax))]
+    rs = []
+    for e in edges:
+        for k in range(-4, 5):
+            r = e
+            for _ in range(abs(k)):
+                r = np.nextafter(r, np.inf if k > 0 else -np.inf)
+            if 0 < r < L / 2 * 0.99:
+                rs.append(r)
+    rs = np.array(rs)
+    rng = np.random.default_rng(12)
+    origin = np.array([[L - 0.3, 0.2, L / 2]])
+    pts = np.zeros((len(rs), 3))
+    axis = rng.integers(0, 3, len(rs)); sign = rng.choice([-1.0, 1.0], len(rs))
+    pts[np.arange(len(rs)), axis] = sign * rs
+    c2 = np.ascontiguousarray((origin + pts) % L)
+    g = RDF(["000"], hmin, hmax, dr, 1, len(c2), 1, len(c2), L, gfn_flags=filt + ",dense")
+    assert g.stats()["kernel"] == kernel
+    o = O.OracleRDF(["000"], hmin, hmax, dr, 1, len(c2), 1, len(c2), L)
+    o.histogram = np.zeros(2 * nb * 7)               # spare row so the Q3 spill stays inspectable
+    for _ in range(2):
+        g.calcFrame(origin, c2); o.calcFrame(origin, c2)
+    got = g.raw_histogram()
+    assert np.array_equal(got[:nb], o.histogram[:nb]) and got[:nb].sum() > 100
+    assert g.overflow == o.histogram[nb:2 * nb].sum()                     # pairs at exactly histo_max (pos == histo_n)
+    assert np.array_equal(got[nb:2 * nb], o.histogram[nb:2 * nb])         # ... land in the next mode's row like the reference's
+
+
+@pytest.mark.parametrize("case", ["self", "self_hmin", "rect", "rect_unwrapped", "self_far", "npt_fine"])
+def test_count_kernel_selfcheck_and_oracle(case, monkeypatch):
+    """g000 count kernel (gfn_count.cu): GFN_DEBUG=8 makes it evaluate EVERY pair in fp64 as well and count the pairs whose
+    fp32 decision (bin / rejection) differs from the exact one - there must be none - and the counts equal the oracle's.
+    Cases: triangular and rectangular frames, histo_min > 0, coordinates far outside the box (large EPS: more pairs take
+    the exact pass, none may be wrong), per-frame boxes with fine bins."""
+    monkeypatch.setenv("GFN_DEBUG", "8")
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    hmin, hmax, dr, L, nf = 0.0, 15.0, 0.05, 31.04, 3
+    n1 = n2 = 1000
+    shift = 0.0
+    if case == "self_hmin":
+        hmin, hmax, dr = 2.0, 14.0, 0.1
+    if case.startswith("rect"):
+        n1, n2 = 300, 1500
+    if case == "rect_unwrapped":
+        shift = 40.0 * L
+    if case == "self_far":
+        shift = 3000.0 * L
+    if case == "npt_fine":
+        dr, nf = 0.01, 4
+    g = RDF(["000"], hmin, hmax, dr, n1, n2, n1, n2, L, gfn_flags="dense")
+    assert g.stats()["kernel"] == "count"
+    o = O.OracleRDF(["000"], hmin, hmax, dr, n1, n2, n1, n2, L)
+    for f in range(nf):
+        if case == "npt_fine":
+            b = L * (1.0 + 0.01 * rng.standard_normal(3))
+            g.update_box(*b); o.update_box(*b)
+        c1 = rng.random((n1, 3)) * L + shift * rng.integers(-1, 2, (n1, 3))
+        c2 = c1 if n1 == n2 else rng.random((n2, 3)) * L + shift * rng.integers(-1, 2, (n2, 3))
+        g.calcFrame(c1, c2); o.calcFrame(c1, c2)
+    hn = int(g.histo_n)
+    got, ref = g.raw_histogram(), o.raw_sum()
+    st = g.stats()
+    assert st["selfcheck_bad"] == 0
+    assert np.array_equal(got[:hn], ref[:hn]) and ref[:hn].sum() > 1000
+    assert st["in_range"] * (2 if n1 == n2 else 1) == ref[:hn].sum() + (2 if n1 == n2 else 1) * st["overflow"]
+    if shift == 0.0:
+        assert st["exact_evals"] < (0.01 if dr >= 0.05 else 0.06) * st["in_range"]      # the fp64 pass stays a small share
+
+
 def test_unwrapped_and_large_coordinates():
     """Coordinates far outside the box (single-shift minimum image, quirk Q8) and a large offset:
     the guard band scales with max|x|, results must still match the oracle exactly."""
@@ -331,7 +434,11 @@ def test_device_resident_frames_equal_host_path():
     b = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
     dc, dd = to_device(c), to_device(d)
     b.calcFramesDevice(nf, dc, dc, dd, dd)
-    assert np.array_equal(a.raw_histogram(), b.raw_histogram())
+    ha, hb = a.raw_histogram(), b.raw_histogram()
+    # same frames, same kernel: counts equal; the dense kernel (this box is dense) hands work units to warps dynamically,
+    # so the order of the fp64 additions - not the set of addends - may differ between two runs
+    assert np.array_equal(ha[:300], hb[:300]) and a.stats()["kernel"] == b.stats()["kernel"]
+    assert_hist_close(hb, ha, 300)
     # legacy pre_*_gpu kwargs of calcFrame: one shared upload, two RDF objects (cfg4 pattern)
     e = RDF(["000"], 0.0, 15.0, 0.05, n, n, n, n, L); f = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
     pc, pd = to_device(c[0]), to_device(d[0])
@@ -562,8 +669,11 @@ def test_atom_frames_self_equal_reference_chain(flags):
     assert a.oneistwo is True and a.ctr == nf
     assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 0
     assert_hist_close(got, ref, 300)
-    # the device-made centres of mass / dipoles are bit-identical to the host-made ones, so the whole histogram is
-    assert np.array_equal(got, host.raw_histogram())
+    # the device-made centres of mass / dipoles are bit-identical to the host-made ones: counts are equal, and the fp64
+    # sums hold the same addends (their order follows the launch's frame batch, which differs between the two feeds)
+    hh = host.raw_histogram()
+    assert np.array_equal(got[:300], hh[:300])
+    assert_hist_close(got, hh, 300)
     st = a.stats()
     assert st["h2d_bytes"] == nf * (3 * nres * 3 * 4 + 48)      # float32 atoms once per frame + the box
 
@@ -710,7 +820,9 @@ def test_trajectory_self_npt_equals_atom_frames_and_oracle(tmp_path, big_endian,
         com, dip = _reference_chain(xyz[sel], masses, charges, apr, rfa)
         o.calcFrame(com, com, dip, dip)
     got, ref = a.raw_histogram(), o.raw_sum()
-    assert np.array_equal(got, b.raw_histogram())
+    hb = b.raw_histogram()
+    assert np.array_equal(got[:300], hb[:300])          # same frames: equal counts, sums in batch-dependent order
+    assert_hist_close(got, hb, 300)
     assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 0
     assert_hist_close(got, ref, 300)
     assert a.ctr == len(frames) and a.oneistwo is True
