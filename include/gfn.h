@@ -130,6 +130,20 @@ int gfn_enqueue_frames(gfn_t *h, int nframes,
                        const double *d1, long long stride_d1, const double *d2, long long stride_d2,
                        const double *box_dims);
 
+/* The same frames WITHOUT the staging copy: every array must be page-locked host memory (gfn_host_alloc below, or
+ * cudaHostRegister'ed by the caller; anything else is GFN_EINVAL) and must stay unchanged until the next gfn_sync /
+ * gfn_readout returns - the DMA engine reads the caller's arrays directly (one strided copy per array and batch), so the
+ * host does no per-frame work at all.  Meant for trajectory decoders that write into page-locked buffers and for one
+ * process feeding several devices.  (The reference has no counterpart: calcFrame, gfunction.pyx:385-464, is synchronous.) */
+int gfn_enqueue_frames_pinned(gfn_t *h, int nframes,
+                              const double *c1, long long stride_c1, const double *c2, long long stride_c2,
+                              const double *d1, long long stride_d1, const double *d2, long long stride_d2,
+                              const double *box_dims);
+
+/* Page-locked host memory for gfn_enqueue_frames_pinned (cudaHostAlloc, portable across devices). */
+int gfn_host_alloc(void **out, unsigned long long bytes);
+int gfn_host_free(void *p);
+
 /* Device-resident frames (inputs already in HBM on one of h's devices; the legacy pre_*_gpu kwargs of
  * calcFrame, gfunction.pyx:390-391,431-453, map here).  Pointers are DEVICE pointers with the same
  * layout as gfn_enqueue_frames, all on the same device; the frames are processed on the device that

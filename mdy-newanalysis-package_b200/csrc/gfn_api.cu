@@ -91,6 +91,14 @@ constexpr int kRing = 3;
 constexpr int kXRing = 4;
 constexpr int kStatusSlots = 2;   // behind the 8*histo_n accumulators: [0] ranks/devices that hit the fp16 range error, [1] ... a zero-norm dipole
 
+// one source of frames for the ring: host selections (coordinates / dipoles [/ shell matrix]) or float32 atom positions
+struct FrameSrc {
+    const double* c1 = nullptr; const double* c2 = nullptr; const double* d1 = nullptr; const double* d2 = nullptr;
+    long long s_c1 = 0, s_c2 = 0, s_d1 = 0, s_d2 = 0;
+    const int* shell_map = nullptr; long long s_map = 0;
+    const float* a1 = nullptr; const float* a2 = nullptr; long long s_a1 = 0, s_a2 = 0;
+};
+
 struct Batch {
     double* h_pin = nullptr;      // pinned staging: [frame][c1 | d1 | c2 | d2] (absent parts omitted)
     double* d_raw = nullptr;      // same layout on the device
@@ -106,6 +114,8 @@ struct Batch {
     float* h_atoms = nullptr;     // pinned [frame][atoms of selection 1 | atoms of selection 2][3] float32 (atom batches)
     float* d_atoms = nullptr;
     bool atoms = false;           // this batch holds atom positions; COM / dipoles are produced on the device
+    bool direct = false;          // the frames are NOT staged in h_pin: the DMA engine reads the caller's page-locked arrays
+    FrameSrc dsrc;                // ... starting here (first frame of the batch)
 };
 
 struct Dev {
@@ -146,6 +156,8 @@ struct gfn_residues {
 struct gfn_handle {
     CopyHelper* helper = nullptr;
     int copy_threads = 1;
+    CopyPool* pool = nullptr;     // block calls: frames of a batch copied in parallel
+    int pool_threads = 0;
     int n1, n2, histo_n, mode_sel;   // histo_n: bins per histogram row (radial bins x shells)
     int histo_nr = 0;                // radial bins
     gfn_shell_cfg shells = {0, 0, 1, 1, 0, 0, 0};   // layout 0: plain g-functions
@@ -344,6 +356,22 @@ int submit(gfn_t* h, Dev& d)
         const long long fa = 3 * (na1 + na2);
         bytes = (size_t)fa * b.nframes * sizeof(float);
         CU(cudaMemcpyAsync(b.d_atoms, b.h_atoms, bytes, cudaMemcpyHostToDevice, d.copy));
+    } else if (b.direct) {
+        // page-locked caller arrays: one strided DMA per part, [frame] rows of the part's width into the frame layout
+        const FrameSrc& q = b.dsrc;
+        const size_t dp = (size_t)fd * sizeof(double);
+        auto part = [&](long long off, const double* srcp, long long stride, size_t width) -> cudaError_t {
+            const size_t sp = b.nframes > 1 ? (size_t)stride * sizeof(double) : width;
+            return cudaMemcpy2DAsync(b.d_raw + off, dp, srcp, sp, width, (size_t)b.nframes, cudaMemcpyHostToDevice, d.copy);
+        };
+        bytes = 0;
+        CU(part(h->off_c1, q.c1, q.s_c1, sizeof(double) * 3 * h->n1)); bytes += sizeof(double) * 3 * h->n1;
+        if (h->need1) { CU(part(h->off_d1, q.d1, q.s_d1, sizeof(double) * 3 * h->n1)); bytes += sizeof(double) * 3 * h->n1; }
+        if (!b.aliased) {
+            CU(part(h->off_c2, q.c2, q.s_c2, sizeof(double) * 3 * h->n2)); bytes += sizeof(double) * 3 * h->n2;
+            if (h->need2) { CU(part(h->off_d2, q.d2, q.s_d2, sizeof(double) * 3 * h->n2)); bytes += sizeof(double) * 3 * h->n2; }
+        }
+        bytes *= (size_t)b.nframes;
     } else {
         CU(cudaMemcpyAsync(b.d_raw, b.h_pin, bytes, cudaMemcpyHostToDevice, d.copy));
     }
@@ -535,6 +563,15 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
         if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) ranks = v; }
         h->copy_threads = (int)std::thread::hardware_concurrency() >= 8 * ranks ? 2 : 1;
         if (const char* e = getenv("GFN_COPY_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 2) h->copy_threads = v; }
+        // block calls: the frames of a batch are copied by a pool - two workers per device this handle feeds, within a fair
+        // share of the box's cores (the caller copies too)
+        const int cores = (int)std::thread::hardware_concurrency() / ranks;
+        int pt = 2 * (int)devs.size();
+        if (pt > cores / 2) pt = cores / 2;
+        if (pt > 16) pt = 16;
+        if (h->copy_threads < 2 && devs.size() < 2) pt = 0;
+        if (const char* e = getenv("GFN_POOL_THREADS")) { const int v = atoi(e); if (v >= 0 && v <= 64) pt = v; }
+        h->pool_threads = pt < 0 ? 0 : pt;
     }
     // an idle device (first frames of a run, right after a readout) should not wait for a full batch: a quarter of
     // one, or ~2^28 pair evaluations (0.2 ms of kernel time) if that is less
@@ -685,21 +722,25 @@ static void copy_frame(gfn_t* h, const CopyHelper::Seg* segs, int nseg)
     h->helper->copy(segs, nseg);
 }
 
-// one source of frames for the ring: host selections (coordinates / dipoles [/ shell matrix]) or float32 atom positions
-struct FrameSrc {
-    const double* c1 = nullptr; const double* c2 = nullptr; const double* d1 = nullptr; const double* d2 = nullptr;
-    long long s_c1 = 0, s_c2 = 0, s_d1 = 0, s_d2 = 0;
-    const int* shell_map = nullptr; long long s_map = 0;
-    const float* a1 = nullptr; const float* a2 = nullptr; long long s_a1 = 0, s_a2 = 0;
-};
-
-static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased, const double* box_dims)
+// Frames go into the ring batch by batch.  Per batch: the caller's frames are copied into their pinned slots (one frame:
+// the caller, split with the helper thread when large; several frames: the copy pool, one frame per task) - or, for
+// page-locked sources (direct), only referenced - then the batch is submitted when it is full or the device is idle.
+static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased, const double* box_dims, bool direct = false)
 {
     const bool atoms = src.a1 != nullptr;
-    for (int f = 0; f < nframes; ++f) {
+    auto device_idle = [](Dev& d) {
+        bool idle = true;
+        for (Batch& o : d.ring)
+            if (o.inflight && cudaEventQuery(o.done) == cudaErrorNotReady) { idle = false; break; }
+        cudaGetLastError();
+        return idle;
+    };
+    int f = 0;
+    while (f < nframes) {
         Dev& d = h->devs[h->next_dev];
         Batch* b = &d.ring[d.cur];
-        if (b->nframes > 0 && (b->aliased != aliased || b->atoms != atoms)) {      // layout change: close the batch
+        if (b->nframes > 0 && (b->aliased != aliased || b->atoms != atoms || b->direct || direct)) {
+            // layout change, or a batch that references caller memory (it never spans two calls): close the batch
             int rc = submit(h, d);
             if (rc) return rc;
             b = &d.ring[d.cur];
@@ -709,43 +750,72 @@ static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased
             if (rc) return rc;
             b->aliased = aliased;
             b->atoms = atoms;
-        }
-        if (box_dims) {
-            int rc = validate_box(h, box_dims + 6ll * f);
-            if (rc) return rc;
-        }
-        CopyHelper::Seg segs[8];
-        int nseg = 0;
-        auto seg = [&](void* dstp, const void* srcp, size_t n) {
-            segs[nseg++] = {static_cast<unsigned char*>(dstp), static_cast<const unsigned char*>(srcp), n};
-        };
-        if (atoms) {
-            const long long na1 = h->na[0], na2 = aliased ? 0 : (h->na[1] ? h->na[1] : h->na[0]);
-            float* dst = b->h_atoms + 3 * (na1 + na2) * b->nframes;
-            seg(dst, src.a1 + src.s_a1 * f, sizeof(float) * 3 * na1);
-            if (!aliased) seg(dst + 3 * na1, src.a2 + src.s_a2 * f, sizeof(float) * 3 * na2);
-        } else {
-            const long long fd = aliased ? h->off_c2 : h->frame_doubles;
-            double* dst = b->h_pin + fd * b->nframes;
-            seg(dst + h->off_c1, src.c1 + src.s_c1 * f, sizeof(double) * 3 * h->n1);
-            if (h->need1) seg(dst + h->off_d1, src.d1 + src.s_d1 * f, sizeof(double) * 3 * h->n1);
-            if (!aliased) {
-                seg(dst + h->off_c2, src.c2 + src.s_c2 * f, sizeof(double) * 3 * h->n2);
-                if (h->need2) seg(dst + h->off_d2, src.d2 + src.s_d2 * f, sizeof(double) * 3 * h->n2);
+            b->direct = direct;
+            if (direct) {
+                b->dsrc = src;
+                b->dsrc.c1 = src.c1 + src.s_c1 * f; b->dsrc.c2 = src.c2 + src.s_c2 * f;
+                if (src.d1) b->dsrc.d1 = src.d1 + src.s_d1 * f;
+                if (src.d2) b->dsrc.d2 = src.d2 + src.s_d2 * f;
             }
-            if (src.shell_map) seg(dst + h->off_map, src.shell_map + src.s_map * f, sizeof(int) * (size_t)h->shells.map_elems);
         }
-        copy_frame(h, segs, nseg);
-        memcpy(b->h_box + 6ll * b->nframes, box_dims ? box_dims + 6ll * f : h->box, sizeof(double) * 6);
-        b->nframes++;
+        // frames of this call that go into the batch now; an idle device (first frames of a run, right after a readout)
+        // gets a short batch instead of waiting for a full one
+        int k = h->batch_frames - b->nframes;
+        if (k > nframes - f) k = nframes - f;
+        const bool idle = device_idle(d);
+        if (idle && b->nframes < h->idle_frames && k > h->idle_frames - b->nframes) k = h->idle_frames - b->nframes;
+        if (box_dims)
+            for (int i = 0; i < k; ++i) {
+                int rc = validate_box(h, box_dims + 6ll * (f + i));
+                if (rc) return rc;
+            }
+        auto frame_segs = [&](int slot, int fr, CopyHelper::Seg* segs) -> int {
+            int nseg = 0;
+            auto seg = [&](void* dstp, const void* srcp, size_t n) {
+                segs[nseg++] = {static_cast<unsigned char*>(dstp), static_cast<const unsigned char*>(srcp), n};
+            };
+            if (atoms) {
+                const long long na1 = h->na[0], na2 = aliased ? 0 : (h->na[1] ? h->na[1] : h->na[0]);
+                float* dst = b->h_atoms + 3 * (na1 + na2) * slot;
+                seg(dst, src.a1 + src.s_a1 * fr, sizeof(float) * 3 * na1);
+                if (!aliased) seg(dst + 3 * na1, src.a2 + src.s_a2 * fr, sizeof(float) * 3 * na2);
+            } else {
+                const long long fd = aliased ? h->off_c2 : h->frame_doubles;
+                double* dst = b->h_pin + fd * slot;
+                seg(dst + h->off_c1, src.c1 + src.s_c1 * fr, sizeof(double) * 3 * h->n1);
+                if (h->need1) seg(dst + h->off_d1, src.d1 + src.s_d1 * fr, sizeof(double) * 3 * h->n1);
+                if (!aliased) {
+                    seg(dst + h->off_c2, src.c2 + src.s_c2 * fr, sizeof(double) * 3 * h->n2);
+                    if (h->need2) seg(dst + h->off_d2, src.d2 + src.s_d2 * fr, sizeof(double) * 3 * h->n2);
+                }
+                if (src.shell_map) seg(dst + h->off_map, src.shell_map + src.s_map * fr, sizeof(int) * (size_t)h->shells.map_elems);
+            }
+            return nseg;
+        };
+        if (!direct) {
+            if (k >= 2 && h->pool_threads > 0) {
+                if (!h->pool) h->pool = new CopyPool(h->pool_threads);
+                const int base = b->nframes;
+                h->pool->run(k, [&](int i) {
+                    CopyHelper::Seg segs[8];
+                    const int nseg = frame_segs(base + i, f + i, segs);
+                    for (int q = 0; q < nseg; ++q) copy_to_ring(segs[q].d, segs[q].s, segs[q].n);
+                });
+            } else {
+                for (int i = 0; i < k; ++i) {
+                    CopyHelper::Seg segs[8];
+                    const int nseg = frame_segs(b->nframes + i, f + i, segs);
+                    copy_frame(h, segs, nseg);
+                }
+            }
+        }
+        for (int i = 0; i < k; ++i)
+            memcpy(b->h_box + 6ll * (b->nframes + i), box_dims ? box_dims + 6ll * (f + i) : h->box, sizeof(double) * 6);
+        b->nframes += k;
+        f += k;
         bool go = b->nframes == h->batch_frames;
-        if (!go && b->nframes >= h->idle_frames) {
-            // the device is idle (e.g. right after a readout): do not make it wait for a full batch
-            go = true;
-            for (Batch& o : d.ring)
-                if (o.inflight && cudaEventQuery(o.done) == cudaErrorNotReady) { go = false; break; }
-            cudaGetLastError();
-        }
+        if (!go && b->nframes >= h->idle_frames) go = idle || device_idle(d);
+        if (!go && direct && f == nframes) go = true;            // the reference to the caller's arrays ends with the call
         if (go) {
             int rc = submit(h, d);
             if (rc) return rc;
@@ -758,7 +828,7 @@ static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased
 static int enqueue_impl(gfn_t* h, int nframes,
                        const double* c1, long long s_c1, const double* c2, long long s_c2,
                        const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims,
-                       const int* shell_map, long long s_map)
+                       const int* shell_map, long long s_map, bool direct = false)
 {
     if (!h) return GFN_EINVAL;
     if (h->shells.layout && !shell_map) return fail(h, GFN_EINVAL, "this handle resolves shells: frames need a shell matrix (gfn_enqueue_frames_shells)");
@@ -771,7 +841,24 @@ static int enqueue_impl(gfn_t* h, int nframes,
     FrameSrc src;
     src.c1 = c1; src.c2 = c2; src.d1 = d1; src.d2 = d2; src.s_c1 = s_c1; src.s_c2 = s_c2; src.s_d1 = s_d1; src.s_d2 = s_d2;
     src.shell_map = shell_map; src.s_map = s_map;
-    return enqueue_loop(h, nframes, src, aliased, box_dims);
+    if (direct) {
+        // the DMA engine reads the caller's arrays: every part must be page-locked, frames must not overlap
+        if (h->shells.layout) return fail(h, GFN_EINVAL, "shell-resolved handles take staged frames (gfn_enqueue_frames_shells)");
+        const void* parts[4] = {c1, h->need1 ? d1 : nullptr, aliased ? nullptr : c2, (!aliased && h->need2) ? d2 : nullptr};
+        const long long strides[4] = {s_c1, s_d1, s_c2, s_d2};
+        const long long widths[4] = {3ll * h->n1, 3ll * h->n1, 3ll * h->n2, 3ll * h->n2};
+        for (int k = 0; k < 4; ++k) {
+            if (!parts[k]) continue;
+            if (nframes > 1 && strides[k] < widths[k]) return fail(h, GFN_EINVAL, "frame stride of part %d is smaller than a frame", k);
+            cudaPointerAttributes at;
+            const cudaError_t e = cudaPointerGetAttributes(&at, parts[k]);
+            if (e != cudaSuccess || at.type != cudaMemoryTypeHost) {
+                cudaGetLastError();
+                return fail(h, GFN_EINVAL, "gfn_enqueue_frames_pinned: part %d is not page-locked host memory (gfn_host_alloc / cudaHostRegister)", k);
+            }
+        }
+    }
+    return enqueue_loop(h, nframes, src, aliased, box_dims, direct);
 }
 
 // ---- N1 + N4: atoms through the ring ---------------------------------------------------------------------
@@ -850,6 +937,30 @@ int gfn_enqueue_frames(gfn_t* h, int nframes,
                        const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims)
 {
     return enqueue_impl(h, nframes, c1, s_c1, c2, s_c2, d1, s_d1, d2, s_d2, box_dims, nullptr, 0);
+}
+
+int gfn_enqueue_frames_pinned(gfn_t* h, int nframes,
+                              const double* c1, long long s_c1, const double* c2, long long s_c2,
+                              const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims)
+{
+    return enqueue_impl(h, nframes, c1, s_c1, c2, s_c2, d1, s_d1, d2, s_d2, box_dims, nullptr, 0, true);
+}
+
+int gfn_host_alloc(void** out, unsigned long long bytes)
+{
+    if (!out) return fail(nullptr, GFN_EINVAL, "NULL argument");
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, e == cudaErrorMemoryAllocation ? GFN_ENOMEM : GFN_ECUDA, "cudaHostAlloc(%llu bytes): %s", bytes, cudaGetErrorString(e)); }
+    return GFN_OK;
+}
+
+int gfn_host_free(void* p)
+{
+    if (!p) return GFN_OK;
+    const cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, GFN_ECUDA, "cudaFreeHost: %s", cudaGetErrorString(e)); }
+    return GFN_OK;
 }
 
 int gfn_enqueue_frames_shells(gfn_t* h, int nframes,
@@ -1058,6 +1169,8 @@ void gfn_destroy(gfn_t* h)
     if (!h) return;
     delete h->helper;
     h->helper = nullptr;
+    delete h->pool;
+    h->pool = nullptr;
     for (Dev& d : h->devs) free_dev(d);
     delete h;
 }

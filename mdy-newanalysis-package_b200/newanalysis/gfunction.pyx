@@ -59,6 +59,10 @@ cdef extern from "gfn.h":
                    unsigned flags) nogil
     int gfn_update_box(gfn_t *h, const double *box_dim) nogil
     int gfn_enqueue_frame(gfn_t *h, const double *c1, const double *c2, const double *d1, const double *d2) nogil
+    int gfn_enqueue_frames_pinned(gfn_t *h, int nframes, const double *c1, long long s1, const double *c2, long long s2,
+                                  const double *d1, long long s3, const double *d2, long long s4, const double *boxes) nogil
+    int gfn_host_alloc(void **out, unsigned long long nbytes) nogil
+    int gfn_host_free(void *p) nogil
     int gfn_enqueue_frames(gfn_t *h, int nframes, const double *c1, long long s1, const double *c2, long long s2,
                            const double *d1, long long s3, const double *d2, long long s4, const double *boxes) nogil
     int gfn_enqueue_device_frames(gfn_t *h, int nframes, const double *c1, long long s1, const double *c2, long long s2,
@@ -231,6 +235,34 @@ cdef class DeviceArray:
     @property
     def address(self):
         return <unsigned long long> <size_t> self.ptr
+
+
+class _PinnedOwner(object):
+    """Frees a gfn_host_alloc block when the last numpy view of it is gone."""
+    def __init__(self, size_t ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        cdef size_t p = self.ptr
+        self.ptr = 0
+        if p:
+            gfn_host_free(<void *> p)
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (cudaHostAlloc through libgfn): the source `RDF.calcFrames(..., pinned=True)`
+    uploads from without a staging copy.  Freed with the last reference."""
+    import ctypes
+    dt = np.dtype(dtype)
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    cdef unsigned long long nbytes = <unsigned long long> (int(np.prod(shape)) * dt.itemsize)
+    cdef void *p = NULL
+    cdef int rc = gfn_host_alloc(&p, nbytes)
+    if rc != 0:
+        raise MemoryError("libgfn: " + gfn_last_error(NULL).decode("utf-8", "replace"))
+    buf = (ctypes.c_char * max(int(nbytes), 1)).from_address(<size_t> p)
+    buf._gfn_owner = _PinnedOwner(<size_t> p)
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
 
 
 def to_device(arr, int device=0):
@@ -508,10 +540,13 @@ cdef class _Backend:
         return self.check(rc)
 
     cdef int enqueue_many(self, int nframes, const double *c1, long long s1, const double *c2, long long s2,
-                          const double *d1, long long s3, const double *d2, long long s4, const double *boxes) except -1:
+                          const double *d1, long long s3, const double *d2, long long s4, const double *boxes, bint pinned=False) except -1:
         cdef int rc
         with nogil:
-            rc = gfn_enqueue_frames(self.h, nframes, c1, s1, c2, s2, d1, s3, d2, s4, boxes)
+            if pinned:
+                rc = gfn_enqueue_frames_pinned(self.h, nframes, c1, s1, c2, s2, d1, s3, d2, s4, boxes)
+            else:
+                rc = gfn_enqueue_frames(self.h, nframes, c1, s1, c2, s2, d1, s3, d2, s4, boxes)
         return self.check(rc)
 
     def enqueue_device(self, int nframes, DeviceArray c1, DeviceArray c2, DeviceArray d1, DeviceArray d2, boxes=None, long long first=0):
@@ -1044,8 +1079,15 @@ class RDF(object):
         self.overflow = ovf
         return hist
 
-    def calcFrames(self, coor_sel1, coor_sel2, dip_sel1=None, dip_sel2=None, boxes=None):
-        """Many frames per call: arrays of shape (nframes, n, 3); boxes (nframes, 3) for NpT or None."""
+    def calcFrames(self, coor_sel1, coor_sel2, dip_sel1=None, dip_sel2=None, boxes=None, pinned=False):
+        """Many frames per call: arrays of shape (nframes, n, 3); boxes (nframes, 3) for NpT or None.
+
+        pinned=True: the arrays are page-locked (`pinned_empty`) float64 C arrays and stay unchanged until the next
+        sync() / histogram readout: the GPU's copy engine reads them directly, nothing is staged on the host."""
+        if pinned:
+            for arr in (coor_sel1, coor_sel2, dip_sel1, dip_sel2):
+                if arr is not None and not (isinstance(arr, np.ndarray) and arr.dtype == np.float64 and arr.flags.c_contiguous):
+                    raise TypeError("pinned=True takes C-contiguous float64 arrays made by pinned_empty (no conversion copy is allowed)")
         cdef np.ndarray[np.float64_t, ndim=3, mode="c"] c1 = np.ascontiguousarray(coor_sel1, dtype=np.float64)
         cdef np.ndarray[np.float64_t, ndim=3, mode="c"] c2 = c1 if coor_sel2 is coor_sel1 else np.ascontiguousarray(coor_sel2, dtype=np.float64)
         cdef np.ndarray[np.float64_t, ndim=3, mode="c"] d1 = None
@@ -1075,13 +1117,15 @@ class RDF(object):
             vols = [self.volume] * nf
         if self._auto_filter and self.ctr == 0:
             self._auto_pick_filter(c1[0], c2[0])
-        self.ctr += nf
-        self.volume_list.extend(vols)
         cdef _Backend be = self._be
         be.enqueue_many(nf, <const double *> c1.data, 3 * <long long> self.n1, <const double *> c2.data, 3 * <long long> self.n2,
                         <const double *> d1.data if d1 is not None else NULL, 3 * <long long> self.n1,
                         <const double *> d2.data if d2 is not None else NULL, 3 * <long long> self.n2,
-                        <const double *> bx.data if bx is not None else NULL)
+                        <const double *> bx.data if bx is not None else NULL, bool(pinned))
+        self.ctr += nf
+        self.volume_list.extend(vols)
+        if pinned:
+            be.keepalive.append(("pinned", c1, c2, d1, d2))          # until the next sync / readout
         if boxes is not None:
             self.update_box(*[float(v) for v in b3[nf - 1]])
 

@@ -425,6 +425,63 @@ def test_ring_recycling_and_npt(monkeypatch):
     assert g.volume_list == o.volume_list
 
 
+@pytest.mark.parametrize("case", ["self_all", "rect_5modes", "g000_npt"])
+def test_pinned_frames_and_pool_copies_equal_staged_frames(case, monkeypatch):
+    """Three host feeds of the same frames: per-frame calcFrame (staged by the caller thread), calcFrames blocks (frames of
+    a batch copied by the pool threads) and calcFrames(pinned=True) (no staging at all: strided DMA from page-locked
+    arrays, gfn_enqueue_frames_pinned).  Small batches so that every feed crosses several ring slots; all against the oracle."""
+    from newanalysis.gfunction import pinned_empty
+    monkeypatch.setenv("GFN_BATCH_FRAMES", "3")
+    monkeypatch.setenv("GFN_POOL_THREADS", "3")
+    rng = np.random.default_rng(515)
+    nf, L = 11, 42.0
+    if case == "self_all":
+        n1 = n2 = 700; modes = ["all"]
+    elif case == "rect_5modes":
+        n1, n2 = 300, 900; modes = ["000", "110", "101", "011", "220"]
+    else:
+        n1 = n2 = 500; modes = ["000"]
+    boxes = L * (1 + 2e-3 * rng.standard_normal((nf, 3))) if case == "g000_npt" else None
+    same = n1 == n2
+    pc1, pd1 = pinned_empty((nf, n1, 3)), pinned_empty((nf, n1, 3))
+    pc1[:] = rng.random((nf, n1, 3)) * L; pd1[:] = rng.standard_normal((nf, n1, 3))
+    if same:
+        pc2, pd2 = pc1, pd1
+    else:
+        pc2, pd2 = pinned_empty((nf, n2, 3)), pinned_empty((nf, n2, 3))
+        pc2[:] = rng.random((nf, n2, 3)) * L; pd2[:] = rng.standard_normal((nf, n2, 3))
+    need_d = modes != ["000"]
+    mk = lambda: RDF(modes, 0.0, 15.0, 0.05, n1, n2, n1, n2, L)      # noqa: E731
+    a, b, c = mk(), mk(), mk()
+    o = O.OracleRDF(modes, 0.0, 15.0, 0.05, n1, n2, n1, n2, L)
+    for f in range(nf):
+        if boxes is not None:
+            a.update_box(*boxes[f]); o.update_box(*boxes[f])
+        args = (pc1[f], pc2[f]) + ((pd1[f], pd2[f]) if need_d else ())
+        a.calcFrame(*args); o.calcFrame(*args)
+    dargs = (pd1, pd2) if need_d else (None, None)
+    # two calls each, the second one starting in the middle of a batch
+    for lo, hi in ((0, 4), (4, nf)):
+        c1v = pc1[lo:hi].copy(); c2v = c1v if same else pc2[lo:hi].copy()
+        d1v = pd1[lo:hi].copy() if need_d else None; d2v = (d1v if same else pd2[lo:hi].copy()) if need_d else None
+        b.calcFrames(c1v, c2v, d1v, d2v, boxes=None if boxes is None else boxes[lo:hi])
+    for lo, hi in ((0, 5), (5, nf)):
+        c1v = pc1[lo:hi]; c2v = c1v if same else pc2[lo:hi]
+        d1v = pd1[lo:hi] if need_d else None; d2v = (d1v if same else pd2[lo:hi]) if need_d else None
+        c.calcFrames(c1v, c2v, d1v, d2v, boxes=None if boxes is None else boxes[lo:hi], pinned=True)
+    ha, hb, hc, ref = a.raw_histogram(), b.raw_histogram(), c.raw_histogram(), o.raw_sum()
+    assert np.array_equal(ha[:300], ref[:300]) and ref[:300].sum() > 1000
+    assert np.array_equal(hb[:300], ref[:300]) and np.array_equal(hc[:300], ref[:300])
+    for h in (ha, hb, hc):
+        assert_hist_close(h, ref, 300)
+    assert c.stats()["h2d_bytes"] == a.stats()["h2d_bytes"]         # the same bytes cross PCIe, without the host copy
+    assert a.volume_list == o.volume_list and c.volume_list == o.volume_list
+    with pytest.raises(ValueError, match="page-locked"):
+        c.calcFrames(pc1[:2].copy(), pc1[:2].copy(), pd1[:2].copy() if need_d else None, pd1[:2].copy() if need_d else None, pinned=True)
+    with pytest.raises(TypeError):
+        c.calcFrames(pc1[:2].astype(np.float32), pc1[:2].astype(np.float32), pinned=True)
+
+
 def test_device_resident_frames_equal_host_path():
     from newanalysis.gfunction import to_device
     n, L, nf = 3000, 45.0, 3
