@@ -65,6 +65,10 @@ extern "C" {
                                           sites in registers) where it supports the handle; default: chosen when the
                                           share of in-range pairs expected from box and histo_max exceeds 10 % */
 #define GFN_FLAG_NO_DENSE          256u /* never use it (the warp-specialised ring kernel serves every handle) */
+#define GFN_FLAG_CELLS             512u /* tile skipping for sparse neighbourhoods: every frame is sorted into Morton order on the device
+                                         * and only the tile pairs whose bounding boxes lie within histo_max of each other are
+                                         * visited (gfn_cells.cu).  Same pairs accepted, same arithmetic: counts bit-exact.  Ignored
+                                         * by handles the dense kernels serve and by shell-resolved handles. */
 #define GFN_FLAG_EXACT_DIV         64u /* orientation cosines by the reference's literal divisions dot/(|a|*|b|)
                                           (gfunction.pyx:155,159,163) instead of reciprocal products: per-pair increments
                                           bit-identical to the reference, see "Arithmetic contract" above */
@@ -96,6 +100,9 @@ typedef struct gfn_stats {
     int    dense;             /* 0 ring kernel, 1 dense-neighbourhood kernel, 2 g000 count kernel (fp32 classification) */
     double exact_evals;       /* count kernel: pairs the fp32 classification could not decide, evaluated in fp64 */
     double selfcheck_bad;     /* count kernel under GFN_DEBUG=8: pairs whose fp32 decision differs from the exact one (must be 0) */
+    double tile_visits;       /* GFN_FLAG_CELLS: (core tile, surround tile) pairs the pair kernel visited so far ... */
+    double tile_visits_dense; /* ... and how many the un-pruned enumeration has for the same frames */
+    int    cells;             /* 1 if tile skipping is active */
 } gfn_stats_t;
 
 /* Number of CUDA devices visible (0 if none / no driver).  Never fails. */

@@ -126,7 +126,7 @@ __host__ __device__ inline size_t replica_bytes(int hn, bool weights)
 
 // The last warp (filter or drain) to finish with a stage refills it with the tile S steps ahead.
 __device__ __forceinline__ void release_stage(Ctrl* c, Site* jsite, const Site* siteB, int st, int nwarps,
-                                              int t, int ntiles, int jt_begin, int lane)
+                                              int t, const Item& it, int lane)
 {
     __syncwarp();
     if (lane == 0) {
@@ -134,9 +134,9 @@ __device__ __forceinline__ void release_stage(Ctrl* c, Site* jsite, const Site* 
         const int old = atomicAdd(&c->done_cnt[st], 1);
         if (old == nwarps - 1) {
             atomicExch(&c->done_cnt[st], 0);
-            if (t + kStages < ntiles) {
+            if (t + kStages < it.ntiles) {
                 mbar_expect_tx(&c->full[st], kTJ * (uint32_t)sizeof(Site));
-                bulk_g2s(jsite + st * kTJ, siteB + (long long)(jt_begin + t + kStages) * kTJ, kTJ * (uint32_t)sizeof(Site), &c->full[st]);
+                bulk_g2s(jsite + st * kTJ, siteB + (long long)run_tile(it, t + kStages) * kTJ, kTJ * (uint32_t)sizeof(Site), &c->full[st]);
             }
         }
     }
@@ -188,7 +188,7 @@ pair_kernel(const PairParams P)
     }
     __syncthreads();
 
-    const long long total_tiles = (long long)P.tiles_per_frame * P.nframes;
+    const long long total_tiles = total_visits(P);
     const long long slice_begin = total_tiles * blockIdx.x / gridDim.x;
     const long long slice_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
     unsigned tcount = 0;        // surround tiles consumed so far by this CTA (stage = g % S, parity = (g / S) & 1)
@@ -218,7 +218,7 @@ pair_kernel(const PairParams P)
                 for (int pre = 0; pre < S && pre < it.ntiles; ++pre) {
                     const int st = (tcount + pre) % S;
                     mbar_expect_tx(&ctrl->full[st], TJ * (uint32_t)sizeof(Site));
-                    bulk_g2s(jsite + st * TJ, siteB + (long long)(it.jt_begin + pre) * TJ, TJ * (uint32_t)sizeof(Site), &ctrl->full[st]);
+                    bulk_g2s(jsite + st * TJ, siteB + (long long)run_tile(it, pre) * TJ, TJ * (uint32_t)sizeof(Site), &ctrl->full[st]);
                 }
             }
             // frame constants (uniform)
@@ -278,7 +278,7 @@ pair_kernel(const PairParams P)
             for (int t = 0; t < it.ntiles; ++t) {
                 const unsigned g = tcount + t;
                 const int st = g % S;
-                const int j0 = (it.jt_begin + t) * TJ;
+                const int j0 = run_tile(it, t) * TJ;
                 mbar_wait(&ctrl->full[st], (g / S) & 1);
                 const Site* js = jsite + st * TJ;
 
@@ -452,7 +452,7 @@ pair_kernel(const PairParams P)
                     __threadfence_block();
                     ctrl->tdone[warp] = g + 1;
                 }
-                release_stage(ctrl, jsite, siteB, st, NW, t, it.ntiles, it.jt_begin, lane);
+                release_stage(ctrl, jsite, siteB, st, NW, t, it, lane);
             }
             tcount += it.ntiles;
         }
@@ -510,6 +510,15 @@ pair_kernel(const PairParams P)
                             ok[u] = have && i < P.n1 && j < P.n2 && !(P.tri && j < i);
                             const double2* ap = reinterpret_cast<const double2*>(isite + il);
                             const double2* bp = reinterpret_cast<const double2*>(js + jl);
+                            if (P.visit_start) {
+                                // cell-sorted frame: i, j are positions in the sorted order, Site.fw keeps the original index.
+                                // A triangular frame visits every unordered pair once BY POSITION; the reference's roles
+                                // (core = the smaller original index, gfunction.pyx:126-130) are restored by exchanging the
+                                // two records - same operands, same operations, same result.
+                                const int oi = __float_as_int(isite[il].fw), oj = __float_as_int(js[jl].fw);
+                                gi[u] = oi;
+                                if (P.tri && oj < oi) { const double2* sw = ap; ap = bp; bp = sw; gi[u] = oj; }
+                            }
                             const double2 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];   // x y | z px | py pz | norm -
                             const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
                             apx[u] = a1.y; apy[u] = a2.x; apz[u] = a2.y; an[u] = a3.x; ian[u] = a3.y;
@@ -728,7 +737,7 @@ pair_kernel(const PairParams P)
                     while (t_wait < it.ntiles && t_wait <= td && t_wait < t_rel + S) {
                         const unsigned g = tcount + t_wait;
                         mbar_wait(&ctrl->full[g % S], (g / S) & 1);
-                        const int j0 = (it.jt_begin + t_wait) * TJ;
+                        const int j0 = run_tile(it, t_wait) * TJ;
                         if (g % S == 0) j0s0 = j0; else if (g % S == 1) j0s1 = j0; else j0s2 = j0;
                         ++t_wait;
                     }
@@ -747,7 +756,7 @@ pair_kernel(const PairParams P)
                         continue;
                     }
                     while (t_rel < it.ntiles && td > t_rel && (int)(head - ctrl->tend[fw][(tcount + t_rel) & 3]) >= 0) {
-                        release_stage(ctrl, jsite, siteB, (int)((tcount + t_rel) % S), NW, t_rel, it.ntiles, it.jt_begin, lane);
+                        release_stage(ctrl, jsite, siteB, (int)((tcount + t_rel) % S), NW, t_rel, it, lane);
                         ++t_rel;
                     }
                     if (t_rel == it.ntiles) break;
@@ -759,7 +768,7 @@ pair_kernel(const PairParams P)
                     const unsigned g = tcount + t;
                     const int st = g % S;
                     mbar_wait(&ctrl->full[st], (g / S) & 1);
-                    const int j0 = (it.jt_begin + t) * TJ;
+                    const int j0 = run_tile(it, t) * TJ;
                     if (st == 0) j0s0 = j0; else if (st == 1) j0s1 = j0; else j0s2 = j0;
 #pragma unroll 1
                     for (int fw = dw; fw < NF; fw += ND) {      // this warp's rings, in this fixed order
@@ -782,7 +791,7 @@ pair_kernel(const PairParams P)
                             head += (unsigned)n;
                         }
                     }
-                    release_stage(ctrl, jsite, siteB, st, NW, t, it.ntiles, it.jt_begin, lane);
+                    release_stage(ctrl, jsite, siteB, st, NW, t, it, lane);
                 }
             }
             tcount += it.ntiles;

@@ -32,7 +32,8 @@ constexpr int kDrainILP = GFN_DRAIN_ILP;     // survivors evaluated per drain la
 constexpr int kRingCap = 2048;   // survivor ring entries (16 bit) per filter warp: one push (<= 32*32) always fits behind < 64 unread ones
 constexpr int kCtrlBytes = 640;  // shared-memory control block
 constexpr int kCounters = 8;     // 0 overflow, 1 error flags (bit 0 zero-norm dipole, bit 1 fp16 filter range), 2 survivors, 3 in-range pairs,
-                                 // 4 count kernel self-check mismatches (GFN_DEBUG=8), 5 count kernel: pairs evaluated in fp64
+                                 // 4 count kernel self-check mismatches (GFN_DEBUG=8), 5 count kernel: pairs evaluated in fp64,
+                                 // 6 tile visits of cell-sorted launches (GFN_FLAG_CELLS)
 
 struct PairParams {
     const Site* siteA;  const float* maxA;   // selection 1 (core)
@@ -63,6 +64,11 @@ struct PairParams {
     int apr1, apr2;                 // sites per molecule: matrix row = i / apr1, column = j / apr2 (:582-583, :601)
     int map_ld;                     // row stride of the matrix as the reference indexes it (:602 uses nsurround)
     int excl_self;                  // skip pairs of the same molecule (calcHistoVoronoiNonSelf :700)
+    // cell-sorted frames with tile skipping (gfn_cells.cu; nullptr = every tile pair is visited): siteA / siteB are then the
+    // SORTED records (Site.fw holds the site's original index), the core tile of entry e = frame * n_itiles + ti visits
+    // the surround tiles visit_list[e * n_jtiles + 0 .. visit_start[e+1] - visit_start[e])
+    const long long* visit_start;   // [nframes * n_itiles + 1] exclusive prefix, last = total visits of the launch
+    const int* visit_list;
     // dense kernel, g000-only handles: the bin of a pair from d^2 without a square root (gfn_dense.cu)
     const double* bin_thr;          // [histo_n + 4]  T[k] = min { t : sqrt(t) >= hmin and floor((sqrt(t) - hmin) * invdx) >= k }
     double acc_lo, acc_hi;          // a pair passes gfunction.pyx:149  <=>  acc_lo <= d^2 <= acc_hi
@@ -130,5 +136,14 @@ cudaError_t peaks_measure(int dev, double* fp64_tflops, double* fp32_tflops);
 cudaError_t arith_selftest(int dev, unsigned long long seed, long long n_operands, unsigned long long out[3]);
 
 int tile_i(const PairConfig& cfg);   // core sites per block tile
+
+// tile skipping (gfn_cells.cu)
+size_t cells_sort_temp_bytes(long long items);
+cudaError_t cells_sort_launch(const Site* site, Site* sorted, int n, int n_pad, int nframes, const double* box,
+                              unsigned long long* keys_in, unsigned long long* keys_out, unsigned* vals_in, unsigned* vals_out,
+                              void* tmp, size_t tmp_bytes, cudaStream_t s);
+cudaError_t cells_bbox_launch(const Site* sorted, int n, int n_pad, int nframes, const double* box, int tile, int ntiles, float* bbox, cudaStream_t s);
+cudaError_t cells_list_launch(const float* boxA, const float* boxB, int n_itiles, int n_jtiles, int TI, int tri, int nframes,
+                              const double* box, double hmax, int* list, int* count, long long* start, unsigned long long* visits, cudaStream_t s);
 
 }  // namespace gfn

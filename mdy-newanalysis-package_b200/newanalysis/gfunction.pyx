@@ -51,6 +51,9 @@ cdef extern from "gfn.h":
         int dense
         double exact_evals
         double selfcheck_bad
+        double tile_visits
+        double tile_visits_dense
+        int cells
     int GFN_OK, GFN_EINVAL, GFN_ECUDA, GFN_ENCCL, GFN_EZERODIV, GFN_ENOMEM, GFN_ENODEV
     unsigned GFN_FLAG_PER_PARTICLE, GFN_FLAG_FILTER_FP64, GFN_FLAG_DISCARD_OVERFLOW, GFN_FLAG_HIST_GLOBAL
     int gfn_device_count() nogil
@@ -125,7 +128,7 @@ cdef extern from "gfn.h":
     int gfn_dev_upload(int dev, void *dptr, const void *host, unsigned long long nbytes) nogil
 
 
-_FLAG_NAMES = {"dense": 128, "nodense": 256, "exact_div": 64, "no_triangle": 32, "fp16": 16, "filter_fp16": 16, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
+_FLAG_NAMES = {"cells": 512, "dense": 128, "nodense": 256, "exact_div": 64, "no_triangle": 32, "fp16": 16, "filter_fp16": 16, "per_particle": 1, "fp64": 2, "filter_fp64": 2, "discard_overflow": 4, "global": 8, "hist_global": 8}
 
 
 def _parse_flags(spec):
@@ -695,7 +698,8 @@ cdef class _Backend:
                     hist_mode=("smem_warp_replicas", "global_atomics", "per_particle")[s.hist_mode],
                     warps_per_block=s.warps_per_block, blocks_per_sm=s.blocks_per_sm, grid=s.grid,
                     smem_bytes=s.smem_bytes, batch_frames=s.batch_frames, ndev=s.ndev, hist_replicas=s.hist_replicas,
-                    kernel=("ring", "dense", "count")[s.dense], exact_evals=s.exact_evals, selfcheck_bad=s.selfcheck_bad)
+                    kernel=("ring", "dense", "count")[s.dense], exact_evals=s.exact_evals, selfcheck_bad=s.selfcheck_bad,
+                    cells=bool(s.cells), tile_visits=s.tile_visits, tile_visits_dense=s.tile_visits_dense)
 
 
 _ts_cache = {}

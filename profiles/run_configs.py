@@ -39,7 +39,8 @@ def run(name, n1, n2, L, modes, hmax, nframes, reps, self_pairs, flags="", env=N
                in_range_fraction=f_in, kernel_ms=st["kernel_ms"] - st0["kernel_ms"], wall_ms=ms, hist=st["hist_mode"],
                warps=st["warps_per_block"], replicas=st["hist_replicas"], batch_frames=st["batch_frames"], filter=st["filter"],
                kernel=st["kernel"], flags=flags, survivor_fraction=(st["survivors"] - st0["survivors"]) / evals,
-               exact_fraction=(st["exact_evals"] - st0["exact_evals"]) / evals)
+               exact_fraction=(st["exact_evals"] - st0["exact_evals"]) / evals,
+               tile_visit_fraction=((st["tile_visits"] - st0["tile_visits"]) / max(st["tile_visits_dense"] - st0["tile_visits_dense"], 1.0)) if st["cells"] else 1.0)
     for k in (env or {}):
         os.environ.pop(k, None)
     print(json.dumps(out), flush=True)
@@ -56,6 +57,9 @@ CONFIGS = {
     "cfg1_all_ring": lambda: run("cfg1 shape, all modes (ring kernel)", 1000, 1000, 31.04, ["all"], 15.0, 100, 20, True, "nodense"),
     "cfg3_dense": lambda: run("cfg3 water 32768 all modes (dense kernel forced)", 32768, 32768, 99.33, ["all"], 15.0, 15, 2, True, "dense"),
     "cfg3": lambda: run("cfg3 water 32768 all modes", 32768, 32768, 99.33, ["all"], 15.0, 15, 4, True),
+    "cfg3_cells": lambda: run("cfg3 water 32768 all modes, tile skipping", 32768, 32768, 99.33, ["all"], 15.0, 15, 4, True, "cells", {"GFN_CELLS_FORCE": "1"}),
+    "cfg5_cells": lambda: run("cfg5 1M sites self all, tile skipping", 1048576, 1048576, 315.4, ["all"], 15.0, 1, 2, True, "cells"),
+    "cfg4b_cells": lambda: run("cfg4 solvent 81920 self all, tile skipping", 81920, 81920, 143.6, ["all"], 15.0, 2, 3, True, "cells", {"GFN_CELLS_FORCE": "1"}),
     "cfg3_g000": lambda: run("cfg3 shape, g000 only", 32768, 32768, 99.33, ["000"], 15.0, 15, 4, True),
     "cfg4a": lambda: run("cfg4 solute COM 1024 x solvent 81920 all", 1024, 81920, 143.6, ["all"], 15.0, 16, 4, False),
     "cfg4b": lambda: run("cfg4 solvent 81920 self all", 81920, 81920, 143.6, ["all"], 15.0, 2, 3, True),

@@ -20,7 +20,7 @@ RTOL = 1e-12
 # "" / fp16 / fp32: the library picks the kernel itself - the dense-neighbourhood kernel for most of the small golden boxes
 # (expected in-range share > 10 %), the warp-specialised ring kernel otherwise; "dense" / "nodense" force one of them
 VARIANTS = ["", "fp32", "fp64", "fp16", "fp32,global", "fp64,global", "fp16,global", "per_particle",
-            "fp16,dense", "fp32,dense", "fp16,nodense", "fp32,nodense"]
+            "fp16,dense", "fp32,dense", "fp16,nodense", "fp32,nodense", "nodense,cells", "fp32,nodense,cells", "nodense,cells,global"]
 
 
 def RDF(*a, **k):
@@ -46,7 +46,9 @@ def assert_hist_close(got, ref, hn, pairw=None):
 
 @pytest.mark.parametrize("flags", VARIANTS)
 @pytest.mark.parametrize("name", sorted(C.CASES))
-def test_golden(golden_dir, name, flags, tmp_path):
+def test_golden(golden_dir, name, flags, tmp_path, monkeypatch):
+    if "cells" in flags:
+        monkeypatch.setenv("GFN_CELLS_FORCE", "1")         # small boxes: the library would not bother to skip tiles
     raw, out, meta = load_golden(golden_dir, name)
     case = C.CASES[name]
     n1, n2 = case["n1"], case["n2"]
@@ -70,6 +72,15 @@ def test_golden(golden_dir, name, flags, tmp_path):
         a = np.loadtxt(str(tmp_path / ("g_g%s.dat" % mode)))
         b = np.array([[float(v) for v in ln.split()] for ln in text.strip().splitlines()])
         assert a.shape == b.shape and np.allclose(a, b, rtol=0, atol=2e-5)
+
+
+def test_tile_skipping_is_used_only_where_it_pays():
+    """GFN_FLAG_CELLS is honoured when the expected share of visited tile pairs is small (a box many tile diameters wide)."""
+    mk = lambda n, L, **kw: RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L, **kw).stats()      # noqa: E731
+    assert mk(32768, 99.33, gfn_flags="cells")["cells"] is False          # BASELINE configs[2]: two thirds of the tile pairs stay
+    assert mk(262144, 198.66, gfn_flags="cells")["cells"] is True         # the same density, eight times the volume
+    assert mk(262144, 198.66)["cells"] is False
+    assert mk(4096, 31.0, gfn_flags="cells")["cells"] is False            # dense kernel: flag ignored
 
 
 def test_kernel_choice_follows_the_expected_in_range_share():
@@ -315,6 +326,68 @@ def test_count_kernel_selfcheck_and_oracle(case, monkeypatch):
         assert st["exact_evals"] < (0.01 if dr >= 0.05 else 0.06) * st["in_range"]      # the fp64 pass stays a small share
 
 
+@pytest.mark.parametrize("case", ["self_all", "self_all_fp32", "rect", "unwrapped_npt", "per_particle", "g000_spill"])
+def test_tile_skipping_equals_the_full_enumeration_and_the_oracle(case, monkeypatch):
+    """GFN_FLAG_CELLS (gfn_cells.cu): frames sorted into Morton order on the device, only tile pairs within histo_max are
+    visited.  Counts must equal the un-pruned run's and the oracle's bit for bit - in a triangular frame that needs the
+    reference's core/surround roles restored from the ORIGINAL indices (modes 101 / 011 / 202 / 022 are not symmetric
+    under the exchange) - weighted sums within the bar, and the visit count must actually drop."""
+    monkeypatch.setenv("GFN_CELLS_FORCE", "1")
+    rng = np.random.default_rng(zlib_seed(case))
+    n1 = n2 = 20000; L, hmax, nf, modes, flags = 200.0, 10.0, 2, ["all"], ""
+    if case == "self_all_fp32":
+        flags = "fp32,"
+    if case == "rect":
+        n1, n2 = 3000, 24000
+    if case == "per_particle":
+        n1 = n2 = 3000; L = 100.0; flags = "per_particle,"
+    if case == "g000_spill":
+        modes, hmax = ["000"], 10.02
+    shift = 0.0
+    a = RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags + "nodense,cells")
+    b = RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags + "nodense")
+    o = O.OracleRDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L)
+    hn = int(a.histo_n)
+    for f in range(nf):
+        if case == "unwrapped_npt":
+            bx = L * (1.0 + 0.02 * rng.standard_normal(3)); shift = 2.0
+            for r in (a, b, o):
+                r.update_box(*bx)
+        c1 = rng.random((n1, 3)) * L; d1 = rng.standard_normal((n1, 3))
+        if shift:
+            c1 = c1 + L * rng.integers(-2, 3, (n1, 3))        # single-shift minimum image (quirk Q8): far images do not count
+        c2, d2 = (c1, d1) if n1 == n2 else (rng.random((n2, 3)) * L, rng.standard_normal((n2, 3)))
+        for r in (a, b, o):
+            if modes == ["000"]:
+                r.calcFrame(c1, c2)
+            else:
+                r.calcFrame(c1, c2, d1, d2)
+    ha, hb = a.raw_histogram(), b.raw_histogram()
+    ref = o.raw_sum()
+    sa, sb = a.stats(), b.stats()
+    assert sa["cells"] and not sb["cells"] and sa["kernel"] == "ring"
+    assert np.array_equal(ha[:hn], ref[:hn]) and np.array_equal(hb[:hn], ref[:hn]) and ref[:hn].sum() > 1000
+    if case == "g000_spill":
+        # pairs in (10.00, 10.02] have pos == histo_n (quirk Q3): they spill into the next row exactly where the un-pruned run puts them
+        assert a.overflow == b.overflow and a.overflow > 0
+        assert np.array_equal(ha, hb) and np.array_equal(ha, ref)
+    else:
+        assert_hist_close(ha, ref, hn); assert_hist_close(hb, ref, hn)
+    assert sa["in_range"] == sb["in_range"]
+    assert 0 < sa["tile_visits"] <= sa["tile_visits_dense"]
+    if case not in ("per_particle", "rect"):
+        assert sa["tile_visits"] < 0.85 * sa["tile_visits_dense"]       # the box is a few tile diameters wide
+    if case == "per_particle":
+        pa, pb = a.histogram, b.histogram           # the reference's [mode][core i][bin] array: rows are ORIGINAL indices
+        assert np.array_equal(pa[:n1 * hn], pb[:n1 * hn])
+        assert np.allclose(pa, pb, rtol=0, atol=1e-9)
+
+
+def zlib_seed(s):
+    import zlib
+    return zlib.crc32(s.encode())
+
+
 def test_unwrapped_and_large_coordinates():
     """Coordinates far outside the box (single-shift minimum image, quirk Q8) and a large offset:
     the guard band scales with max|x|, results must still match the oracle exactly."""
@@ -477,9 +550,9 @@ def test_pinned_frames_and_pool_copies_equal_staged_frames(case, monkeypatch):
     assert c.stats()["h2d_bytes"] == a.stats()["h2d_bytes"]         # the same bytes cross PCIe, without the host copy
     assert a.volume_list == o.volume_list and c.volume_list == o.volume_list
     with pytest.raises(ValueError, match="page-locked"):
-        c.calcFrames(pc1[:2].copy(), pc1[:2].copy(), pd1[:2].copy() if need_d else None, pd1[:2].copy() if need_d else None, pinned=True)
+        c.calcFrames(pc1[:2].copy(), pc2[:2].copy(), pd1[:2].copy() if need_d else None, pd2[:2].copy() if need_d else None, pinned=True)
     with pytest.raises(TypeError):
-        c.calcFrames(pc1[:2].astype(np.float32), pc1[:2].astype(np.float32), pinned=True)
+        c.calcFrames(pc1[:2].astype(np.float32), pc2[:2].astype(np.float32), pinned=True)
 
 
 def test_device_resident_frames_equal_host_path():
