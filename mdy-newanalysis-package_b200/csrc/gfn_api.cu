@@ -123,6 +123,7 @@ struct Dev {
     cudaStream_t copy = nullptr, comp = nullptr;
     Batch ring[kRing];
     int cur = 0;
+    int ramp = 2;                         // page-locked feeds: size of the next batch (reset by every sync)
     double* gacc = nullptr;               // [8][histo_n] + kStatusSlots status words (filled at readout, summed over ranks)
     double* gsum = nullptr;               // all-reduce result, same layout
     double* h_out = nullptr;              // pinned: readout lands here ([8][histo_n] + status, then kCounters u64)
@@ -828,6 +829,11 @@ static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased
         int k = h->batch_frames - b->nframes;
         if (k > nframes - f) k = nframes - f;
         const bool idle = device_idle(d);
+        if (direct) {
+            // page-locked frames cost the host nothing, but a batch runs only after ALL its frames have crossed PCIe: an idle
+            // device (after a sync / readout) starts with two frames and the batches double while it works (2, 4, 8, ... batch_frames)
+            if (d.ramp < h->batch_frames && b->nframes == 0 && k > d.ramp) k = d.ramp;
+        }
         if (idle && !direct) {
             // staged frames: what the copy threads move in one go costs the idle device no more than a single frame would
             int first = h->idle_frames;
@@ -885,10 +891,11 @@ static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased
         f += k;
         bool go = b->nframes == h->batch_frames;
         if (!go && b->nframes >= h->idle_frames) go = idle || device_idle(d);
-        if (!go && direct && f == nframes) go = true;            // the reference to the caller's arrays ends with the call
+        if (!go && direct) go = true;                            // a direct batch is exactly what this pass referenced (it never spans calls)
         if (go) {
             int rc = submit(h, d);
             if (rc) return rc;
+            if (direct && d.ramp < h->batch_frames) d.ramp *= 2;
             h->next_dev = (h->next_dev + 1) % (int)h->devs.size();
         }
     }
@@ -1135,6 +1142,7 @@ int gfn_sync(gfn_t* h)
         CU(cudaStreamSynchronize(d.copy));
         CU(cudaStreamSynchronize(d.comp));
         for (Batch& b : d.ring) { b.inflight = false; harvest_timing(h, b); }
+        d.ramp = 2;
         for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms; x.timed = false; }
     }
     return check_zerodiv(h);
@@ -1180,6 +1188,7 @@ int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overf
         CU(cudaSetDevice(d.dev));
         CU(cudaStreamSynchronize(d.comp));       // the one wait: frames, all-reduce and copies are all behind it
         for (Batch& b : d.ring) { b.inflight = false; harvest_timing(h, b); }
+        d.ramp = 2;
         for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms; x.timed = false; }
         ovf += reinterpret_cast<const unsigned long long*>(d.h_out + nall)[0];
     }
