@@ -625,7 +625,7 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
         // expected share of in-range pairs in a uniform box: decides between the ring kernel and the dense kernel
         const double vol = box_dim[0] * box_dim[1] * box_dim[2];
         const double share = fmin(1.0, 4.18879020478639098 * (double)histo_max * (double)histo_max * (double)histo_max / vol);
-        const HandleGeom geom = {(double)(float)histo_max, inv_dr, fmax(box_dim[0], fmax(box_dim[1], box_dim[2]))};
+        const HandleGeom geom = {(double)(float)histo_max, inv_dr, fmax(box_dim[0], fmax(box_dim[1], box_dim[2])), n1, n2, tri_create ? 1 : 0};
         CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, share, geom, &d.cfg));
     }
     std::vector<double> thr;
@@ -636,7 +636,7 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
         h->flags = flags;
         for (Dev& d : h->devs) {
             CUC(cudaSetDevice(d.dev));
-            CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, 0.0, HandleGeom{0.0, 0.0, 0.0}, &d.cfg));
+            CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, 0.0, HandleGeom{0.0, 0.0, 0.0, n1, n2, tri_create ? 1 : 0}, &d.cfg));
         }
     }
     h->cells = (flags & GFN_FLAG_CELLS) && !h->devs[0].cfg.dense && !sc;
@@ -670,6 +670,13 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
                 start[jt + 1] = start[jt] + (int)cnt;
             }
             h->tiles_per_frame = start[h->n_jtiles];
+            if (c.dense == 1) {
+                // fixed-point sums of the dense kernel: a launch holds at most dense_max_units units
+                long long cap = dense_max_units(c) / (h->tiles_per_frame > 0 ? h->tiles_per_frame : 1);
+                if (cap < 1) cap = 1;             // (dense_configure has checked that one frame fits)
+                if (cap < h->batch_frames) h->batch_frames = (int)cap;
+                if (h->idle_frames > h->batch_frames) h->idle_frames = h->batch_frames;
+            }
         } else {
             // prefix of surround-tile visits per core tile (the triangle starts at the tile holding the diagonal)
             start.assign(h->n_itiles + 1, 0);
@@ -1191,6 +1198,8 @@ int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overf
         d.ramp = 2;
         for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms; x.timed = false; }
         ovf += reinterpret_cast<const unsigned long long*>(d.h_out + nall)[0];
+        if (reinterpret_cast<const unsigned long long*>(d.h_out + nall)[1] & 4ull)
+            return fail(h, GFN_ECUDA, "internal: the dense kernel's fixed-point sums left their range (launch larger than dense_max_units)");
     }
     const double* out = h->devs[0].h_out;
     if (out[n8] != 0.0)

@@ -102,7 +102,7 @@ count_kernel(const PairParams P)
     const float qmid = (float)qmid_d;
     const float invdx_f = (float)P.invdx, nhminv_f = -(float)(P.hmin * P.invdx);
 
-    unsigned long long n_amb = 0, n_amb_acc = 0, n_ovf = 0, n_bad = 0;
+    unsigned long long n_amb = 0, n_amb_acc = 0, n_ovf = 0, n_bad = 0, n_w1 = 0;
     int f_cur = -1;
     Box bx; bx.Lx = bx.Ly = bx.Lz = bx.hx = bx.hy = bx.hz = 0.0;
     float hxf = 0.f, hyf = 0.f, hzf = 0.f, e1 = 0.f, hc = 0.f, hwid = 0.f;
@@ -231,6 +231,9 @@ count_kernel(const PairParams P)
                         }
                         amb[r] |= loc << (jo * 8);
                     }
+                    // j == i itself: distance 0 between identical selections (never accepted), but a real pair with
+                    // off_diag = 1 between two DIFFERENT selections of equal size (quirk Q1) - always through the exact pass
+                    if (r == jc) amb[r] |= 1u << lane;
                 }
             }
             if (selfcheck) {
@@ -253,6 +256,7 @@ count_kernel(const PairParams P)
                         const float g = q - (bf - 8388607.5f);
                         const float m = q - qmid;
                         const int row = i0 + 32 * r + lane, j = j0 + jc * 32 + jj;
+                        if (diag && j == row) continue;              // always taken by the exact pass
                         const bool cond = !diag || j > row;
                         const bool cert = (fabsf(g) < e1) && (fabsf(m) <= hc) && cond;
                         const bool wide = (fabsf(m) <= hwid) && cond;
@@ -276,7 +280,7 @@ count_kernel(const PairParams P)
                     if (pos >= 0) {
                         ++n_amb_acc;
                         const unsigned w = (P.tri && row != j) ? 2u : 1u;                                    // :131-134
-                        if (pos < hn) red_shared_u32(hraw + ((unsigned)pos << 2), w);                           // :152
+                        if (pos < hn) { red_shared_u32(hraw + ((unsigned)pos << 2), w); if (TRI && w == 1u) ++n_w1; }   // :152
                         else {                                  // quirk Q3: the flat index runs into the next row / mode
                             ++n_ovf;
                             if (!(P.flags & GFN_FLAG_DISCARD_OVERFLOW)) global_add(P, 1, 0, row, pos, (double)w);
@@ -300,23 +304,32 @@ count_kernel(const PairParams P)
         out[k] = (double)s;
         sum += s;
     }
-    // pairs accepted in the row itself = sum / weight - but the exact pass may have added weight 1 to a triangular
-    // frame's histogram only for i == j, which :149 never accepts, so every addend is wt
-    unsigned long long inr = sum / wt + n_ovf;
-    unsigned long long surv = inr + (n_amb - n_amb_acc);
+    // Counters.  The histogram holds S = wt * (pairs accepted in the rows with weight wt) + (pairs accepted with weight 1:
+    // i == j of two different selections in a triangular frame), so accepted-in-rows = (S + W1) / 2 for wt = 2, S for wt = 1 -
+    // exact per CTA (its replicas hold exactly its own pairs).
+    __shared__ unsigned long long red[5];
+    if (tid < 5) red[tid] = 0ull;
+    __syncthreads();
+    unsigned long long rej = n_amb - n_amb_acc;
     for (int d = 16; d; d >>= 1) {
-        inr += __shfl_xor_sync(0xffffffffu, inr, d);
-        surv += __shfl_xor_sync(0xffffffffu, surv, d);
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        n_w1 += __shfl_xor_sync(0xffffffffu, n_w1, d);
         n_ovf += __shfl_xor_sync(0xffffffffu, n_ovf, d);
+        rej += __shfl_xor_sync(0xffffffffu, rej, d);
         n_bad += __shfl_xor_sync(0xffffffffu, n_bad, d);
         n_amb += __shfl_xor_sync(0xffffffffu, n_amb, d);
     }
     if (lane == 0) {
-        if (n_ovf) atomicAdd(P.counters + 0, n_ovf);
-        if (surv)  atomicAdd(P.counters + 2, surv);
-        if (inr)   atomicAdd(P.counters + 3, inr);
+        atomicAdd(&red[0], sum); atomicAdd(&red[1], n_w1); atomicAdd(&red[2], n_ovf); atomicAdd(&red[3], rej);
         if (n_bad) atomicAdd(P.counters + 4, n_bad);
         if (n_amb) atomicAdd(P.counters + 5, n_amb);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long inr = (TRI ? (red[0] + red[1]) / 2ull : red[0]) + red[2];
+        if (red[2]) atomicAdd(P.counters + 0, red[2]);
+        if (inr + red[3]) atomicAdd(P.counters + 2, inr + red[3]);
+        if (inr) atomicAdd(P.counters + 3, inr);
     }
 }
 

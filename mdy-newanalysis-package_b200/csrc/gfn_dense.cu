@@ -17,13 +17,15 @@
 //     REGISTERS, so the exact path never gathers a core record.
 //   * per unit the warp runs the packed-fp16 (or fp32) range pre-filter of pair_kernel - two core rows per instruction -
 //     and keeps the survivor masks in registers: 4 chunks x 2 rows x 32 bits.
-//   * then every lane WALKS ITS OWN masks, two survivors of one row per step (two independent fp64 chains): it gathers
-//     only the surround record, evaluates distance, bin and weights in the reference's arithmetic and adds into the warp's
-//     PRIVATE histogram replica.  Pair counts use native shared-memory integer atomics (2 clocks per warp instruction
-//     on B200, profiles/microbench/warp_ops.cu).  fp64 sums must not use atomics (CAS loops) and must not use match.any
-//     either (73 clocks per warp instruction and SM when the keys differ - it was the top stall of the first version):
-//     lanes that hit the same bin are serialised by a write-and-check on a per-warp tag array (every contender stores its
-//     id, the one that reads its own id back adds, the rest retry), on average 1.5 rounds.
+//   * then the warp goes through the surround sites that survived against ANY of its rows: the site's record is read as a
+//     broadcast, every lane evaluates it against its two rows (two independent fp64 chains) masked by the rows' filter
+//     bits - distance, bin and weights in the reference's arithmetic.  (Letting every lane walk its OWN survivors keeps all
+//     lanes busy but makes every record a gather of 32 random rows: 9 shared-memory wavefronts per 128-bit load instead
+//     of 1; with that layout the shared-memory pipe was the limiter at 74 % of its peak, profiles/r2/.)
+//   * ONE histogram per CTA: pair counts with native shared-memory integer atomics; orientation sums as 64-bit FIXED POINT
+//     under a per-bin lock word (native exchange), stored in 8 bank-group stripes so that the read-modify-write of random
+//     bins is conflict-free.  Integer sums are associative: any order gives the same bits, so the warps pull units
+//     dynamically and share the histogram, and the result is reproducible.
 //   * the acceptance test :149 is taken on d^2: acc_lo <= d^2 <= acc_hi with the exact thresholds the host finds by
 //     bisection over the reference's own expressions (gfn_api.cu bin_thresholds), so rejected pairs never reach the
 //     square root.  g000-only handles are not served here: gfn_count.cu decides their bins in fp32.
@@ -63,10 +65,29 @@ __host__ __device__ constexpr int dense_col(int msel, int k)
 }
 
 __host__ __device__ inline size_t pad16(size_t b) { return (b + 15) & ~(size_t)15; }
-// per-warp replica: [bin][NCOL] fp64 sums, [bin] u32 pair weights, [bin] u8 tags
-__host__ __device__ inline size_t dense_replica_bytes(int hn, int msel)
+// ONE histogram per CTA, shared by all its warps:
+//   sums   [bin][chunk][Q] 16-byte words: two int64 fixed-point columns (2^-43) per word, Q copies ("stripes") of every
+//          word, copy q at the 16-byte slot q of its group.  A lane only ever touches stripe lane % Q: the 8 lanes of a
+//          quarter warp - what one shared-memory wavefront of a 128-bit access serves - hit 8 different bank groups
+//          whatever their bins are, so the read-modify-write of random bins is free of bank conflicts (with [bin][column]
+//          records it replayed 2.2 times, and the shared-memory pipe was the kernel's limiter at 74 % of its peak)
+//   counts [bin] u32 (native atomics), locks [bin][Q] u32
+__host__ __device__ inline size_t dense_hist_bytes(int hn, int msel, int Q)
 {
-    return pad16((size_t)hn * dense_ncol(msel) * 8) + pad16((size_t)hn * 4) + pad16((size_t)hn);
+    return (size_t)hn * ((size_t)(dense_ncol(msel) / 2) * Q * 16 + 4 + 4 * (size_t)Q);
+}
+
+// Orientation sums are kept as 64-bit fixed point, 2^-43 per unit: integer addition is associative, so a bin's sum does
+// not depend on which warp or lane got there first - all warps of a CTA can share one histogram and pull their work
+// dynamically, and the result is still reproducible bit for bit.  One addend is off by at most
+// 2^-44 = 5.7e-14 (the bar is 1e-12 per unit of pair weight); |sum| < 2^20 per bin and stripe is guaranteed by the launch
+// size (dense_max_units) and checked when the kernel starts.
+constexpr double kFixScale = 8796093022208.0;              // 2^43
+constexpr long long kFixPairs = (1ll << 20) - 1;           // accepted pairs one stripe of a bin may take per launch
+__device__ __forceinline__ long long to_fixed(double v)
+{
+    // v * 2^43 + 1.5 * 2^52 has its integer part in the mantissa: |v| <= 2^7 keeps the exponent fixed
+    return __double_as_longlong(fma(v, kFixScale, 6755399441055744.0)) - 0x4338000000000000ll;
 }
 
 template <typename F, int NW, int MSEL>
@@ -86,10 +107,10 @@ dense_kernel(const PairParams P)
     const int hn = P.histo_n;
     unsigned char* hist = reinterpret_cast<unsigned char*>(ctrl) + kDCtrlBytes;                      // [NW] replicas
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t rbytes = dense_replica_bytes(hn, MSEL);
+    const int tid = threadIdx.x, lane = tid & 31;
     const int mode_sel = MSEL == 0 ? P.mode_sel : MSEL;
     const bool m_cs = mode_sel & (2 | 16), m_cd = mode_sel & (4 | 32), m_sd = mode_sel & (8 | 64);
+    const double wt_d = P.tri ? 2.0 : 1.0;                   // off_diag of every accepted pair of this launch (:131-134)
 
     // this CTA's range of units and the surround tiles it touches (tile index gt = frame * n_jtiles + jt)
     const int upf = P.tiles_per_frame;                        // units per frame
@@ -120,9 +141,11 @@ dense_kernel(const PairParams P)
     const long long gt_first = ubeg < uend ? tile_of(ubeg, dummy_iu) : 0;
     const long long gt_last = ubeg < uend ? tile_of(uend - 1, dummy_iu) : -1;
 
+    const int Q = P.nrep;                                    // stripes (8, 4, 2 or 1)
+    const size_t hbytes = dense_hist_bytes(hn, MSEL, Q);
     {
         unsigned* z = reinterpret_cast<unsigned*>(hist);
-        for (size_t k = tid; k < (size_t)NW * rbytes / 4; k += NW * 32) z[k] = 0u;
+        for (size_t k = tid; k < hbytes / 4; k += NW * 32) z[k] = 0u;
     }
     if (tid < 4) ctrl->done[tid] = 0;
     if (tid == 0) {
@@ -133,15 +156,20 @@ dense_kernel(const PairParams P)
     __syncthreads();
     if (tid == 0) for (int k = 0; k < S && gt_first + k <= gt_last; ++k) load_tile(gt_first + k, k);
 
-    unsigned char* rep = hist + (size_t)warp * rbytes;
-    double* wsum = reinterpret_cast<double*>(rep);                                                            // [bin][NCOL]
-    unsigned* cnt = reinterpret_cast<unsigned*>(rep + pad16((size_t)hn * NCOL * 8));          // [bin]
-    unsigned char* tag = rep + pad16((size_t)hn * NCOL * 8) + pad16((size_t)hn * 4);          // [bin]
+    constexpr int NCH = NCOL / 2;                            // 16-byte words per bin
+    const int q = lane & (Q - 1);
+    longlong2* wsum = reinterpret_cast<longlong2*>(hist) + q;                                        // word (bin, c): [(bin * NCH + c) * Q]
+    unsigned* cnt = reinterpret_cast<unsigned*>(hist + (size_t)hn * NCH * Q * 16);                   // [bin]
+    unsigned* lock = cnt + hn + q;                                                                   // lock (bin): [bin * Q]
+    // the fixed-point range: a stripe takes the pairs of 32 / Q lanes per warp, 8192 / Q per unit
+    if (uend - ubeg > (kFixPairs + 1) * Q / (64 * TJ)) {
+        if (tid == 0) atomicOr(P.counters + 1, 4ull);
+        return;
+    }
 
     unsigned n_surv = 0, n_inr = 0, n_ovf = 0;
     bool zerodiv = false;
     const double acc_lo = P.acc_lo, acc_hi = P.acc_hi;
-    const bool dynamic = P.debug & 4;                        // experiments: units pulled from a counter (not reproducible)
 
     // frame constants, refreshed when a unit belongs to another frame
     int f_cur = -1;
@@ -151,14 +179,12 @@ dense_kernel(const PairParams P)
     __half2 hTg, hLx, hLy, hLz;
     hTg = hLx = hLy = hLz = __halves2half2(__ushort_as_half(0), __ushort_as_half(0));
 
-    for (int iter = 0;; ++iter) {
-        // units of the range go round-robin over the warps (fixed assignment: the summation order, and with it every bit of
-        // the result, is reproducible); a surround tile's units are consecutive, so they spread evenly over the warps
-        int un = warp + NW * iter;
-        if (dynamic) {
-            if (lane == 0) un = atomicAdd(&ctrl->next, 1);
-            un = __shfl_sync(0xffffffffu, un, 0);
-        }
+    for (;;) {
+        // the warps PULL the units of the CTA's range from a shared-memory counter: nobody waits for a slower warp, the
+        // triangle balances itself, and - the sums being integers - the result does not depend on who got which unit
+        int un = 0;
+        if (lane == 0) un = atomicAdd(&ctrl->next, 1);
+        un = __shfl_sync(0xffffffffu, un, 0);
         const long long u = ubeg + un;
         if (u >= uend) break;
         int iu;
@@ -276,141 +302,157 @@ dense_kernel(const PairParams P)
             n_surv += __popc(m0) + __popc(m1);
         }
 
-        // ---- walk: per row and chunk, every lane pops two of its survivors per step -------------------------------
+        // ---- walk: per core row every lane pops two of its survivors per step (two independent fp64 chains).  The four
+        //      chunk masks of a row form one stream (a shift register of words): lanes only wait for each other once per row.
+        //      (Going through the surround sites one by one instead - the record read as a broadcast, every lane evaluating it
+        //      against its two rows under the rows' filter bits - removes the gathers' bank conflicts but idles the lanes whose
+        //      rows did not survive: measured equal in dense boxes, four times slower in sparse ones.)
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int row = row0 + r;
-#pragma unroll 1
-            for (int jc = 0; jc < 4; ++jc) {
-                unsigned m = jc == 0 ? mk[0][r] : jc == 1 ? mk[1][r] : jc == 2 ? mk[2][r] : mk[3][r];
-                const int jbase = jc * 32;
-                while (__any_sync(0xffffffffu, m != 0u)) {
-                    bool ok[2]; int pos[2], jg[2];
-                    {
-                        // ======== weighted modes: the reference's arithmetic as in pair_kernel's drain warps
-                        bool self_pair[2]; double w[2], v[2][6];
-                        double dxa[2], dya[2], dza[2], d2[2], dist[2], idist[2];
-                        double bpx[2], bpy[2], bpz[2], bn[2], ibn[2];
+            unsigned m0 = mk[0][r], m1 = mk[1][r], m2 = mk[2][r], m3 = mk[3][r];
+            int jb = 0;
+            while (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u)) {
+                int jg[2];
+                double bpx[2], bpy[2], bpz[2], bn[2], ibn[2];
+                double bx0[2], by0[2], bz0[2];
+                bool have[2];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int fl = 31 - __clz(m);                  // highest set bit = first surround site; -1: none left
-                            const bool have = fl >= 0;
-                            m &= ~(1u << (fl & 31));
-                            const int jl = jbase + 31 - fl;
-                            jg[u] = j0 + jl;
-                            self_pair[u] = (row == jg[u]);
-                            const double2* bp = reinterpret_cast<const double2*>(js + jl);
-                            const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];   // x y | z px | py pz | norm 1/norm
-                            bpx[u] = b1.y; bpy[u] = b2.x; bpz[u] = b2.y; bn[u] = b3.x; ibn[u] = b3.y;
-                            dxa[u] = wrap_signed(b0.x, cx[r], bx.hx, bx.Lx);                         // :141-147
-                            dya[u] = wrap_signed(b0.y, cy[r], bx.hy, bx.Ly);
-                            dza[u] = wrap_signed(b1.x, cz[r], bx.hz, bx.Lz);
-                            d2[u] = DOT3(dxa[u], dya[u], dza[u], dxa[u], dya[u], dza[u]);
-                            // :149 as an interval of d^2 (exact thresholds from the host; false for NaN).  Accepted values lie
-                            // far inside the range where the straight-line square root below is exact (gfn_create checks
-                            // histo_max and inv_dr), the others are replaced by 1.
-                            ok[u] = have && d2[u] >= acc_lo && d2[u] <= acc_hi;
-                            if (!ok[u]) d2[u] = 1.0;
+                for (int u = 0; u < 2; ++u) {
+                    if (m0 == 0u) { m0 = m1; m1 = m2; m2 = m3; m3 = 0u; jb += 32; }      // next chunk of this row's stream
+                    const int fl = 31 - __clz(m0);                 // highest set bit = first surround site; -1: none left
+                    have[u] = fl >= 0;
+                    m0 &= ~(1u << (fl & 31));
+                    const int jl = (jb + 31 - fl) & (TJ - 1);
+                    jg[u] = j0 + jl;
+                    const double2* bp = reinterpret_cast<const double2*>(js + jl);
+                    const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];   // x y | z px | py pz | norm 1/norm
+                    bx0[u] = b0.x; by0[u] = b0.y; bz0[u] = b1.x;
+                    bpx[u] = b1.y; bpy[u] = b2.x; bpz[u] = b2.y; bn[u] = b3.x; ibn[u] = b3.y;
+                }
+                bool ok[2]; int pos[2];
+                double v[2][6];
+                double dxa[2], dya[2], dza[2], d2[2], dist[2], idist[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    dxa[u] = wrap_signed(bx0[u], cx[r], bx.hx, bx.Lx);                       // :141-147
+                    dya[u] = wrap_signed(by0[u], cy[r], bx.hy, bx.Ly);
+                    dza[u] = wrap_signed(bz0[u], cz[r], bx.hz, bx.Lz);
+                    d2[u] = DOT3(dxa[u], dya[u], dza[u], dxa[u], dya[u], dza[u]);
+                    // :149 as an interval of d^2 (exact thresholds from the host; false for NaN).  Accepted values lie
+                    // far inside the range where the straight-line square root below is exact (gfn_create checks
+                    // histo_max and inv_dr), the others are replaced by 1.
+                    ok[u] = have[u] && d2[u] >= acc_lo && d2[u] <= acc_hi;
+                    if (!ok[u]) d2[u] = 1.0;
+                }
+                // --- distance :148, bin :150
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    dist[u] = sqrt_rsqrt_inrange(d2[u], idist[u]);
+                    pos[u] = __double2int_rd(DMUL(DSUB(dist[u], P.hmin), P.invdx));
+                }
+                n_inr += (ok[0] ? 1u : 0u) + (ok[1] ? 1u : 0u);
+                // --- orientation weights :154-165: reciprocal form (see pair_kernel) unless this frame holds a norm that
+                //     is zero / out of range or the caller asked for the literal divisions
+                double c[2][3];
+                if (!exact_div) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        c[u][0] = DMUL(DOT3(cpx[r], cpy[r], cpz[r], bpx[u], bpy[u], bpz[u]), DMUL(icn[r], ibn[u]));
+                        c[u][1] = DMUL(DOT3(cpx[r], cpy[r], cpz[r], dxa[u], dya[u], dza[u]), DMUL(icn[r], idist[u]));
+                        c[u][2] = DMUL(DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]), DMUL(ibn[u], idist[u]));
+                    }
+                } else {
+                    double den[2][3], num[2][3];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        den[u][0] = DMUL(cn[r], bn[u]);
+                        den[u][1] = DMUL(cn[r], dist[u]);
+                        den[u][2] = DMUL(bn[u], dist[u]);
+                        num[u][0] = DOT3(cpx[r], cpy[r], cpz[r], bpx[u], bpy[u], bpz[u]);
+                        num[u][1] = DOT3(cpx[r], cpy[r], cpz[r], dxa[u], dya[u], dza[u]);
+                        num[u][2] = DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const bool sel = k == 0 ? m_cs : (k == 1 ? m_cd : m_sd);
+                            if (ok[u] && sel && den[u][k] == 0.0) zerodiv = true;          // quirk Q5
+                            if (!ok[u] || !sel || den[u][k] == 0.0) { den[u][k] = 1.0; num[u][k] = 0.0; }
+                            c[u][k] = DDIV(num[u][k], den[u][k]);
                         }
-                        // --- distance :148, bin :150, weight :131-134
+                    }
+                }
+                // every accepted pair of a launch carries the same weight off_diag (:131-134: 2 in a triangular frame, else 1 -
+                // but see i == j below): the sums are kept unweighted and multiplied at the flush (exact, a power of two)
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            dist[u] = sqrt_rsqrt_inrange(d2[u], idist[u]);
-                            pos[u] = __double2int_rd(DMUL(DSUB(dist[u], P.hmin), P.invdx));
-                            w[u] = (P.tri && !self_pair[u]) ? 2.0 : 1.0;
-                        }
-                        n_inr += (ok[0] ? 1u : 0u) + (ok[1] ? 1u : 0u);
-                        // --- orientation weights :154-165: reciprocal form (see pair_kernel) unless this frame holds a norm that
-                        //     is zero / out of range or the caller asked for the literal divisions
-                        double c[2][3];
-                        if (!exact_div) {
+                for (int u = 0; u < 2; ++u)
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                c[u][0] = DMUL(DOT3(cpx[r], cpy[r], cpz[r], bpx[u], bpy[u], bpz[u]), DMUL(icn[r], ibn[u]));
-                                c[u][1] = DMUL(DOT3(cpx[r], cpy[r], cpz[r], dxa[u], dya[u], dza[u]), DMUL(icn[r], idist[u]));
-                                c[u][2] = DMUL(DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]), DMUL(ibn[u], idist[u]));
-                            }
+                    for (int k = 0; k < 3; ++k) {
+                        v[u][k] = c[u][k];                                                       // incr
+                        v[u][3 + k] = DSUB(DMUL(DMUL(1.5, c[u][k]), c[u][k]), 0.5);              // 1.5*incr*incr-0.5
+                    }
+                // ---- accumulate -------------------------------------------------------------------------------
+                bool pend[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (ok[u] && P.tri && row == jg[u]) {
+                        // i == j of two DIFFERENT selections of equal size (quirk Q1; identical selections have d = 0 here
+                        // and were rejected): the one pair of the triangle with off_diag = 1 - straight to the global rows
+                        if (pos[u] < hn) {
+                            atomicAdd(P.gacc + 7ll * hn + pos[u], 1.0);
+                            if (mode_sel & 1) atomicAdd(P.gacc + pos[u], 1.0);
+#pragma unroll
+                            for (int k = 1; k <= 6; ++k)
+                                if (mode_sel & (1 << k)) atomicAdd(P.gacc + (long long)k * hn + pos[u], v[u][k - 1]);
                         } else {
-                            double den[2][3], num[2][3];
+                            ++n_ovf;
+                            if (!(P.flags & GFN_FLAG_DISCARD_OVERFLOW)) {
+                                if (mode_sel & 1) global_add(P, 1, 0, row, pos[u], 1.0);
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                den[u][0] = DMUL(cn[r], bn[u]);
-                                den[u][1] = DMUL(cn[r], dist[u]);
-                                den[u][2] = DMUL(bn[u], dist[u]);
-                                num[u][0] = DOT3(cpx[r], cpy[r], cpz[r], bpx[u], bpy[u], bpz[u]);
-                                num[u][1] = DOT3(cpx[r], cpy[r], cpz[r], dxa[u], dya[u], dza[u]);
-                                num[u][2] = DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]);
-#pragma unroll
-                                for (int q = 0; q < 3; ++q) {
-                                    const bool sel = q == 0 ? m_cs : (q == 1 ? m_cd : m_sd);
-                                    if (ok[u] && sel && den[u][q] == 0.0) zerodiv = true;          // quirk Q5
-                                    if (!ok[u] || !sel || den[u][q] == 0.0) { den[u][q] = 1.0; num[u][q] = 0.0; }
-                                    c[u][q] = DDIV(num[u][q], den[u][q]);
-                                }
+                                for (int k = 1; k <= 6; ++k)
+                                    if (mode_sel & (1 << k)) global_add(P, 1, k, row, pos[u], v[u][k - 1]);
                             }
                         }
+                        ok[u] = false;
+                    }
+                    pend[u] = ok[u] && pos[u] < hn;
+                    if (pend[u]) atomicAdd(cnt + pos[u], 1u);                                    // :152 and the weight row
+                    if (ok[u] && pos[u] >= hn) {
+                        // quirk Q3: the reference's flat index runs into the next row / mode; global accumulators
+                        ++n_ovf;
+                        if (!(P.flags & GFN_FLAG_DISCARD_OVERFLOW)) {
+                            const double w = wt_d;
+                            if (mode_sel & 1)  global_add(P, 1, 0, row, pos[u], w);
 #pragma unroll
-                        for (int u = 0; u < 2; ++u)
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                v[u][q] = DMUL(c[u][q], w[u]);                                          // incr*off_diag
-                                v[u][3 + q] = DMUL(DSUB(DMUL(DMUL(1.5, c[u][q]), c[u][q]), 0.5), w[u]);   // (1.5*incr*incr-0.5)*off_diag
-                            }
-                        // ---- accumulate -------------------------------------------------------------------------------
-                        bool pend[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            pend[u] = ok[u] && pos[u] < hn;
-                            if (pend[u]) atomicAdd(cnt + pos[u], (P.tri && !self_pair[u]) ? 2u : 1u);     // :152 and the weight row
-                            if (ok[u] && pos[u] >= hn) {
-                                // quirk Q3: the reference's flat index runs into the next row / mode; global accumulators
-                                ++n_ovf;
-                                if (!(P.flags & GFN_FLAG_DISCARD_OVERFLOW)) {
-                                    if (mode_sel & 1)  global_add(P, 1, 0, row, pos[u], w[u]);
-                                    if (mode_sel & 2)  global_add(P, 1, 1, row, pos[u], v[u][0]);
-                                    if (mode_sel & 4)  global_add(P, 1, 2, row, pos[u], v[u][1]);
-                                    if (mode_sel & 8)  global_add(P, 1, 3, row, pos[u], v[u][2]);
-                                    if (mode_sel & 16) global_add(P, 1, 4, row, pos[u], v[u][3]);
-                                    if (mode_sel & 32) global_add(P, 1, 5, row, pos[u], v[u][4]);
-                                    if (mode_sel & 64) global_add(P, 1, 6, row, pos[u], v[u][5]);
-                                }
-                            }
+                            for (int k = 1; k <= 6; ++k)
+                                if (mode_sel & (1 << k)) global_add(P, 1, k, row, pos[u], DMUL(v[u][k - 1], w));
                         }
-                        // fp64 sums: contenders for a bin store their id into the bin's tag; whoever reads its own id back
-                        // owns the bin for this round (exactly one per bin), the others retry
-                        const unsigned char id0 = (unsigned char)(2 * lane), id1 = (unsigned char)(2 * lane + 1);
-                        while (__any_sync(0xffffffffu, pend[0] || pend[1])) {
-                            if (pend[0]) tag[pos[0]] = id0;
-                            if (pend[1]) tag[pos[1]] = id1;
-                            __syncwarp();
-                            const bool win0 = pend[0] && tag[pos[0]] == id0;
-                            const bool win1 = pend[1] && tag[pos[1]] == id1;
-                            __syncwarp();
+                    }
+                }
+                // sums: the lane claims its stripe of the bin with a native shared-memory exchange on the lock word (one winner
+                // among all lanes of the CTA that use this stripe), updates it with plain 128-bit loads / stores, releases it
+                while (__any_sync(0xffffffffu, pend[0] || pend[1])) {
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                if (u == 0 ? win0 : win1) {
-                                    // column c of the record holds mode bit q with dense_col(MSEL, q) == c (a compile-time
-                                    // map; MSEL == 0: all six columns, unselected ones are never added to)
-                                    double addv[NCOL];
+                    for (int u = 0; u < 2; ++u) {
+                        if (pend[u] && atomicExch(lock + (size_t)pos[u] * Q, 1u) == 0u) {
+                            // column k of the bin holds mode bit b with dense_col(MSEL, b) == k (a compile-time map;
+                            // MSEL == 0: all six columns, unselected ones are never added to)
+                            long long addv[NCOL];
 #pragma unroll
-                                    for (int q = 1; q <= 6; ++q) {
-                                        const int col = dense_col(MSEL, q);
-                                        if (col >= 0) addv[col] = (MSEL != 0 || (mode_sel & (1 << q))) ? v[u][q - 1] : 0.0;
-                                    }
-                                    static_assert(NCOL % 2 == 0, "bin records are read and written as double2");
-                                    double2* h2 = reinterpret_cast<double2*>(wsum + (size_t)pos[u] * NCOL);
-                                    double2 hv[NCOL / 2];
-#pragma unroll
-                                    for (int c2 = 0; c2 < NCOL / 2; ++c2) hv[c2] = h2[c2];
-#pragma unroll
-                                    for (int c2 = 0; c2 < NCOL / 2; ++c2) { hv[c2].x += addv[2 * c2]; hv[c2].y += addv[2 * c2 + 1]; }
-#pragma unroll
-                                    for (int c2 = 0; c2 < NCOL / 2; ++c2) h2[c2] = hv[c2];
-                                }
+                            for (int b = 1; b <= 6; ++b) {
+                                const int col = dense_col(MSEL, b);
+                                if (col >= 0) addv[col] = (MSEL != 0 || (mode_sel & (1 << b))) ? to_fixed(v[u][b - 1]) : 0ll;
                             }
-                            pend[0] = pend[0] && !win0;
-                            pend[1] = pend[1] && !win1;
-                            __syncwarp();
+                            longlong2* h2 = wsum + (size_t)pos[u] * NCH * Q;
+                            longlong2 hv[NCH];
+#pragma unroll
+                            for (int c2 = 0; c2 < NCH; ++c2) hv[c2] = h2[c2 * Q];
+#pragma unroll
+                            for (int c2 = 0; c2 < NCH; ++c2) { hv[c2].x += addv[2 * c2]; hv[c2].y += addv[2 * c2 + 1]; }
+#pragma unroll
+                            for (int c2 = 0; c2 < NCH; ++c2) h2[c2 * Q] = hv[c2];
+                            __threadfence_block();
+                            *reinterpret_cast<volatile unsigned*>(lock + (size_t)pos[u] * Q) = 0u;
+                            pend[u] = false;
                         }
                     }
                 }
@@ -442,26 +484,30 @@ dense_kernel(const PairParams P)
         if (anyz)   atomicOr(P.counters + 1, 1ull);
     }
 
-    // ---- flush: replicas summed in a fixed order -> this CTA's partial histogram (layout of pair_kernel) --------
+    // ---- flush: stripes summed -> this CTA's partial histogram (layout of pair_kernel) -----------------------------
     __syncthreads();
     {
         constexpr int PS = 8;
         double* out = P.partials + (size_t)blockIdx.x * hn * PS;
+        const long long* sums = reinterpret_cast<const long long*>(hist);
+        const unsigned* counts = reinterpret_cast<const unsigned*>(hist + (size_t)hn * NCH * Q * 16);
         for (int k = tid; k < hn * PS; k += NW * 32) {
             const int bin = k / PS, sl = k - bin * PS;
             double s = 0.0;
             int col = -1;
             if (sl >= 1 && sl <= 6) col = MSEL == 0 ? sl - 1 : dense_col(MSEL, sl);
-            for (int r = 0; r < NW; ++r) {
-                const unsigned char* base = hist + (size_t)r * rbytes;
-                if (sl == 0 || sl == 7) {
-                    const unsigned c = reinterpret_cast<const unsigned*>(base + pad16((size_t)hn * NCOL * 8))[bin];
-                    if (sl == 7 || (mode_sel & 1)) s += (double)c;
-                } else if (col >= 0) {
-                    s += reinterpret_cast<const double*>(base)[(size_t)bin * NCOL + col];
+            if (sl == 0 || sl == 7) {
+                if (sl == 7 || (mode_sel & 1)) s = (double)counts[bin];
+            } else if (col >= 0) {
+                long long t = 0;                                   // |sum of the stripes| < Q * 2^63 / 2^43 ... each < 2^62: add as doubles
+                double acc = 0.0;
+                for (int z = 0; z < Q; ++z) {
+                    t = sums[(((size_t)bin * NCH + (col >> 1)) * Q + z) * 2 + (col & 1)];
+                    acc += (double)t;
                 }
+                s = acc * (1.0 / kFixScale);
             }
-            out[k] = s;
+            out[k] = s * wt_d;
         }
     }
 }
@@ -471,58 +517,75 @@ dense_kernel(const PairParams P)
 // ------------------------------------------------------------------------------------------------
 typedef void (*pair_fn_t)(const PairParams);
 
-static size_t dense_smem(int nw, int hn, int msel)
-{
-    return (size_t)kDStages * kTJ * sizeof(Site) + kDCtrlBytes + (size_t)nw * dense_replica_bytes(hn, msel);
-}
+constexpr int kDW = 16;             // warps per CTA
+long long dense_max_units(const PairConfig& cfg);
 
-template <typename F, int MSEL>
-static pair_fn_t dense_pick_w(int nw)
+static size_t dense_smem(int Q, int hn, int msel)
 {
-    return nw == 16 ? dense_kernel<F, 16, MSEL> : (nw == 12 ? dense_kernel<F, 12, MSEL> : dense_kernel<F, 8, MSEL>);
+    return (size_t)kDStages * kTJ * sizeof(Site) + kDCtrlBytes + dense_hist_bytes(hn, msel, Q);
 }
 
 template <typename F>
-static pair_fn_t dense_pick_t(int msel, int nw)
+static pair_fn_t dense_pick_t(int msel)
 {
     switch (msel) {
-        case 127: return dense_pick_w<F, 127>(nw);
-        case 31:  return dense_pick_w<F, 31>(nw);
-        default:  return dense_pick_w<F, 0>(nw);
+        case 127: return dense_kernel<F, kDW, 127>;
+        case 31:  return dense_kernel<F, kDW, 31>;
+        default:  return dense_kernel<F, kDW, 0>;
     }
 }
 
 static pair_fn_t dense_pick(const PairConfig& c)
 {
-    return c.filter_fp64 == 2 ? dense_pick_t<__half>(c.dense_msel, c.warps) : dense_pick_t<float>(c.dense_msel, c.warps);
+    return c.filter_fp64 == 2 ? dense_pick_t<__half>(c.dense_msel) : dense_pick_t<float>(c.dense_msel);
 }
 
-// Fills the dense fields of cfg (dense, dense_msel, warps, smem_bytes, nslot, grid) when the dense kernel can serve this
-// handle; returns false (cfg untouched) otherwise.
-bool dense_configure(int dev, int histo_n, int mode_sel, int max_smem, int sms, PairConfig* cfg, cudaError_t* err)
+// Fills the dense fields of cfg (dense, dense_msel, warps, nrep, smem_bytes, nslot, grid) when the dense kernel can serve
+// this handle; returns false (cfg untouched) otherwise.
+long long dense_units_per_frame(int n1, int n2, int tri)
+{
+    const long long ni = (n1 + 63) / 64, nj = (n2 + kTJ - 1) / kTJ;
+    if (!tri) return ni * nj;
+    long long u = 0;
+    for (long long jt = 0; jt < nj; ++jt) u += (2 * jt + 2 < ni) ? 2 * jt + 2 : ni;     // row blocks that reach the tile's last column
+    return u;
+}
+
+bool dense_configure(int dev, int histo_n, int mode_sel, int max_smem, int sms, const HandleGeom& geom, PairConfig* cfg, cudaError_t* err)
 {
     *err = cudaSuccess;
     if (cfg->filter_fp64 == 1 || cfg->shells || cfg->hist_mode != 0) return false;
     if (mode_sel == 0 || mode_sel == 1) return false;     // g000 only: gfn_count.cu (or the ring kernel)
     const int msel = mode_sel == 127 ? 127 : (mode_sel == 31 ? 31 : 0);
-    int nw = 0;
-    for (int cand : {12, 8}) if (!nw && dense_smem(cand, histo_n, msel) <= (size_t)max_smem) nw = cand;
-    // (16 warps leave the weighted path 128 registers per thread and spill ~100 bytes: experiments only)
-    if (const char* env = getenv("GFN_DENSE_WARPS")) {
+    // stripes of the CTA's histogram: 8 make its updates conflict-free, fewer when 8 do not fit
+    int nrep = 0;
+    for (int cand = 8; cand >= 1 && !nrep; cand >>= 1)
+        if (dense_smem(cand, histo_n, msel) <= (size_t)max_smem) nrep = cand;
+    if (const char* env = getenv("GFN_DENSE_STRIPES")) {
         const int v = atoi(env);
-        if ((v == 8 || v == 12 || v == 16) && dense_smem(v, histo_n, msel) <= (size_t)max_smem) nw = v;
+        if ((v == 1 || v == 2 || v == 4 || v == 8) && dense_smem(v, histo_n, msel) <= (size_t)max_smem) nrep = v;
     }
-    if (!nw) return false;                            // the replicas do not fit: the ring kernel takes the handle
+    if (!nrep) return false;                          // the histogram does not fit: the ring kernel takes the handle
     PairConfig c = *cfg;
     c.dense = 1; c.dense_msel = msel;
-    c.warps = nw; c.drain_warps = 0; c.nrep = nw;
+    c.warps = kDW; c.drain_warps = 0; c.nrep = nrep;
     c.nslot = 8;
-    c.smem_bytes = (int)dense_smem(nw, histo_n, msel);
+    c.smem_bytes = (int)dense_smem(nrep, histo_n, msel);
     c.blocks_per_sm = 1; c.grid = sms;
+    if (dense_max_units(c) < dense_units_per_frame(geom.n1, geom.n2, geom.tri)) return false;     // a single frame would not fit a launch
     pair_fn_t fn = dense_pick(c);
     if ((*err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes)) != cudaSuccess) return false;
     *cfg = c;
     return true;
+}
+
+// Units (64 core rows x 128 surround sites) one launch may hold so that no stripe of a bin can take more than kFixPairs
+// accepted pairs even if every pair of every unit is accepted and lands in one bin: a CTA gets at most ceil(units / grid)
+// units, a stripe the pairs of 32 / Q lanes of each of them.
+long long dense_max_units(const PairConfig& cfg)
+{
+    const long long per_cta = (kFixPairs + 1) * cfg.nrep / (64ll * kTJ) - 1;
+    return per_cta * cfg.grid;
 }
 
 cudaError_t dense_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s)

@@ -992,7 +992,7 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
         // g000 only: the count kernel (fp32 classification, fp64 for the ambiguous pairs), else the dense walk kernel
         if (count_configure(dev, histo_n, mode_sel, geom.invdx, geom.hmax, geom.box_max, max_smem, sms, cfg, &de)) return cudaSuccess;
         if (de != cudaSuccess) return de;
-        if (!dense_configure(dev, histo_n, mode_sel, max_smem, sms, cfg, &de) && de != cudaSuccess) return de;
+        if (!dense_configure(dev, histo_n, mode_sel, max_smem, sms, geom, cfg, &de) && de != cudaSuccess) return de;
     }
     return cudaSuccess;
 }

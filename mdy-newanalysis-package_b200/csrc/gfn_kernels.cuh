@@ -96,12 +96,14 @@ struct PairConfig {
 //   in_range_hint: expected share of pairs inside histo_max, (4/3) pi hmax^3 / V of the handle's box: above kDenseShare
 //   the dense kernel is chosen when it supports the handle (GFN_FLAG_DENSE / GFN_FLAG_NO_DENSE override the hint).
 constexpr double kDenseShare = 0.10;
-struct HandleGeom { double hmax, invdx, box_max; };    // what the kernel choice looks at besides the in-range share
+struct HandleGeom { double hmax, invdx, box_max; int n1, n2, tri; };    // what the kernel choice looks at besides the in-range share
 cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, int shells, double in_range_hint, const HandleGeom& geom, PairConfig* cfg);
 bool count_configure(int dev, int histo_n, int mode_sel, double invdx, double hmax, double box_max, int max_smem, int sms, PairConfig* cfg, cudaError_t* err);
 cudaError_t count_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
-bool dense_configure(int dev, int histo_n, int mode_sel, int max_smem, int sms, PairConfig* cfg, cudaError_t* err);
+bool dense_configure(int dev, int histo_n, int mode_sel, int max_smem, int sms, const HandleGeom& geom, PairConfig* cfg, cudaError_t* err);
+long long dense_units_per_frame(int n1, int n2, int tri);
 cudaError_t dense_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
+long long dense_max_units(const PairConfig& cfg);     // launch-size bound of the dense kernel's fixed-point sums
 cudaError_t pair_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
 
 // Converts nframes frames of one selection into Site records and the per-frame max |coordinate|.
