@@ -673,6 +673,17 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def counts_ok(g000_sum, accepted, n1, n2, self_pairs, frames):
+    """Exact relation between the g000 row and the number of accepted pairs: every accepted pair weighs 2 in a triangular
+    frame and 1 otherwise - except i == j between two DIFFERENT selections of equal size (quirk Q1), which weighs 1: then
+    the row lies between 2 * accepted - n * frames and 2 * accepted."""
+    if n1 != n2:
+        return bool(float(g000_sum) == accepted)
+    if self_pairs:
+        return bool(float(g000_sum) == 2.0 * accepted)
+    return bool(2.0 * accepted - n1 * frames <= float(g000_sum) <= 2.0 * accepted)
+
+
 def mode_mask(modes):
     bits = {"000": 1, "110": 2, "101": 4, "011": 8, "220": 16, "202": 32, "022": 64}
     if modes == ["all"]:
@@ -718,7 +729,7 @@ def other_config(G, name, dev, fp64_peak):
     return {"workload": name, "n1": n1, "n2": n2, "modes": "+".join(c["modes"]), "frames": F * reps, "value": evals / ms / 1e6, "unit": UNIT,
             "kernel": s1["kernel"], "filter": s1["filter"], "in_range_fraction": f_in, "flops_per_eval": fl,
             "achieved_tflops": ach, "frac": ach / fp64_peak, "kernel_share": kms / ms,
-            "bins": hn, "counts_exact": bool(float(hist[:hn].sum()) == wt * (s1["in_range"] - s1["overflow"]))}
+            "bins": hn, "counts_exact": counts_ok(hist[:hn].sum(), s1["in_range"] - s1["overflow"], n1, n2, c["self_pairs"], F * (reps + 1))}
 
 
 def atom_arms(args, G, c, mk, pool_c, F, K, W, per, POOL):

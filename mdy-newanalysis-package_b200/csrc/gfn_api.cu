@@ -448,6 +448,7 @@ int check_zerodiv(gfn_t* h)
         CU(cudaSetDevice(d.dev));
         CU(cudaMemcpy(c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
         if (c[1] & 2ull) return fail(h, GFN_EINVAL, "coordinates lie more than 30000 box lengths from the origin: the fp16 pre-filter cannot represent them, create the handle without GFN_FLAG_FILTER_FP16");
+        if (c[1] & 8ull) return fail(h, GFN_ECUDA, "checked build: a device-side index / protocol check failed");
         if (c[1] & 1ull) return fail(h, GFN_EZERODIV, "float division");
     }
     return GFN_OK;
@@ -1198,6 +1199,8 @@ int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overf
         d.ramp = 2;
         for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms; x.timed = false; }
         ovf += reinterpret_cast<const unsigned long long*>(d.h_out + nall)[0];
+        if (reinterpret_cast<const unsigned long long*>(d.h_out + nall)[1] & 8ull)
+            return fail(h, GFN_ECUDA, "checked build: a device-side index / protocol check failed");
         if (reinterpret_cast<const unsigned long long*>(d.h_out + nall)[1] & 4ull)
             return fail(h, GFN_ECUDA, "internal: the dense kernel's fixed-point sums left their range (launch larger than dense_max_units)");
     }

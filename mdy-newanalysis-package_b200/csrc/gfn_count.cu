@@ -165,7 +165,8 @@ count_kernel(const PairParams P)
             const float bf = __fadd_rd(q, 8388608.0f);                 /* floor(q) + 2^23 for 0 <= q < 2^23 */        \
             const float g = q - (bf - 8388607.5f);                     /* q - (floor(q) + 0.5) */                    \
             const float m = q - qmid;                                                                                 \
-            const unsigned addr = hbase + (__float_as_uint(bf) << 2);
+            const unsigned addr = hbase + (__float_as_uint(bf) << 2);                                                 \
+            GFN_CHECK(P, !((fabsf(g) < e1) && (fabsf(m) <= hc)) || (addr - hraw) < 4u * (unsigned)hn);
 #define GFN_COUNT_PAIR(R, BIT, LOC)                                                                                   \
         do {                                                                                                          \
             GFN_COUNT_HEAD(R)                                                                                         \
@@ -280,6 +281,7 @@ count_kernel(const PairParams P)
                     if (pos >= 0) {
                         ++n_amb_acc;
                         const unsigned w = (P.tri && row != j) ? 2u : 1u;                                    // :131-134
+                        GFN_CHECK(P, jj >= 0 && jj < 32 && row < P.strideA && j < P.strideB);
                         if (pos < hn) { red_shared_u32(hraw + ((unsigned)pos << 2), w); if (TRI && w == 1u) ++n_w1; }   // :152
                         else {                                  // quirk Q3: the flat index runs into the next row / mode
                             ++n_ovf;

@@ -415,6 +415,8 @@ dense_kernel(const PairParams P)
                         ok[u] = false;
                     }
                     pend[u] = ok[u] && pos[u] < hn;
+                    GFN_CHECK(P, !pend[u] || (pos[u] >= 0 && (size_t)(((size_t)pos[u] * NCH + NCH - 1) * Q + q) * 16 + 16 <= (size_t)hn * NCH * Q * 16));
+                    GFN_CHECK(P, !have[u] || (jg[u] - j0 >= 0 && jg[u] - j0 < TJ && st < S));
                     if (pend[u]) atomicAdd(cnt + pos[u], 1u);                                    // :152 and the weight row
                     if (ok[u] && pos[u] >= hn) {
                         // quirk Q3: the reference's flat index runs into the next row / mode; global accumulators

@@ -373,6 +373,7 @@ pair_kernel(const PairParams P)
                         for (int s2 = 0; s2 < 2; ++s2) {
                             const bool hv = m != 0u;
                             const int jj = __clz(m);
+                            GFN_CHECK(P, !hv || (at - ctrl->head[warp]) < (unsigned)kRingCap);        // never over an unread entry
                             if (hv) q[at & RMASK] = (unsigned short)(tag + (unsigned)jj);
                             m = hv ? (m & ~(0x80000000u >> (jj & 31))) : 0u;
                             at += hv ? 1u : 0u;
@@ -382,6 +383,7 @@ pair_kernel(const PairParams P)
                     auto emit_rest = [&](unsigned m, unsigned tag, unsigned at) {
                         while (m) {
                             const int jj = __clz(m);
+                            GFN_CHECK(P, (at - ctrl->head[warp]) < (unsigned)kRingCap);
                             q[at & RMASK] = (unsigned short)(tag + (unsigned)jj);
                             m &= ~(0x80000000u >> jj);
                             ++at;
@@ -503,6 +505,7 @@ pair_kernel(const PairParams P)
                             const unsigned e = have ? q[(head + idx) & RMASK] : 0u;
                             const int il = fw * (32 * kIPT) + (int)((e >> 7) & 63u), jl = e & 127;
                             const int stg = (int)(e >> 13);
+                            GFN_CHECK(P, stg < S && il < TI && (int)(head + idx - ctrl->tail[fw]) < 0 || !have);   // a published entry of a loaded stage
                             const Site* js = jsite + stg * TJ;
                             const int i = it.i0 + il, j = (stg == 0 ? j0s0 : (stg == 1 ? j0s1 : j0s2)) + jl;
                             gi[u] = i; if (SHELLS) gj[u] = j;
@@ -674,8 +677,10 @@ pair_kernel(const PairParams P)
                         }
                         if (HIST == 0) {
 #pragma unroll
-                            for (int u = 0; u < kU; ++u)
+                            for (int u = 0; u < kU; ++u) {
+                                GFN_CHECK(P, !addf[u] || (pos[u] >= 0 && pos[u] < hn));
                                 if (addf[u]) atomicAdd(cnt + pos[u], (P.tri && !self_pair[u]) ? 2u : 1u);   // :152 and the weight row
+                            }
                             if (WEIGHTS) {
                                 if (use_lock) {
                                     if (lane == 0) { while (atomicCAS(&ctrl->locks[rep], 0, 1) != 0) __nanosleep(40); }

@@ -20,7 +20,8 @@ from newanalysis.gfunction import RDF, RDF_voronoi, calcHistoTS   # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
 names = ["rect_all", "self_odd", "hmin_pos", "tiny_1x5", "g000_nodip", "cfg2_shape"] if not quick else ["self_odd", "tiny_1x5"]
-variants = ["", "fp32", "fp64", "fp16,global", "per_particle", "fp16,dense", "fp16,nodense"] if not quick else ["", "fp64"]
+os.environ["GFN_CELLS_FORCE"] = "1"
+variants = ["", "fp32", "fp64", "fp16,global", "per_particle", "fp16,dense", "fp16,nodense", "nodense,cells"] if not quick else ["", "fp64"]
 done = 0
 for name in names:
     case = dict(C.CASES[name], frames=1)
@@ -46,4 +47,5 @@ if not quick:
         done += 1
     C.drive_ts(calcHistoTS, C.TS_CASES["ts_edge"])
     done += 1
-print("sanitizer cases done:", done)
+libs = sorted(set(ln.split()[-1] for ln in open("/proc/self/maps") if "libgfn" in ln))
+print("sanitizer cases done:", done, "with", ", ".join(os.path.relpath(p, ROOT) for p in libs))

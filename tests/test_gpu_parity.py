@@ -15,6 +15,7 @@ import cases as C
 import oracle as O
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 RTOL = 1e-12
 # "" / fp16 / fp32: the library picks the kernel itself - the dense-neighbourhood kernel for most of the small golden boxes
@@ -72,6 +73,22 @@ def test_golden(golden_dir, name, flags, tmp_path, monkeypatch):
         a = np.loadtxt(str(tmp_path / ("g_g%s.dat" % mode)))
         b = np.array([[float(v) for v in ln.split()] for ln in text.strip().splitlines()])
         assert a.shape == b.shape and np.allclose(a, b, rtol=0, atol=2e-5)
+
+
+def test_checked_build_runs_the_small_cases_clean():
+    """compute-sanitizer is closed on the GPU pool (profiles/sanitizer/README.md).  Its stand-in: libgfn compiled with
+    -DGFN_CHECKED (every ring / stage / tile / histogram index and protocol invariant is tested on the device and raises a
+    sticky error) runs the small golden cases of every kernel variant - ring, count, dense, tile skipping, shells, time
+    series - in a child process that finds the checked library first."""
+    import subprocess
+    import sys
+    chk = os.path.join(ROOT, "mdy-newanalysis-package_b200", "newanalysis", "checked")
+    if not os.path.exists(os.path.join(chk, "libgfn.so")):
+        pytest.skip("checked library not built (make -C mdy-newanalysis-package_b200/csrc checked)")
+    env = dict(os.environ, LD_LIBRARY_PATH=chk + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "sanitizer", "run_cases.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "sanitizer cases done" in out.stdout and "checked/libgfn.so" in out.stdout, out.stdout[-500:]
 
 
 def test_tile_skipping_is_used_only_where_it_pays():
