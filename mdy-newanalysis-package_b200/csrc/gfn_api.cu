@@ -146,7 +146,7 @@ struct Dev {
         unsigned long long* keys[2] = {nullptr, nullptr}; unsigned* vals[2] = {nullptr, nullptr};
         void* tmp = nullptr; size_t tmp_bytes = 0;
         float* boxA = nullptr; float* boxB = nullptr;                  // [batch_frames][tiles][6]
-        int* list = nullptr; int* count = nullptr; long long* start = nullptr;
+        int* list = nullptr; int* count = nullptr; long long* start = nullptr; long long list_cap = 0;
     } cells;
     cudaEvent_t mark[2] = {nullptr, nullptr};
     gfn_residues_t* res[2] = {nullptr, nullptr};   // topology of selection 1 / 2 on this device (gfn_attach_topology)
@@ -337,6 +337,8 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
     // between the original indices of two arrays - not a triangle of positions once each is sorted on its own.  Such
     // launches keep the full enumeration.
     const bool tri_launch = (h->n1 == h->n2) && !(h->flags & GFN_FLAG_NO_TRIANGLE);
+    if (h->cells && d.cfg.dense == 1 && tri_launch && !aliased && (long long)h->tiles_per_frame * nframes > dense_max_units(d.cfg))
+        return fail(h, GFN_EINVAL, "two different selections of equal size cannot use tile skipping (their triangle relates original indices, quirk Q1) and a full frame of this size does not fit the dense kernel: create the handle without GFN_FLAG_CELLS");
     if (h->cells && !(tri_launch && !aliased)) {
         // Morton order + visit lists: the pair kernel runs on the sorted copies
         Dev::Cells& c = d.cells;
@@ -349,7 +351,12 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
         const int tri = (h->n1 == h->n2) && !(h->flags & GFN_FLAG_NO_TRIANGLE);
         double reach = (double)h->hmax_f;
         if (const char* e = getenv("GFN_CELLS_REACH")) reach = atof(e);          // experiments: a larger reach visits more tiles (never fewer pairs)
-        CU(cells_list_launch(c.boxA, c.boxB, h->n_itiles, h->n_jtiles, TI, tri, nframes, d_box, reach, c.list, c.count, c.start, d.counters + 6, s));
+        if (d.cfg.dense == 1) {
+            CU(cells_dense_lists_launch(c.boxA, c.boxB, h->n_itiles, h->n_jtiles, tri, nframes, d_box, reach, c.list, c.list_cap, c.count, c.start, d.counters, s));
+            p.visit_cap = c.list_cap;
+        } else {
+            CU(cells_list_launch(c.boxA, c.boxB, h->n_itiles, h->n_jtiles, TI, tri, nframes, d_box, reach, c.list, c.count, c.start, d.counters + 6, s));
+        }
         h->st_launches += aliased ? 8 : 12;
         h->st_visits_dense += (double)h->tiles_per_frame * nframes;
         siteA = c.sortA; siteB = sb;
@@ -448,6 +455,8 @@ int check_zerodiv(gfn_t* h)
         CU(cudaSetDevice(d.dev));
         CU(cudaMemcpy(c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
         if (c[1] & 2ull) return fail(h, GFN_EINVAL, "coordinates lie more than 30000 box lengths from the origin: the fp16 pre-filter cannot represent them, create the handle without GFN_FLAG_FILTER_FP16");
+        if (c[1] & 16ull) return fail(h, GFN_ECUDA, "internal: the visit list of a cell-sorted launch overflowed its buffer");
+        if (c[1] & 4ull) return fail(h, GFN_ECUDA, "a bin of one CTA took more than 2^20 pairs in one launch: beyond the dense kernel's fixed-point range (create the handle with GFN_FLAG_NO_DENSE)");
         if (c[1] & 8ull) return fail(h, GFN_ECUDA, "checked build: a device-side index / protocol check failed");
         if (c[1] & 1ull) return fail(h, GFN_EZERODIV, "float division");
     }
@@ -619,6 +628,24 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
     }
 
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(nullptr, GFN_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); for (Dev& dd : h->devs) free_dev(dd); delete h; return GFN_ECUDA; } } while (0)
+    double cells_share = 0.05;        // expected share of visited tile pairs (forced handles: assume few)
+    if ((flags & GFN_FLAG_CELLS) && !getenv("GFN_CELLS_FORCE")) {
+        // Tile skipping is worth it only when enough tile pairs can be skipped.  Expected share of visited tile pairs: a tile of
+        // T sorted sites fills a blob of edge (V T / n)^(1/3); Morton blobs measure ~1.5 cubes across; a core blob sees the
+        // surround blobs within histo_max of it.  Orientation modes run on the dense kernel (64-row core blocks): worth it
+        // below one half; g000-only handles stay on pair_kernel (512-row core tiles), whose survivor path is built for evenly
+        // sparse tiles: worth it below 15 % (measured: 0.67 at BASELINE configs[2] is 3 x slower, 0.024 at configs[4] 4 x faster).
+        const double vol = box_dim[0] * box_dim[1] * box_dim[2];
+        const bool g000 = mode_sel == 1;
+        const double ec = cbrt(vol * (g000 ? 512.0 : 64.0) / (double)(n1 > 0 ? n1 : 1)), es = cbrt(vol * kTJ / (double)(n2 > 0 ? n2 : 1));
+        const double w = 1.5 * (ec + es) + 2.0 * (double)histo_max;
+        double share = 1.0;
+        for (int k = 0; k < 3; ++k) share *= fmin(1.0, w / box_dim[k]);
+        if (share > (g000 ? 0.15 : 0.08)) flags &= ~GFN_FLAG_CELLS;
+        h->flags = flags;
+        cells_share = share;
+    }
+    if (sc) { flags &= ~GFN_FLAG_CELLS; h->flags = flags; }
     h->devs.resize(devs.size());
     for (size_t i = 0; i < devs.size(); ++i) h->devs[i].dev = devs[i];
     for (Dev& d : h->devs) {
@@ -626,7 +653,7 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
         // expected share of in-range pairs in a uniform box: decides between the ring kernel and the dense kernel
         const double vol = box_dim[0] * box_dim[1] * box_dim[2];
         const double share = fmin(1.0, 4.18879020478639098 * (double)histo_max * (double)histo_max * (double)histo_max / vol);
-        const HandleGeom geom = {(double)(float)histo_max, inv_dr, fmax(box_dim[0], fmax(box_dim[1], box_dim[2])), n1, n2, tri_create ? 1 : 0};
+        const HandleGeom geom = {(double)(float)histo_max, inv_dr, fmax(box_dim[0], fmax(box_dim[1], box_dim[2])), n1, n2, tri_create ? 1 : 0, (flags & GFN_FLAG_CELLS) ? cells_share : 0.0};
         CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, share, geom, &d.cfg));
     }
     std::vector<double> thr;
@@ -637,22 +664,10 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
         h->flags = flags;
         for (Dev& d : h->devs) {
             CUC(cudaSetDevice(d.dev));
-            CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, 0.0, HandleGeom{0.0, 0.0, 0.0, n1, n2, tri_create ? 1 : 0}, &d.cfg));
+            CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, 0.0, HandleGeom{0.0, 0.0, 0.0, n1, n2, tri_create ? 1 : 0, 0.0}, &d.cfg));
         }
     }
-    h->cells = (flags & GFN_FLAG_CELLS) && !h->devs[0].cfg.dense && !sc;
-    if (h->cells && !getenv("GFN_CELLS_FORCE")) {
-        // Worth it only when most tile pairs can be skipped.  Expected share of visited tile pairs: a tile of T sorted sites
-        // fills a blob of edge (V T / n)^(1/3); Morton blobs measure ~1.5 cubes across; a core blob sees the surround blobs
-        // within histo_max of it.  (Measured visit shares: 0.67 at BASELINE configs[2] - slower than the full enumeration,
-        // the pair kernel's survivor path is built for evenly sparse tiles -, 0.26 at configs[3], 0.024 at configs[4].)
-        const double vol = box_dim[0] * box_dim[1] * box_dim[2];
-        const double ec = cbrt(vol * tile_i(h->devs[0].cfg) / (double)(n1 > 0 ? n1 : 1)), es = cbrt(vol * kTJ / (double)(n2 > 0 ? n2 : 1));
-        const double w = 1.5 * (ec + es) + 2.0 * (double)histo_max;
-        double share = 1.0;
-        for (int k = 0; k < 3; ++k) share *= fmin(1.0, w / box_dim[k]);
-        if (share > 0.15) h->cells = false;
-    }
+    h->cells = (flags & GFN_FLAG_CELLS) && h->devs[0].cfg.dense != 2 && !sc;
     // work decomposition (identical on all devices)
     {
         const PairConfig& c = h->devs[0].cfg;
@@ -673,7 +688,9 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
             h->tiles_per_frame = start[h->n_jtiles];
             if (c.dense == 1) {
                 // fixed-point sums of the dense kernel: a launch holds at most dense_max_units units
-                long long cap = dense_max_units(c) / (h->tiles_per_frame > 0 ? h->tiles_per_frame : 1);
+                double upf = (double)(h->tiles_per_frame > 0 ? h->tiles_per_frame : 1);
+                if (flags & GFN_FLAG_CELLS) upf *= fmin(1.0, 2.0 * cells_share);
+                long long cap = (long long)((double)dense_max_units(c) / fmax(upf, 1.0));
                 if (cap < 1) cap = 1;             // (dense_configure has checked that one frame fits)
                 if (cap < h->batch_frames) h->batch_frames = (int)cap;
                 if (h->idle_frames > h->batch_frames) h->idle_frames = h->batch_frames;
@@ -723,9 +740,17 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
             CUC(cudaMalloc(&c.tmp, c.tmp_bytes ? c.tmp_bytes : 16));
             CUC(cudaMalloc(&c.boxA, sizeof(float) * 6 * (size_t)h->n_itiles * bf));
             CUC(cudaMalloc(&c.boxB, sizeof(float) * 6 * (size_t)h->n_jtiles * bf));
-            CUC(cudaMalloc(&c.list, sizeof(int) * (size_t)h->n_itiles * (size_t)h->n_jtiles * bf));
-            CUC(cudaMalloc(&c.count, sizeof(int) * (size_t)h->n_itiles * bf));
-            CUC(cudaMalloc(&c.start, sizeof(long long) * ((size_t)h->n_itiles * bf + 1)));
+            if (d.cfg.dense == 1) {
+                // dense kernel: entries are (frame, surround tile), lists are compact; room for the un-pruned unit count
+                c.list_cap = (long long)h->tiles_per_frame * (long long)bf;
+                CUC(cudaMalloc(&c.list, sizeof(int) * (size_t)c.list_cap));
+                CUC(cudaMalloc(&c.count, sizeof(int) * (size_t)h->n_jtiles * bf));
+                CUC(cudaMalloc(&c.start, sizeof(long long) * ((size_t)h->n_jtiles * bf + 1)));
+            } else {
+                CUC(cudaMalloc(&c.list, sizeof(int) * (size_t)h->n_itiles * (size_t)h->n_jtiles * bf));
+                CUC(cudaMalloc(&c.count, sizeof(int) * (size_t)h->n_itiles * bf));
+                CUC(cudaMalloc(&c.start, sizeof(long long) * ((size_t)h->n_itiles * bf + 1)));
+            }
         }
         if (flags & GFN_FLAG_PER_PARTICLE) {
             const size_t bytes = sizeof(double) * 7ull * n1 * histo_n;
@@ -1202,7 +1227,9 @@ int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overf
         if (reinterpret_cast<const unsigned long long*>(d.h_out + nall)[1] & 8ull)
             return fail(h, GFN_ECUDA, "checked build: a device-side index / protocol check failed");
         if (reinterpret_cast<const unsigned long long*>(d.h_out + nall)[1] & 4ull)
-            return fail(h, GFN_ECUDA, "internal: the dense kernel's fixed-point sums left their range (launch larger than dense_max_units)");
+            return fail(h, GFN_ECUDA, "a bin of one CTA took more than 2^20 pairs in one launch: beyond the dense kernel's fixed-point range (create the handle with GFN_FLAG_NO_DENSE)");
+        if (reinterpret_cast<const unsigned long long*>(d.h_out + nall)[1] & 16ull)
+            return fail(h, GFN_ECUDA, "internal: the visit list of a cell-sorted launch overflowed its buffer");
     }
     const double* out = h->devs[0].h_out;
     if (out[n8] != 0.0)

@@ -155,6 +155,49 @@ cells_list_kernel(const float* __restrict__ boxA, const float* __restrict__ boxB
     if (lane == 0) count[(long long)f * n_itiles + ti] = nout;
 }
 
+// Dense-kernel units of cell-sorted frames: one warp per (frame, surround tile jt) lists the 64-row core BLOCKS whose box
+// lies within reach of the tile's box, in ascending order - a triangular frame only the blocks that reach the tile's last
+// column (ib <= 2 jt + 1, as in the un-pruned enumeration).  An entry is never empty (block 0 stands in: the kernel's tile
+// ring counts the units of every tile).  Two passes: fill == 0 counts, fill == 1 writes the lists at their prefix offsets
+// (compact storage, capacity checked: an overflowing launch raises the error flag and lists nothing beyond).
+__global__ void __launch_bounds__(256)
+cells_dense_list_kernel(const float* __restrict__ boxBlk, const float* __restrict__ boxTile, int n_blk, int n_jtiles, int tri,
+                        const double* __restrict__ box, float reach, int fill, int* __restrict__ count, const long long* __restrict__ start,
+                        int* __restrict__ list, long long capacity, unsigned long long* __restrict__ counters)
+{
+    const int f = blockIdx.y;
+    const int jt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (jt >= n_jtiles) return;
+    const long long e = (long long)f * n_jtiles + jt;
+    const float* a = boxTile + e * 6;
+    const double* b = box + 6ll * f;
+    const float Lx = __double2float_rd(b[0]), Ly = __double2float_rd(b[1]), Lz = __double2float_rd(b[2]);
+    const float r = reach * (1.0f + 4e-6f) + 4e-6f * fmaxf(Lx, fmaxf(Ly, Lz));
+    const float r2 = r * r * (1.0f + 1e-6f);
+    const long long base = fill ? start[e] : 0;
+    const bool room = !fill || start[e + 1] <= capacity;
+    if (fill && !room) { if (lane == 0) atomicOr(counters + 1, 16ull); return; }
+    int nout = 0;
+    const int ib_end = tri ? min(2 * jt + 2, n_blk) : n_blk;
+    for (int b0 = 0; b0 < ib_end; b0 += 32) {
+        const int ib = b0 + lane;
+        bool hit = false;
+        if (ib < ib_end) {
+            const float* q = boxBlk + ((long long)f * n_blk + ib) * 6;
+            const float gx = interval_gap(a[0], a[3], q[0], q[3], Lx);
+            const float gy = interval_gap(a[1], a[4], q[1], q[4], Ly);
+            const float gz = interval_gap(a[2], a[5], q[2], q[5], Lz);
+            hit = (a[0] <= a[3]) && (q[0] <= q[3]) && gx * gx + gy * gy + gz * gz <= r2;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (fill && hit) list[base + nout + __popc(m & ((1u << lane) - 1u))] = ib;
+        nout += __popc(m);
+    }
+    if (nout == 0) { if (fill && lane == 0) list[base] = 0; nout = 1; }
+    if (!fill && lane == 0) count[e] = nout;
+}
+
 // exclusive prefix of count[0 .. nent) -> start[0 .. nent]; one block
 __global__ void __launch_bounds__(1024)
 cells_scan_kernel(const int* __restrict__ count, long long* __restrict__ start, long long nent, unsigned long long* __restrict__ visits)
@@ -216,6 +259,19 @@ cudaError_t cells_list_launch(const float* boxA, const float* boxB, int n_itiles
 {
     cells_list_kernel<<<dim3((n_itiles + 7) / 8, nframes), 256, 0, s>>>(boxA, boxB, n_itiles, n_jtiles, TI, tri, box, (float)hmax * (1.0f + 1e-6f), list, count);
     cells_scan_kernel<<<1, 1024, 0, s>>>(count, start, (long long)nframes * n_itiles, visits);
+    return cudaGetLastError();
+}
+
+// Visit lists of the dense kernel's units (count, prefix, fill).  capacity: ints the list buffer holds.
+cudaError_t cells_dense_lists_launch(const float* boxBlk, const float* boxTile, int n_blk, int n_jtiles, int tri, int nframes,
+                                     const double* box, double hmax, int* list, long long capacity, int* count, long long* start,
+                                     unsigned long long* counters, cudaStream_t s)
+{
+    const dim3 grid((n_jtiles + 7) / 8, nframes);
+    const float reach = (float)hmax * (1.0f + 1e-6f);
+    cells_dense_list_kernel<<<grid, 256, 0, s>>>(boxBlk, boxTile, n_blk, n_jtiles, tri, box, reach, 0, count, nullptr, nullptr, capacity, counters);
+    cells_scan_kernel<<<1, 1024, 0, s>>>(count, start, (long long)nframes * n_jtiles, counters + 6);
+    cells_dense_list_kernel<<<grid, 256, 0, s>>>(boxBlk, boxTile, n_blk, n_jtiles, tri, box, reach, 1, count, start, list, capacity, counters);
     return cudaGetLastError();
 }
 

@@ -44,7 +44,7 @@ struct DCtrl {
     uint64_t full[kDStages];     // TMA landed in stage s
     int done[4];                 // units finished on the tile held by stage s (the last one refills the stage)
     int next;                    // next unit of this CTA's range to hand out
-    int pad[3];
+    volatile int gen[3];         // ordinal (inside the CTA's range) of the tile stage s holds or is being loaded with
 };
 constexpr int kDCtrlBytes = 64;
 static_assert(sizeof(DCtrl) <= kDCtrlBytes, "control block");
@@ -80,10 +80,10 @@ __host__ __device__ inline size_t dense_hist_bytes(int hn, int msel, int Q)
 // Orientation sums are kept as 64-bit fixed point, 2^-43 per unit: integer addition is associative, so a bin's sum does
 // not depend on which warp or lane got there first - all warps of a CTA can share one histogram and pull their work
 // dynamically, and the result is still reproducible bit for bit.  One addend is off by at most
-// 2^-44 = 5.7e-14 (the bar is 1e-12 per unit of pair weight); |sum| < 2^20 per bin and stripe is guaranteed by the launch
-// size (dense_max_units) and checked when the kernel starts.
+// 2^-44 = 5.7e-14 (the bar is 1e-12 per unit of pair weight); |sum| < 2^20 per bin and stripe holds as long as no bin of a CTA
+// takes 2^20 pairs in one launch: checked at the flush (error, not a wrap-around); launches are sized far below (dense_max_units).
 constexpr double kFixScale = 8796093022208.0;              // 2^43
-constexpr long long kFixPairs = (1ll << 20) - 1;           // accepted pairs one stripe of a bin may take per launch
+constexpr long long kFixPairs = (1ll << 20) - 1;           // accepted pairs one bin of a CTA's histogram may take per launch
 __device__ __forceinline__ long long to_fixed(double v)
 {
     // v * 2^43 + 1.5 * 2^52 has its integer part in the mantissa: |v| <= 2^7 keeps the exponent fixed
@@ -114,10 +114,21 @@ dense_kernel(const PairParams P)
 
     // this CTA's range of units and the surround tiles it touches (tile index gt = frame * n_jtiles + jt)
     const int upf = P.tiles_per_frame;                        // units per frame
-    const long long total_units = (long long)upf * P.nframes;
+    // cell-sorted frames (gfn_cells.cu): entry gt = frame * n_jtiles + jt lists the 64-row core blocks within histo_max of
+    // surround tile jt (never empty), visit_start is the exclusive prefix of the list lengths = the flat unit sequence
+    const bool listed = P.visit_start != nullptr;
+    const long long nent = (long long)P.nframes * P.n_jtiles;
+    long long total_units = listed ? P.visit_start[nent] : (long long)upf * P.nframes;
+    if (listed && total_units > P.visit_cap) total_units = 0;       // the list buffer overflowed (flagged by gfn_cells.cu): only the flush runs
     const long long ubeg = total_units * blockIdx.x / gridDim.x;
     const long long uend = total_units * (blockIdx.x + 1) / gridDim.x;
     auto tile_of = [&](long long u, int& iu) -> long long {
+        if (listed) {
+            long long lo = 0, hi = nent;           // the last entry with start <= u (entries are never empty)
+            while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (P.visit_start[mid] <= u) lo = mid; else hi = mid; }
+            iu = __ldg(P.visit_list + u);
+            return lo;
+        }
         const int f = (int)(u / upf);
         const int r = (int)(u - (long long)f * upf);
         int lo = 0, hi = P.n_jtiles;       // jt with tile_start[jt] <= r < tile_start[jt+1]
@@ -126,21 +137,27 @@ dense_kernel(const PairParams P)
         return (long long)f * P.n_jtiles + lo;
     };
     auto units_in_range = [&](long long gt) -> int {          // units of tile gt that belong to this CTA
-        const int f = (int)(gt / P.n_jtiles), jt = (int)(gt - (long long)f * P.n_jtiles);
-        long long b = (long long)f * upf + P.tile_start[jt], e = (long long)f * upf + P.tile_start[jt + 1];
+        long long b, e;
+        if (listed) { b = P.visit_start[gt]; e = P.visit_start[gt + 1]; }
+        else {
+            const int f = (int)(gt / P.n_jtiles), jt = (int)(gt - (long long)f * P.n_jtiles);
+            b = (long long)f * upf + P.tile_start[jt]; e = (long long)f * upf + P.tile_start[jt + 1];
+        }
         if (b < ubeg) b = ubeg;
         if (e > uend) e = uend;
         return (int)(e - b);
-    };
-    auto load_tile = [&](long long gt, int st) {
-        const int f = (int)(gt / P.n_jtiles), jt = (int)(gt - (long long)f * P.n_jtiles);
-        mbar_expect_tx(&ctrl->full[st], TJ * (uint32_t)sizeof(Site));
-        bulk_g2s(jsite + st * TJ, P.siteB + (long long)f * P.strideB + (long long)jt * TJ, TJ * (uint32_t)sizeof(Site), &ctrl->full[st]);
     };
     int dummy_iu;
     const long long gt_first = ubeg < uend ? tile_of(ubeg, dummy_iu) : 0;
     const long long gt_last = ubeg < uend ? tile_of(uend - 1, dummy_iu) : -1;
 
+    auto load_tile = [&](long long gt, int st) {
+        const int f = (int)(gt / P.n_jtiles), jt = (int)(gt - (long long)f * P.n_jtiles);
+        ctrl->gen[st] = (int)(gt - gt_first);          // a waiter first sees WHICH tile the stage is for, then waits for its bytes
+        __threadfence_block();
+        mbar_expect_tx(&ctrl->full[st], TJ * (uint32_t)sizeof(Site));
+        bulk_g2s(jsite + st * TJ, P.siteB + (long long)f * P.strideB + (long long)jt * TJ, TJ * (uint32_t)sizeof(Site), &ctrl->full[st]);
+    };
     const int Q = P.nrep;                                    // stripes (8, 4, 2 or 1)
     const size_t hbytes = dense_hist_bytes(hn, MSEL, Q);
     {
@@ -148,6 +165,7 @@ dense_kernel(const PairParams P)
         for (size_t k = tid; k < hbytes / 4; k += NW * 32) z[k] = 0u;
     }
     if (tid < 4) ctrl->done[tid] = 0;
+    if (tid < 3) ctrl->gen[tid] = -1;
     if (tid == 0) {
         ctrl->next = 0;
         for (int k = 0; k < S; ++k) mbar_init(&ctrl->full[k], 1);
@@ -161,12 +179,6 @@ dense_kernel(const PairParams P)
     longlong2* wsum = reinterpret_cast<longlong2*>(hist) + q;                                        // word (bin, c): [(bin * NCH + c) * Q]
     unsigned* cnt = reinterpret_cast<unsigned*>(hist + (size_t)hn * NCH * Q * 16);                   // [bin]
     unsigned* lock = cnt + hn + q;                                                                   // lock (bin): [bin * Q]
-    // the fixed-point range: a stripe takes the pairs of 32 / Q lanes per warp, 8192 / Q per unit
-    if (uend - ubeg > (kFixPairs + 1) * Q / (64 * TJ)) {
-        if (tid == 0) atomicOr(P.counters + 1, 4ull);
-        return;
-    }
-
     unsigned n_surv = 0, n_inr = 0, n_ovf = 0;
     bool zerodiv = false;
     const double acc_lo = P.acc_lo, acc_hi = P.acc_hi;
@@ -223,7 +235,7 @@ dense_kernel(const PairParams P)
         // ---- this lane's two core rows -----------------------------------------------------------------------------
         const int row0 = iu * 64 + 2 * lane;
         double cx[2], cy[2], cz[2], cpx[2], cpy[2], cpz[2], cn[2], icn[2];
-        unsigned fxb[2], fyb[2], fzb[2];
+        unsigned fxb[2], fyb[2], fzb[2]; int corig[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const double2* rp = reinterpret_cast<const double2*>(siteA + row0 + r);
@@ -232,7 +244,7 @@ dense_kernel(const PairParams P)
             const double2 a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
             cpy[r] = a2.x; cpz[r] = a2.y; cn[r] = a3.x; icn[r] = a3.y;
             const uint4 f4 = __ldg(reinterpret_cast<const uint4*>(&siteA[row0 + r].fx));
-            fxb[r] = f4.x; fyb[r] = f4.y; fzb[r] = f4.z;
+            fxb[r] = f4.x; fyb[r] = f4.y; fzb[r] = f4.z; corig[r] = (int)f4.w;      // Site.fw: original index in cell-sorted frames
         }
         __half2 hcx, hcy, hcz;
         float fcx[2], fcy[2], fcz[2];
@@ -243,6 +255,9 @@ dense_kernel(const PairParams P)
             for (int r = 0; r < 2; ++r) { fcx[r] = __uint_as_float(fxb[r]); fcy[r] = __uint_as_float(fyb[r]); fcz[r] = __uint_as_float(fzb[r]); }
         }
 
+        // the stage may still hold (or be waiting for) an EARLIER tile: with few units per tile the 16 warps run several tiles
+        // ahead of the ring, and an mbarrier parity alone cannot tell a tile from the one two uses before it
+        while (ctrl->gen[st] != (int)k) __nanosleep(40);
         mbar_wait(&ctrl->full[st], (unsigned)((k / S) & 1));
         const Site* js = jsite + st * TJ;
 
@@ -313,7 +328,7 @@ dense_kernel(const PairParams P)
             unsigned m0 = mk[0][r], m1 = mk[1][r], m2 = mk[2][r], m3 = mk[3][r];
             int jb = 0;
             while (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u)) {
-                int jg[2];
+                int jg[2], sorig[2];
                 double bpx[2], bpy[2], bpz[2], bn[2], ibn[2];
                 double bx0[2], by0[2], bz0[2];
                 bool have[2];
@@ -325,6 +340,7 @@ dense_kernel(const PairParams P)
                     m0 &= ~(1u << (fl & 31));
                     const int jl = (jb + 31 - fl) & (TJ - 1);
                     jg[u] = j0 + jl;
+                    sorig[u] = listed ? __float_as_int(js[jl].fw) : 0;
                     const double2* bp = reinterpret_cast<const double2*>(js + jl);
                     const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];   // x y | z px | py pz | norm 1/norm
                     bx0[u] = b0.x; by0[u] = b0.y; bz0[u] = b1.x;
@@ -381,6 +397,19 @@ dense_kernel(const PairParams P)
                         }
                     }
                 }
+                // cell-sorted triangular frame: the pair was found by POSITION; the reference's core is the site with the smaller
+                // ORIGINAL index (:126-130).  Exchanging the roles exchanges cos(core dipole, d) and cos(surround dipole, d) and
+                // flips d: the same products, negated - exact.
+                int rowo[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    rowo[u] = listed ? corig[r] : row;
+                    if (listed && P.tri && sorig[u] < corig[r]) {
+                        const double t = c[u][1];
+                        c[u][1] = -c[u][2]; c[u][2] = -t;
+                        rowo[u] = sorig[u];
+                    }
+                }
                 // every accepted pair of a launch carries the same weight off_diag (:131-134: 2 in a triangular frame, else 1 -
                 // but see i == j below): the sums are kept unweighted and multiplied at the flush (exact, a power of two)
 #pragma unroll
@@ -406,10 +435,10 @@ dense_kernel(const PairParams P)
                         } else {
                             ++n_ovf;
                             if (!(P.flags & GFN_FLAG_DISCARD_OVERFLOW)) {
-                                if (mode_sel & 1) global_add(P, 1, 0, row, pos[u], 1.0);
+                                if (mode_sel & 1) global_add(P, 1, 0, rowo[u], pos[u], 1.0);
 #pragma unroll
                                 for (int k = 1; k <= 6; ++k)
-                                    if (mode_sel & (1 << k)) global_add(P, 1, k, row, pos[u], v[u][k - 1]);
+                                    if (mode_sel & (1 << k)) global_add(P, 1, k, rowo[u], pos[u], v[u][k - 1]);
                             }
                         }
                         ok[u] = false;
@@ -423,10 +452,10 @@ dense_kernel(const PairParams P)
                         ++n_ovf;
                         if (!(P.flags & GFN_FLAG_DISCARD_OVERFLOW)) {
                             const double w = wt_d;
-                            if (mode_sel & 1)  global_add(P, 1, 0, row, pos[u], w);
+                            if (mode_sel & 1)  global_add(P, 1, 0, rowo[u], pos[u], w);
 #pragma unroll
                             for (int k = 1; k <= 6; ++k)
-                                if (mode_sel & (1 << k)) global_add(P, 1, k, row, pos[u], DMUL(v[u][k - 1], w));
+                                if (mode_sel & (1 << k)) global_add(P, 1, k, rowo[u], pos[u], DMUL(v[u][k - 1], w));
                         }
                     }
                 }
@@ -511,6 +540,9 @@ dense_kernel(const PairParams P)
             }
             out[k] = s * wt_d;
         }
+        // the fixed-point range: a stripe of a bin holds at most as many addends as the bin's count
+        for (int k = tid; k < hn; k += NW * 32)
+            if (counts[k] > (unsigned)kFixPairs) atomicOr(P.counters + 1, 4ull);
     }
 }
 
@@ -574,20 +606,23 @@ bool dense_configure(int dev, int histo_n, int mode_sel, int max_smem, int sms, 
     c.nslot = 8;
     c.smem_bytes = (int)dense_smem(nrep, histo_n, msel);
     c.blocks_per_sm = 1; c.grid = sms;
-    if (dense_max_units(c) < dense_units_per_frame(geom.n1, geom.n2, geom.tri)) return false;     // a single frame would not fit a launch
+    {
+        // a single frame must fit a launch; under tile skipping only the listed units count (twice the expected share)
+        double units = (double)dense_units_per_frame(geom.n1, geom.n2, geom.tri);
+        if (geom.cells_share > 0.0) units *= fmin(1.0, 2.0 * geom.cells_share);
+        if ((double)dense_max_units(c) < units) return false;
+    }
     pair_fn_t fn = dense_pick(c);
     if ((*err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes)) != cudaSuccess) return false;
     *cfg = c;
     return true;
 }
 
-// Units (64 core rows x 128 surround sites) one launch may hold so that no stripe of a bin can take more than kFixPairs
-// accepted pairs even if every pair of every unit is accepted and lands in one bin: a CTA gets at most ceil(units / grid)
-// units, a stripe the pairs of 32 / Q lanes of each of them.
+// Units (64 core rows x 128 surround sites) per launch: small enough that a CTA's 2^20-pairs-per-bin limit is out of reach
+// for any but pathological frames (a CTA then sees at most 2^27 pairs; a bin of a uniform box takes < 1 % of them).
 long long dense_max_units(const PairConfig& cfg)
 {
-    const long long per_cta = (kFixPairs + 1) * cfg.nrep / (64ll * kTJ) - 1;
-    return per_cta * cfg.grid;
+    return (1ll << 14) * cfg.grid;
 }
 
 cudaError_t dense_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s)

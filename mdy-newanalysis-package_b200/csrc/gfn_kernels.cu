@@ -991,7 +991,10 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
     cfg->blocks_per_sm = 1;
     cfg->grid = sms;
     // dense neighbourhoods: the symmetric kernel, when it supports the handle
-    const bool want_dense = (flags & GFN_FLAG_DENSE) || (!(flags & GFN_FLAG_NO_DENSE) && in_range_hint > kDenseShare);
+    // tile skipping with orientation modes runs on the dense kernel (its warps all filter AND evaluate, so the survivors a
+    // cell-sorted frame concentrates in its near tiles do not stall anybody)
+    const bool cells_dense = (flags & GFN_FLAG_CELLS) && mode_sel != 1 && !(flags & GFN_FLAG_NO_DENSE);
+    const bool want_dense = (flags & GFN_FLAG_DENSE) || cells_dense || (!(flags & GFN_FLAG_NO_DENSE) && in_range_hint > kDenseShare);
     if (want_dense) {
         cudaError_t de = cudaSuccess;
         // g000 only: the count kernel (fp32 classification, fp64 for the ambiguous pairs), else the dense walk kernel

@@ -69,6 +69,7 @@ struct PairParams {
     // the surround tiles visit_list[e * n_jtiles + 0 .. visit_start[e+1] - visit_start[e])
     const long long* visit_start;   // [nframes * n_itiles + 1] exclusive prefix, last = total visits of the launch
     const int* visit_list;
+    long long visit_cap;            // dense kernel: entries the compact list buffer holds (a launch that lists more does nothing and flags it)
     // dense kernel, g000-only handles: the bin of a pair from d^2 without a square root (gfn_dense.cu)
     const double* bin_thr;          // [histo_n + 4]  T[k] = min { t : sqrt(t) >= hmin and floor((sqrt(t) - hmin) * invdx) >= k }
     double acc_lo, acc_hi;          // a pair passes gfunction.pyx:149  <=>  acc_lo <= d^2 <= acc_hi
@@ -96,7 +97,7 @@ struct PairConfig {
 //   in_range_hint: expected share of pairs inside histo_max, (4/3) pi hmax^3 / V of the handle's box: above kDenseShare
 //   the dense kernel is chosen when it supports the handle (GFN_FLAG_DENSE / GFN_FLAG_NO_DENSE override the hint).
 constexpr double kDenseShare = 0.10;
-struct HandleGeom { double hmax, invdx, box_max; int n1, n2, tri; };    // what the kernel choice looks at besides the in-range share
+struct HandleGeom { double hmax, invdx, box_max; int n1, n2, tri; double cells_share; };   // cells_share: expected share of visited units under tile skipping (0: off)    // what the kernel choice looks at besides the in-range share
 cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned flags, int shells, double in_range_hint, const HandleGeom& geom, PairConfig* cfg);
 bool count_configure(int dev, int histo_n, int mode_sel, double invdx, double hmax, double box_max, int max_smem, int sms, PairConfig* cfg, cudaError_t* err);
 cudaError_t count_launch(const PairConfig& cfg, const PairParams& p, cudaStream_t s);
@@ -141,6 +142,9 @@ int tile_i(const PairConfig& cfg);   // core sites per block tile
 
 // tile skipping (gfn_cells.cu)
 size_t cells_sort_temp_bytes(long long items);
+cudaError_t cells_dense_lists_launch(const float* boxBlk, const float* boxTile, int n_blk, int n_jtiles, int tri, int nframes,
+                                     const double* box, double hmax, int* list, long long capacity, int* count, long long* start,
+                                     unsigned long long* counters, cudaStream_t s);
 cudaError_t cells_sort_launch(const Site* site, Site* sorted, int n, int n_pad, int nframes, const double* box,
                               unsigned long long* keys_in, unsigned long long* keys_out, unsigned* vals_in, unsigned* vals_out,
                               void* tmp, size_t tmp_bytes, cudaStream_t s);

@@ -91,13 +91,33 @@ def test_checked_build_runs_the_small_cases_clean():
     assert "sanitizer cases done" in out.stdout and "checked/libgfn.so" in out.stdout, out.stdout[-500:]
 
 
+@pytest.mark.parametrize("n1,n2", [(100, 6000), (64, 3000), (200, 200 * 13)])
+def test_dense_kernel_few_units_per_tile(n1, n2):
+    """A small core selection against a large surround one in a dense box: one to four 64-row units per surround tile, so the
+    dense kernel's 16 warps run many tiles ahead of its 3-stage TMA ring.  (An mbarrier parity cannot tell a tile from the
+    one two uses before it: the kernel checks the stage's generation word first.)"""
+    rng = np.random.default_rng(n1 * 7 + n2)
+    L, nf = 36.0, 6
+    g = RDF(["all"], 0.0, 15.0, 0.05, n1, n2, n1, n2, L, gfn_flags="dense")
+    assert g.stats()["kernel"] == "dense"
+    o = O.OracleRDF(["all"], 0.0, 15.0, 0.05, n1, n2, n1, n2, L)
+    for f in range(nf):
+        c1 = rng.random((n1, 3)) * L; d1 = rng.standard_normal((n1, 3))
+        c2 = rng.random((n2, 3)) * L; d2 = rng.standard_normal((n2, 3))
+        g.calcFrame(c1, c2, d1, d2); o.calcFrame(c1, c2, d1, d2)
+    got, ref = g.raw_histogram(), o.raw_sum()
+    assert np.array_equal(got[:300], ref[:300]) and ref[:300].sum() > 1000
+    assert_hist_close(got, ref, 300)
+
+
 def test_tile_skipping_is_used_only_where_it_pays():
     """GFN_FLAG_CELLS is honoured when the expected share of visited tile pairs is small (a box many tile diameters wide)."""
     mk = lambda n, L, **kw: RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L, **kw).stats()      # noqa: E731
-    assert mk(32768, 99.33, gfn_flags="cells")["cells"] is False          # BASELINE configs[2]: two thirds of the tile pairs stay
-    assert mk(262144, 198.66, gfn_flags="cells")["cells"] is True         # the same density, eight times the volume
+    assert mk(32768, 99.33, gfn_flags="cells")["cells"] is False          # BASELINE configs[2]: most tile pairs stay
+    st = mk(262144, 198.66, gfn_flags="cells")                            # the same density, eight times the volume
+    assert st["cells"] is True
     assert mk(262144, 198.66)["cells"] is False
-    assert mk(4096, 31.0, gfn_flags="cells")["cells"] is False            # dense kernel: flag ignored
+    assert mk(4096, 31.0, gfn_flags="cells")["cells"] is False            # a box of two tile diameters
 
 
 def test_kernel_choice_follows_the_expected_in_range_share():
@@ -351,7 +371,8 @@ def test_count_kernel_selfcheck_and_oracle(case, monkeypatch):
         assert st["exact_evals"] < (0.01 if dr >= 0.05 else 0.06) * st["in_range"]      # the fp64 pass stays a small share
 
 
-@pytest.mark.parametrize("case", ["self_all", "self_all_fp32", "rect", "unwrapped_npt", "per_particle", "g000_spill"])
+@pytest.mark.parametrize("case", ["self_all", "self_all_fp32", "rect", "unwrapped_npt", "per_particle", "g000_spill",
+                                  "dense_self_all", "dense_rect_5modes", "dense_unwrapped_npt", "dense_two_selections"])
 def test_tile_skipping_equals_the_full_enumeration_and_the_oracle(case, monkeypatch):
     """GFN_FLAG_CELLS (gfn_cells.cu): frames sorted into Morton order on the device, only tile pairs within histo_max are
     visited.  Counts must equal the un-pruned run's and the oracle's bit for bit - in a triangular frame that needs the
@@ -368,8 +389,15 @@ def test_tile_skipping_equals_the_full_enumeration_and_the_oracle(case, monkeypa
         n1 = n2 = 3000; L = 100.0; flags = "per_particle,"
     if case == "g000_spill":
         modes, hmax = ["000"], 10.02
+    # "dense_*": orientation modes with tile skipping run on the dense kernel (visit lists of 64-row blocks per surround tile)
+    kern = "dense" if case.startswith("dense") else "ring"
+    if case == "dense_rect_5modes":
+        n1, n2, modes = 3000, 24000, ["000", "110", "101", "011", "220"]
+    if case == "dense_two_selections":
+        n1 = n2 = 6000; L = 130.0
+    case = case.replace("dense_", "") if case != "dense_two_selections" else case
     shift = 0.0
-    a = RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags + "nodense,cells")
+    a = RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags + ("nodense,cells" if kern == "ring" else "cells"))
     b = RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags + "nodense")
     o = O.OracleRDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L)
     hn = int(a.histo_n)
@@ -382,6 +410,8 @@ def test_tile_skipping_equals_the_full_enumeration_and_the_oracle(case, monkeypa
         if shift:
             c1 = c1 + L * rng.integers(-2, 3, (n1, 3))        # single-shift minimum image (quirk Q8): far images do not count
         c2, d2 = (c1, d1) if n1 == n2 else (rng.random((n2, 3)) * L, rng.standard_normal((n2, 3)))
+        if case == "dense_two_selections":          # equal sizes, different arrays (quirk Q1): such launches keep the full enumeration
+            c2, d2 = rng.random((n2, 3)) * L, rng.standard_normal((n2, 3))
         for r in (a, b, o):
             if modes == ["000"]:
                 r.calcFrame(c1, c2)
@@ -390,7 +420,7 @@ def test_tile_skipping_equals_the_full_enumeration_and_the_oracle(case, monkeypa
     ha, hb = a.raw_histogram(), b.raw_histogram()
     ref = o.raw_sum()
     sa, sb = a.stats(), b.stats()
-    assert sa["cells"] and not sb["cells"] and sa["kernel"] == "ring"
+    assert sa["cells"] and not sb["cells"] and sa["kernel"] == kern
     assert np.array_equal(ha[:hn], ref[:hn]) and np.array_equal(hb[:hn], ref[:hn]) and ref[:hn].sum() > 1000
     if case == "g000_spill":
         # pairs in (10.00, 10.02] have pos == histo_n (quirk Q3): they spill into the next row exactly where the un-pruned run puts them
@@ -399,8 +429,10 @@ def test_tile_skipping_equals_the_full_enumeration_and_the_oracle(case, monkeypa
     else:
         assert_hist_close(ha, ref, hn); assert_hist_close(hb, ref, hn)
     assert sa["in_range"] == sb["in_range"]
-    assert 0 < sa["tile_visits"] <= sa["tile_visits_dense"]
-    if case not in ("per_particle", "rect"):
+    assert 0 <= sa["tile_visits"] <= max(sa["tile_visits_dense"], 1)
+    if case == "dense_two_selections":
+        assert sa["tile_visits"] == 0
+    elif case not in ("per_particle", "rect"):
         assert sa["tile_visits"] < 0.85 * sa["tile_visits_dense"]       # the box is a few tile diameters wide
     if case == "per_particle":
         pa, pb = a.histogram, b.histogram           # the reference's [mode][core i][bin] array: rows are ORIGINAL indices
