@@ -609,6 +609,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and name == "cfg3" and not args.no_other_configs:
         del e
         others = [other_config(G, nm, local_rank, fp64_peak) for nm in ("cfg1", "cfg2", "cfg5")]
+        others.append(other_config(G, "cfg5", local_rank, fp64_peak, flags="cells"))
     sampler.stop()
     e2e_value = world * K * F * per / dt / 1e9
     h2d = (se1["h2d_bytes"] - se0["h2d_bytes"]) / K
@@ -694,8 +695,11 @@ def mode_mask(modes):
     return m
 
 
-def other_config(G, name, dev, fp64_peak):
-    """One of the other BASELINE configurations, frames resident in HBM, device-timed: value, flops/eval, roofline fraction."""
+def other_config(G, name, dev, fp64_peak, flags=None):
+    """One of the other BASELINE configurations, frames resident in HBM, device-timed: value, flops/eval, roofline fraction.
+    flags="cells": tile skipping - `value` then counts REFERENCE-EQUIVALENT evaluations (the pairs the reference's loop visits),
+    `visited_value` the pairs of the tile pairs the kernel actually went through; no roofline fraction (the flop count of
+    SURVEY 8d assumes every pair is evaluated)."""
     c = cfg(name)
     n1, n2, L = c["n1"], c["n2"], c["L"]
     F = c["F"]
@@ -704,7 +708,7 @@ def other_config(G, name, dev, fp64_peak):
     need_d = c["modes"] != ["000"]
     rng = np.random.default_rng(50 + c["cfg"])
     c1 = rng.random((F, n1, 3)) * L
-    r = G.RDF(c["modes"], c["hmin"], c["hmax"], c["dr"], n1, n2, n1, n2, L, devices=[dev])
+    r = G.RDF(c["modes"], c["hmin"], c["hmax"], c["dr"], n1, n2, n1, n2, L, devices=[dev], gfn_flags=flags)
     dc1 = G.to_device(c1, dev); dd1 = G.to_device(rng.standard_normal((F, n1, 3)), dev) if need_d else None
     if c["self_pairs"]:
         dc2, dd2 = dc1, dd1
@@ -726,10 +730,15 @@ def other_config(G, name, dev, fp64_peak):
     hist = r.raw_histogram()
     wt = 2.0 if n1 == n2 else 1.0
     hn = int(r.histo_n)
-    return {"workload": name, "n1": n1, "n2": n2, "modes": "+".join(c["modes"]), "frames": F * reps, "value": evals / ms / 1e6, "unit": UNIT,
-            "kernel": s1["kernel"], "filter": s1["filter"], "in_range_fraction": f_in, "flops_per_eval": fl,
-            "achieved_tflops": ach, "frac": ach / fp64_peak, "kernel_share": kms / ms,
-            "bins": hn, "counts_exact": counts_ok(hist[:hn].sum(), s1["in_range"] - s1["overflow"], n1, n2, c["self_pairs"], F * (reps + 1))}
+    out = {"workload": name, "n1": n1, "n2": n2, "modes": "+".join(c["modes"]), "frames": F * reps, "value": evals / ms / 1e6, "unit": UNIT,
+           "kernel": s1["kernel"], "filter": s1["filter"], "in_range_fraction": f_in, "flops_per_eval": fl,
+           "achieved_tflops": ach, "frac": ach / fp64_peak, "kernel_share": kms / ms, "ms_per_frame": ms / (F * reps)}
+    if s1["cells"]:
+        share = (s1["tile_visits"] - s0["tile_visits"]) / max(s1["tile_visits_dense"] - s0["tile_visits_dense"], 1.0)
+        out.update(flags=flags, tile_skipping=True, visited_share=share, visited_value=share * evals / ms / 1e6,
+                   value_counts="reference-equivalent pair evaluations (all pairs the reference's loop visits)", achieved_tflops=None, frac=None)
+    return dict(out,
+                bins=hn, counts_exact=counts_ok(hist[:hn].sum(), s1["in_range"] - s1["overflow"], n1, n2, c["self_pairs"], F * (reps + 1)))
 
 
 def atom_arms(args, G, c, mk, pool_c, F, K, W, per, POOL):
