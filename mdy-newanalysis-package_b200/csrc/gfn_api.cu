@@ -124,6 +124,8 @@ struct Dev {
     Batch ring[kRing];
     int cur = 0;
     int ramp = 2;                         // page-locked feeds: size of the next batch (reset by every sync)
+    // per-device share of the handle's statistics (a device is only ever driven by one thread at a time)
+    struct Stats { double pairs = 0, frames = 0, h2d = 0, launches = 0, pair_launches = 0, kernel_ms = 0, visits_dense = 0; } st;
     double* gacc = nullptr;               // [8][histo_n] + kStatusSlots status words (filled at readout, summed over ranks)
     double* gsum = nullptr;               // all-reduce result, same layout
     double* h_out = nullptr;              // pinned: readout lands here ([8][histo_n] + status, then kCounters u64)
@@ -222,11 +224,11 @@ int validate_box(gfn_t* h, const double* b)
     return GFN_OK;
 }
 
-void harvest_timing(gfn_t* h, Batch& b)
+void harvest_timing(Dev& d, Batch& b)
 {
     if (b.timed) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, b.k0, b.k1) == cudaSuccess) h->st_kernel_ms += ms;
+        if (cudaEventElapsedTime(&ms, b.k0, b.k1) == cudaSuccess) d.st.kernel_ms += ms;
         b.timed = false;
     }
 }
@@ -237,7 +239,7 @@ int wait_batch(gfn_t* h, Dev& d, Batch& b)
         CU(cudaSetDevice(d.dev));
         CU(cudaEventSynchronize(b.done));
         b.inflight = false;
-        harvest_timing(h, b);
+        harvest_timing(d, b);
     }
     return GFN_OK;
 }
@@ -326,10 +328,10 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
     unsigned* nflag = reinterpret_cast<unsigned*>(maxab + 2 * nframes);
     const int hf = d.cfg.filter_fp64 == 2;
     CU(prep_launch(c1, s_c1, h->need1 ? d1 : nullptr, s_d1, siteA, maxab, nflag, h->n1, h->n1_pad, nframes, d_box, hf, d.counters, s));
-    h->st_launches += 1;
+    d.st.launches += 1;
     if (!aliased) {
         CU(prep_launch(c2, s_c2, h->need2 ? d2 : nullptr, s_d2, siteB, maxab + nframes, nflag + nframes, h->n2, h->n2_pad, nframes, d_box, hf, d.counters, s));
-        h->st_launches += 1;
+        d.st.launches += 1;
     }
     PairParams p;
     fill_params(h, d, p);
@@ -357,8 +359,8 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
         } else {
             CU(cells_list_launch(c.boxA, c.boxB, h->n_itiles, h->n_jtiles, TI, tri, nframes, d_box, reach, c.list, c.count, c.start, d.counters + 6, s));
         }
-        h->st_launches += aliased ? 8 : 12;
-        h->st_visits_dense += (double)h->tiles_per_frame * nframes;
+        d.st.launches += aliased ? 8 : 12;
+        d.st.visits_dense += (double)h->tiles_per_frame * nframes;
         siteA = c.sortA; siteB = sb;
         p.visit_start = c.start; p.visit_list = c.list;
     }
@@ -370,15 +372,15 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
     CU(cudaEventRecord(k0, s));
     CU(pair_launch(d.cfg, p, s));
     CU(cudaEventRecord(k1, s));
-    h->st_launches += 1; h->st_pair_launches += 1;
+    d.st.launches += 1; d.st.pair_launches += 1;
     if (d.cfg.hist_mode == 0) {
         CU(finalize_launch(d.partials, d.cfg.grid, h->histo_n, d.cfg.nslot, d.gacc, s));
-        h->st_launches += 1;
+        d.st.launches += 1;
     }
     const bool tri = (h->n1 == h->n2) && !(h->flags & GFN_FLAG_NO_TRIANGLE);
     const double per = tri ? 0.5 * (double)h->n1 * ((double)h->n1 + 1.0) : (double)h->n1 * (double)h->n2;
-    h->st_pairs += per * nframes;
-    h->st_frames += nframes;
+    d.st.pairs += per * nframes;
+    d.st.frames += nframes;
     return GFN_OK;
 }
 
@@ -418,7 +420,7 @@ int submit(gfn_t* h, Dev& d)
     CU(cudaMemcpyAsync(b.d_box, b.h_box, sizeof(double) * 6 * b.nframes, cudaMemcpyHostToDevice, d.copy));
     CU(cudaEventRecord(b.uploaded, d.copy));
     CU(cudaStreamWaitEvent(d.comp, b.uploaded, 0));
-    h->st_h2d += (double)bytes + 48.0 * b.nframes;
+    d.st.h2d += (double)bytes + 48.0 * b.nframes;
     if (b.atoms) {
         const long long na1 = h->na[0], na2 = b.aliased ? 0 : (h->na[1] ? h->na[1] : h->na[0]);
         const long long fa = 3 * (na1 + na2);
@@ -430,7 +432,7 @@ int submit(gfn_t* h, Dev& d)
             const bool need = k == 0 ? h->need1 : h->need2;
             CU(residue_com_launch_f32(at, fa, r->masses, r->apr, r->rfa, r->nres, b.nframes, com, fd, d.comp));
             if (need) CU(residue_dip_launch_f32(at, fa, r->charges, r->apr, r->rfa, r->nres, b.nframes, com, dip, fd, d.comp));
-            h->st_launches += need ? 2 : 1;
+            d.st.launches += need ? 2 : 1;
         }
     }
     int rc = launch_frames(h, d, b.nframes,
@@ -824,9 +826,61 @@ static void copy_frame(gfn_t* h, const CopyHelper::Seg* segs, int nseg)
 // Frames go into the ring batch by batch.  Per batch: the caller's frames are copied into their pinned slots (one frame:
 // the caller, split with the helper thread when large; several frames: the copy pool, one frame per task) - or, for
 // page-locked sources (direct), only referenced - then the batch is submitted when it is full or the device is idle.
+// Page-locked frames on a multi-device handle: nothing is copied on the host, so all the calling thread would do is issue
+// ~14 CUDA calls per batch and device, one device after the other - with 8 devices that serial submission, not the GPUs,
+// bounds the rate.  The call's frames are dealt to the devices exactly as the serial loop would (round-robin by batch, ramp
+// after a sync) and each device's batches are then submitted by its own worker.
+static int enqueue_direct_parallel(gfn_t* h, int nframes, const FrameSrc& src, bool aliased, const double* box_dims)
+{
+    struct Job { int f, k; };
+    const int nd = (int)h->devs.size();
+    std::vector<std::vector<Job>> jobs(nd);
+    // batches that hold staged frames of an earlier call go first (serial: rare)
+    for (Dev& d : h->devs) {
+        Batch& b = d.ring[d.cur];
+        if (b.nframes > 0) { int rc = submit(h, d); if (rc) return rc; }
+    }
+    if (box_dims)
+        for (int f = 0; f < nframes; ++f) { int rc = validate_box(h, box_dims + 6ll * f); if (rc) return rc; }
+    for (int f = 0; f < nframes; ) {
+        Dev& d = h->devs[h->next_dev];
+        int k = h->batch_frames;
+        if (d.ramp < h->batch_frames && k > d.ramp) k = d.ramp;
+        if (k > nframes - f) k = nframes - f;
+        jobs[h->next_dev].push_back(Job{f, k});
+        if (d.ramp < h->batch_frames) d.ramp *= 2;
+        f += k;
+        h->next_dev = (h->next_dev + 1) % nd;
+    }
+    std::vector<int> rcs(nd, GFN_OK);
+    if (!h->pool) h->pool = new CopyPool(h->pool_threads);
+    h->pool->run(nd, [&](int di) {
+        Dev& d = h->devs[di];
+        for (const Job& j : jobs[di]) {
+            Batch* b = &d.ring[d.cur];
+            int rc = wait_batch(h, d, *b);
+            if (rc) { rcs[di] = rc; return; }
+            b->aliased = aliased; b->atoms = false; b->direct = true;
+            b->dsrc = src;
+            b->dsrc.c1 = src.c1 + src.s_c1 * j.f; b->dsrc.c2 = src.c2 + src.s_c2 * j.f;
+            if (src.d1) b->dsrc.d1 = src.d1 + src.s_d1 * j.f;
+            if (src.d2) b->dsrc.d2 = src.d2 + src.s_d2 * j.f;
+            for (int i = 0; i < j.k; ++i)
+                memcpy(b->h_box + 6ll * i, box_dims ? box_dims + 6ll * (j.f + i) : h->box, sizeof(double) * 6);
+            b->nframes = j.k;
+            rc = submit(h, d);
+            if (rc) { rcs[di] = rc; return; }
+        }
+    });
+    for (int rc : rcs) if (rc) return rc;
+    return GFN_OK;
+}
+
 static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased, const double* box_dims, bool direct = false)
 {
     const bool atoms = src.a1 != nullptr;
+    if (direct && !atoms && h->devs.size() > 1 && h->pool_threads > 0 && !getenv("GFN_SERIAL_SUBMIT"))
+        return enqueue_direct_parallel(h, nframes, src, aliased, box_dims);
     auto device_idle = [](Dev& d) {
         bool idle = true;
         for (Batch& o : d.ring)
@@ -1135,7 +1189,7 @@ int gfn_enqueue_device_frames(gfn_t* h, int nframes,
         if (x.timed) {          // slot reuse: its previous launch is kXRing chunks old
             CU(cudaEventSynchronize(x.k1));
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms;
+            if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) d.st.kernel_ms += ms;
             x.timed = false;
         }
         for (int f = 0; f < nf; ++f) {
@@ -1174,9 +1228,9 @@ int gfn_sync(gfn_t* h)
         CU(cudaSetDevice(d.dev));
         CU(cudaStreamSynchronize(d.copy));
         CU(cudaStreamSynchronize(d.comp));
-        for (Batch& b : d.ring) { b.inflight = false; harvest_timing(h, b); }
+        for (Batch& b : d.ring) { b.inflight = false; harvest_timing(d, b); }
         d.ramp = 2;
-        for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms; x.timed = false; }
+        for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) d.st.kernel_ms += ms; x.timed = false; }
     }
     return check_zerodiv(h);
 }
@@ -1192,7 +1246,11 @@ int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overf
     int rc = gfn_flush(h);
     if (rc) return rc;
     const size_t n8 = 8ull * h->histo_n, nall = n8 + kStatusSlots;
-    const bool collective = h->devs.size() > 1 || h->ext_comm;
+    // one process, several devices, no external communicator: every device copies its 19 KB into pinned memory and the host
+    // adds them in device order (deterministic; no NCCL needed, and an in-process group all-reduce over 8 communicators
+    // costs more launch latency than the eight copies)
+    const bool host_sum = h->devs.size() > 1 && !h->ext_comm;
+    const bool collective = (h->devs.size() > 1 || h->ext_comm) && !host_sum;
     if (collective && (rc = setup_comm(h))) return rc;
     for (Dev& d : h->devs) {
         CU(cudaSetDevice(d.dev));
@@ -1213,16 +1271,16 @@ int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overf
     for (size_t i = 0; i < h->devs.size(); ++i) {
         Dev& d = h->devs[i];
         CU(cudaSetDevice(d.dev));
-        if (i == 0) CU(cudaMemcpyAsync(d.h_out, collective ? d.gsum : d.gacc, sizeof(double) * nall, cudaMemcpyDeviceToHost, d.comp));
+        if (i == 0 || host_sum) CU(cudaMemcpyAsync(d.h_out, collective ? d.gsum : d.gacc, sizeof(double) * nall, cudaMemcpyDeviceToHost, d.comp));
         CU(cudaMemcpyAsync(d.h_out + nall, d.counters, sizeof(unsigned long long) * kCounters, cudaMemcpyDeviceToHost, d.comp));
     }
     unsigned long long ovf = 0;
     for (Dev& d : h->devs) {
         CU(cudaSetDevice(d.dev));
         CU(cudaStreamSynchronize(d.comp));       // the one wait: frames, all-reduce and copies are all behind it
-        for (Batch& b : d.ring) { b.inflight = false; harvest_timing(h, b); }
+        for (Batch& b : d.ring) { b.inflight = false; harvest_timing(d, b); }
         d.ramp = 2;
-        for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) h->st_kernel_ms += ms; x.timed = false; }
+        for (Dev::XSlot& x : d.xs) if (x.timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.k0, x.k1) == cudaSuccess) d.st.kernel_ms += ms; x.timed = false; }
         ovf += reinterpret_cast<const unsigned long long*>(d.h_out + nall)[0];
         if (reinterpret_cast<const unsigned long long*>(d.h_out + nall)[1] & 8ull)
             return fail(h, GFN_ECUDA, "checked build: a device-side index / protocol check failed");
@@ -1230,6 +1288,13 @@ int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overf
             return fail(h, GFN_ECUDA, "a bin of one CTA took more than 2^20 pairs in one launch: beyond the dense kernel's fixed-point range (create the handle with GFN_FLAG_NO_DENSE)");
         if (reinterpret_cast<const unsigned long long*>(d.h_out + nall)[1] & 16ull)
             return fail(h, GFN_ECUDA, "internal: the visit list of a cell-sorted launch overflowed its buffer");
+    }
+    if (host_sum) {
+        double* acc = h->devs[0].h_out;
+        for (size_t i = 1; i < h->devs.size(); ++i) {
+            const double* src = h->devs[i].h_out;
+            for (size_t k = 0; k < nall; ++k) acc[k] += src[k];
+        }
     }
     const double* out = h->devs[0].h_out;
     if (out[n8] != 0.0)
@@ -1299,6 +1364,11 @@ int gfn_stats(gfn_t* h, gfn_stats_t* out)
     memset(out, 0, sizeof(*out));
     out->pair_evals = h->st_pairs; out->frames = h->st_frames; out->h2d_bytes = h->st_h2d;
     out->kernel_launches = h->st_launches; out->pair_launches = h->st_pair_launches; out->kernel_ms = h->st_kernel_ms;
+    double visits_dense = h->st_visits_dense;
+    for (Dev& d : h->devs) {
+        out->pair_evals += d.st.pairs; out->frames += d.st.frames; out->h2d_bytes += d.st.h2d; out->kernel_launches += d.st.launches;
+        out->pair_launches += d.st.pair_launches; out->kernel_ms += d.st.kernel_ms; visits_dense += d.st.visits_dense;
+    }
     for (Dev& d : h->devs) {
         unsigned long long c[kCounters];
         CU(cudaSetDevice(d.dev));
@@ -1310,7 +1380,7 @@ int gfn_stats(gfn_t* h, gfn_stats_t* out)
     out->filter_fp64 = c.filter_fp64; out->hist_mode = c.hist_mode; out->warps_per_block = c.warps; out->hist_replicas = c.nrep;
     out->blocks_per_sm = c.blocks_per_sm; out->grid = c.grid; out->smem_bytes = c.smem_bytes;
     out->batch_frames = h->batch_frames; out->ndev = (int)h->devs.size(); out->dense = c.dense;
-    out->cells = h->cells ? 1 : 0; out->tile_visits_dense = h->st_visits_dense;
+    out->cells = h->cells ? 1 : 0; out->tile_visits_dense = visits_dense;
     return GFN_OK;
 }
 

@@ -665,7 +665,7 @@ def _ngpu():
 @pytest.mark.skipif("_ngpu() < 2")
 def test_single_process_two_devices_frame_sharding(monkeypatch):
     """NEWANALYSIS_GPUS=2: one handle deals frame batches round-robin to two GPUs and sums the per-device
-    histograms with one ncclAllReduce (communicator from ncclCommInitAll) at readout."""
+    histograms on the host at readout (device order: deterministic)."""
     monkeypatch.setenv("GFN_BATCH_FRAMES", "2")
     n, L, nf = 900, 40.0, 9
     rng = np.random.default_rng(123)
@@ -680,6 +680,36 @@ def test_single_process_two_devices_frame_sharding(monkeypatch):
     assert_hist_close(b, a, 300)
     two.calcFrame(c[0], c[0], d[0], d[0]); one.calcFrame(c[0], c[0], d[0], d[0])     # accumulation continues after a readout
     assert np.array_equal(one.raw_histogram()[:300], two.raw_histogram()[:300])
+
+
+@pytest.mark.skipif("_ngpu() < 2")
+@pytest.mark.parametrize("serial", [False, True])
+def test_two_devices_block_and_page_locked_feeds(serial, monkeypatch):
+    """One process, two devices: block calls staged by the copy pool and page-locked blocks whose batches are submitted by one
+    worker per device (or, GFN_SERIAL_SUBMIT, by the calling thread); NpT boxes, several calls and readouts in between; the
+    histograms of the devices are added on the host in device order."""
+    from newanalysis.gfunction import pinned_empty
+    monkeypatch.setenv("GFN_BATCH_FRAMES", "3")
+    if serial:
+        monkeypatch.setenv("GFN_SERIAL_SUBMIT", "1")
+    n, L, nf = 1200, 60.0, 23
+    rng = np.random.default_rng(321)
+    c, d = pinned_empty((nf, n, 3)), pinned_empty((nf, n, 3))
+    c[:] = rng.random((nf, n, 3)) * L; d[:] = rng.standard_normal((nf, n, 3))
+    boxes = L * (1 + 2e-3 * rng.standard_normal((nf, 3)))
+    a = RDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L, devices=[0, 1])
+    b = RDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L, devices=[0, 1])
+    o = O.OracleRDF(["all"], 0.0, 14.0, 0.05, n, n, n, n, L)
+    for lo, hi in ((0, 9), (9, 10), (10, nf)):
+        a.calcFrames(c[lo:hi], c[lo:hi], d[lo:hi], d[lo:hi], boxes=boxes[lo:hi], pinned=True)
+        cc, dd = np.array(c[lo:hi]), np.array(d[lo:hi])
+        b.calcFrames(cc, cc, dd, dd, boxes=boxes[lo:hi])
+        for f in range(lo, hi):
+            o.update_box(*boxes[f]); o.calcFrame(c[f], c[f], d[f], d[f])
+        ha, hb, ref = a.raw_histogram(), b.raw_histogram(), o.raw_sum()
+        assert np.array_equal(ha[:280], ref[:280]) and np.array_equal(hb[:280], ref[:280])
+        assert_hist_close(ha, ref, 280); assert_hist_close(hb, ref, 280)
+    assert a.stats()["frames"] == nf and a.stats()["ndev"] == 2 and a.volume_list == o.volume_list
 
 
 @pytest.mark.skipif("_ngpu() < 2")
