@@ -353,8 +353,8 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
         const int tri = (h->n1 == h->n2) && !(h->flags & GFN_FLAG_NO_TRIANGLE);
         double reach = (double)h->hmax_f;
         if (const char* e = getenv("GFN_CELLS_REACH")) reach = atof(e);          // experiments: a larger reach visits more tiles (never fewer pairs)
-        if (d.cfg.dense == 1) {
-            CU(cells_dense_lists_launch(c.boxA, c.boxB, h->n_itiles, h->n_jtiles, tri, nframes, d_box, reach, c.list, c.list_cap, c.count, c.start, d.counters, s));
+        if (d.cfg.dense) {
+            CU(cells_dense_lists_launch(c.boxA, c.boxB, h->n_itiles, h->n_jtiles, tri, kTJ / TI, nframes, d_box, reach, c.list, c.list_cap, c.count, c.start, d.counters, s));
             p.visit_cap = c.list_cap;
         } else {
             CU(cells_list_launch(c.boxA, c.boxB, h->n_itiles, h->n_jtiles, TI, tri, nframes, d_box, reach, c.list, c.count, c.start, d.counters + 6, s));
@@ -634,16 +634,19 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
     if ((flags & GFN_FLAG_CELLS) && !getenv("GFN_CELLS_FORCE")) {
         // Tile skipping is worth it only when enough tile pairs can be skipped.  Expected share of visited tile pairs: a tile of
         // T sorted sites fills a blob of edge (V T / n)^(1/3); Morton blobs measure ~1.5 cubes across; a core blob sees the
-        // surround blobs within histo_max of it.  Orientation modes run on the dense kernel (64-row core blocks): worth it
-        // below one half; g000-only handles stay on pair_kernel (512-row core tiles), whose survivor path is built for evenly
-        // sparse tiles: worth it below 15 % (measured: 0.67 at BASELINE configs[2] is 3 x slower, 0.024 at configs[4] 4 x faster).
+        // surround blobs within histo_max of it.  Measured: orientation modes (dense kernel, 64-row core blocks) gain below ~8 %
+        // (configs[4]: 1.3 % visited, 11 x faster; configs[3] solvent: 14 %, 1.1 x slower); g000-only handles (count kernel,
+        // 128-row blocks, ~1000 x 10^9 visited pairs/s whatever the density: configs[2] shape 47 % visited, 1.17 x faster; configs[4]
+        // shape 1.3 %, 36 x faster) gain below ~50 %; pair_kernel (GFN_FLAG_NO_DENSE,
+        // 512-row core tiles), whose survivor path is built for evenly sparse tiles, below 15 %.
         const double vol = box_dim[0] * box_dim[1] * box_dim[2];
         const bool g000 = mode_sel == 1;
-        const double ec = cbrt(vol * (g000 ? 512.0 : 64.0) / (double)(n1 > 0 ? n1 : 1)), es = cbrt(vol * kTJ / (double)(n2 > 0 ? n2 : 1));
+        const bool ring = (flags & GFN_FLAG_NO_DENSE) != 0;          // pair_kernel: 512-row core tiles; count / dense kernel: 128 / 64 rows
+        const double ec = cbrt(vol * (ring ? 512.0 : (g000 ? 128.0 : 64.0)) / (double)(n1 > 0 ? n1 : 1)), es = cbrt(vol * kTJ / (double)(n2 > 0 ? n2 : 1));
         const double w = 1.5 * (ec + es) + 2.0 * (double)histo_max;
         double share = 1.0;
         for (int k = 0; k < 3; ++k) share *= fmin(1.0, w / box_dim[k]);
-        if (share > (g000 ? 0.15 : 0.08)) flags &= ~GFN_FLAG_CELLS;
+        if (share > (ring ? 0.15 : (g000 ? 0.5 : 0.08))) flags &= ~GFN_FLAG_CELLS;
         h->flags = flags;
         cells_share = share;
     }
@@ -669,7 +672,7 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
             CUC(pair_configure(d.dev, n1, histo_n, mode_sel, flags, sc ? 1 : 0, 0.0, HandleGeom{0.0, 0.0, 0.0, n1, n2, tri_create ? 1 : 0, 0.0}, &d.cfg));
         }
     }
-    h->cells = (flags & GFN_FLAG_CELLS) && h->devs[0].cfg.dense != 2 && !sc;
+    h->cells = (flags & GFN_FLAG_CELLS) && !sc;
     // work decomposition (identical on all devices)
     {
         const PairConfig& c = h->devs[0].cfg;
@@ -742,8 +745,8 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
             CUC(cudaMalloc(&c.tmp, c.tmp_bytes ? c.tmp_bytes : 16));
             CUC(cudaMalloc(&c.boxA, sizeof(float) * 6 * (size_t)h->n_itiles * bf));
             CUC(cudaMalloc(&c.boxB, sizeof(float) * 6 * (size_t)h->n_jtiles * bf));
-            if (d.cfg.dense == 1) {
-                // dense kernel: entries are (frame, surround tile), lists are compact; room for the un-pruned unit count
+            if (d.cfg.dense) {
+                // dense / count kernel: entries are (frame, surround tile), lists are compact; room for the un-pruned unit count
                 c.list_cap = (long long)h->tiles_per_frame * (long long)bf;
                 CUC(cudaMalloc(&c.list, sizeof(int) * (size_t)c.list_cap));
                 CUC(cudaMalloc(&c.count, sizeof(int) * (size_t)h->n_jtiles * bf));

@@ -157,11 +157,12 @@ cells_list_kernel(const float* __restrict__ boxA, const float* __restrict__ boxB
 
 // Dense-kernel units of cell-sorted frames: one warp per (frame, surround tile jt) lists the 64-row core BLOCKS whose box
 // lies within reach of the tile's box, in ascending order - a triangular frame only the blocks that reach the tile's last
-// column (ib <= 2 jt + 1, as in the un-pruned enumeration).  An entry is never empty (block 0 stands in: the kernel's tile
+// column (64-row blocks of the dense kernel: ib <= 2 jt + 1; 128-row blocks of the count kernel: ib <= jt - as in the un-pruned
+// enumerations).  An entry is never empty (block 0 stands in: the kernel's tile
 // ring counts the units of every tile).  Two passes: fill == 0 counts, fill == 1 writes the lists at their prefix offsets
 // (compact storage, capacity checked: an overflowing launch raises the error flag and lists nothing beyond).
 __global__ void __launch_bounds__(256)
-cells_dense_list_kernel(const float* __restrict__ boxBlk, const float* __restrict__ boxTile, int n_blk, int n_jtiles, int tri,
+cells_dense_list_kernel(const float* __restrict__ boxBlk, const float* __restrict__ boxTile, int n_blk, int n_jtiles, int tri, int blk_per_tile,
                         const double* __restrict__ box, float reach, int fill, int* __restrict__ count, const long long* __restrict__ start,
                         int* __restrict__ list, long long capacity, unsigned long long* __restrict__ counters)
 {
@@ -179,7 +180,7 @@ cells_dense_list_kernel(const float* __restrict__ boxBlk, const float* __restric
     const bool room = !fill || start[e + 1] <= capacity;
     if (fill && !room) { if (lane == 0) atomicOr(counters + 1, 16ull); return; }
     int nout = 0;
-    const int ib_end = tri ? min(2 * jt + 2, n_blk) : n_blk;
+    const int ib_end = tri ? min(blk_per_tile * jt + blk_per_tile, n_blk) : n_blk;
     for (int b0 = 0; b0 < ib_end; b0 += 32) {
         const int ib = b0 + lane;
         bool hit = false;
@@ -263,15 +264,15 @@ cudaError_t cells_list_launch(const float* boxA, const float* boxB, int n_itiles
 }
 
 // Visit lists of the dense kernel's units (count, prefix, fill).  capacity: ints the list buffer holds.
-cudaError_t cells_dense_lists_launch(const float* boxBlk, const float* boxTile, int n_blk, int n_jtiles, int tri, int nframes,
+cudaError_t cells_dense_lists_launch(const float* boxBlk, const float* boxTile, int n_blk, int n_jtiles, int tri, int blk_per_tile, int nframes,
                                      const double* box, double hmax, int* list, long long capacity, int* count, long long* start,
                                      unsigned long long* counters, cudaStream_t s)
 {
     const dim3 grid((n_jtiles + 7) / 8, nframes);
     const float reach = (float)hmax * (1.0f + 1e-6f);
-    cells_dense_list_kernel<<<grid, 256, 0, s>>>(boxBlk, boxTile, n_blk, n_jtiles, tri, box, reach, 0, count, nullptr, nullptr, capacity, counters);
+    cells_dense_list_kernel<<<grid, 256, 0, s>>>(boxBlk, boxTile, n_blk, n_jtiles, tri, blk_per_tile, box, reach, 0, count, nullptr, nullptr, capacity, counters);
     cells_scan_kernel<<<1, 1024, 0, s>>>(count, start, (long long)nframes * n_jtiles, counters + 6);
-    cells_dense_list_kernel<<<grid, 256, 0, s>>>(boxBlk, boxTile, n_blk, n_jtiles, tri, box, reach, 1, count, start, list, capacity, counters);
+    cells_dense_list_kernel<<<grid, 256, 0, s>>>(boxBlk, boxTile, n_blk, n_jtiles, tri, blk_per_tile, box, reach, 1, count, start, list, capacity, counters);
     return cudaGetLastError();
 }
 

@@ -89,8 +89,13 @@ count_kernel(const PairParams P)
     const unsigned wt = TRI ? 2u : 1u;                     // :131-134 (i == j has dist 0 and is never accepted, :149)
     const bool selfcheck = P.debug & 8;
 
+    // cell-sorted frames (gfn_cells.cu): entry gt = frame * n_jtiles + jt lists the 128-row core blocks within histo_max of
+    // surround tile jt; visit_start is the exclusive prefix of the list lengths = the flat unit sequence
+    const bool listed = P.visit_start != nullptr;
+    const long long nent = (long long)P.nframes * P.n_jtiles;
     const int upf = P.tiles_per_frame;
-    const long long total_units = (long long)upf * P.nframes;
+    long long total_units = listed ? P.visit_start[nent] : (long long)upf * P.nframes;
+    if (listed && total_units > P.visit_cap) total_units = 0;       // the list buffer overflowed (flagged by gfn_cells.cu)
     const long long ubeg = total_units * blockIdx.x / gridDim.x;
     const long long uend = total_units * (blockIdx.x + 1) / gridDim.x;
 
@@ -110,11 +115,19 @@ count_kernel(const PairParams P)
     for (int iter = 0;; ++iter) {
         const long long u = ubeg + warp + (long long)kCW * iter;
         if (u >= uend) break;
-        const int f = (int)(u / upf);
-        const int ru = (int)(u - (long long)f * upf);
-        int lo = 0, hi = P.n_jtiles;                       // surround tile jt with tile_start[jt] <= ru < tile_start[jt+1]
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.tile_start[mid] <= ru) lo = mid; else hi = mid; }
-        const int jt = lo, ib = ru - P.tile_start[lo];
+        int f, jt, ib;
+        if (listed) {
+            long long lo = 0, hi = nent;                       // the last entry with start <= u (entries are never empty)
+            while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (P.visit_start[mid] <= u) lo = mid; else hi = mid; }
+            f = (int)(lo / P.n_jtiles); jt = (int)(lo - (long long)f * P.n_jtiles);
+            ib = __ldg(P.visit_list + u);
+        } else {
+            f = (int)(u / upf);
+            const int ru = (int)(u - (long long)f * upf);
+            int lo = 0, hi = P.n_jtiles;                       // surround tile jt with tile_start[jt] <= ru < tile_start[jt+1]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.tile_start[mid] <= ru) lo = mid; else hi = mid; }
+            jt = lo; ib = ru - P.tile_start[lo];
+        }
         const int j0 = jt * kTJ, i0 = ib * kCRows;
         const bool diag = TRI && ib == jt;
         const Site* sa = P.siteA + (long long)f * P.strideA;
@@ -285,7 +298,7 @@ count_kernel(const PairParams P)
                         if (pos < hn) { red_shared_u32(hraw + ((unsigned)pos << 2), w); if (TRI && w == 1u) ++n_w1; }   // :152
                         else {                                  // quirk Q3: the flat index runs into the next row / mode
                             ++n_ovf;
-                            if (!(P.flags & GFN_FLAG_DISCARD_OVERFLOW)) global_add(P, 1, 0, row, pos, (double)w);
+                            if (!(P.flags & GFN_FLAG_DISCARD_OVERFLOW)) global_add(P, 1, 0, listed ? __float_as_int(sa[row].fw) : row, pos, (double)w);
                         }
                     }
                 }

@@ -71,10 +71,10 @@ __host__ __device__ inline size_t pad16(size_t b) { return (b + 15) & ~(size_t)1
 //          quarter warp - what one shared-memory wavefront of a 128-bit access serves - hit 8 different bank groups
 //          whatever their bins are, so the read-modify-write of random bins is free of bank conflicts (with [bin][column]
 //          records it replayed 2.2 times, and the shared-memory pipe was the kernel's limiter at 74 % of its peak)
-//   counts [bin] u32 (native atomics), locks [bin][Q] u32
+//   count / lock words [bin][Q] u32: bit 31 = the stripe of the bin is being updated, bits 0-30 = pairs it has taken
 __host__ __device__ inline size_t dense_hist_bytes(int hn, int msel, int Q)
 {
-    return (size_t)hn * ((size_t)(dense_ncol(msel) / 2) * Q * 16 + 4 + 4 * (size_t)Q);
+    return (size_t)hn * ((size_t)(dense_ncol(msel) / 2) * Q * 16 + 4 * (size_t)Q);
 }
 
 // Orientation sums are kept as 64-bit fixed point, 2^-43 per unit: integer addition is associative, so a bin's sum does
@@ -83,7 +83,7 @@ __host__ __device__ inline size_t dense_hist_bytes(int hn, int msel, int Q)
 // 2^-44 = 5.7e-14 (the bar is 1e-12 per unit of pair weight); |sum| < 2^20 per bin and stripe holds as long as no bin of a CTA
 // takes 2^20 pairs in one launch: checked at the flush (error, not a wrap-around); launches are sized far below (dense_max_units).
 constexpr double kFixScale = 8796093022208.0;              // 2^43
-constexpr long long kFixPairs = (1ll << 20) - 1;           // accepted pairs one bin of a CTA's histogram may take per launch
+constexpr long long kFixPairs = (1ll << 20) - 1;           // accepted pairs one stripe of a bin may take per launch
 __device__ __forceinline__ long long to_fixed(double v)
 {
     // v * 2^43 + 1.5 * 2^52 has its integer part in the mantissa: |v| <= 2^7 keeps the exponent fixed
@@ -177,8 +177,7 @@ dense_kernel(const PairParams P)
     constexpr int NCH = NCOL / 2;                            // 16-byte words per bin
     const int q = lane & (Q - 1);
     longlong2* wsum = reinterpret_cast<longlong2*>(hist) + q;                                        // word (bin, c): [(bin * NCH + c) * Q]
-    unsigned* cnt = reinterpret_cast<unsigned*>(hist + (size_t)hn * NCH * Q * 16);                   // [bin]
-    unsigned* lock = cnt + hn + q;                                                                   // lock (bin): [bin * Q]
+    unsigned* lock = reinterpret_cast<unsigned*>(hist + (size_t)hn * NCH * Q * 16) + q;              // count / lock word (bin): [bin * Q]
     unsigned n_surv = 0, n_inr = 0, n_ovf = 0;
     bool zerodiv = false;
     const double acc_lo = P.acc_lo, acc_hi = P.acc_hi;
@@ -446,7 +445,6 @@ dense_kernel(const PairParams P)
                     pend[u] = ok[u] && pos[u] < hn;
                     GFN_CHECK(P, !pend[u] || (pos[u] >= 0 && (size_t)(((size_t)pos[u] * NCH + NCH - 1) * Q + q) * 16 + 16 <= (size_t)hn * NCH * Q * 16));
                     GFN_CHECK(P, !have[u] || (jg[u] - j0 >= 0 && jg[u] - j0 < TJ && st < S));
-                    if (pend[u]) atomicAdd(cnt + pos[u], 1u);                                    // :152 and the weight row
                     if (ok[u] && pos[u] >= hn) {
                         // quirk Q3: the reference's flat index runs into the next row / mode; global accumulators
                         ++n_ovf;
@@ -459,12 +457,15 @@ dense_kernel(const PairParams P)
                         }
                     }
                 }
-                // sums: the lane claims its stripe of the bin with a native shared-memory exchange on the lock word (one winner
-                // among all lanes of the CTA that use this stripe), updates it with plain 128-bit loads / stores, releases it
+                // sums: the lane claims its stripe of the bin by setting bit 31 of the stripe's count word (native shared-memory
+                // atomic OR: one winner among all lanes of the CTA that use this stripe), updates the sums with plain 128-bit
+                // loads / stores and releases by storing the count + 1
                 while (__any_sync(0xffffffffu, pend[0] || pend[1])) {
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        if (pend[u] && atomicExch(lock + (size_t)pos[u] * Q, 1u) == 0u) {
+                        unsigned held = 0x80000000u;
+                        if (pend[u]) held = atomicOr(lock + (size_t)pos[u] * Q, 0x80000000u);       // old value: the lock bit and the count
+                        if (pend[u] && !(held & 0x80000000u)) {
                             // column k of the bin holds mode bit b with dense_col(MSEL, b) == k (a compile-time map;
                             // MSEL == 0: all six columns, unselected ones are never added to)
                             long long addv[NCOL];
@@ -482,7 +483,7 @@ dense_kernel(const PairParams P)
 #pragma unroll
                             for (int c2 = 0; c2 < NCH; ++c2) h2[c2 * Q] = hv[c2];
                             __threadfence_block();
-                            *reinterpret_cast<volatile unsigned*>(lock + (size_t)pos[u] * Q) = 0u;
+                            *reinterpret_cast<volatile unsigned*>(lock + (size_t)pos[u] * Q) = held + 1u;      // :152 and the weight row; releases
                             pend[u] = false;
                         }
                     }
@@ -521,27 +522,27 @@ dense_kernel(const PairParams P)
         constexpr int PS = 8;
         double* out = P.partials + (size_t)blockIdx.x * hn * PS;
         const long long* sums = reinterpret_cast<const long long*>(hist);
-        const unsigned* counts = reinterpret_cast<const unsigned*>(hist + (size_t)hn * NCH * Q * 16);
+        const unsigned* counts = reinterpret_cast<const unsigned*>(hist + (size_t)hn * NCH * Q * 16);      // [bin][Q]
         for (int k = tid; k < hn * PS; k += NW * 32) {
             const int bin = k / PS, sl = k - bin * PS;
             double s = 0.0;
             int col = -1;
             if (sl >= 1 && sl <= 6) col = MSEL == 0 ? sl - 1 : dense_col(MSEL, sl);
             if (sl == 0 || sl == 7) {
-                if (sl == 7 || (mode_sel & 1)) s = (double)counts[bin];
-            } else if (col >= 0) {
-                long long t = 0;                                   // |sum of the stripes| < Q * 2^63 / 2^43 ... each < 2^62: add as doubles
-                double acc = 0.0;
-                for (int z = 0; z < Q; ++z) {
-                    t = sums[(((size_t)bin * NCH + (col >> 1)) * Q + z) * 2 + (col & 1)];
-                    acc += (double)t;
+                if (sl == 7 || (mode_sel & 1)) {
+                    unsigned long long c = 0;
+                    for (int z = 0; z < Q; ++z) c += counts[(size_t)bin * Q + z];
+                    s = (double)c;
                 }
+            } else if (col >= 0) {
+                double acc = 0.0;                                  // each stripe < 2^63: add as doubles, in stripe order
+                for (int z = 0; z < Q; ++z) acc += (double)sums[(((size_t)bin * NCH + (col >> 1)) * Q + z) * 2 + (col & 1)];
                 s = acc * (1.0 / kFixScale);
             }
             out[k] = s * wt_d;
         }
-        // the fixed-point range: a stripe of a bin holds at most as many addends as the bin's count
-        for (int k = tid; k < hn; k += NW * 32)
+        // the fixed-point range: a stripe of a bin holds exactly as many addends as its count word says
+        for (int k = tid; k < hn * Q; k += NW * 32)
             if (counts[k] > (unsigned)kFixPairs) atomicOr(P.counters + 1, 4ull);
     }
 }

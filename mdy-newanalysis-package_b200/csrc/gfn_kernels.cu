@@ -993,7 +993,8 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
     // dense neighbourhoods: the symmetric kernel, when it supports the handle
     // tile skipping with orientation modes runs on the dense kernel (its warps all filter AND evaluate, so the survivors a
     // cell-sorted frame concentrates in its near tiles do not stall anybody)
-    const bool cells_dense = (flags & GFN_FLAG_CELLS) && mode_sel != 1 && !(flags & GFN_FLAG_NO_DENSE);
+    // (g000-only handles: the count kernel, whose warps are independent anyway)
+    const bool cells_dense = (flags & GFN_FLAG_CELLS) && !(flags & GFN_FLAG_NO_DENSE);
     const bool want_dense = (flags & GFN_FLAG_DENSE) || cells_dense || (!(flags & GFN_FLAG_NO_DENSE) && in_range_hint > kDenseShare);
     if (want_dense) {
         cudaError_t de = cudaSuccess;

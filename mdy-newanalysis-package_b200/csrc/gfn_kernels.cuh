@@ -142,7 +142,7 @@ int tile_i(const PairConfig& cfg);   // core sites per block tile
 
 // tile skipping (gfn_cells.cu)
 size_t cells_sort_temp_bytes(long long items);
-cudaError_t cells_dense_lists_launch(const float* boxBlk, const float* boxTile, int n_blk, int n_jtiles, int tri, int nframes,
+cudaError_t cells_dense_lists_launch(const float* boxBlk, const float* boxTile, int n_blk, int n_jtiles, int tri, int blk_per_tile, int nframes,
                                      const double* box, double hmax, int* list, long long capacity, int* count, long long* start,
                                      unsigned long long* counters, cudaStream_t s);
 cudaError_t cells_sort_launch(const Site* site, Site* sorted, int n, int n_pad, int nframes, const double* box,

@@ -60,6 +60,9 @@ CONFIGS = {
     "cfg3_cells_ring": lambda: run("cfg3, tile skipping on pair_kernel", 32768, 32768, 99.33, ["all"], 15.0, 15, 4, True, "nodense,cells", {"GFN_CELLS_FORCE": "1"}),
     "cfg5_cells_ring": lambda: run("cfg5, tile skipping on pair_kernel", 1048576, 1048576, 315.4, ["all"], 15.0, 1, 2, True, "nodense,cells"),
     "cfg4a_cells": lambda: run("cfg4 solute COM 1024 x solvent 81920 all, tile skipping", 1024, 81920, 143.6, ["all"], 15.0, 16, 4, False, "cells", {"GFN_CELLS_FORCE": "1"}),
+    "cfg5_g000": lambda: run("cfg5 shape, g000 only", 1048576, 1048576, 315.4, ["000"], 15.0, 1, 1, True),
+    "cfg5_g000_cells": lambda: run("cfg5 shape, g000 only, tile skipping", 1048576, 1048576, 315.4, ["000"], 15.0, 1, 2, True, "cells"),
+    "cfg3_g000_cells": lambda: run("cfg3 shape, g000 only, tile skipping", 32768, 32768, 99.33, ["000"], 15.0, 15, 4, True, "cells", {"GFN_CELLS_FORCE": "1"}),
     "cfg3_cells": lambda: run("cfg3 water 32768 all modes, tile skipping", 32768, 32768, 99.33, ["all"], 15.0, 15, 4, True, "cells", {"GFN_CELLS_FORCE": "1"}),
     "cfg5_cells": lambda: run("cfg5 1M sites self all, tile skipping", 1048576, 1048576, 315.4, ["all"], 15.0, 1, 2, True, "cells"),
     "cfg4b_cells": lambda: run("cfg4 solvent 81920 self all, tile skipping", 81920, 81920, 143.6, ["all"], 15.0, 2, 3, True, "cells", {"GFN_CELLS_FORCE": "1"}),

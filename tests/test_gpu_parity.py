@@ -372,7 +372,8 @@ def test_count_kernel_selfcheck_and_oracle(case, monkeypatch):
 
 
 @pytest.mark.parametrize("case", ["self_all", "self_all_fp32", "rect", "unwrapped_npt", "per_particle", "g000_spill",
-                                  "dense_self_all", "dense_rect_5modes", "dense_unwrapped_npt", "dense_two_selections"])
+                                  "dense_self_all", "dense_rect_5modes", "dense_unwrapped_npt", "dense_two_selections",
+                                  "count_self", "count_rect", "count_spill", "count_unwrapped_npt"])
 def test_tile_skipping_equals_the_full_enumeration_and_the_oracle(case, monkeypatch):
     """GFN_FLAG_CELLS (gfn_cells.cu): frames sorted into Morton order on the device, only tile pairs within histo_max are
     visited.  Counts must equal the un-pruned run's and the oracle's bit for bit - in a triangular frame that needs the
@@ -390,14 +391,21 @@ def test_tile_skipping_equals_the_full_enumeration_and_the_oracle(case, monkeypa
     if case == "g000_spill":
         modes, hmax = ["000"], 10.02
     # "dense_*": orientation modes with tile skipping run on the dense kernel (visit lists of 64-row blocks per surround tile)
-    kern = "dense" if case.startswith("dense") else "ring"
+    kern = "dense" if case.startswith("dense") else ("count" if case.startswith("count") else "ring")
+    if kern == "count":                                   # g000 only: the count kernel walks lists of 128-row blocks
+        modes = ["000"]
+        if case == "count_rect":
+            n1, n2 = 3000, 24000
+        if case == "count_spill":
+            hmax = 10.02
+        case = {"count_self": "g000", "count_rect": "g000_rect", "count_spill": "g000_spill", "count_unwrapped_npt": "unwrapped_npt"}[case]
     if case == "dense_rect_5modes":
         n1, n2, modes = 3000, 24000, ["000", "110", "101", "011", "220"]
     if case == "dense_two_selections":
         n1 = n2 = 6000; L = 130.0
     case = case.replace("dense_", "") if case != "dense_two_selections" else case
     shift = 0.0
-    a = RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags + ("nodense,cells" if kern == "ring" else "cells"))
+    a = RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags + ("nodense,cells" if kern == "ring" else ("cells,dense" if kern == "count" else "cells")))
     b = RDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L, gfn_flags=flags + "nodense")
     o = O.OracleRDF(modes, 0.0, hmax, 0.05, n1, n2, n1, n2, L)
     hn = int(a.histo_n)
@@ -432,7 +440,7 @@ def test_tile_skipping_equals_the_full_enumeration_and_the_oracle(case, monkeypa
     assert 0 <= sa["tile_visits"] <= max(sa["tile_visits_dense"], 1)
     if case == "dense_two_selections":
         assert sa["tile_visits"] == 0
-    elif case not in ("per_particle", "rect"):
+    elif case not in ("per_particle", "rect", "g000_rect"):
         assert sa["tile_visits"] < 0.85 * sa["tile_visits_dense"]       # the box is a few tile diameters wide
     if case == "per_particle":
         pa, pb = a.histogram, b.histogram           # the reference's [mode][core i][bin] array: rows are ORIGINAL indices
