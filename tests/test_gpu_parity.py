@@ -21,7 +21,8 @@ RTOL = 1e-12
 # "" / fp16 / fp32: the library picks the kernel itself - the dense-neighbourhood kernel for most of the small golden boxes
 # (expected in-range share > 10 %), the warp-specialised ring kernel otherwise; "dense" / "nodense" force one of them
 VARIANTS = ["", "fp32", "fp64", "fp16", "fp32,global", "fp64,global", "fp16,global", "per_particle",
-            "fp16,dense", "fp32,dense", "fp16,nodense", "fp32,nodense", "nodense,cells", "fp32,nodense,cells", "nodense,cells,global"]
+            "fp16,dense", "fp32,dense", "fp16,nodense", "fp32,nodense", "nodense,cells", "fp32,nodense,cells", "nodense,cells,global",
+            "cells", "fp32,cells"]           # tile skipping on the dense / count kernels (forced: the golden boxes are small)
 
 
 def RDF(*a, **k):
