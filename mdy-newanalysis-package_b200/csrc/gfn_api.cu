@@ -634,8 +634,8 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
     if ((flags & GFN_FLAG_CELLS) && !getenv("GFN_CELLS_FORCE")) {
         // Tile skipping is worth it only when enough tile pairs can be skipped.  Expected share of visited tile pairs: a tile of
         // T sorted sites fills a blob of edge (V T / n)^(1/3); Morton blobs measure ~1.5 cubes across; a core blob sees the
-        // surround blobs within histo_max of it.  Measured: orientation modes (dense kernel, 64-row core blocks) gain below ~8 %
-        // (configs[4]: 1.3 % visited, 11 x faster; configs[3] solvent: 14 %, 1.1 x slower); g000-only handles (count kernel,
+        // surround blobs within histo_max of it.  Measured: orientation modes (dense kernel, 64-row core blocks) gain below ~15 %
+        // (configs[4]: 1.3 % visited, 13 x faster; configs[3] solvent: 14 %, 1.09 x faster; configs[2]: 46 %, 1.9 x slower); g000-only handles (count kernel,
         // 128-row blocks, ~1000 x 10^9 visited pairs/s whatever the density: configs[2] shape 47 % visited, 1.17 x faster; configs[4]
         // shape 1.3 %, 36 x faster) gain below ~50 %; pair_kernel (GFN_FLAG_NO_DENSE,
         // 512-row core tiles), whose survivor path is built for evenly sparse tiles, below 15 %.
@@ -646,7 +646,7 @@ static int create_impl(gfn_t** out, int n1, int n2, int histo_nr, float histo_mi
         const double w = 1.5 * (ec + es) + 2.0 * (double)histo_max;
         double share = 1.0;
         for (int k = 0; k < 3; ++k) share *= fmin(1.0, w / box_dim[k]);
-        if (share > (ring ? 0.15 : (g000 ? 0.5 : 0.08))) flags &= ~GFN_FLAG_CELLS;
+        if (share > (ring ? 0.15 : (g000 ? 0.5 : 0.15))) flags &= ~GFN_FLAG_CELLS;
         h->flags = flags;
         cells_share = share;
     }

@@ -316,28 +316,33 @@ dense_kernel(const PairParams P)
             n_surv += __popc(m0) + __popc(m1);
         }
 
-        // ---- walk: per core row every lane pops two of its survivors per step (two independent fp64 chains).  The four
-        //      chunk masks of a row form one stream (a shift register of words): lanes only wait for each other once per row.
+        // ---- walk: every lane pops one survivor of EACH of its two rows per step (two independent fp64 chains).  The four
+        //      chunk masks of a row form one stream (a shift register of words), so lanes wait for each other once per unit;
+        //      a step costs the same whether one or both chains are live, and taking one survivor from each row needs
+        //      max(c0, c1) steps where two per row would need ceil(c0/2) + ceil(c1/2) - the same in a dense unit, half in the
+        //      sparse units a cell-sorted frame is full of.
         //      (Going through the surround sites one by one instead - the record read as a broadcast, every lane evaluating it
         //      against its two rows under the rows' filter bits - removes the gathers' bank conflicts but idles the lanes whose
         //      rows did not survive: measured equal in dense boxes, four times slower in sparse ones.)
+        {
+            unsigned ms[2][4];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int row = row0 + r;
-            unsigned m0 = mk[0][r], m1 = mk[1][r], m2 = mk[2][r], m3 = mk[3][r];
-            int jb = 0;
-            while (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u)) {
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int jc = 0; jc < 4; ++jc) ms[u][jc] = mk[jc][u];
+            int jb[2] = {0, 0};
+            while (__any_sync(0xffffffffu, (ms[0][0] | ms[0][1] | ms[0][2] | ms[0][3] | ms[1][0] | ms[1][1] | ms[1][2] | ms[1][3]) != 0u)) {
                 int jg[2], sorig[2];
                 double bpx[2], bpy[2], bpz[2], bn[2], ibn[2];
                 double bx0[2], by0[2], bz0[2];
                 bool have[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    if (m0 == 0u) { m0 = m1; m1 = m2; m2 = m3; m3 = 0u; jb += 32; }      // next chunk of this row's stream
-                    const int fl = 31 - __clz(m0);                 // highest set bit = first surround site; -1: none left
+                    if (ms[u][0] == 0u) { ms[u][0] = ms[u][1]; ms[u][1] = ms[u][2]; ms[u][2] = ms[u][3]; ms[u][3] = 0u; jb[u] += 32; }   // next chunk of the row's stream
+                    const int fl = 31 - __clz(ms[u][0]);           // highest set bit = first surround site; -1: none left
                     have[u] = fl >= 0;
-                    m0 &= ~(1u << (fl & 31));
-                    const int jl = (jb + 31 - fl) & (TJ - 1);
+                    ms[u][0] &= ~(1u << (fl & 31));
+                    const int jl = (jb[u] + 31 - fl) & (TJ - 1);
                     jg[u] = j0 + jl;
                     sorig[u] = listed ? __float_as_int(js[jl].fw) : 0;
                     const double2* bp = reinterpret_cast<const double2*>(js + jl);
@@ -350,9 +355,9 @@ dense_kernel(const PairParams P)
                 double dxa[2], dya[2], dza[2], d2[2], dist[2], idist[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    dxa[u] = wrap_signed(bx0[u], cx[r], bx.hx, bx.Lx);                       // :141-147
-                    dya[u] = wrap_signed(by0[u], cy[r], bx.hy, bx.Ly);
-                    dza[u] = wrap_signed(bz0[u], cz[r], bx.hz, bx.Lz);
+                    dxa[u] = wrap_signed(bx0[u], cx[u], bx.hx, bx.Lx);                       // :141-147
+                    dya[u] = wrap_signed(by0[u], cy[u], bx.hy, bx.Ly);
+                    dza[u] = wrap_signed(bz0[u], cz[u], bx.hz, bx.Lz);
                     d2[u] = DOT3(dxa[u], dya[u], dza[u], dxa[u], dya[u], dza[u]);
                     // :149 as an interval of d^2 (exact thresholds from the host; false for NaN).  Accepted values lie
                     // far inside the range where the straight-line square root below is exact (gfn_create checks
@@ -373,19 +378,19 @@ dense_kernel(const PairParams P)
                 if (!exact_div) {
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        c[u][0] = DMUL(DOT3(cpx[r], cpy[r], cpz[r], bpx[u], bpy[u], bpz[u]), DMUL(icn[r], ibn[u]));
-                        c[u][1] = DMUL(DOT3(cpx[r], cpy[r], cpz[r], dxa[u], dya[u], dza[u]), DMUL(icn[r], idist[u]));
+                        c[u][0] = DMUL(DOT3(cpx[u], cpy[u], cpz[u], bpx[u], bpy[u], bpz[u]), DMUL(icn[u], ibn[u]));
+                        c[u][1] = DMUL(DOT3(cpx[u], cpy[u], cpz[u], dxa[u], dya[u], dza[u]), DMUL(icn[u], idist[u]));
                         c[u][2] = DMUL(DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]), DMUL(ibn[u], idist[u]));
                     }
                 } else {
                     double den[2][3], num[2][3];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        den[u][0] = DMUL(cn[r], bn[u]);
-                        den[u][1] = DMUL(cn[r], dist[u]);
+                        den[u][0] = DMUL(cn[u], bn[u]);
+                        den[u][1] = DMUL(cn[u], dist[u]);
                         den[u][2] = DMUL(bn[u], dist[u]);
-                        num[u][0] = DOT3(cpx[r], cpy[r], cpz[r], bpx[u], bpy[u], bpz[u]);
-                        num[u][1] = DOT3(cpx[r], cpy[r], cpz[r], dxa[u], dya[u], dza[u]);
+                        num[u][0] = DOT3(cpx[u], cpy[u], cpz[u], bpx[u], bpy[u], bpz[u]);
+                        num[u][1] = DOT3(cpx[u], cpy[u], cpz[u], dxa[u], dya[u], dza[u]);
                         num[u][2] = DOT3(bpx[u], bpy[u], bpz[u], dxa[u], dya[u], dza[u]);
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
@@ -402,8 +407,8 @@ dense_kernel(const PairParams P)
                 int rowo[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    rowo[u] = listed ? corig[r] : row;
-                    if (listed && P.tri && sorig[u] < corig[r]) {
+                    rowo[u] = listed ? corig[u] : row0 + u;
+                    if (listed && P.tri && sorig[u] < corig[u]) {
                         const double t = c[u][1];
                         c[u][1] = -c[u][2]; c[u][2] = -t;
                         rowo[u] = sorig[u];
@@ -422,7 +427,7 @@ dense_kernel(const PairParams P)
                 bool pend[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    if (ok[u] && P.tri && row == jg[u]) {
+                    if (ok[u] && P.tri && row0 + u == jg[u]) {
                         // i == j of two DIFFERENT selections of equal size (quirk Q1; identical selections have d = 0 here
                         // and were rejected): the one pair of the triangle with off_diag = 1 - straight to the global rows
                         if (pos[u] < hn) {
