@@ -5,7 +5,7 @@
 out=gpurun_out/r2; mkdir -p $out
 set -x
 timeout 300 python bench.py > $out/bench.json 2> $out/bench.err || exit 1
-timeout 400 python profiles/run_configs.py cfg1 cfg2 cfg1_all cfg3 cfg3_g000 cfg4a cfg4b cfg4c cfg5 cfg5_cells cfg4b_cells > $out/configs.jsonl 2> $out/configs.err
+timeout 600 python profiles/run_configs.py cfg1 cfg2 cfg1_all cfg3 cfg3_g000 cfg3_dense cfg4a cfg4b cfg4c cfg5 cfg5_g000 cfg5_cells cfg5_cells_ring cfg5_g000_cells cfg4b_cells cfg3_cells cfg3_cells_ring cfg3_g000_cells > $out/configs.jsonl 2> $out/configs.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs > $out/ncu_launches.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:pair_kernel -s 2 -c 1 -f -o $out/prof_pair \
