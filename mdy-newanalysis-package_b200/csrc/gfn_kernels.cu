@@ -998,10 +998,16 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
     const bool want_dense = (flags & GFN_FLAG_DENSE) || cells_dense || (!(flags & GFN_FLAG_NO_DENSE) && in_range_hint > kDenseShare);
     if (want_dense) {
         cudaError_t de = cudaSuccess;
+        // (a histogram too large for pair_kernel's per-warp replicas sent it to global atomics above; the dense-box kernels
+        // have their own, smaller shared layouts and refuse only what the CALLER forced to global / per-particle)
+        const int ring_hist = cfg->hist_mode;
+        if (!(flags & (GFN_FLAG_PER_PARTICLE | GFN_FLAG_HIST_GLOBAL))) cfg->hist_mode = 0;
         // g000 only: the count kernel (fp32 classification, fp64 for the ambiguous pairs), else the dense walk kernel
         if (count_configure(dev, histo_n, mode_sel, geom.invdx, geom.hmax, geom.box_max, max_smem, sms, cfg, &de)) return cudaSuccess;
         if (de != cudaSuccess) return de;
-        if (!dense_configure(dev, histo_n, mode_sel, max_smem, sms, geom, cfg, &de) && de != cudaSuccess) return de;
+        if (dense_configure(dev, histo_n, mode_sel, max_smem, sms, geom, cfg, &de)) return cudaSuccess;
+        if (de != cudaSuccess) return de;
+        cfg->hist_mode = ring_hist;
     }
     return cudaSuccess;
 }

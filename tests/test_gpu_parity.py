@@ -92,6 +92,29 @@ def test_checked_build_runs_the_small_cases_clean():
     assert "sanitizer cases done" in out.stdout and "checked/libgfn.so" in out.stdout, out.stdout[-500:]
 
 
+@pytest.mark.parametrize("modes,dr,stripes,kernel", [(["all"], 0.0125, 2, "dense"), (["all"], 0.005, 1, "dense"), (["000", "110", "220"], 0.02, 4, "dense"),
+                                                    (["000"], 0.004, 1, "count"), (["000"], 0.0125, 16, "count")])
+def test_dense_box_kernels_with_many_bins(modes, dr, stripes, kernel):
+    """Histograms too large for the preferred shared-memory layout: the dense kernel falls back from 8 bank-group stripes to
+    4, 2 or 1 (bin updates then replay, results do not change), the count kernel from one replica per warp to one per CTA."""
+    rng = np.random.default_rng(int(dr * 1e5))
+    n, L, nf, hmax = 900, 33.0, 3, 15.0
+    g = RDF(modes, 0.0, hmax, dr, n, n, n, n, L)
+    o = O.OracleRDF(modes, 0.0, hmax, dr, n, n, n, n, L)
+    st = g.stats()
+    assert st["kernel"] == kernel and st["hist_replicas"] == stripes, st
+    for f in range(nf):
+        c = rng.random((n, 3)) * L; d = rng.standard_normal((n, 3))
+        if modes == ["000"]:
+            g.calcFrame(c, c); o.calcFrame(c, c)
+        else:
+            g.calcFrame(c, c, d, d); o.calcFrame(c, c, d, d)
+    hn = int(g.histo_n)
+    got, ref = g.raw_histogram(), o.raw_sum()
+    assert np.array_equal(got[:hn], ref[:hn]) and ref[:hn].sum() > 1000
+    assert_hist_close(got, ref, hn)
+
+
 @pytest.mark.parametrize("n1,n2", [(100, 6000), (64, 3000), (200, 200 * 13)])
 def test_dense_kernel_few_units_per_tile(n1, n2):
     """A small core selection against a large surround one in a dense box: one to four 64-row units per surround tile, so the
