@@ -23,11 +23,17 @@
  * Arithmetic contract (DESIGN.md sections 3 and 6):
  *   - Distances and bins: IEEE fp64 with exactly the reference's operation order and one rounding per operation (no
  *     fused multiply-add), so every pair lands in the reference's bin and the g000 row / pair counts are bit-exact.
+ *     g000-only handles in dense boxes (count kernel, gfn_count.cu) decide a pair's bin in fp32 when the estimate is farther
+ *     than a proven error bound from every bin edge and from both ends of the accepted range, and in fp64 otherwise: the
+ *     same bins, bit for bit.
  *   - Orientation weights (gfunction.pyx:154-165): by default each cosine is formed as  dot * (1/|a| * 1/|b|)  with
  *     separately rounded reciprocals (1/norm per site, 1/dist from the square-root iteration) instead of the
  *     reference's  dot / (|a|*|b|):  a per-pair increment can differ from the reference's by up to 4 ulp (relative
  *     4.5e-16), far inside the 1e-12 bar of the weighted rows; sums additionally differ by summation order.  A pair
  *     whose needed norm is zero / outside [2^-300, 2^300] always takes the literal divisions (quirk Q5 semantics).
+ *     The dense-box kernel (gfn_dense.cu) accumulates the weighted rows in 64-bit fixed point, 2^-43 per unit: one
+ *     addend is off by at most 5.7e-14 absolute (bar: 1e-12 per unit of pair weight), sums are exact integers and
+ *     therefore identical for any order of evaluation.
  *   - GFN_FLAG_EXACT_DIV makes every pair take the literal IEEE divisions: per-pair increments are then bit-identical to
  *     the reference's and the weighted rows differ from it by summation order only.
  */
@@ -61,14 +67,18 @@ extern "C" {
                                           units, wider guard band); results identical, see DESIGN.md section 4 */
 #define GFN_FLAG_NO_TRIANGLE       32u /* evaluate all n1 x n2 pairs with weight 1 even when n1 == n2 (calcHistoTS,
                                           gfunction.pyx:168-192, has no j >= i shortcut) */
-#define GFN_FLAG_DENSE             128u /* force the dense-neighbourhood kernel (every warp filters AND evaluates, core
-                                          sites in registers) where it supports the handle; default: chosen when the
-                                          share of in-range pairs expected from box and histo_max exceeds 10 % */
-#define GFN_FLAG_NO_DENSE          256u /* never use it (the warp-specialised ring kernel serves every handle) */
+#define GFN_FLAG_DENSE             128u /* force the dense-box kernels (g000 only: count kernel, fp32 bin classification + fp64 for
+                                          the ambiguous pairs; other mode sets: every warp filters AND evaluates, core sites in
+                                          registers) where they support the handle; default: chosen when the share of in-range
+                                          pairs expected from box and histo_max exceeds 10 % */
+#define GFN_FLAG_NO_DENSE          256u /* never use them (the warp-specialised ring kernel serves every handle) */
 #define GFN_FLAG_CELLS             512u /* tile skipping for sparse neighbourhoods: every frame is sorted into Morton order on the device
                                          * and only the tile pairs whose bounding boxes lie within histo_max of each other are
-                                         * visited (gfn_cells.cu).  Same pairs accepted, same arithmetic: counts bit-exact.  Ignored
-                                         * by handles the dense kernels serve and by shell-resolved handles. */
+                                         * visited (gfn_cells.cu).  Same pairs accepted, same arithmetic: counts bit-exact.  Honoured
+                                         * where the expected share of visited tile pairs is small enough to pay (a box many tile
+                                         * diameters wide, e.g. 10^6 sites: 269 -> 20 ms per frame, g000 only 251 -> 7 ms); ignored by
+                                         * shell-resolved handles.  Launches of two DIFFERENT selections of equal size keep the full
+                                         * enumeration (quirk Q1: their triangle relates original indices). */
 #define GFN_FLAG_EXACT_DIV         64u /* orientation cosines by the reference's literal divisions dot/(|a|*|b|)
                                           (gfunction.pyx:155,159,163) instead of reciprocal products: per-pair increments
                                           bit-identical to the reference, see "Arithmetic contract" above */
