@@ -87,6 +87,34 @@ Nccl& nccl()
 // ------------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------------
+// Readers of caller-managed device arrays (gfn_enqueue_device_frames: the legacy pre_*_gpu path): the only kernel that reads
+// the raw arrays of a frame is prep_kernel, and launch_frames records an event right behind it.  gfn_dev_upload waits for the
+// events recorded on its device since the last upload - not for the whole device - before it overwrites a buffer, so the
+// upload of the next frame overlaps the pair kernels of the previous one.
+struct ReaderFence {
+    std::mutex mu;
+    std::vector<cudaEvent_t> ev[64];
+    void add(int dev, cudaEvent_t e) { if (dev < 0 || dev >= 64) return; std::lock_guard<std::mutex> lk(mu); ev[dev].push_back(e); }
+    void forget(int dev, cudaEvent_t e)
+    {
+        if (dev < 0 || dev >= 64) return;
+        std::lock_guard<std::mutex> lk(mu);
+        std::vector<cudaEvent_t>& v = ev[dev];
+        for (size_t k = 0; k < v.size(); ) { if (v[k] == e) { v[k] = v.back(); v.pop_back(); } else ++k; }
+    }
+    // waits with the lock held: a handle cannot be destroyed (forget) under the events being waited for
+    cudaError_t wait(int dev)
+    {
+        if (dev < 0 || dev >= 64) return cudaDeviceSynchronize();
+        std::lock_guard<std::mutex> lk(mu);
+        cudaError_t rc = cudaSuccess;
+        for (cudaEvent_t e : ev[dev]) { const cudaError_t r = cudaEventSynchronize(e); if (r != cudaSuccess) rc = r; }
+        ev[dev].clear();
+        return rc;
+    }
+};
+ReaderFence& reader_fence() { static ReaderFence f; return f; }
+
 constexpr int kRing = 3;
 constexpr int kXRing = 4;
 constexpr int kStatusSlots = 2;   // behind the 8*histo_n accumulators: [0] ranks/devices that hit the fp16 range error, [1] ... a zero-norm dipole
@@ -505,6 +533,7 @@ void free_dev(Dev& d)
     cudaFree(d.cells.sortA); cudaFree(d.cells.sortB); cudaFree(d.cells.keys[0]); cudaFree(d.cells.keys[1]); cudaFree(d.cells.vals[0]); cudaFree(d.cells.vals[1]);
     cudaFree(d.cells.tmp); cudaFree(d.cells.boxA); cudaFree(d.cells.boxB); cudaFree(d.cells.list); cudaFree(d.cells.count); cudaFree(d.cells.start);
     for (Dev::XSlot& x : d.xs) {
+        if (x.k0) reader_fence().forget(d.dev, x.k0);
         if (x.h_box) cudaFreeHost(x.h_box);
         cudaFree(x.d_box);
         if (x.k0) cudaEventDestroy(x.k0);
@@ -1208,6 +1237,7 @@ int gfn_enqueue_device_frames(gfn_t* h, int nframes,
                                d.xsiteA, d.xsiteB, d.xmax, x.d_box, x.k0, x.k1);
         if (rc) return rc;
         x.timed = true;
+        reader_fence().add(d.dev, x.k0);          // recorded right behind prep_kernel, the only reader of the caller's arrays
     }
     return GFN_OK;
 }
@@ -1568,7 +1598,7 @@ int gfn_dev_upload(int dev, void* dptr, const void* host, unsigned long long byt
 {
     gfn_t* h = nullptr;
     CU(cudaSetDevice(dev));
-    CU(cudaDeviceSynchronize());      // frames enqueued earlier may still be reading this buffer
+    CU(reader_fence().wait(dev));     // frames enqueued earlier may still be reading this buffer: wait for their prep kernels only
     CU(cudaMemcpy(dptr, host, bytes, cudaMemcpyHostToDevice));
     return GFN_OK;
 }

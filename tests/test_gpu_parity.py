@@ -1188,6 +1188,28 @@ def _cfg4_box(rng, ns, nu, apu, L):
     return solv_c, solv_d, solv_o, solu_c, solu_d, solu_a
 
 
+def test_device_arrays_reused_frame_after_frame():
+    """The upload slots of the pre_*_gpu path are overwritten every frame while earlier frames are still queued: upload()
+    waits for the prep kernels that read the slot (not for the whole device), so no frame may see its successor's data."""
+    from newanalysis.gfunction import to_device
+    n, L, nf = 12000, 70.0, 7
+    rng = np.random.default_rng(808)
+    frames = [(rng.random((n, 3)) * L, rng.standard_normal((n, 3))) for _ in range(nf)]
+    a = RDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
+    b = RDF(["000"], 0.0, 15.0, 0.05, n, n, n, n, L)
+    gc, gd = to_device(frames[0][0]), to_device(frames[0][1])
+    o = O.OracleRDF(["all"], 0.0, 15.0, 0.05, n, n, n, n, L)
+    for c, d in frames:
+        gc.upload(c); gd.upload(d)
+        a.calcFrame(c, c, d, d, pre_coor_sel1_gpu=gc, pre_coor_sel2_gpu=gc, pre_dip_sel1_gpu=gd, pre_dip_sel2_gpu=gd)
+        b.calcFrame(c, c, pre_coor_sel1_gpu=gc, pre_coor_sel2_gpu=gc)
+        o.calcFrame(c, c, d, d)
+    ref = o.raw_sum()
+    ha, hb = a.raw_histogram(), b.raw_histogram()
+    assert np.array_equal(ha[:300], ref[:300]) and np.array_equal(hb[:300], ref[:300]) and ref[:300].sum() > 1e5
+    assert_hist_close(ha, ref, 300)
+
+
 def test_cfg4_four_objects_share_one_upload():
     """BASELINE configs[3] as north_star states it: four RDF objects per frame on ONE shared upload of the frame's arrays
     (the reference's pre_*_gpu kwargs, gfunction.pyx:390-391, 431-453): solute COM x solvent COM "all", solvent self
