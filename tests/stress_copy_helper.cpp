@@ -9,11 +9,47 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 #include <thread>
 #include <vector>
 
+// "pool" mode: stress_copy_helper pool <pools> <rounds> - several CopyPool instances (more threads than cores), rounds of
+// parallel frame copies with 1 .. 40 tasks each, pauses in between so that the workers sleep on their condition variable;
+// every task must run exactly once per round and every copy is verified.
+static int pool_mode(int pools, int rounds)
+{
+    std::atomic<int> bad{0};
+    std::vector<std::thread> th;
+    for (int p = 0; p < pools; ++p) th.emplace_back([&, p] {
+        std::mt19937_64 rng(99 + p);
+        const size_t frame = 200u << 10;
+        const int maxn = 40;
+        std::vector<unsigned char> src(frame * maxn), dst(frame * maxn);
+        for (size_t k = 0; k < src.size(); ++k) src[k] = (unsigned char)(rng() >> 56);
+        gfn::CopyPool pool(1 + (int)(rng() % 5));
+        std::vector<std::atomic<int>> hits(maxn);
+        for (int r = 0; r < rounds; ++r) {
+            const int n = 1 + (int)(rng() % maxn);
+            for (auto& h : hits) h.store(0);
+            memset(dst.data(), 0, frame * n);
+            pool.run(n, [&](int i) {
+                hits[i].fetch_add(1);
+                gfn::copy_to_ring(dst.data() + frame * i, src.data() + frame * i, frame - (size_t)(i % 3) * 17);
+            });
+            for (int i = 0; i < n; ++i) {
+                if (hits[i].load() != 1 || memcmp(dst.data() + frame * i, src.data() + frame * i, frame - (size_t)(i % 3) * 17) != 0) { bad.fetch_add(1); return; }
+            }
+            if (r % 4 == 0) std::this_thread::sleep_for(std::chrono::microseconds(100 + rng() % 400));
+        }
+    });
+    for (auto& t : th) t.join();
+    printf("pools %d rounds %d bad %d\n", pools, rounds, bad.load());
+    return bad.load() ? 1 : 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc > 1 && std::string(argv[1]) == "pool") return pool_mode(argc > 2 ? atoi(argv[2]) : 4, argc > 3 ? atoi(argv[3]) : 2000);
     const int pairs = argc > 1 ? atoi(argv[1]) : 8;
     const int iters = argc > 2 ? atoi(argv[2]) : 20000;
     const int sleep_every = argc > 3 ? atoi(argv[3]) : 3;

@@ -91,3 +91,7 @@ def test_copy_helper_stress(tmp_path):
     out = subprocess.run([exe, "16", "3000", "3"], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "bad 0" in out.stdout
+    # the copy pool of the block calls: 6 pools of 1-5 workers each, 1500 rounds of 1-40 frame copies, every task exactly once
+    out = subprocess.run([exe, "pool", "6", "1500"], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "bad 0" in out.stdout
