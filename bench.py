@@ -669,11 +669,53 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu
     if atoms is not None:
         line["e2e_atoms"] = atoms
+    if world == 1 and name == "cfg3" and not args.no_other_configs:
+        line["time_series"] = time_series_arm(args)
     if others is not None:
         line["other_configs"] = others
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def time_series_arm(args):
+    """calcHistoTS (gfunction.pyx:168-192), one call per frame with host arrays, result[t] written on
+    the host: 1,024 core sites x 32,768 surround sites, 240 bins.  The reference function on all host threads runs the same
+    frames (fewer of them); the two results must be equal."""
+    from newanalysis.gfunction import calcHistoTS
+    import oracle as O
+    n1, n2, nb, T = 1024, 32768, 240, 12
+    L = (n2 / 0.0334) ** (1.0 / 3.0)
+    rng = np.random.default_rng(77)
+    surr = [rng.random((n2, 3)) * L for _ in range(T)]
+    core = [np.ascontiguousarray(x[:n1]) + 0.37 for x in surr]
+    res = np.zeros((T, n1, nb))
+    calcHistoTS(core[0], surr[0], res, L, 0, 0.0, 12.0, 20.0)               # builds the handle
+    res[:] = 0.0
+    t0 = time.perf_counter()
+    for t in range(T):
+        calcHistoTS(core[t], surr[t], res, L, t, 0.0, 12.0, 20.0)
+    ms = (time.perf_counter() - t0) / T * 1e3
+    out = {"what": "calcHistoTS, %d x %d sites, %d bins, host arrays in, result[t] out, per call" % (n1, n2, nb),
+           "ms_per_frame": ms, "value": n1 * n2 / ms / 1e6, "unit": UNIT, "d2h_bytes_per_frame": 8 * (n1 + 1) * nb}
+    if not args.no_cpu_baseline:
+        ref = O.load_ref()
+        use_all_host_threads()
+        fn = ref.calcHistoTS if ref is not None else None
+        TR = 2
+        rr = np.zeros((TR, n1, nb))
+        t0 = time.perf_counter()
+        for t in range(TR):
+            if fn is not None:
+                fn(core[t], surr[t], rr, L, t, 0.0, 12.0, 20.0)
+            else:
+                O.calc_histo_ts_c(core[t], surr[t], rr[t], L, 0.0, 12.0, 20.0)
+        rms = (time.perf_counter() - t0) / TR * 1e3
+        out["reference_ms_per_frame"] = rms
+        out["reference_kind"] = "reference" if fn is not None else "port"
+        out["reference_cores"] = host_threads() if fn is not None else 1
+        out["equal_to_reference"] = bool(np.array_equal(res[:TR], rr))
+    return out
 
 
 def counts_ok(g000_sum, accepted, n1, n2, self_pairs, frames):

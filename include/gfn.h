@@ -221,6 +221,11 @@ int gfn_readout(gfn_t *h, double *hist, double *pairw, unsigned long long *overf
 /* Per-particle histogram (GFN_FLAG_PER_PARTICLE only): 7*n1*histo_n doubles, reference layout :332. */
 int gfn_readout_per_particle(gfn_t *h, double *hist);
 
+/* A slice of the same array added to the caller's: dst[k] += per_particle[first + k], k < count.  This is the
+ * reference's `result[t,i,pos] += 1.0` of calcHistoTS (gfunction.pyx:168-192) for a whole frame: the shim passes
+ * &result[t,0,0] and only the g000 rows of the frame cross PCIe (through a pinned staging buffer the handle keeps). */
+int gfn_readout_per_particle_add(gfn_t *h, double *dst, unsigned long long first, unsigned long long count);
+
 /* RDF.scale (gfunction.pyx:513-515) and RDF.resetArrays (:552-557) on the device accumulators. */
 int gfn_scale(gfn_t *h, double value);
 int gfn_reset(gfn_t *h);

@@ -27,11 +27,22 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "copy_helper.h"
 
 using namespace gfn;
 
 namespace {
+
+// NVTX range of one host-side stage (the reference has no tracing; Nsight shows these next to the
+// kernels).  Header-only NVTX 3: without an attached tool a push/pop is one load and one branch.
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range&) = delete;
+    Range& operator=(const Range&) = delete;
+};
 
 thread_local char g_create_err[512] = "";
 
@@ -158,6 +169,8 @@ struct Dev {
     double* gsum = nullptr;               // all-reduce result, same layout
     double* h_out = nullptr;              // pinned: readout lands here ([8][histo_n] + status, then kCounters u64)
     double* gpp = nullptr;                // per-particle
+    double* h_pp = nullptr;               // pinned staging of gfn_readout_per_particle_add
+    size_t h_pp_cap = 0;                  // ... its capacity in doubles
     double* partials = nullptr;
     unsigned long long* counters = nullptr;
     int* item_start = nullptr;
@@ -351,6 +364,7 @@ int launch_frames(gfn_t* h, Dev& d, int nframes,
                   Site* siteA, Site* siteB, float* maxab, const double* d_box,
                   cudaEvent_t k0, cudaEvent_t k1, const int* d_map = nullptr, long long s_map = 0)
 {
+    Range nvtx_range("gfn: launch batch");
     cudaStream_t s = d.comp;
     CU(cudaMemsetAsync(maxab, 0, sizeof(float) * 4 * nframes, s));
     unsigned* nflag = reinterpret_cast<unsigned*>(maxab + 2 * nframes);
@@ -528,6 +542,7 @@ void free_dev(Dev& d)
         if (b.k1) cudaEventDestroy(b.k1);
     }
     if (d.h_out) cudaFreeHost(d.h_out);
+    if (d.h_pp) cudaFreeHost(d.h_pp);
     cudaFree(d.gacc); cudaFree(d.gsum); cudaFree(d.gpp); cudaFree(d.partials); cudaFree(d.counters); cudaFree(d.item_start); cudaFree(d.bin_thr);
     cudaFree(d.xsiteA); cudaFree(d.xsiteB); cudaFree(d.xmax);
     cudaFree(d.cells.sortA); cudaFree(d.cells.sortB); cudaFree(d.cells.keys[0]); cudaFree(d.cells.keys[1]); cudaFree(d.cells.vals[0]); cudaFree(d.cells.vals[1]);
@@ -1107,6 +1122,7 @@ int gfn_topology_natoms(gfn_t* h, int* natoms1, int* natoms2)
 int gfn_enqueue_atom_frames(gfn_t* h, int nframes, const float* a1, long long stride_a1,
                             const float* a2, long long stride_a2, const double* box_dims)
 {
+    Range nvtx_range("gfn_enqueue_atom_frames");
     if (!h) return GFN_EINVAL;
     if (!h->na[0]) return fail(h, GFN_EINVAL, "no topology attached (gfn_attach_topology)");
     if (nframes < 0) return fail(h, GFN_EINVAL, "nframes < 0");
@@ -1132,6 +1148,7 @@ int gfn_enqueue_frames(gfn_t* h, int nframes,
                        const double* c1, long long s_c1, const double* c2, long long s_c2,
                        const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims)
 {
+    Range nvtx_range("gfn_enqueue_frames");
     return enqueue_impl(h, nframes, c1, s_c1, c2, s_c2, d1, s_d1, d2, s_d2, box_dims, nullptr, 0);
 }
 
@@ -1139,6 +1156,7 @@ int gfn_enqueue_frames_pinned(gfn_t* h, int nframes,
                               const double* c1, long long s_c1, const double* c2, long long s_c2,
                               const double* d1, long long s_d1, const double* d2, long long s_d2, const double* box_dims)
 {
+    Range nvtx_range("gfn_enqueue_frames_pinned");
     return enqueue_impl(h, nframes, c1, s_c1, c2, s_c2, d1, s_d1, d2, s_d2, box_dims, nullptr, 0, true);
 }
 
@@ -1164,6 +1182,7 @@ int gfn_enqueue_frames_shells(gfn_t* h, int nframes,
                               const double* d1, long long s_d1, const double* d2, long long s_d2,
                               const double* box_dims, const int* shell_map, long long s_map)
 {
+    Range nvtx_range("gfn_enqueue_frames_shells");
     if (h && !shell_map) return fail(h, GFN_EINVAL, "shell matrix is NULL");
     return enqueue_impl(h, nframes, c1, s_c1, c2, s_c2, d1, s_d1, d2, s_d2, box_dims, shell_map, s_map);
 }
@@ -1177,6 +1196,7 @@ int gfn_enqueue_device_frames(gfn_t* h, int nframes,
                               const double* dc1, long long s_c1, const double* dc2, long long s_c2,
                               const double* dd1, long long s_d1, const double* dd2, long long s_d2, const double* box_dims)
 {
+    Range nvtx_range("gfn_enqueue_device_frames");
     if (!h) return GFN_EINVAL;
     if (nframes < 0) return fail(h, GFN_EINVAL, "nframes < 0");
     if (!dc1 || !dc2) return fail(h, GFN_EINVAL, "coordinate array is NULL");
@@ -1254,6 +1274,7 @@ int gfn_flush(gfn_t* h)
 
 int gfn_sync(gfn_t* h)
 {
+    Range nvtx_range("gfn_sync");
     if (!h) return GFN_EINVAL;
     int rc = gfn_flush(h);
     if (rc) return rc;
@@ -1275,6 +1296,7 @@ int gfn_sync(gfn_t* h)
 // in a collective the failing rank never entered.
 int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overflow)
 {
+    Range nvtx_range("gfn_readout");
     if (!h || !hist) return fail(h, GFN_EINVAL, "NULL argument");
     int rc = gfn_flush(h);
     if (rc) return rc;
@@ -1342,6 +1364,7 @@ int gfn_readout(gfn_t* h, double* hist, double* pairw, unsigned long long* overf
 
 int gfn_readout_per_particle(gfn_t* h, double* hist)
 {
+    Range nvtx_range("gfn_readout_per_particle");
     if (!h || !hist) return fail(h, GFN_EINVAL, "NULL argument");
     if (!(h->flags & GFN_FLAG_PER_PARTICLE)) return fail(h, GFN_EINVAL, "handle was not created with GFN_FLAG_PER_PARTICLE");
     int rc = gfn_sync(h);
@@ -1349,6 +1372,31 @@ int gfn_readout_per_particle(gfn_t* h, double* hist)
     Dev& d = h->devs[0];
     CU(cudaSetDevice(d.dev));
     CU(cudaMemcpy(hist, d.gpp, sizeof(double) * 7ull * h->n1 * h->histo_n, cudaMemcpyDeviceToHost));
+    return rc;
+}
+
+int gfn_readout_per_particle_add(gfn_t* h, double* dst, unsigned long long first, unsigned long long count)
+{
+    Range nvtx_range("gfn_readout_per_particle_add");
+    if (!h || !dst) return fail(h, GFN_EINVAL, "NULL argument");
+    if (!(h->flags & GFN_FLAG_PER_PARTICLE)) return fail(h, GFN_EINVAL, "handle was not created with GFN_FLAG_PER_PARTICLE");
+    const unsigned long long total = 7ull * h->n1 * h->histo_n;
+    if (first > total || count > total - first) return fail(h, GFN_EINVAL, "slice [%llu, +%llu) exceeds the per-particle array of %llu values", first, count, total);
+    int rc = gfn_flush(h);
+    if (rc) return rc;
+    Dev& d = h->devs[0];
+    CU(cudaSetDevice(d.dev));
+    if (count > d.h_pp_cap) {
+        if (d.h_pp) { CU(cudaFreeHost(d.h_pp)); d.h_pp = nullptr; d.h_pp_cap = 0; }
+        CU(cudaHostAlloc(&d.h_pp, sizeof(double) * count, cudaHostAllocDefault));
+        d.h_pp_cap = count;
+    }
+    // enqueued behind the last frame; gfn_sync below is the one wait (and reports the deferred errors)
+    if (count) CU(cudaMemcpyAsync(d.h_pp, d.gpp + first, sizeof(double) * count, cudaMemcpyDeviceToHost, d.comp));
+    rc = gfn_sync(h);
+    if (rc && rc != GFN_EZERODIV) return rc;
+    const double* src = d.h_pp;
+    for (unsigned long long k = 0; k < count; ++k) dst[k] += src[k];
     return rc;
 }
 

@@ -88,6 +88,7 @@ cdef extern from "gfn.h":
     int gfn_sync(gfn_t *h) nogil
     int gfn_readout(gfn_t *h, double *hist, double *pairw, unsigned long long *overflow) nogil
     int gfn_readout_per_particle(gfn_t *h, double *hist) nogil
+    int gfn_readout_per_particle_add(gfn_t *h, double *dst, unsigned long long first, unsigned long long count) nogil
     int gfn_scale(gfn_t *h, double value) nogil
     int gfn_reset(gfn_t *h) nogil
     void gfn_destroy(gfn_t *h) nogil
@@ -653,6 +654,13 @@ cdef class _Backend:
         self.check(rc)
         return hist
 
+    cdef int add_per_particle(self, double *dst, unsigned long long first, unsigned long long count) except -1:
+        cdef int rc
+        with nogil:
+            rc = gfn_readout_per_particle_add(self.h, dst, first, count)
+        self.check(rc)
+        return 0
+
     def scale(self, double v):
         self.check(gfn_scale(self.h, v))
 
@@ -737,11 +745,17 @@ def calcHistoTS(core_xyz, surr_xyz, np.ndarray[np.float64_t, ndim=3] result, dou
     cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a1 = c1
     cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a2 = c2
     b.enqueue(<const double *> a1.data, <const double *> a2.data, NULL, NULL)
-    pp = b.readout_per_particle()
-    result[t] += pp[:n1 * nb].reshape(n1, nb)
-    # Q3 spill of the last core row: the device keeps it right behind the frame's slab (first row of the next mode)
-    if t + 1 < result.shape[0] and result.flags.c_contiguous:
-        result[t + 1, 0, :] += pp[n1 * nb:n1 * nb + nb]
+    # Q3 spill of the last core row: the device keeps it right behind the frame's slab (first row of the next mode), and
+    # in a C-contiguous result that is the first row of frame t+1 - one add over (n1 + 1) rows covers both
+    cdef unsigned long long slab = <unsigned long long> n1 * nb
+    cdef bint spill = t + 1 < result.shape[0]
+    cdef np.ndarray[np.float64_t, ndim=2] tmp
+    if result.flags.c_contiguous:
+        b.add_per_particle(<double *> result.data + <unsigned long long> t * slab, 0, slab + (nb if spill else 0))
+    else:
+        tmp = np.zeros((n1, nb))
+        b.add_per_particle(<double *> tmp.data, 0, slab)
+        result[t] += tmp
 
 
 def calcHistoTSVoro(core_xyz, surr_xyz, np.ndarray[np.float64_t, ndim=4] result, ds, int maxshell,
@@ -779,8 +793,11 @@ def calcHistoTSVoro(core_xyz, surr_xyz, np.ndarray[np.float64_t, ndim=4] result,
     cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a1 = c1
     cdef np.ndarray[np.float64_t, ndim=2, mode="c"] a2 = c2
     b.enqueue_shells(<const double *> a1.data, <const double *> a2.data, NULL, NULL, <const int *> shells.data)
-    rows = b.readout_per_particle()[:<long long> n1 * maxshell * nb].reshape(n1, maxshell, nb)
-    result[t] += rows
+    cdef unsigned long long slab = <unsigned long long> n1 * maxshell * nb
+    if result.flags.c_contiguous:
+        b.add_per_particle(<double *> result.data + <unsigned long long> t * slab, 0, slab)
+    else:
+        result[t] += b.readout_per_particle()[:slab].reshape(n1, maxshell, nb)
 
 
 class RDF(object):

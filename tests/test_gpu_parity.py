@@ -1324,6 +1324,81 @@ def test_calc_histo_ts_matches_oracle():
     assert np.array_equal(r2, o2)
 
 
+def test_calc_histo_ts_adds_into_result_and_takes_strided_results():
+    """The reference adds (`result[t,i,pos] += 1.0`, gfunction.pyx:192): what is already in `result` stays, a second call on
+    the same frame doubles the counts, and a result array that is not C-contiguous gets the same rows."""
+    from newanalysis.gfunction import calcHistoTS
+    n1, n2, nb, L = 96, 700, 240, 28.0
+    rng = np.random.default_rng(43)
+    c1 = rng.random((n1, 3)) * L; c2 = rng.random((n2, 3)) * L
+    want = np.zeros((n1, nb)); O.calc_histo_ts_c(c1, c2, want, L, 0.0, 12.0, 20.0)
+    res = np.full((2, n1, nb), 3.0)
+    calcHistoTS(c1, c2, res, L, 1, 0.0, 12.0, 20.0)
+    calcHistoTS(c1, c2, res, L, 1, 0.0, 12.0, 20.0)
+    assert np.array_equal(res[1], 3.0 + 2.0 * want) and np.array_equal(res[0], np.full((n1, nb), 3.0))
+    wide = np.zeros((2, n1, 2 * nb))
+    view = wide[:, :, ::2]
+    assert not view.flags.c_contiguous
+    calcHistoTS(c1, c2, view, L, 0, 0.0, 12.0, 20.0)
+    assert np.array_equal(wide[0, :, ::2], want) and not wide[:, :, 1::2].any() and not wide[1].any()
+
+
+def test_readout_per_particle_add_slices_and_errors():
+    """gfn_readout_per_particle_add through raw ctypes: a slice of the [mode][core site][bin] array is ADDED to the
+    caller's values; slices beyond the array and handles without GFN_FLAG_PER_PARTICLE are refused."""
+    import ctypes
+    import newanalysis
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(newanalysis.__file__), "libgfn.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    U = ctypes.c_ulonglong
+    lib.gfn_create.restype = ctypes.c_int
+    lib.gfn_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                               ctypes.c_float, ctypes.c_double, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                               ctypes.c_uint]
+    lib.gfn_enqueue_frame.restype = ctypes.c_int
+    lib.gfn_enqueue_frame.argtypes = [ctypes.c_void_p, dp, dp, dp, dp]
+    lib.gfn_readout_per_particle.restype = ctypes.c_int
+    lib.gfn_readout_per_particle.argtypes = [ctypes.c_void_p, dp]
+    lib.gfn_readout_per_particle_add.restype = ctypes.c_int
+    lib.gfn_readout_per_particle_add.argtypes = [ctypes.c_void_p, dp, U, U]
+    lib.gfn_destroy.restype = None
+    lib.gfn_destroy.argtypes = [ctypes.c_void_p]
+    lib.gfn_last_error.restype = ctypes.c_char_p
+    lib.gfn_last_error.argtypes = [ctypes.c_void_p]
+    n, hn, L = 64, 100, 20.0
+    rng = np.random.default_rng(44)
+    c = np.ascontiguousarray(rng.random((n, 3)) * L)
+    box = (ctypes.c_double * 6)(L, L, L, L / 2, L / 2, L / 2)
+    ptr = lambda a: a.ctypes.data_as(dp)
+
+    def handle(flags):
+        h = ctypes.c_void_p()
+        rc = lib.gfn_create(ctypes.byref(h), n, n, hn, 0.0, 10.0, 10.0, 1, box, None, 0, flags)
+        assert rc == 0, lib.gfn_last_error(None)
+        return h
+
+    h = handle(1 | 32)                                            # per-particle, no triangle
+    try:
+        assert lib.gfn_enqueue_frame(h, ptr(c), ptr(c), None, None) == 0, lib.gfn_last_error(h)
+        full = np.zeros(7 * n * hn)
+        assert lib.gfn_readout_per_particle(h, ptr(full)) == 0 and full[:n * hn].sum() > 100
+        part = np.full(3 * hn, 5.0)
+        assert lib.gfn_readout_per_particle_add(h, ptr(part), 7 * hn, 3 * hn) == 0, lib.gfn_last_error(h)
+        assert np.array_equal(part, 5.0 + full[7 * hn:10 * hn]) and full[7 * hn:10 * hn].sum() > 0
+        assert lib.gfn_readout_per_particle_add(h, ptr(part), 0, 0) == 0
+        assert lib.gfn_readout_per_particle_add(h, ptr(part), 7 * n * hn - 2, 3) != 0
+        assert b"exceeds" in lib.gfn_last_error(h)
+        assert lib.gfn_readout_per_particle_add(h, None, 0, 1) != 0
+    finally:
+        lib.gfn_destroy(h)
+    g = handle(0)
+    try:
+        assert lib.gfn_readout_per_particle_add(g, ptr(part), 0, 1) != 0
+        assert b"PER_PARTICLE" in lib.gfn_last_error(g)
+    finally:
+        lib.gfn_destroy(g)
+
+
 @pytest.mark.parametrize("name", sorted(C.TS_CASES))
 def test_calc_histo_ts_golden(golden_dir, name):
     """calcHistoTS against what the UNMODIFIED reference function wrote (tests/golden/ts.npz), including the quirk-Q3
