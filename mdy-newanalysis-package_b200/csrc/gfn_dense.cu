@@ -17,11 +17,13 @@
 //     REGISTERS, so the exact path never gathers a core record.
 //   * per unit the warp runs the packed-fp16 (or fp32) range pre-filter of pair_kernel - two core rows per instruction -
 //     and keeps the survivor masks in registers: 4 chunks x 2 rows x 32 bits.
-//   * then the warp goes through the surround sites that survived against ANY of its rows: the site's record is read as a
-//     broadcast, every lane evaluates it against its two rows (two independent fp64 chains) masked by the rows' filter
-//     bits - distance, bin and weights in the reference's arithmetic.  (Letting every lane walk its OWN survivors keeps all
-//     lanes busy but makes every record a gather of 32 random rows: 9 shared-memory wavefronts per 128-bit load instead
-//     of 1; with that layout the shared-memory pipe was the limiter at 74 % of its peak, profiles/r2/.)
+//   * then every lane walks the survivors of its OWN two rows, one survivor of each row per step (two independent fp64
+//     chains): the surround record is gathered from the shared-memory stage (four 128-bit loads per survivor; the
+//     80-byte record stride spreads random rows over all bank groups), distance, bin and weights in the reference's
+//     arithmetic.  These gathers make the shared-memory pipe the busiest unit of the kernel (profiles/r2/); the
+//     alternative - going through the surround sites one by one with the record read as a broadcast and every lane
+//     testing it against its two rows - has no gathers but idles the lanes whose rows did not survive: measured equal in
+//     dense boxes and four times slower in the sparse units of a cell-sorted frame.
 //   * ONE histogram per CTA: pair counts with native shared-memory integer atomics; orientation sums as 64-bit FIXED POINT
 //     under a per-bin lock word (native exchange), stored in 8 bank-group stripes so that the read-modify-write of random
 //     bins is conflict-free.  Integer sums are associative: any order gives the same bits, so the warps pull units
