@@ -152,7 +152,7 @@ __global__ void __launch_bounds__((NF + ND) * 32, 1)
 pair_kernel(const PairParams P)
 {
     constexpr int NW = NF + ND;
-    static_assert(ND == 4 || (ND == 8 && NF == 8), "4 drain warps (rings d, d+4, d+8), or 8 behind 8 filter warps (ring d)");
+    static_assert(ND == 4 || (ND == 8 && NF == 8) || (ND == 6 && NF == 12), "4 drain warps (rings d, d+4, d+8), 6 behind 12 (rings d, d+6), or 8 behind 8 filter warps (ring d)");
     constexpr int TI = NF * 32 * kIPT;
     constexpr int TJ = kTJ;
     constexpr int S = kStages;
@@ -199,7 +199,12 @@ pair_kernel(const PairParams P)
 #define GFN_REGS_F "104"
 #define GFN_REGS_D "152"
 #endif
+#ifndef GFN_REGS_F6
+#define GFN_REGS_F6 "72"
+#define GFN_REGS_D6 "128"
+#endif
         if (ND == 8)   asm volatile("setmaxnreg.dec.sync.aligned.u32 " GFN_REGS_F ";");
+        else if (ND == 6) asm volatile("setmaxnreg.dec.sync.aligned.u32 " GFN_REGS_F6 ";");    // experiment (profiles/exp_build.sh): 576 threads launch with 96 registers; 384*F + 192*D must stay BELOW 576*96
         else if (kF32 || kH16) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         else           asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         unsigned short* q = rings + warp * kRingCap;
@@ -461,6 +466,7 @@ pair_kernel(const PairParams P)
     } else {
         // =========================================== DRAIN ============================================
         if (ND == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 " GFN_REGS_D ";");
+        else if (ND == 6) asm volatile("setmaxnreg.inc.sync.aligned.u32 " GFN_REGS_D6 ";");
         else         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int dw = warp - NF;                   // drain warp: serves the rings of filter warps dw, dw+ND, ...
         const int rep = dw % nrep;
@@ -932,7 +938,9 @@ static pair_fn_t pick_fn(const PairConfig& c)
     return c.drain_warps == 8 ? pick_shape<F, 8, 8, false>(c.hist_mode, weights, allm) : pick_shape<F, 8, 4, false>(c.hist_mode, weights, allm);
 }
 
-#ifdef GFN_EXP_ONLY_F32
+#ifdef GFN_EXP_12_6
+static pair_fn_t pick(const PairConfig& c) { return pair_kernel<__half, 12, 6, true, 0, true, false>; }
+#elif defined(GFN_EXP_ONLY_F32)
 static pair_fn_t pick(const PairConfig& c) { return pair_kernel<float, 8, 8, true, 0, true, false>; }
 #elif defined(GFN_EXP_ONLY_H16)      // experiment builds (profiles/exp.sh): one instantiation, seconds to compile; cfg3 fp16 shape only
 static pair_fn_t pick(const PairConfig& c) { return pair_kernel<__half, 8, 8, true, 0, true, false>; }
@@ -956,7 +964,11 @@ cudaError_t pair_configure(int dev, int n1, int histo_n, int mode_sel, unsigned 
     cfg->all_modes = (mode_sel == 127) ? 1 : 0;
     cfg->nrep = 1;
     // CTA shapes in order of preference: 8 filter + 8 drain warps, 8 + 4 (fewer histogram replicas to fit)
+#ifdef GFN_EXP_12_6
+    const int shapes[2][2] = {{12, 6}, {12, 6}};
+#else
     const int shapes[2][2] = {{8, 8}, {8, 4}};
+#endif
     int force_nf = 0, force_nd = 0;
     if (const char* env = getenv("GFN_FILTER_WARPS")) force_nf = atoi(env);
     if (const char* env = getenv("GFN_DRAIN_WARPS")) force_nd = atoi(env);

@@ -24,12 +24,20 @@ static_assert(sizeof(Site) == 80, "Site must be 80 bytes");
 constexpr int kTJ      = 128;    // surround sites per shared-memory stage
 constexpr int kStages  = 3;      // surround stages in flight
 constexpr int kIPT     = 2;      // core sites held in registers per thread
+#ifdef GFN_EXP_12_6   // experiment: 12 filter + 6 drain warps (768-site core tiles)
+constexpr int kPadTo   = 3072;   // a multiple of the 768-site core tile and of 1024
+#else
 constexpr int kPadTo   = 1024;   // selections are padded to a multiple of this many sites on the device
+#endif
 #ifndef GFN_DRAIN_ILP
 #define GFN_DRAIN_ILP 2
 #endif
 constexpr int kDrainILP = GFN_DRAIN_ILP;     // survivors evaluated per drain lane per batch
+#ifdef GFN_EXP_12_6
+constexpr int kRingCap = 1024;   // 12 rings must fit next to 6 replicas (sparse tiles only: a fully dense mask push needs 2048)
+#else
 constexpr int kRingCap = 2048;   // survivor ring entries (16 bit) per filter warp: one push (<= 32*32) always fits behind < 64 unread ones
+#endif
 constexpr int kCtrlBytes = 640;  // shared-memory control block
 constexpr int kCounters = 8;     // 0 overflow, 1 error flags (bit 0 zero-norm dipole, bit 1 fp16 filter range), 2 survivors, 3 in-range pairs,
                                  // 4 count kernel self-check mismatches (GFN_DEBUG=8), 5 count kernel: pairs evaluated in fp64,
