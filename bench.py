@@ -884,6 +884,8 @@ def run_single_process(args):
         s1 = r.stats()
         out[label] = {"value": K * F * per / dt / 1e9, "ms_per_step": dt / K * 1e3, "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) / K,
                       "kernel_ms_sum_over_devices_per_step": (s1["kernel_ms"] - s0["kernel_ms"]) / K, "ndev": s1["ndev"],
+                      "kernel_ms_busiest_device_per_step": (s1["kernel_ms_max_device"] - s0["kernel_ms_max_device"]) / K,
+                      "frames_per_device_min_max": [s1["frames_min_device"] - s0["frames_min_device"], s1["frames_max_device"] - s0["frames_max_device"]],
                       "counts_exact": bool(float(hist[:HN].sum()) == 2.0 * (s1["in_range"] - s1["overflow"]))}
         del r
     print(json.dumps(out), flush=True)

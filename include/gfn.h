@@ -113,6 +113,9 @@ typedef struct gfn_stats {
     double tile_visits;       /* GFN_FLAG_CELLS: (core tile, surround tile) pairs the pair kernel visited so far ... */
     double tile_visits_dense; /* ... and how many the un-pruned enumeration has for the same frames */
     int    cells;             /* 1 if tile skipping is active */
+    double frames_max_device; /* frames submitted to the device that got the most / the fewest of them (block calls deal */
+    double frames_min_device; /* ... every device the same number +- 1) */
+    double kernel_ms_max_device;  /* pair-kernel time of the busiest device */
 } gfn_stats_t;
 
 /* Number of CUDA devices visible (0 if none / no driver).  Never fails. */

@@ -889,14 +889,21 @@ static int enqueue_direct_parallel(gfn_t* h, int nframes, const FrameSrc& src, b
     }
     if (box_dims)
         for (int f = 0; f < nframes; ++f) { int rc = validate_box(h, box_dims + 6ll * f); if (rc) return rc; }
+    // every device gets the same number of frames of this call (+- 1, the extra ones starting at the device whose turn it
+    // is): dealing whole batches round-robin until the frames run out leaves the first devices up to a batch ahead of the
+    // last ones, and the call takes as long as the fullest device (8 devices, 512 frames, batches of 15: 74 vs 59 frames)
+    std::vector<int> quota(nd, nframes / nd);
+    for (int r = 0; r < nframes % nd; ++r) quota[(h->next_dev + r) % nd] += 1;
     for (int f = 0; f < nframes; ) {
+        if (quota[h->next_dev] == 0) { h->next_dev = (h->next_dev + 1) % nd; continue; }
         Dev& d = h->devs[h->next_dev];
         int k = h->batch_frames;
         if (d.ramp < h->batch_frames && k > d.ramp) k = d.ramp;
-        if (k > nframes - f) k = nframes - f;
+        if (k > quota[h->next_dev]) k = quota[h->next_dev];
         jobs[h->next_dev].push_back(Job{f, k});
         if (d.ramp < h->batch_frames) d.ramp *= 2;
         f += k;
+        quota[h->next_dev] -= k;
         h->next_dev = (h->next_dev + 1) % nd;
     }
     std::vector<int> rcs(nd, GFN_OK);
@@ -935,9 +942,19 @@ static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased
         cudaGetLastError();
         return idle;
     };
+    // a block call on several devices gives every device the same number of frames (see enqueue_direct_parallel); frame by
+    // frame calls keep filling one device's batch at a time
+    const int nd = (int)h->devs.size();
+    std::vector<int> quota;
+    if (nd > 1 && nframes >= 2 * nd) {
+        quota.assign(nd, nframes / nd);
+        for (int r = 0; r < nframes % nd; ++r) quota[(h->next_dev + r) % nd] += 1;
+    }
     int f = 0;
     while (f < nframes) {
-        Dev& d = h->devs[h->next_dev];
+        if (!quota.empty() && quota[h->next_dev] == 0) { h->next_dev = (h->next_dev + 1) % nd; continue; }
+        const int di = h->next_dev;
+        Dev& d = h->devs[di];
         Batch* b = &d.ring[d.cur];
         if (b->nframes > 0 && (b->aliased != aliased || b->atoms != atoms || b->direct || direct)) {
             // layout change, or a batch that references caller memory (it never spans two calls): close the batch
@@ -962,6 +979,7 @@ static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased
         // gets a short batch instead of waiting for a full one
         int k = h->batch_frames - b->nframes;
         if (k > nframes - f) k = nframes - f;
+        if (!quota.empty() && k > quota[di]) k = quota[di];
         const bool idle = device_idle(d);
         if (direct) {
             // page-locked frames cost the host nothing, but a batch runs only after ALL its frames have crossed PCIe: an idle
@@ -1026,11 +1044,14 @@ static int enqueue_loop(gfn_t* h, int nframes, const FrameSrc& src, bool aliased
         bool go = b->nframes == h->batch_frames;
         if (!go && b->nframes >= h->idle_frames) go = idle || device_idle(d);
         if (!go && direct) go = true;                            // a direct batch is exactly what this pass referenced (it never spans calls)
+        if (!quota.empty()) quota[di] -= k;
         if (go) {
             int rc = submit(h, d);
             if (rc) return rc;
             if (direct && d.ramp < h->batch_frames) d.ramp *= 2;
-            h->next_dev = (h->next_dev + 1) % (int)h->devs.size();
+            h->next_dev = (h->next_dev + 1) % nd;
+        } else if (!quota.empty() && quota[di] == 0) {
+            h->next_dev = (h->next_dev + 1) % nd;                // this device has its share; the open batch goes out with the next call or flush
         }
     }
     return GFN_OK;
@@ -1456,6 +1477,12 @@ int gfn_stats(gfn_t* h, gfn_stats_t* out)
         CU(cudaMemcpy(c, d.counters, sizeof(c), cudaMemcpyDeviceToHost));
         out->overflow += (double)c[0]; out->survivors += (double)c[2]; out->in_range += (double)c[3];
         out->selfcheck_bad += (double)c[4]; out->exact_evals += (double)c[5]; out->tile_visits += (double)c[6];
+    }
+    out->frames_min_device = h->devs.empty() ? 0.0 : h->devs[0].st.frames;
+    for (Dev& d : h->devs) {
+        if (d.st.frames > out->frames_max_device) out->frames_max_device = d.st.frames;
+        if (d.st.frames < out->frames_min_device) out->frames_min_device = d.st.frames;
+        if (d.st.kernel_ms > out->kernel_ms_max_device) out->kernel_ms_max_device = d.st.kernel_ms;
     }
     const PairConfig& c = h->devs[0].cfg;
     out->filter_fp64 = c.filter_fp64; out->hist_mode = c.hist_mode; out->warps_per_block = c.warps; out->hist_replicas = c.nrep;

@@ -54,6 +54,9 @@ cdef extern from "gfn.h":
         double tile_visits
         double tile_visits_dense
         int cells
+        double frames_max_device
+        double frames_min_device
+        double kernel_ms_max_device
     int GFN_OK, GFN_EINVAL, GFN_ECUDA, GFN_ENCCL, GFN_EZERODIV, GFN_ENOMEM, GFN_ENODEV
     unsigned GFN_FLAG_PER_PARTICLE, GFN_FLAG_FILTER_FP64, GFN_FLAG_DISCARD_OVERFLOW, GFN_FLAG_HIST_GLOBAL
     int gfn_device_count() nogil
@@ -707,7 +710,9 @@ cdef class _Backend:
                     warps_per_block=s.warps_per_block, blocks_per_sm=s.blocks_per_sm, grid=s.grid,
                     smem_bytes=s.smem_bytes, batch_frames=s.batch_frames, ndev=s.ndev, hist_replicas=s.hist_replicas,
                     kernel=("ring", "dense", "count")[s.dense], exact_evals=s.exact_evals, selfcheck_bad=s.selfcheck_bad,
-                    cells=bool(s.cells), tile_visits=s.tile_visits, tile_visits_dense=s.tile_visits_dense)
+                    cells=bool(s.cells), tile_visits=s.tile_visits, tile_visits_dense=s.tile_visits_dense,
+                    frames_max_device=s.frames_max_device, frames_min_device=s.frames_min_device,
+                    kernel_ms_max_device=s.kernel_ms_max_device)
 
 
 _ts_cache = {}

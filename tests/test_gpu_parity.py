@@ -742,6 +742,35 @@ def test_two_devices_block_and_page_locked_feeds(serial, monkeypatch):
         assert np.array_equal(ha[:280], ref[:280]) and np.array_equal(hb[:280], ref[:280])
         assert_hist_close(ha, ref, 280); assert_hist_close(hb, ref, 280)
     assert a.stats()["frames"] == nf and a.stats()["ndev"] == 2 and a.volume_list == o.volume_list
+    for r in (a, b):                                     # three calls, each dealt evenly (+- 1 frame)
+        st = r.stats()
+        assert st["frames_max_device"] - st["frames_min_device"] <= 3 and st["frames_min_device"] >= 9
+
+
+@pytest.mark.skipif("_ngpu() < 2")
+@pytest.mark.parametrize("pinned", [True, False])
+def test_two_devices_block_call_is_dealt_evenly(pinned, monkeypatch):
+    """A block call gives every device the same number of frames: dealing whole batches round-robin until the frames run
+    out would leave device 0 a batch ahead (46 frames in batches of 5: 25 vs 21), and the call lasts as long as the
+    fullest device."""
+    from newanalysis.gfunction import pinned_empty
+    monkeypatch.setenv("GFN_BATCH_FRAMES", "5")
+    n, L, nf = 700, 50.0, 46
+    rng = np.random.default_rng(99)
+    c = pinned_empty((nf, n, 3)) if pinned else np.empty((nf, n, 3))
+    c[:] = rng.random((nf, n, 3)) * L
+    two = RDF(["000"], 0.0, 12.0, 0.05, n, n, n, n, L, devices=[0, 1])
+    one = RDF(["000"], 0.0, 12.0, 0.05, n, n, n, n, L)
+    two.calcFrames(c, c, None, None, pinned=pinned)
+    cc = np.array(c)
+    one.calcFrames(cc, cc, None, None)
+    assert np.array_equal(two.raw_histogram()[:240], one.raw_histogram()[:240])
+    st = two.stats()
+    assert st["frames"] == nf and st["frames_max_device"] == 23 and st["frames_min_device"] == 23
+    two.calcFrames(c[:7], c[:7], None, None, pinned=pinned)          # odd count: one device gets the extra frame
+    two.sync()
+    st = two.stats()
+    assert st["frames"] == nf + 7 and st["frames_max_device"] - st["frames_min_device"] == 1
 
 
 @pytest.mark.skipif("_ngpu() < 2")
