@@ -144,7 +144,9 @@ int gfn_update_box(gfn_t *h, const double box_dim[6]);
 int gfn_enqueue_frame(gfn_t *h, const double *c1, const double *c2, const double *d1, const double *d2);
 
 /* Batch extension: nframes frames, frame f of every array starts stride_k doubles after frame f-1
- * (stride 0 is not allowed).  box_dims: NULL = current box for all, else 6 doubles per frame. */
+ * (stride 0 is not allowed).  box_dims: NULL = current box for all, else 6 doubles per frame.
+ * On a handle with several devices a call of at least two frames per device gives every device the same number of
+ * frames (+- 1): the call lasts as long as its fullest device (gfn_stats: frames_max_device / frames_min_device). */
 int gfn_enqueue_frames(gfn_t *h, int nframes,
                        const double *c1, long long stride_c1, const double *c2, long long stride_c2,
                        const double *d1, long long stride_d1, const double *d2, long long stride_d2,
